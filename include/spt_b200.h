@@ -1,0 +1,199 @@
+/*
+ * spt_b200.h — C ABI of libspt_b200.so, the B200 (sm_100a) implementation of the SPT hot path:
+ * PQ sparse multi-head attention (cdist -> lookup -> sddmm -> softmax -> spmm, fwd + bwd, CSR->CSC)
+ * and the routed-FFN grouped GEMM.
+ *
+ * This is the drop-in boundary: it replaces the 7 pybind entry points of the reference's torch
+ * extension `naive_gpt.ext` (reference extension/entry.cpp:43-56) and adds the fused / FFN entry
+ * points listed in SURVEY.md section 8(b).  Plain pointers and sizes only — no torch types.
+ * The Python binding that mirrors the reference's `naive_gpt.ext` on top of this ABI is
+ * spt_proto_b200/ext.py; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - tensors are dense, row-major, contiguous (the reference's CHECK_DIM requires contiguity,
+ *     extension/common.h:13-18);
+ *   - `dtype` selects the element type of q/k/v-like operands: SPT_F32 or SPT_BF16.  Indices are
+ *     int32, CSR values / probabilities / distances are always fp32, accumulation is fp32;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Every kernel is
+ *     launched on it; nothing synchronises the device;
+ *   - the return value is an spt_status; spt_last_error() returns a thread-local message;
+ *   - the callee never allocates device memory: outputs and workspaces are caller-provided
+ *     (ownership rule of SURVEY.md section 8(b): the torch caching allocator owns everything).
+ */
+#ifndef SPT_B200_H
+#define SPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *spt_stream_t; /* cudaStream_t */
+
+typedef enum {
+    SPT_OK = 0,
+    SPT_ERR_INVALID_ARGUMENT = 1, /* bad shape / null pointer; maps to TORCH_CHECK -> RuntimeError */
+    SPT_ERR_UNSUPPORTED = 2,      /* legal in principle, no kernel instantiated                    */
+    SPT_ERR_CUDA = 3              /* launch or runtime error (cudaGetLastError)                    */
+} spt_status;
+
+typedef enum { SPT_F32 = 0, SPT_BF16 = 1 } spt_dtype;
+
+#define SPT_ABI_VERSION 1
+
+int spt_abi_version(void);
+const char *spt_last_error(void);
+/* Number of kernel launches issued through this library by the calling process (all threads).
+ * bench.py uses the difference across the timed region for its `gpu_launches` claim. */
+uint64_t spt_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) cdist — replaces cdist_forward_cuda / cdist_backward_cuda (extension/cdist.cu:185-333).
+ * query [m, n, dc] (dtype), table [m, c, dc] fp32.
+ * distance [m, n, c] fp32 (may be NULL: codes only), indices [m, n] int32.
+ * L1 distance summed over i ascending in fp32, strict-< running minimum: lowest index wins ties.
+ * Lifted restrictions vs the reference: any n, any c >= 1, dc in [1, 64].
+ * ------------------------------------------------------------------------------------------ */
+int spt_cdist_fwd(const void *query, const float *table, float *distance, int32_t *indices,
+                  int m, int64_t n, int c, int dc, int dtype, spt_stream_t stream);
+
+/* grad_distance [m, n, c] -> grad_query [m, n, dc], grad_table [m, c, dc] (all fp32).
+ * sgn(q - t) = +1 if q - t > 0 else -1 (cdist.cu:117,168).  grad_table is accumulated with a
+ * deterministic two-stage reduction; `workspace` must hold spt_cdist_bwd_workspace_bytes(). */
+size_t spt_cdist_bwd_workspace_bytes(int m, int64_t n, int c, int dc);
+int spt_cdist_bwd(const float *query, const float *table, const float *grad_distance,
+                  float *grad_query, float *grad_table, void *workspace,
+                  int m, int64_t n, int c, int dc, spt_stream_t stream);
+
+/* Fused PQBase.forward(mode='encode') (naive_gpt/layers/basic/quantizer.py:26-77): z [rows, m*dc]
+ * (dtype) in its natural head-major layout -> codes [rows, m] int32.  No transposed copy, no
+ * distance tensor. */
+int spt_pq_encode(const void *z, const float *table, int32_t *codes,
+                  int64_t rows, int m, int c, int dc, int dtype, spt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) lookup — replaces lookup_forward_cuda (extension/lookup.cu:87-174).
+ * query_codes, key_codes [B, S, m] int32 -> output [B, S, nnz] int32, nnz = S / sparse_coeff.
+ * Bit-exact with the reference kernel's semantics (bucketed causal candidate selection, zero
+ * padding; see oracle/spt_oracle.py::lookup_spec).  Codes are compared modulo 2^16 like the
+ * reference's uint16 shared-memory caches.  Every output element is written (no pre-zeroing).
+ * Requirements: m >= 4, nnz % 4 == 0, nnz >= 8, S <= 65536.  The (m, nnz) whitelist of the
+ * reference (lookup.cu:113-169) is lifted.
+ * `workspace` must hold spt_lookup_workspace_bytes(); it may be NULL when that returns 0.
+ * ------------------------------------------------------------------------------------------ */
+size_t spt_lookup_workspace_bytes(int B, int S, int m, int nnz);
+int spt_lookup_fwd(const int32_t *query_codes, const int32_t *key_codes, int32_t *output,
+                   void *workspace, int B, int S, int m, int nnz, spt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) sddmm — replaces sddmm_forward_cuda (extension/sddmm.cpp:3-73) for op(A)=N, op(B)=T:
+ * values[b, e] = <query[b, row(e), :], key[b, indices[b, e], :]>.
+ * indptr [S+1] int32 is shared by the whole batch (stride-0 batch, sddmm.cpp:49);
+ * indices [B, nnz] int32; query, key [B, S, d] (dtype); values [B, nnz] fp32.
+ * `scale`/`clamp`: values = clamp(scale * dot, -clamp, +clamp) when clamp > 0 (fuses
+ * attention.py:125-127); pass scale = 1, clamp = 0 for the plain reference semantics.
+ * ------------------------------------------------------------------------------------------ */
+int spt_sddmm_fwd(const int32_t *indptr, const int32_t *indices, const void *query, const void *key,
+                  float *values, int B, int S, int d, int64_t nnz, float scale, float clamp,
+                  int dtype, spt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (5) spmm — replaces spmm_forward_cuda (extension/spmm.cpp:3-72).
+ * trans = 0: y[b, r, :]  = sum_{e in row r} values[b, e] * x[b, indices[b, e], :]
+ * trans = 1: y[b, c, :]  = sum_{e : indices[b,e] = c} values[b, e] * x[b, row(e), :]
+ *            (the reference's CUSPARSE_OPERATION_TRANSPOSE path used for dK / dV).
+ * x, y [B, S, d]; x is (dtype), y is (out_dtype).  trans = 1 needs the CSC built by
+ * spt_csr2csc (col_ptr, row_idx, perm); summation order is (row ascending, CSR order inside a
+ * row) => bit-reproducible run to run, unlike the atomics-based cuSPARSE path.
+ * ------------------------------------------------------------------------------------------ */
+int spt_spmm_fwd(const int32_t *indptr, const int32_t *indices, const float *values, const void *x,
+                 void *y, int B, int S, int d, int64_t nnz, int dtype, int out_dtype,
+                 spt_stream_t stream);
+int spt_spmm_t_fwd(const int32_t *col_ptr, const int32_t *row_idx, const int32_t *perm,
+                   const float *values, const void *x, void *y, int B, int S, int d, int64_t nnz,
+                   int dtype, int out_dtype, spt_stream_t stream);
+
+/* (a-7) CSR -> CSC (implicit in the reference's transposed cuSPARSE calls, explicit in
+ * legacy/csr2csc.cpp:3-54).  indptr [S+1] shared, indices [B, nnz] ->
+ * col_ptr [B, S+1], row_idx [B, nnz], perm [B, nnz] (values_csc = values[perm]).
+ * Stable: rows ascending inside a column, duplicates keep CSR order. */
+size_t spt_csr2csc_workspace_bytes(int B, int S, int64_t nnz);
+int spt_csr2csc(const int32_t *indptr, const int32_t *indices, int32_t *col_ptr, int32_t *row_idx,
+                int32_t *perm, void *workspace, int B, int S, int64_t nnz, spt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (4) softmax — replaces softmax_forward_cuda / softmax_backward_cuda (extension/softmax.cu:84-148).
+ * Row softmax over the stored entries with the causal predicate (indices[e] <= row) as a 0/1
+ * factor, no max subtraction, denominator clamped to >= 1e-9 (softmax.cu:16-46).
+ * Backward is the TRUE gradient y * (dy - sum(y*dy)) — the reference kernel's clamp of the sum to
+ * >= 1e-9 (softmax.cu:69) is a bug and is not reproduced.
+ * ------------------------------------------------------------------------------------------ */
+int spt_softmax_fwd(const int32_t *indptr, const int32_t *indices, const float *values, float *output,
+                    int B, int S, int64_t nnz, spt_stream_t stream);
+int spt_softmax_bwd(const int32_t *indptr, const int32_t *indices, const float *output,
+                    const float *grad_output, float *grad_values, int B, int S, int64_t nnz,
+                    spt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused sparse attention on the fixed-stride CSR the layer produces (attention.py:115-141):
+ * every row has exactly `k` entries (indices [B, S, k]).  One pass computes
+ *   p = softmax_causal(clamp(scale * q.K[idx], -10, 10)),  y = p . V[idx]
+ * probs [B, S, k] fp32 is written for the backward pass.  q, k, v, y [B, S, d] (dtype).
+ * Backward: grad_y [B,S,d] (dtype) -> grad_q, grad_k, grad_v [B,S,d] fp32 or dtype (out_dtype).
+ * grad_k / grad_v are accumulated through the CSC (deterministic).
+ * ------------------------------------------------------------------------------------------ */
+int spt_sparse_attn_fwd(const int32_t *indices, const void *q, const void *k, const void *v,
+                        float *probs, void *y, int B, int S, int d, int topk, float scale,
+                        float clamp, int dtype, spt_stream_t stream);
+size_t spt_sparse_attn_bwd_workspace_bytes(int B, int S, int d, int topk);
+int spt_sparse_attn_bwd(const int32_t *indices, const int32_t *col_ptr, const int32_t *row_idx,
+                        const int32_t *perm, const void *q, const void *k, const void *v,
+                        const float *probs, const void *grad_y, void *grad_q, void *grad_k,
+                        void *grad_v, void *workspace, int B, int S, int d, int topk, float scale,
+                        float clamp, int dtype, spt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (6) routed FFN — the grouped GEMM the reference only sketches (legacy/routed.cpp:10-68,
+ * legacy/test_routed.py:9-26) and ships as a Python loop (layers/sparse/feedforward.py:47-85).
+ *
+ * spt_route_bucket: prob [T, nb] fp32 (router output) -> top-`k_active` blocks per token
+ * (ties: lowest block index) bucketed by block:
+ *   bucket_ptr [nb+1] int32, bucket_tokens [T*k_active] int32 (token ids, ascending per block),
+ *   token_slots [T, k_active] int32 (position of the token's j-th active block, blocks ascending,
+ *   inside bucket_tokens; used for the deterministic block-ordered combine).
+ * ------------------------------------------------------------------------------------------ */
+size_t spt_route_bucket_workspace_bytes(int64_t T, int nb);
+int spt_route_bucket(const float *prob, int32_t *bucket_ptr, int32_t *bucket_tokens,
+                     int32_t *token_slots, void *workspace, int64_t T, int nb, int k_active,
+                     spt_stream_t stream);
+
+/* Gather rows: dst[i, :] = src[index[i], :] (bf16, `cols` elements per row, cols % 8 == 0). */
+int spt_gather_rows_bf16(const void *src, const int32_t *index, void *dst, int64_t n_rows, int cols,
+                         spt_stream_t stream);
+
+/* Grouped GEMM on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM):
+ *   for every group g and row i in [group_ptr[g], group_ptr[g+1]):
+ *       C[i, :] = epilogue( A[i, :] . B_g^T + bias_g )          A [M_total, K] bf16 (row-major)
+ *   B_g = B + g * b_group_stride, [N, K] bf16 with row stride ldb (K-major), bias_g = bias + g*N
+ *   epilogue: act = 0 none, 1 relu, 2 silu;  optional per-row scale row_scale[i];
+ *   C [M_total, N] bf16 or fp32 (c_dtype) with row stride ldc.
+ * Used for fc1 (A = bucketed tokens, B_g = W1 block g) and fc2 (A = bucketed hidden, B_g = W2
+ * column block g) of the routed FFN, and for the backward products after operand transposes. */
+size_t spt_grouped_gemm_workspace_bytes(int n_groups);
+int spt_grouped_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t ldb, int64_t b_group_stride,
+                          const float *bias, const float *row_scale, void *C, int64_t ldc,
+                          const int32_t *group_ptr, int n_groups, int64_t M_total, int N, int K,
+                          int act, int c_dtype, void *workspace, spt_stream_t stream);
+
+/* Deterministic combine: y[t, :] = bias + sum_j partial[token_slots[t, j], :] in ascending block
+ * order (the accumulation order of feedforward.py:66-81).  partial [T*k_active, d] fp32 or bf16. */
+int spt_ffn_combine(const void *partial, const int32_t *token_slots, const float *bias, void *y,
+                    int64_t T, int d, int k_active, int partial_dtype, int y_dtype, spt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPT_B200_H */

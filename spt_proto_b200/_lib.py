@@ -1,0 +1,60 @@
+"""ctypes loader for libspt_b200.so.  There is NO fallback: if the CUDA library is missing the
+import fails loudly (the product path never routes through torch-eager or the oracle)."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libspt_b200.so")
+
+SPT_OK = 0
+SPT_F32 = 0
+SPT_BF16 = 1
+
+
+class SptLibraryMissing(ImportError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise SptLibraryMissing(
+            f"{LIB_PATH} not found. Build it with `python -m spt_proto_b200.build` "
+            "(or __graft_entry__.build()). spt_proto_b200 has no CPU / eager fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, i32, i64, f32, sz = c.c_void_p, c.c_int, c.c_int64, c.c_float, c.c_size_t
+    sig = {
+        "spt_abi_version": (c.c_int, []),
+        "spt_last_error": (c.c_char_p, []),
+        "spt_launch_count": (c.c_uint64, []),
+        "spt_cdist_fwd": (i32, [vp, vp, vp, vp, i32, i64, i32, i32, i32, vp]),
+        "spt_cdist_bwd_workspace_bytes": (sz, [i32, i64, i32, i32]),
+        "spt_cdist_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp]),
+        "spt_pq_encode": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+        "spt_lookup_workspace_bytes": (sz, [i32, i32, i32, i32]),
+        "spt_lookup_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+        "spt_sddmm_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i64, f32, f32, i32, vp]),
+        "spt_spmm_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, vp]),
+        "spt_spmm_t_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, vp]),
+        "spt_csr2csc_workspace_bytes": (sz, [i32, i32, i64]),
+        "spt_csr2csc": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp]),
+        "spt_softmax_fwd": (i32, [vp, vp, vp, vp, i32, i32, i64, vp]),
+        "spt_softmax_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i64, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError => header/library mismatch, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    # optional symbols added by later ABI revisions are bound lazily in their own modules
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int) -> None:
+    """Map an spt_status to the exception type the reference raises from TORCH_CHECK (RuntimeError)."""
+    if rc != SPT_OK:
+        raise RuntimeError(f"spt_b200: {lib.spt_last_error().decode()} (status {rc})")

@@ -1,0 +1,73 @@
+"""Build libspt_b200.so (sm_100a) in-tree with nvcc.  No torch headers are involved: every TU in
+csrc/ is plain CUDA C++ behind the C ABI of include/spt_b200.h, so the whole library compiles in
+seconds and cross-compiles on a box without a GPU.
+
+    python -m spt_proto_b200.build [--force]
+"""
+from __future__ import annotations
+
+import concurrent.futures
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
+LIB_PATH = os.path.join(LIB_DIR, "libspt_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found; libspt_b200.so cannot be built")
+    return cand
+
+
+def _deps_mtime() -> float:
+    files = glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "spt_b200.h")]
+    return max(os.path.getmtime(f) for f in files)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    dep_t = _deps_mtime()
+    jobs = []
+    objs = []
+    for src in sources:
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if (not force and os.path.exists(obj)
+                and os.path.getmtime(obj) >= max(os.path.getmtime(src), dep_t)):
+            continue
+        jobs.append([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj])
+    if jobs:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as pool:
+            for cmd, res in zip(jobs, pool.map(
+                    lambda c: subprocess.run(c, capture_output=True, text=True), jobs)):
+                if res.returncode != 0:
+                    raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+                if verbose and (res.stdout or res.stderr):
+                    print(res.stdout + res.stderr)
+    if jobs or not os.path.exists(LIB_PATH):
+        cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,545 @@
+// (3) sddmm, (4) CSR softmax, (5) spmm / transposed spmm, (a-7) CSR->CSC on a batched CSR whose
+// indptr is shared by the whole batch (reference: extension/sddmm.cpp, softmax.cu, spmm.cpp,
+// legacy/csr2csc.cpp; call sites naive_gpt/kernels/{sddmm,softmax,spmm}.py).
+//
+// All kernels are warp-per-row (or warp-per-column for the transposed product) over a general CSR:
+// arbitrary indptr, unsorted and possibly duplicated column indices (the lookup stage emits bucket
+// order and zero padding).  Memory-bound stages: the index / value streams are read with coalesced
+// 128-byte warp accesses; dense rows of q/k/v/x are gathered with 16-byte lane loads, L lanes per
+// gathered row (L * 16 B >= row bytes) so that each gathered 128-byte line is touched once.
+#include "common.cuh"
+
+namespace spt {
+
+constexpr int CSR_WARPS = 8;  // warps per block for the warp-per-row kernels
+
+// ---- sddmm -------------------------------------------------------------------------------------
+// values[b,e] = scale * <q[b,row(e),:], k[b,idx[b,e],:]> (optionally clamped).
+// L lanes per gathered key row, G = 32 / L keys in flight per warp instruction.
+template <typename T, int L>
+__global__ void __launch_bounds__(CSR_WARPS * 32)
+sddmm_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, const T *__restrict__ q,
+             const T *__restrict__ k, float *__restrict__ values, int B, int S, int d, int64_t nnz, float scale,
+             float clamp) {
+    constexpr int VEC = Vec16<T>::N;
+    constexpr int G = 32 / L;
+    const int lane = threadIdx.x & 31;
+    const int64_t row_id = (int64_t)blockIdx.x * CSR_WARPS + (threadIdx.x >> 5);
+    if (row_id >= (int64_t)B * S) return;
+    const int b = (int)(row_id / S), r = (int)(row_id % S);
+    const int sub = lane % L, grp = lane / L;
+    const bool has = sub * VEC < d;
+    float qv[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) qv[i] = 0.0f;
+    if (has) Vec16<T>::load(q + ((size_t)b * S + r) * d + sub * VEC, qv);
+    const int e0 = indptr[r], e1 = indptr[r + 1];
+    const int32_t *ip = indices + (size_t)b * nnz;
+    float *vp = values + (size_t)b * nnz;
+    const T *kb = k + (size_t)b * S * d;
+    for (int base = e0; base < e1; base += 32) {
+        const int e = base + lane;
+        const int my_idx = e < e1 ? ip[e] : 0;
+        float mine = 0.0f;
+        const int cnt = min(32, e1 - base);
+#pragma unroll
+        for (int st = 0; st < L; ++st) {  // 32 entries = L steps of G entries
+            if (st * G >= cnt) break;     // warp-uniform
+            const int col = __shfl_sync(FULL, my_idx, st * G + grp);
+            float kv[VEC], acc = 0.0f;
+            if (has) {
+                Vec16<T>::load(kb + (size_t)col * d + sub * VEC, kv);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc = fmaf(qv[i], kv[i], acc);
+            }
+            acc = group_sum<L>(acc);
+            // entry (st*G + g) was computed by group g; lane l wants entry l
+            const float got = __shfl_sync(FULL, acc, (lane % G) * L);
+            if (lane / G == st) mine = got;
+        }
+        if (e < e1) {
+            float v = mine * scale;
+            if (clamp > 0.0f) v = fminf(fmaxf(v, -clamp), clamp);
+            vp[e] = v;
+        }
+    }
+}
+
+// scalar fallback for head dims that are not a multiple of the 16-byte vector
+template <typename T>
+__global__ void __launch_bounds__(CSR_WARPS * 32)
+sddmm_scalar_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, const T *__restrict__ q,
+                    const T *__restrict__ k, float *__restrict__ values, int B, int S, int d, int64_t nnz,
+                    float scale, float clamp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row_id = (int64_t)blockIdx.x * CSR_WARPS + (threadIdx.x >> 5);
+    if (row_id >= (int64_t)B * S) return;
+    const int b = (int)(row_id / S), r = (int)(row_id % S);
+    const T *qp = q + ((size_t)b * S + r) * d;
+    for (int e = indptr[r] + lane; e < indptr[r + 1]; e += 32) {
+        const T *kp = k + ((size_t)b * S + indices[(size_t)b * nnz + e]) * d;
+        float acc = 0.0f;
+        for (int i = 0; i < d; ++i) acc = fmaf(to_f32(qp[i]), to_f32(kp[i]), acc);
+        float v = acc * scale;
+        if (clamp > 0.0f) v = fminf(fmaxf(v, -clamp), clamp);
+        values[(size_t)b * nnz + e] = v;
+    }
+}
+
+// ---- spmm (y = A x) and transposed spmm (y = A^T x through the CSC) ------------------------------
+// One warp per output row.  TRANS = false: entries e in [indptr[r], indptr[r+1]), source row
+// indices[b,e], weight values[b,e].  TRANS = true: entries e' in [col_ptr[b,c], col_ptr[b,c+1]),
+// source row row_idx[b,e'], weight values[b, perm[b,e']].  Accumulation order inside a group is the
+// entry order; groups are combined by a fixed butterfly => deterministic.
+template <typename T, typename TO, int L, bool TRANS>
+__global__ void __launch_bounds__(CSR_WARPS * 32)
+spmm_kernel(const int32_t *__restrict__ ptr, const int32_t *__restrict__ src_idx, const int32_t *__restrict__ perm,
+            const float *__restrict__ values, const T *__restrict__ x, TO *__restrict__ y, int B, int S, int d,
+            int64_t nnz) {
+    constexpr int VEC = Vec16<T>::N;
+    constexpr int G = 32 / L;
+    const int lane = threadIdx.x & 31;
+    const int64_t row_id = (int64_t)blockIdx.x * CSR_WARPS + (threadIdx.x >> 5);
+    if (row_id >= (int64_t)B * S) return;
+    const int b = (int)(row_id / S), r = (int)(row_id % S);
+    const int sub = lane % L, grp = lane / L;
+    const bool has = sub * VEC < d;
+    const int32_t *pp = TRANS ? ptr + (size_t)b * (S + 1) : ptr;
+    const int e0 = pp[r], e1 = pp[r + 1];
+    const int32_t *ip = src_idx + (size_t)b * nnz;
+    const int32_t *pm = TRANS ? perm + (size_t)b * nnz : nullptr;
+    const float *vp = values + (size_t)b * nnz;
+    const T *xb = x + (size_t)b * S * d;
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.0f;
+    for (int base = e0; base < e1; base += 32) {
+        const int e = base + lane;
+        int my_idx = 0;
+        float my_val = 0.0f;
+        if (e < e1) {
+            my_idx = ip[e];
+            my_val = TRANS ? vp[pm[e]] : vp[e];
+        }
+        const int cnt = min(32, e1 - base);
+#pragma unroll
+        for (int st = 0; st < L; ++st) {
+            if (st * G >= cnt) break;  // warp-uniform
+            const int src = st * G + grp;
+            const int col = __shfl_sync(FULL, my_idx, src);
+            const float w = __shfl_sync(FULL, my_val, src);  // 0 for padding lanes
+            if (has) {
+                float xv[VEC];
+                Vec16<T>::load(xb + (size_t)col * d + sub * VEC, xv);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w, xv[i], acc[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+#pragma unroll
+        for (int o = L; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
+    }
+    if (grp == 0 && has) {
+        TO *yp = y + ((size_t)b * S + r) * d + sub * VEC;
+        if constexpr (sizeof(TO) == 4 && VEC == 8) {
+            float lo[4] = {acc[0], acc[1], acc[2], acc[3]}, hi[4] = {acc[4], acc[5], acc[6], acc[7]};
+            Vec16<float>::store(reinterpret_cast<float *>(yp), lo);
+            Vec16<float>::store(reinterpret_cast<float *>(yp) + 4, hi);
+        } else if constexpr (sizeof(TO) == 4) {
+            Vec16<float>::store(reinterpret_cast<float *>(yp), acc);
+        } else if constexpr (VEC == 8) {
+            Vec16<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16 *>(yp), acc);
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) yp[i] = from_f32<TO>(acc[i]);
+        }
+    }
+}
+
+template <typename T, typename TO, bool TRANS>
+__global__ void __launch_bounds__(CSR_WARPS * 32)
+spmm_scalar_kernel(const int32_t *__restrict__ ptr, const int32_t *__restrict__ src_idx,
+                   const int32_t *__restrict__ perm, const float *__restrict__ values, const T *__restrict__ x,
+                   TO *__restrict__ y, int B, int S, int d, int64_t nnz) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row_id = (int64_t)blockIdx.x * CSR_WARPS + (threadIdx.x >> 5);
+    if (row_id >= (int64_t)B * S) return;
+    const int b = (int)(row_id / S), r = (int)(row_id % S);
+    const int32_t *pp = TRANS ? ptr + (size_t)b * (S + 1) : ptr;
+    for (int i = lane; i < d; i += 32) {
+        float acc = 0.0f;
+        for (int e = pp[r]; e < pp[r + 1]; ++e) {
+            const size_t be = (size_t)b * nnz + e;
+            const float w = TRANS ? values[(size_t)b * nnz + perm[be]] : values[be];
+            acc = fmaf(w, to_f32(x[((size_t)b * S + src_idx[be]) * d + i]), acc);
+        }
+        y[((size_t)b * S + r) * d + i] = from_f32<TO>(acc);
+    }
+}
+
+// ---- CSR softmax -------------------------------------------------------------------------------
+// Warp per row; entries strided over lanes (coalesced).  exp without max subtraction, causal
+// predicate as a 0/1 factor, denominator >= 1e-9 (softmax.cu:16-46).
+__global__ void __launch_bounds__(CSR_WARPS * 32)
+softmax_fwd_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                   const float *__restrict__ values, float *__restrict__ output, int B, int S, int64_t nnz) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row_id = (int64_t)blockIdx.x * CSR_WARPS + (threadIdx.x >> 5);
+    if (row_id >= (int64_t)B * S) return;
+    const int b = (int)(row_id / S), r = (int)(row_id % S);
+    const int e0 = indptr[r], e1 = indptr[r + 1];
+    const int32_t *ip = indices + (size_t)b * nnz;
+    const float *vp = values + (size_t)b * nnz;
+    float *op = output + (size_t)b * nnz;
+    constexpr int KEEP = 8;  // rows up to 256 entries stay in registers (the layer's k = S/8 at S = 2048)
+    float ex[KEEP];
+    float sum = 0.0f;
+    int it = 0;
+    for (int e = e0 + lane; e < e1; e += 32, ++it) {
+        const float v = (ip[e] <= r) ? __expf(vp[e]) : 0.0f;
+        if (it < KEEP) ex[it] = v;
+        sum += v;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / fmaxf(1e-9f, sum);
+    it = 0;
+    for (int e = e0 + lane; e < e1; e += 32, ++it) {
+        const float v = it < KEEP ? ex[it] : ((ip[e] <= r) ? __expf(vp[e]) : 0.0f);
+        op[e] = v * inv;
+    }
+}
+
+// dv = y * (dy - sum(y * dy)) on kept entries (true gradient; see header comment in spt_b200.h).
+__global__ void __launch_bounds__(CSR_WARPS * 32)
+softmax_bwd_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                   const float *__restrict__ output, const float *__restrict__ grad_output,
+                   float *__restrict__ grad_values, int B, int S, int64_t nnz) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row_id = (int64_t)blockIdx.x * CSR_WARPS + (threadIdx.x >> 5);
+    if (row_id >= (int64_t)B * S) return;
+    const int b = (int)(row_id / S), r = (int)(row_id % S);
+    const int e0 = indptr[r], e1 = indptr[r + 1];
+    const int32_t *ip = indices + (size_t)b * nnz;
+    const float *yp = output + (size_t)b * nnz;
+    const float *gp = grad_output + (size_t)b * nnz;
+    float *op = grad_values + (size_t)b * nnz;
+    constexpr int KEEP = 8;
+    float ys[KEEP], gs[KEEP];
+    float sum = 0.0f;
+    int it = 0;
+    for (int e = e0 + lane; e < e1; e += 32, ++it) {
+        const bool keep = ip[e] <= r;
+        const float yv = keep ? yp[e] : 0.0f, gv = gp[e];
+        if (it < KEEP) { ys[it] = yv; gs[it] = gv; }
+        sum = fmaf(yv, gv, sum);
+    }
+    sum = warp_sum(sum);
+    it = 0;
+    for (int e = e0 + lane; e < e1; e += 32, ++it) {
+        float yv, gv;
+        if (it < KEEP) { yv = ys[it]; gv = gs[it]; }
+        else { yv = (ip[e] <= r) ? yp[e] : 0.0f; gv = gp[e]; }
+        op[e] = yv * (gv - sum);
+    }
+}
+
+// ---- CSR -> CSC ----------------------------------------------------------------------------------
+// Deterministic, stable counting sort by column, tiled over rows:
+//   K1  per (tile of TR rows, batch): shared-memory histogram of the tile's columns -> tile_cnt[b][tile][c]
+//   K2  per batch: exclusive scan over tiles for every column, then exclusive scan over columns ->
+//       col_ptr[b][c]; tile_cnt becomes the start offset of (tile, column)
+//   K3  one warp per (tile, batch): walks the tile's rows in order, 32 entries at a time; equal
+//       columns inside a chunk are ranked by lane with __match_any_sync, so the result does not
+//       depend on scheduling.
+constexpr int C2C_TR = 32;
+
+__global__ void __launch_bounds__(256)
+csr2csc_count_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                     int32_t *__restrict__ tile_cnt, int S, int64_t nnz, int n_tiles) {
+    extern __shared__ int32_t s_cnt[];
+    const int tile = blockIdx.x, b = blockIdx.y;
+    for (int c = threadIdx.x; c < S; c += blockDim.x) s_cnt[c] = 0;
+    __syncthreads();
+    const int r0 = tile * C2C_TR, r1 = min(S, r0 + C2C_TR);
+    const int e0 = indptr[r0], e1 = indptr[r1];
+    const int32_t *ip = indices + (size_t)b * nnz;
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int c = ip[e];
+        if ((unsigned)c < (unsigned)S) atomicAdd(&s_cnt[c], 1);
+    }
+    __syncthreads();
+    int32_t *out = tile_cnt + ((size_t)b * n_tiles + tile) * S;
+    for (int c = threadIdx.x; c < S; c += blockDim.x) out[c] = s_cnt[c];
+}
+
+__global__ void __launch_bounds__(1024)
+csr2csc_scan_kernel(int32_t *__restrict__ tile_cnt, int32_t *__restrict__ col_ptr, int S, int n_tiles) {
+    extern __shared__ int32_t s_tot[];  // [S] column totals, then their exclusive scan
+    __shared__ int32_t s_warp[32];
+    __shared__ int32_t s_carry;
+    const int b = blockIdx.x;
+    int32_t *tc = tile_cnt + (size_t)b * n_tiles * S;
+    for (int c = threadIdx.x; c < S; c += blockDim.x) {
+        int32_t run = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int32_t v = tc[(size_t)t * S + c];
+            tc[(size_t)t * S + c] = run;
+            run += v;
+        }
+        s_tot[c] = run;
+    }
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    // block-wide exclusive scan of s_tot in slabs of blockDim.x
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int base = 0; base < S; base += blockDim.x) {
+        const int c = base + threadIdx.x;
+        const int32_t v = c < S ? s_tot[c] : 0;
+        int32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t n = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int32_t w = lane < nw ? s_warp[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t n = __shfl_up_sync(FULL, w, o);
+                if (lane >= o) w += n;
+            }
+            s_warp[lane] = w;  // inclusive
+        }
+        __syncthreads();
+        const int32_t carry = s_carry;
+        const int32_t warp_off = wid > 0 ? s_warp[wid - 1] : 0;
+        if (c < S) s_tot[c] = carry + warp_off + inc - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + s_warp[nw - 1];
+        __syncthreads();
+    }
+    for (int c = threadIdx.x; c < S; c += blockDim.x) col_ptr[(size_t)b * (S + 1) + c] = s_tot[c];
+    if (threadIdx.x == 0) col_ptr[(size_t)b * (S + 1) + S] = s_carry;
+}
+
+__global__ void csr2csc_place_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                                     const int32_t *__restrict__ tile_cnt, const int32_t *__restrict__ col_ptr,
+                                     int32_t *__restrict__ row_idx, int32_t *__restrict__ perm, int S, int64_t nnz,
+                                     int n_tiles) {
+    extern __shared__ int32_t s_all[];  // [warps][S] running cursors
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int tile = blockIdx.x * nw + wid, b = blockIdx.y;
+    if (tile >= n_tiles) return;
+    int32_t *cur = s_all + (size_t)wid * S;
+    const int32_t *tc = tile_cnt + ((size_t)b * n_tiles + tile) * S;
+    const int32_t *cp = col_ptr + (size_t)b * (S + 1);
+    for (int c = lane; c < S; c += 32) cur[c] = cp[c] + tc[c];
+    __syncwarp();
+    const int32_t *ip = indices + (size_t)b * nnz;
+    int32_t *ro = row_idx + (size_t)b * nnz, *po = perm + (size_t)b * nnz;
+    const int r0 = tile * C2C_TR, r1 = min(S, r0 + C2C_TR);
+    for (int r = r0; r < r1; ++r) {
+        const int e0 = indptr[r], e1 = indptr[r + 1];
+        for (int base = e0; base < e1; base += 32) {
+            const int e = base + lane;
+            const int c = e < e1 ? ip[e] : -1;
+            const bool ok = (unsigned)c < (unsigned)S;  // out-of-range columns are dropped (as in K1)
+            const unsigned active = __ballot_sync(FULL, ok);
+            if (ok) {
+                const unsigned same = __match_any_sync(active, c);
+                const int rank = __popc(same & ((1u << lane) - 1u));
+                const int leader = __ffs(same) - 1;
+                int32_t start = 0;
+                if (lane == leader) {
+                    start = cur[c];
+                    cur[c] = start + __popc(same);
+                }
+                start = __shfl_sync(same, start, leader);
+                ro[start + rank] = r;
+                po[start + rank] = e;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---- launch helpers ------------------------------------------------------------------------------
+static inline int lanes_for(int d, int vec) {
+    int need = (d + vec - 1) / vec, L = 1;
+    while (L < need) L <<= 1;
+    return L;
+}
+
+template <typename T>
+static int launch_sddmm(const int32_t *indptr, const int32_t *indices, const T *q, const T *k, float *values, int B,
+                        int S, int d, int64_t nnz, float scale, float clamp, cudaStream_t st) {
+    constexpr int VEC = Vec16<T>::N;
+    const int64_t rows = (int64_t)B * S;
+    const unsigned grid = (unsigned)((rows + CSR_WARPS - 1) / CSR_WARPS);
+    const bool vec_ok = (d % VEC == 0) && (d <= 32 * VEC) && ((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0);
+    if (!vec_ok) {
+        sddmm_scalar_kernel<T><<<grid, CSR_WARPS * 32, 0, st>>>(indptr, indices, q, k, values, B, S, d, nnz, scale, clamp);
+        return after_launch("sddmm_scalar_kernel");
+    }
+#define SPT_SDDMM_CASE(LL)                                                                                       \
+    case LL:                                                                                                     \
+        sddmm_kernel<T, LL><<<grid, CSR_WARPS * 32, 0, st>>>(indptr, indices, q, k, values, B, S, d, nnz, scale, clamp); \
+        break;
+    switch (lanes_for(d, VEC)) {
+        SPT_SDDMM_CASE(1)
+        SPT_SDDMM_CASE(2)
+        SPT_SDDMM_CASE(4)
+        SPT_SDDMM_CASE(8)
+        SPT_SDDMM_CASE(16)
+        SPT_SDDMM_CASE(32)
+    }
+#undef SPT_SDDMM_CASE
+    return after_launch("sddmm_kernel");
+}
+
+template <typename T, typename TO, bool TRANS>
+static int launch_spmm(const int32_t *ptr, const int32_t *src_idx, const int32_t *perm, const float *values,
+                       const T *x, TO *y, int B, int S, int d, int64_t nnz, cudaStream_t st) {
+    constexpr int VEC = Vec16<T>::N;
+    const int64_t rows = (int64_t)B * S;
+    const unsigned grid = (unsigned)((rows + CSR_WARPS - 1) / CSR_WARPS);
+    const bool vec_ok = (d % VEC == 0) && (d <= 32 * VEC) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+    if (!vec_ok) {
+        spmm_scalar_kernel<T, TO, TRANS><<<grid, CSR_WARPS * 32, 0, st>>>(ptr, src_idx, perm, values, x, y, B, S, d, nnz);
+        return after_launch("spmm_scalar_kernel");
+    }
+#define SPT_SPMM_CASE(LL)                                                                                        \
+    case LL:                                                                                                     \
+        spmm_kernel<T, TO, LL, TRANS><<<grid, CSR_WARPS * 32, 0, st>>>(ptr, src_idx, perm, values, x, y, B, S, d, nnz); \
+        break;
+    switch (lanes_for(d, VEC)) {
+        SPT_SPMM_CASE(1)
+        SPT_SPMM_CASE(2)
+        SPT_SPMM_CASE(4)
+        SPT_SPMM_CASE(8)
+        SPT_SPMM_CASE(16)
+        SPT_SPMM_CASE(32)
+    }
+#undef SPT_SPMM_CASE
+    return after_launch("spmm_kernel");
+}
+
+template <bool TRANS>
+static int dispatch_spmm(const int32_t *ptr, const int32_t *src_idx, const int32_t *perm, const float *values,
+                         const void *x, void *y, int B, int S, int d, int64_t nnz, int dtype, int out_dtype,
+                         cudaStream_t st) {
+    using bf16 = __nv_bfloat16;
+    if (dtype == SPT_F32 && out_dtype == SPT_F32)
+        return launch_spmm<float, float, TRANS>(ptr, src_idx, perm, values, (const float *)x, (float *)y, B, S, d, nnz, st);
+    if (dtype == SPT_BF16 && out_dtype == SPT_F32)
+        return launch_spmm<bf16, float, TRANS>(ptr, src_idx, perm, values, (const bf16 *)x, (float *)y, B, S, d, nnz, st);
+    if (dtype == SPT_BF16 && out_dtype == SPT_BF16)
+        return launch_spmm<bf16, bf16, TRANS>(ptr, src_idx, perm, values, (const bf16 *)x, (bf16 *)y, B, S, d, nnz, st);
+    return fail(SPT_ERR_UNSUPPORTED, "spmm: dtype combination (%d -> %d) not supported", dtype, out_dtype);
+}
+
+static int c2c_warps_per_block(int S) {
+    int w = (int)((160 * 1024) / ((size_t)S * 4));
+    return w < 1 ? 1 : (w > 4 ? 4 : w);
+}
+
+}  // namespace spt
+
+using namespace spt;
+
+#define SPT_CHECK_CSR(name)                                                                              \
+    SPT_REQUIRE(B >= 1 && S >= 1 && nnz >= 0, name ": bad sizes B=%d S=%d nnz=%lld", B, S, (long long)nnz); \
+    SPT_REQUIRE((int64_t)B * S < ((int64_t)1 << 31) * CSR_WARPS, name ": B*S too large")
+
+extern "C" int spt_sddmm_fwd(const int32_t *indptr, const int32_t *indices, const void *query, const void *key,
+                             float *values, int B, int S, int d, int64_t nnz, float scale, float clamp, int dtype,
+                             spt_stream_t stream) {
+    SPT_REQUIRE(indptr && indices && query && key && values, "sddmm_fwd: null pointer");
+    SPT_CHECK_CSR("sddmm_fwd");
+    SPT_REQUIRE(d >= 1, "sddmm_fwd: bad head dim %d", d);
+    if (nnz == 0) return SPT_OK;
+    if (dtype == SPT_F32)
+        return launch_sddmm(indptr, indices, (const float *)query, (const float *)key, values, B, S, d, nnz, scale, clamp, as_stream(stream));
+    if (dtype == SPT_BF16)
+        return launch_sddmm(indptr, indices, (const __nv_bfloat16 *)query, (const __nv_bfloat16 *)key, values, B, S, d, nnz, scale, clamp, as_stream(stream));
+    return fail(SPT_ERR_INVALID_ARGUMENT, "sddmm_fwd: unknown dtype %d", dtype);
+}
+
+extern "C" int spt_spmm_fwd(const int32_t *indptr, const int32_t *indices, const float *values, const void *x, void *y,
+                            int B, int S, int d, int64_t nnz, int dtype, int out_dtype, spt_stream_t stream) {
+    SPT_REQUIRE(indptr && indices && values && x && y, "spmm_fwd: null pointer");
+    SPT_CHECK_CSR("spmm_fwd");
+    SPT_REQUIRE(d >= 1, "spmm_fwd: bad feature dim %d", d);
+    return dispatch_spmm<false>(indptr, indices, nullptr, values, x, y, B, S, d, nnz, dtype, out_dtype, as_stream(stream));
+}
+
+extern "C" int spt_spmm_t_fwd(const int32_t *col_ptr, const int32_t *row_idx, const int32_t *perm, const float *values,
+                              const void *x, void *y, int B, int S, int d, int64_t nnz, int dtype, int out_dtype,
+                              spt_stream_t stream) {
+    SPT_REQUIRE(col_ptr && row_idx && perm && values && x && y, "spmm_t_fwd: null pointer");
+    SPT_CHECK_CSR("spmm_t_fwd");
+    SPT_REQUIRE(d >= 1, "spmm_t_fwd: bad feature dim %d", d);
+    return dispatch_spmm<true>(col_ptr, row_idx, perm, values, x, y, B, S, d, nnz, dtype, out_dtype, as_stream(stream));
+}
+
+extern "C" int spt_softmax_fwd(const int32_t *indptr, const int32_t *indices, const float *values, float *output, int B,
+                               int S, int64_t nnz, spt_stream_t stream) {
+    SPT_REQUIRE(indptr && indices && values && output, "softmax_fwd: null pointer");
+    SPT_CHECK_CSR("softmax_fwd");
+    if (nnz == 0) return SPT_OK;
+    const int64_t rows = (int64_t)B * S;
+    softmax_fwd_kernel<<<(unsigned)((rows + CSR_WARPS - 1) / CSR_WARPS), CSR_WARPS * 32, 0, as_stream(stream)>>>(
+        indptr, indices, values, output, B, S, nnz);
+    return after_launch("softmax_fwd_kernel");
+}
+
+extern "C" int spt_softmax_bwd(const int32_t *indptr, const int32_t *indices, const float *output,
+                               const float *grad_output, float *grad_values, int B, int S, int64_t nnz,
+                               spt_stream_t stream) {
+    SPT_REQUIRE(indptr && indices && output && grad_output && grad_values, "softmax_bwd: null pointer");
+    SPT_CHECK_CSR("softmax_bwd");
+    if (nnz == 0) return SPT_OK;
+    const int64_t rows = (int64_t)B * S;
+    softmax_bwd_kernel<<<(unsigned)((rows + CSR_WARPS - 1) / CSR_WARPS), CSR_WARPS * 32, 0, as_stream(stream)>>>(
+        indptr, indices, output, grad_output, grad_values, B, S, nnz);
+    return after_launch("softmax_bwd_kernel");
+}
+
+extern "C" size_t spt_csr2csc_workspace_bytes(int B, int S, int64_t nnz) {
+    (void)nnz;
+    const size_t n_tiles = (size_t)(S + C2C_TR - 1) / C2C_TR;
+    return (size_t)B * n_tiles * S * sizeof(int32_t);
+}
+
+extern "C" int spt_csr2csc(const int32_t *indptr, const int32_t *indices, int32_t *col_ptr, int32_t *row_idx,
+                           int32_t *perm, void *workspace, int B, int S, int64_t nnz, spt_stream_t stream) {
+    SPT_REQUIRE(indptr && indices && col_ptr && row_idx && perm && workspace, "csr2csc: null pointer");
+    SPT_CHECK_CSR("csr2csc");
+    SPT_REQUIRE(B <= 65535, "csr2csc: batch %d exceeds grid limit", B);
+    SPT_REQUIRE((size_t)S * 4 <= 200 * 1024, "csr2csc: S=%d too large for the shared-memory column cursors", S);
+    SPT_REQUIRE(nnz < ((int64_t)1 << 31), "csr2csc: nnz too large");
+    cudaStream_t st = as_stream(stream);
+    const int n_tiles = (S + C2C_TR - 1) / C2C_TR;
+    int32_t *tile_cnt = (int32_t *)workspace;
+    const size_t smem_s = (size_t)S * 4;
+    if (smem_s > 48 * 1024) {
+        cudaFuncSetAttribute(csr2csc_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+        cudaFuncSetAttribute(csr2csc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+    }
+    csr2csc_count_kernel<<<dim3(n_tiles, B), 256, smem_s, st>>>(indptr, indices, tile_cnt, S, nnz, n_tiles);
+    SPT_LAUNCH_CHECK("csr2csc_count_kernel");
+    csr2csc_scan_kernel<<<B, 1024, smem_s, st>>>(tile_cnt, col_ptr, S, n_tiles);
+    SPT_LAUNCH_CHECK("csr2csc_scan_kernel");
+    const int nw = c2c_warps_per_block(S);
+    const size_t smem_p = smem_s * nw;
+    if (smem_p > 48 * 1024)
+        cudaFuncSetAttribute(csr2csc_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+    csr2csc_place_kernel<<<dim3((n_tiles + nw - 1) / nw, B), nw * 32, smem_p, st>>>(indptr, indices, tile_cnt, col_ptr,
+                                                                                   row_idx, perm, S, nnz, n_tiles);
+    SPT_LAUNCH_CHECK("csr2csc_place_kernel");
+    return SPT_OK;
+}

@@ -1,0 +1,450 @@
+// (2) lookup: PQ-code match counting + bucketed causal candidate selection -> fixed-stride CSR.
+//
+// Replaces lookup_forward_cuda (reference extension/lookup.cu:87-174).  The output is bit-exact with
+// the reference kernel's semantics (restated in oracle/spt_oracle.py::lookup_spec):
+//   row r, lane t in 0..3 owns keys j = t (mod 4), j <= r (ascending); bucket(j) = min(3, matches /
+//   (m/4)); lane t fills output positions t, t+4, ... < min(r+1, nnz) with its keys ordered (bucket
+//   desc, j asc); a (lane, bucket) list holds cap_t = nnz/4 (t < 2) or nnz/4 - 1 (t >= 2) entries;
+//   overflow of lanes 2/3 lands on lane 1/0's last slot of that bucket (latest j wins); unfilled
+//   positions are 0.
+//
+// B200 design (not a port of the reference's 64-thread, serial-per-lane kernel):
+//   * Bit-sliced matching.  A pre-pass turns the key codes of a head into bitmaps
+//       KB[s][w][v][t] : bit i set  <=>  key j = 128 w + 4 i + t has code v in subspace s,
+//     i.e. the keys of one reference "lane" t are contiguous bits.  For query row r the match
+//     indicator of subspace s over 32 keys is ONE shared-memory word KB[s][w][code_r(s)][t]; the m
+//     words are summed with a carry-save adder tree (LOP3) and compared against the bucket
+//     thresholds — about 1 integer instruction per (query, key) pair instead of ~20.
+//   * One thread per (row, lane t): pass 1 popcounts bucket sizes, pass 2 walks set bits and writes
+//     only the entries that survive (<= nnz/4 per thread) into a shared-memory row image, which is
+//     flushed with coalesced 128-bit stores.  Every output element is written (zeros included).
+//   * Codes >= 16 (or m without a specialised adder) take a generic compare path with the same
+//     selection logic; the choice is made on the device through a flag, no host sync.
+//
+// Bound: integer-issue (S^2/2 * m bit-ops per head) and the S*nnz*4-byte index write; see DESIGN.md.
+#include "common.cuh"
+
+namespace spt {
+
+constexpr int LK_ROWS = 32;                  // query rows per block
+constexpr int LK_THREADS = LK_ROWS * 4;      // one thread per (row, lane t)
+constexpr int LK_CV = 16;                    // code values covered by the bitmap path
+constexpr int LK_WORD_U32 = LK_CV * 4;       // u32 per (subspace, 128-key word): [v][t]
+
+// ------------------------------------------------------------------------------------------
+// Pre-pass: key codes [B, S, m] -> bitmaps KB[b][s][w][v][t], overflow flag if any code >= 16.
+// grid (W, B), block 128: warp = lane t, lane = bit i  (key j = 128 w + 4 i + t).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+lookup_pack_kernel(const int32_t *__restrict__ key_codes, uint32_t *__restrict__ kb, int *__restrict__ flag,
+                   int S, int m, int W) {
+    const int w = blockIdx.x, b = blockIdx.y;
+    const int t = threadIdx.x >> 5, i = threadIdx.x & 31;
+    const int j = 128 * w + 4 * i + t;
+    const int32_t *kp = key_codes + ((size_t)b * S + j) * m;
+    bool overflow = false;
+    for (int s = 0; s < m; ++s) {
+        const unsigned code = (j < S) ? ((unsigned)kp[s] & 0xffffu) : 0xffffu;
+        overflow |= (j < S) && (code >= (unsigned)LK_CV);
+        unsigned mine = 0;
+#pragma unroll
+        for (int v = 0; v < LK_CV; ++v) {
+            const unsigned word = __ballot_sync(FULL, code == (unsigned)v);
+            if (i == v) mine = word;
+        }
+        if (i < LK_CV) kb[(((size_t)b * m + s) * W + w) * LK_WORD_U32 + i * 4 + t] = mine;
+    }
+    if (__any_sync(FULL, overflow) && i == 0) atomicOr(flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// Bit-sliced population count of M one-bit inputs (32 keys per word) -> NB count bit-planes.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t &s, uint32_t &cy) {
+    s = a ^ b ^ c;
+    cy = (a & b) | (c & (a ^ b));
+}
+
+template <int M>
+struct BitCount {
+    static constexpr int NB = (M >= 32) ? 6 : (M >= 16) ? 5 : (M >= 8) ? 4 : (M >= 4) ? 3 : 2;
+    // generic ripple-carry accumulate
+    __device__ __forceinline__ static void run(const uint32_t (&x)[M], uint32_t (&bits)[NB]) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) bits[b] = 0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            uint32_t carry = x[i];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const uint32_t t = bits[b] & carry;
+                bits[b] ^= carry;
+                carry = t;
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ void count8(const uint32_t *x, uint32_t *bits /*4*/) {
+    uint32_t s0, c0, s1, c1, s2, c2, s4, c4;
+    full_add(x[0], x[1], x[2], s0, c0);
+    full_add(x[3], x[4], x[5], s1, c1);
+    full_add(x[6], x[7], s0, s2, c2);
+    bits[0] = s1 ^ s2;
+    const uint32_t c3 = s1 & s2;
+    full_add(c0, c1, c2, s4, c4);
+    bits[1] = s4 ^ c3;
+    const uint32_t c5 = s4 & c3;
+    bits[2] = c4 ^ c5;
+    bits[3] = c4 & c5;
+}
+
+template <>
+struct BitCount<8> {
+    static constexpr int NB = 4;
+    __device__ __forceinline__ static void run(const uint32_t (&x)[8], uint32_t (&bits)[4]) { count8(x, bits); }
+};
+
+template <>
+struct BitCount<16> {
+    static constexpr int NB = 5;
+    __device__ __forceinline__ static void run(const uint32_t (&x)[16], uint32_t (&bits)[5]) {
+        uint32_t s[7], c[8];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) full_add(x[3 * i], x[3 * i + 1], x[3 * i + 2], s[i], c[i]);
+        full_add(s[0], s[1], s[2], s[5], c[5]);
+        full_add(s[3], s[4], x[15], s[6], c[6]);
+        bits[0] = s[5] ^ s[6];
+        c[7] = s[5] & s[6];
+        count8(c, bits + 1);
+    }
+};
+
+// count >= T (compile-time T) on bit-planes, LSB first.
+template <int NB>
+__device__ __forceinline__ uint32_t ge_const(const uint32_t (&bits)[NB], int T) {
+    uint32_t ge = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) ge = ((T >> b) & 1) ? (bits[b] & ge) : (bits[b] | ge);
+    if (T >> NB) ge = 0;
+    return ge;
+}
+
+// ------------------------------------------------------------------------------------------
+// Bucket providers: masks[s] bit i set <=> own key index 32*w + i (j = 4*(32w+i) + t) is in bucket s.
+// ------------------------------------------------------------------------------------------
+template <int M>
+struct BitmapMatcher {
+    const uint32_t *s_kb;  // shared: [M][cw][16][4] for the current chunk
+    int cw;                // words in the chunk
+    int w0;                // first word of the chunk
+    unsigned q[M];         // query codes (mod 2^16)
+    int t;
+    __device__ __forceinline__ void buckets(int w, uint32_t valid, uint32_t (&mask)[4]) const {
+        uint32_t x[M];
+#pragma unroll
+        for (int s = 0; s < M; ++s)
+            x[s] = (q[s] < (unsigned)LK_CV) ? s_kb[((s * cw + (w - w0)) * LK_CV + q[s]) * 4 + t] : 0u;
+        uint32_t bits[BitCount<M>::NB];
+        BitCount<M>::run(x, bits);
+        constexpr int DIV = M / 4;
+        const uint32_t g1 = ge_const(bits, DIV), g2 = ge_const(bits, 2 * DIV), g3 = ge_const(bits, 3 * DIV);
+        mask[3] = g3 & valid;
+        mask[2] = g2 & ~g3 & valid;
+        mask[1] = g1 & ~g2 & valid;
+        mask[0] = ~g1 & valid;
+    }
+};
+
+struct GenericMatcher {
+    const int32_t *kc;     // key codes of this head [S][m]
+    const uint16_t *s_q;   // shared: this row's query codes [m]
+    int m, div, t;
+    __device__ __forceinline__ void buckets(int w, uint32_t valid, uint32_t (&mask)[4]) const {
+        mask[0] = mask[1] = mask[2] = mask[3] = 0;
+        uint32_t v = valid;
+        while (v) {
+            const int i = __ffs(v) - 1;
+            v &= v - 1;
+            const int j = 4 * (32 * w + i) + t;
+            const int32_t *kp = kc + (size_t)j * m;
+            int cnt = 0;
+            for (int s = 0; s < m; ++s) cnt += ((unsigned)s_q[s] == ((unsigned)kp[s] & 0xffffu));
+            const int bucket = min(3, cnt / div);
+            mask[bucket] |= 1u << i;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Selection core shared by both paths.  Thread = (row, t).
+// ------------------------------------------------------------------------------------------
+struct LaneState {
+    int len[4], take[4], start[4], done[4];
+    int s_need, track, last_j;
+};
+
+__device__ __forceinline__ uint32_t valid_mask(int w, int nkeys) {
+    const int rem = nkeys - 32 * w;
+    return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+}
+
+__device__ __forceinline__ void plan_lane(LaneState &st, int t, int n_t, int quarter) {
+    const int cap = (t < 2) ? quarter : quarter - 1;
+    int rem = n_t, acc = 0;
+    st.s_need = -1;
+#pragma unroll
+    for (int s = 3; s >= 0; --s) {
+        const int stored = min(st.len[s], cap);
+        st.take[s] = min(stored, rem);
+        st.start[s] = acc;
+        acc += st.take[s];
+        rem -= st.take[s];
+        st.done[s] = 0;
+        if (t < 2 && st.take[s] == quarter) st.s_need = s;
+    }
+    // lanes 2/3 learn which bucket (if any) their partner (lane 3 - t == tid ^ 3) reads its clobbered slot from
+    const int partner_need = __shfl_xor_sync(FULL, st.s_need, 3);
+    st.track = -1;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+        if (partner_need == s && st.len[s] >= quarter) st.track = s;
+    st.last_j = -1;
+}
+
+__device__ __forceinline__ void place_word(LaneState &st, const uint32_t (&mask)[4], int w, int t,
+                                           uint16_t *row_img) {
+#pragma unroll
+    for (int s = 3; s >= 0; --s) {
+        uint32_t mk = mask[s];
+        if (st.track == s && mk) st.last_j = 4 * (32 * w + 31 - __clz(mk)) + t;
+        while (mk && st.done[s] < st.take[s]) {
+            const int i = __ffs(mk) - 1;
+            mk &= mk - 1;
+            row_img[t + 4 * (st.start[s] + st.done[s])] = (uint16_t)(4 * (32 * w + i) + t);
+            st.done[s] += 1;
+        }
+    }
+}
+
+__device__ __forceinline__ void fix_clobber(const LaneState &st, int t, int quarter, uint16_t *row_img) {
+    const int recv = __shfl_xor_sync(FULL, st.track >= 0 ? st.last_j : -1, 3);
+    if (st.s_need >= 0 && recv >= 0) {
+        const int p = t + 4 * (quarter - 1);
+        if (recv > (int)row_img[p]) row_img[p] = (uint16_t)recv;
+    }
+}
+
+__device__ __forceinline__ void flush_rows(const uint16_t *s_out, int32_t *out, int b, int r0, int S, int nnz) {
+    const int per_row = nnz / 4;
+    for (int idx = threadIdx.x; idx < LK_ROWS * per_row; idx += blockDim.x) {
+        const int rl = idx / per_row, c4 = idx % per_row;
+        const int r = r0 + rl;
+        if (r >= S) break;
+        const uint2 v = *reinterpret_cast<const uint2 *>(s_out + rl * nnz + 4 * c4);
+        int4 o;
+        o.x = v.x & 0xffff; o.y = v.x >> 16; o.z = v.y & 0xffff; o.w = v.y >> 16;
+        st_stream(reinterpret_cast<int4 *>(out + ((size_t)b * S + r) * nnz) + c4, o);
+    }
+}
+
+// ---- bitmap path ---------------------------------------------------------------------------
+// smem: [ out image: LK_ROWS * nnz u16 ][ bitmaps: M * cw * 64 u32 ]
+template <int M>
+__global__ void __launch_bounds__(LK_THREADS)
+lookup_bitmap_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__restrict__ kb,
+                     const int *__restrict__ flag, int32_t *__restrict__ out, int S, int nnz, int W, int chunk_words) {
+    if (*flag) return;  // some key code >= 16: the generic kernel handles this call
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint16_t *s_out = reinterpret_cast<uint16_t *>(smem_raw);
+    uint32_t *s_kb = reinterpret_cast<uint32_t *>(smem_raw + (((size_t)LK_ROWS * nnz * 2 + 15) & ~(size_t)15));
+    const int b = blockIdx.y;
+    const int tile = gridDim.x - 1 - blockIdx.x;  // heaviest (last) rows first
+    const int r0 = tile * LK_ROWS;
+    const int rl = threadIdx.x >> 2, t = threadIdx.x & 3;
+    const int r = r0 + rl;
+    const bool live = r < S;
+    const int quarter = nnz / 4;
+    const int nkeys = (live && r >= t) ? (r - t) / 4 + 1 : 0;
+    const int lim = live ? min(r + 1, nnz) : 0;
+    const int n_t = lim > t ? (lim - t + 3) / 4 : 0;
+    const int tile_words = min(W, (min(S, r0 + LK_ROWS) + 127) / 128);  // words any row of the tile needs
+
+    for (int i = threadIdx.x; i < LK_ROWS * nnz / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(s_out)[i] = 0;
+
+    BitmapMatcher<M> mt;
+    mt.s_kb = s_kb;
+    mt.t = t;
+#pragma unroll
+    for (int s = 0; s < M; ++s)
+        mt.q[s] = live ? ((unsigned)query_codes[((size_t)b * S + r) * M + s] & 0xffffu) : 0xffffu;
+
+    LaneState st;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) st.len[s] = 0;
+    const uint32_t *kb_head = kb + (size_t)b * M * W * LK_WORD_U32;
+    const int my_words = (nkeys + 31) / 32;
+
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int w0 = 0; w0 < tile_words; w0 += chunk_words) {
+            const int cw = min(chunk_words, tile_words - w0);
+            if (pass == 0 || tile_words > chunk_words) {  // single-chunk tiles keep the bitmaps for pass 2
+                __syncthreads();
+                const int per_s = cw * LK_WORD_U32 / 4;  // uint4 per subspace
+                for (int i = threadIdx.x; i < M * per_s; i += blockDim.x) {
+                    const int s = i / per_s, o = i % per_s;
+                    reinterpret_cast<uint4 *>(s_kb)[s * per_s + o] =
+                        reinterpret_cast<const uint4 *>(kb_head + ((size_t)s * W + w0) * LK_WORD_U32)[o];
+                }
+                __syncthreads();
+            }
+            mt.cw = cw;
+            mt.w0 = w0;
+            const int w_end = min(w0 + cw, my_words);
+            for (int w = w0; w < w_end; ++w) {
+                uint32_t mask[4];
+                mt.buckets(w, valid_mask(w, nkeys), mask);
+                if (pass == 0) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) st.len[s] += __popc(mask[s]);
+                } else {
+                    place_word(st, mask, w, t, s_out + rl * nnz);
+                }
+            }
+        }
+        if (pass == 0) plan_lane(st, t, n_t, quarter);
+    }
+    fix_clobber(st, t, quarter, s_out + rl * nnz);
+    __syncthreads();
+    flush_rows(s_out, out, b, r0, S, nnz);
+}
+
+// ---- generic path ----------------------------------------------------------------------------
+// smem: [ out image ][ query codes LK_ROWS * m u16 ]
+__global__ void __launch_bounds__(LK_THREADS)
+lookup_generic_kernel(const int32_t *__restrict__ query_codes, const int32_t *__restrict__ key_codes,
+                      const int *__restrict__ flag, int flag_expect, int32_t *__restrict__ out, int S, int m, int nnz) {
+    if (flag && (*flag != 0) != (flag_expect != 0)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint16_t *s_out = reinterpret_cast<uint16_t *>(smem_raw);
+    uint16_t *s_q = reinterpret_cast<uint16_t *>(smem_raw + (((size_t)LK_ROWS * nnz * 2 + 15) & ~(size_t)15));
+    const int b = blockIdx.y;
+    const int tile = gridDim.x - 1 - blockIdx.x;
+    const int r0 = tile * LK_ROWS;
+    const int rl = threadIdx.x >> 2, t = threadIdx.x & 3;
+    const int r = r0 + rl;
+    const bool live = r < S;
+    const int quarter = nnz / 4;
+    const int nkeys = (live && r >= t) ? (r - t) / 4 + 1 : 0;
+    const int lim = live ? min(r + 1, nnz) : 0;
+    const int n_t = lim > t ? (lim - t + 3) / 4 : 0;
+
+    for (int i = threadIdx.x; i < LK_ROWS * nnz / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(s_out)[i] = 0;
+    for (int i = threadIdx.x; i < LK_ROWS * m; i += blockDim.x) {
+        const int rr = r0 + i / m;
+        s_q[i] = rr < S ? (uint16_t)((unsigned)query_codes[((size_t)b * S + rr) * m + i % m] & 0xffffu) : 0;
+    }
+    __syncthreads();
+
+    GenericMatcher mt;
+    mt.kc = key_codes + (size_t)b * S * m;
+    mt.s_q = s_q + rl * m;
+    mt.m = m;
+    mt.div = m / 4;
+    mt.t = t;
+    LaneState st;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) st.len[s] = 0;
+    const int my_words = (nkeys + 31) / 32;
+    for (int w = 0; w < my_words; ++w) {
+        uint32_t mask[4];
+        mt.buckets(w, valid_mask(w, nkeys), mask);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) st.len[s] += __popc(mask[s]);
+    }
+    plan_lane(st, t, n_t, quarter);
+    for (int w = 0; w < my_words; ++w) {
+        uint32_t mask[4];
+        mt.buckets(w, valid_mask(w, nkeys), mask);
+        place_word(st, mask, w, t, s_out + rl * nnz);
+    }
+    fix_clobber(st, t, quarter, s_out + rl * nnz);
+    __syncthreads();
+    flush_rows(s_out, out, b, r0, S, nnz);
+}
+
+static bool bitmap_m_supported(int m) { return m == 4 || m == 8 || m == 10 || m == 12 || m == 16 || m == 32; }
+
+constexpr size_t LK_SMEM_BUDGET = 160 * 1024;
+
+static size_t out_image_bytes(int nnz) { return (((size_t)LK_ROWS * nnz * 2) + 15) & ~(size_t)15; }
+
+}  // namespace spt
+
+using namespace spt;
+
+extern "C" size_t spt_lookup_workspace_bytes(int B, int S, int m, int nnz) {
+    (void)nnz;
+    if (!bitmap_m_supported(m)) return 16;
+    const size_t W = (size_t)(S + 127) / 128;
+    return 16 + (size_t)B * m * W * LK_WORD_U32 * sizeof(uint32_t);
+}
+
+extern "C" int spt_lookup_fwd(const int32_t *query_codes, const int32_t *key_codes, int32_t *output, void *workspace,
+                              int B, int S, int m, int nnz, spt_stream_t stream) {
+    SPT_REQUIRE(query_codes && key_codes && output, "lookup_fwd: null pointer");
+    SPT_REQUIRE(B >= 1 && S >= 1 && S <= 65536, "lookup_fwd: bad batch/seq (B=%d, S=%d; S must be <= 65536)", B, S);
+    SPT_REQUIRE(B <= 65535, "lookup_fwd: batch %d exceeds grid limit", B);
+    SPT_REQUIRE(m >= 4, "lookup_fwd: n_subspaces must be >= 4 (got %d)", m);
+    SPT_REQUIRE(nnz >= 8 && nnz % 4 == 0 && nnz <= S, "lookup_fwd: nonzeros per row must be a multiple of 4 in [8, S] (got %d)", nnz);
+    cudaStream_t st = as_stream(stream);
+    const int tiles = (S + LK_ROWS - 1) / LK_ROWS;
+    dim3 grid(tiles, B);
+    const size_t img = out_image_bytes(nnz);
+    const size_t gen_smem = img + (size_t)LK_ROWS * m * 2;
+    SPT_REQUIRE(gen_smem <= 200 * 1024, "lookup_fwd: nnz=%d too large for the shared-memory row image", nnz);
+    if (gen_smem > 48 * 1024)
+        cudaFuncSetAttribute(lookup_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem);
+
+    if (!bitmap_m_supported(m)) {
+        lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, nullptr, 0, output, S, m, nnz);
+        SPT_LAUNCH_CHECK("lookup_generic_kernel");
+        return SPT_OK;
+    }
+    SPT_REQUIRE(workspace, "lookup_fwd: workspace required");
+    int *flag = reinterpret_cast<int *>(workspace);
+    uint32_t *kb = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(workspace) + 16);
+    const int W = (S + 127) / 128;
+    cudaError_t e = cudaMemsetAsync(flag, 0, 16, st);
+    if (e != cudaSuccess) return fail(SPT_ERR_CUDA, "lookup_fwd: memset: %s", cudaGetErrorString(e));
+    lookup_pack_kernel<<<dim3(W, B), 128, 0, st>>>(key_codes, kb, flag, S, m, W);
+    SPT_LAUNCH_CHECK("lookup_pack_kernel");
+
+    // bitmaps per 128-key word: m * 256 B; pick the chunk so that image + chunk fits the budget
+    const size_t per_word = (size_t)m * LK_WORD_U32 * 4;
+    int chunk_words = (int)((LK_SMEM_BUDGET - img) / per_word);
+    SPT_REQUIRE(img < LK_SMEM_BUDGET && chunk_words >= 1, "lookup_fwd: nnz=%d too large", nnz);
+    if (chunk_words > W) chunk_words = W;
+    const size_t smem = img + per_word * chunk_words;
+#define SPT_LK_CASE(MM)                                                                                          \
+    case MM:                                                                                                     \
+        if (smem > 48 * 1024)                                                                                    \
+            cudaFuncSetAttribute(lookup_bitmap_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        lookup_bitmap_kernel<MM><<<grid, LK_THREADS, smem, st>>>(query_codes, kb, flag, output, S, nnz, W, chunk_words); \
+        break;
+    switch (m) {
+        SPT_LK_CASE(4)
+        SPT_LK_CASE(8)
+        SPT_LK_CASE(10)
+        SPT_LK_CASE(12)
+        SPT_LK_CASE(16)
+        SPT_LK_CASE(32)
+        default:
+            return fail(SPT_ERR_UNSUPPORTED, "lookup_fwd: unreachable m=%d", m);
+    }
+#undef SPT_LK_CASE
+    SPT_LAUNCH_CHECK("lookup_bitmap_kernel");
+    lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, S, m, nnz);
+    SPT_LAUNCH_CHECK("lookup_generic_kernel(fallback)");
+    return SPT_OK;
+}

@@ -1,0 +1,301 @@
+"""Drop-in replacement for the reference's torch CUDA extension `naive_gpt.ext`
+(reference extension/entry.cpp:43-56): the same 7 function names, arity, argument meaning, return
+values and error type (RuntimeError, as TORCH_CHECK raises), implemented as a thin ctypes binding
+over the C ABI of include/spt_b200.h (libspt_b200.so, hand-written sm_100a kernels).
+
+Differences from the reference, all relaxations:
+  * bf16 operands are accepted next to fp32 (outputs that are "values" stay fp32);
+  * the shape whitelists are lifted (cdist: any n / n_codewords; lookup: any (m, nnz) with m >= 4,
+    nnz % 4 == 0; softmax: any row length);
+  * every kernel runs on torch's CURRENT stream (the reference launches its hand kernels on the
+    legacy default stream, extension/cdist.cu:214 — a latent ordering hazard).
+
+Extra entry points: pq_encode, csr2csc, spmm_csc, sddmm_scaled, ffn_*.
+There is no CPU path: tensors must be CUDA tensors and the library must be built.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+
+from ._lib import SPT_BF16, SPT_F32, check, lib
+
+_DTYPES = {torch.float32: SPT_F32, torch.bfloat16: SPT_BF16}
+
+
+# ---- validation helpers (mirror CHECK_DIM / CHECK_TYPE, extension/common.h:13-21) -----------------
+def _check_dim(x: torch.Tensor, d: int, name: str) -> None:
+    if not isinstance(x, torch.Tensor):
+        raise RuntimeError(f"{name} must be a tensor")
+    if not x.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if x.dim() != d:
+        raise RuntimeError(f"{name} must be of dim {d}")
+    if not x.is_contiguous():
+        raise RuntimeError(f"{name} custom kernel requires contiguous tensor")
+
+
+def _check_type(x: torch.Tensor, t: torch.dtype, name: str) -> None:
+    if x.dtype != t:
+        raise RuntimeError(f"{name} must be type of {t}")
+
+
+def _float_code(x: torch.Tensor, name: str) -> int:
+    code = _DTYPES.get(x.dtype)
+    if code is None:
+        raise RuntimeError(f"{name} must be type of torch.float32 or torch.bfloat16")
+    return code
+
+
+def _stream(x: torch.Tensor) -> int:
+    return torch.cuda.current_stream(x.device).cuda_stream
+
+
+def _p(x) -> int:
+    return 0 if x is None else x.data_ptr()
+
+
+class _on_device:
+    """Make x's device current for the duration of a launch (no-op in the common case)."""
+
+    def __init__(self, x: torch.Tensor):
+        self.idx = x.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is not None and self.idx != cur:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+def _workspace(nbytes: int, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=like.device)
+
+
+# ---- (1) cdist ---------------------------------------------------------------------------------------
+def cdist_forward_cuda(query: torch.Tensor, table: torch.Tensor) -> List[torch.Tensor]:
+    """query [m, n, dc], table [m, c, dc] -> [distance [m, n, c] f32, indices [m, n] i32]
+    (extension/cdist.cu:185-249)."""
+    _check_dim(query, 3, "query")
+    _check_dim(table, 3, "table")
+    code = _float_code(query, "query")
+    if query.size(0) != table.size(0) or query.size(-1) != table.size(-1):
+        raise RuntimeError("query and table must agree in n_subspaces and d_code")
+    table32 = table if table.dtype == torch.float32 else table.float()
+    m, n, dc = query.shape
+    c = table.size(1)
+    distance = torch.empty((m, n, c), dtype=torch.float32, device=query.device)
+    indices = torch.empty((m, n), dtype=torch.int32, device=query.device)
+    with _on_device(query):
+        check(lib.spt_cdist_fwd(_p(query), _p(table32), _p(distance), _p(indices), m, n, c, dc, code,
+                                _stream(query)))
+    return [distance, indices]
+
+
+def cdist_backward_cuda(query: torch.Tensor, table: torch.Tensor, grad_output: torch.Tensor) -> List[torch.Tensor]:
+    """-> [grad_query [m,n,dc], grad_table [m,c,dc]] (extension/cdist.cu:251-333)."""
+    _check_dim(query, 3, "query")
+    _check_dim(table, 3, "table")
+    _check_dim(grad_output, 3, "grad_output")
+    _check_type(query, torch.float32, "query")
+    _check_type(table, torch.float32, "table")
+    _check_type(grad_output, torch.float32, "grad_output")
+    m, n, dc = query.shape
+    c = table.size(1)
+    if (table.size(0) != m or table.size(2) != dc or grad_output.size(0) != m
+            or grad_output.size(1) != n or grad_output.size(2) != c):
+        raise RuntimeError("cdist_backward: shape mismatch")
+    grad_query = torch.empty_like(query)
+    grad_table = torch.empty_like(table)
+    ws = _workspace(lib.spt_cdist_bwd_workspace_bytes(m, n, c, dc), query)
+    with _on_device(query):
+        check(lib.spt_cdist_bwd(_p(query), _p(table), _p(grad_output), _p(grad_query), _p(grad_table), _p(ws),
+                                m, n, c, dc, _stream(query)))
+    return [grad_query, grad_table]
+
+
+def pq_encode(z: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """Fused PQBase.forward(mode='encode') (quantizer.py:26-77): z [..., m*dc] -> codes [..., m] int32,
+    straight from the head-major layout (no [m, n, dc] transposed copy, no distance tensor)."""
+    if not z.is_cuda or not z.is_contiguous():
+        raise RuntimeError("z must be a contiguous CUDA tensor")
+    _check_dim(table, 3, "table")
+    code = _float_code(z, "z")
+    m, c, dc = table.shape
+    if z.size(-1) != m * dc:
+        raise RuntimeError("z last dim must equal n_subspaces * d_codeword")
+    table32 = table if table.dtype == torch.float32 else table.float()
+    rows = z.numel() // (m * dc)
+    codes = torch.empty(list(z.shape[:-1]) + [m], dtype=torch.int32, device=z.device)
+    with _on_device(z):
+        check(lib.spt_pq_encode(_p(z), _p(table32), _p(codes), rows, m, c, dc, code, _stream(z)))
+    return codes
+
+
+# ---- (2) lookup --------------------------------------------------------------------------------------
+def lookup_forward_cuda(config: torch.Tensor, query: torch.Tensor, key: torch.Tensor) -> torch.Tensor:
+    """config carries sparse_coeff in its SHAPE (kernels/lookup.py:23, lookup.cu:99);
+    query, key [B, S, m] int32 codes -> [B, S, S // sparse_coeff] int32 (extension/lookup.cu:87-174)."""
+    _check_dim(key, 3, "key")
+    _check_dim(query, 3, "query")
+    _check_type(key, torch.int32, "key")
+    _check_type(query, torch.int32, "query")
+    if query.shape != key.shape:
+        raise RuntimeError("query and key must have the same shape")
+    sparsity = int(config.size(0))
+    B, S, m = query.shape
+    if sparsity <= 0 or S % sparsity != 0:
+        raise RuntimeError("seq_length must be divisible by sparse_coeff")
+    nnz = S // sparsity
+    output = torch.empty((B, S, nnz), dtype=torch.int32, device=query.device)
+    ws = _workspace(lib.spt_lookup_workspace_bytes(B, S, m, nnz), query)
+    with _on_device(query):
+        check(lib.spt_lookup_fwd(_p(query), _p(key), _p(output), _p(ws), B, S, m, nnz, _stream(query)))
+    return output
+
+
+# ---- (3) sddmm ---------------------------------------------------------------------------------------
+def _flag(t) -> bool:
+    return bool(t.item()) if isinstance(t, torch.Tensor) else bool(t)
+
+
+def _check_csr(indptr, indices, S: int) -> None:
+    _check_dim(indptr, 1, "indptr")
+    _check_dim(indices, 2, "indices")
+    _check_type(indptr, torch.int32, "indptr")
+    _check_type(indices, torch.int32, "indices")
+    if indptr.size(-1) != S + 1:
+        raise RuntimeError("indptr must have seq_length + 1 entries")
+
+
+def sddmm_scaled(indptr, indices, query, key, scale: float = 1.0, clamp: float = 0.0) -> torch.Tensor:
+    _check_dim(key, 3, "key")
+    _check_dim(query, 3, "query")
+    if query.shape != key.shape or query.dtype != key.dtype:
+        raise RuntimeError("query and key must have the same shape and dtype")
+    B, S, d = query.shape
+    _check_csr(indptr, indices, S)
+    if indices.size(0) != B:
+        raise RuntimeError("indices batch must match query batch")
+    code = _float_code(query, "query")
+    nnz = indices.size(-1)
+    values = torch.empty((B, nnz), dtype=torch.float32, device=query.device)
+    with _on_device(query):
+        check(lib.spt_sddmm_fwd(_p(indptr), _p(indices), _p(query), _p(key), _p(values), B, S, d, nnz,
+                                float(scale), float(clamp), code, _stream(query)))
+    return values
+
+
+def sddmm_forward_cuda(trans_lhs, trans_rhs, indptr, indices, query, key) -> torch.Tensor:
+    """values[b, e] = <query[b, row(e)], key[b, indices[b, e]]> (extension/sddmm.cpp:3-73).  Only the
+    (N, T) operand layout the reference ever uses (kernels/sddmm.py:19-22, kernels/spmm.py:37-40)."""
+    if _flag(trans_lhs) or not _flag(trans_rhs):
+        raise RuntimeError("sddmm_forward_cuda: only trans_lhs=False, trans_rhs=True is supported")
+    return sddmm_scaled(indptr, indices, query, key)
+
+
+# ---- (a-7) csr2csc + (5) spmm ------------------------------------------------------------------------
+def csr2csc(indptr: torch.Tensor, indices: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (col_ptr [B, S+1], row_idx [B, nnz], perm [B, nnz]); stable (rows ascending per column)."""
+    S = indptr.size(-1) - 1
+    _check_csr(indptr, indices, S)
+    B, nnz = indices.shape
+    dev = indices.device
+    col_ptr = torch.empty((B, S + 1), dtype=torch.int32, device=dev)
+    row_idx = torch.empty((B, nnz), dtype=torch.int32, device=dev)
+    perm = torch.empty((B, nnz), dtype=torch.int32, device=dev)
+    ws = _workspace(lib.spt_csr2csc_workspace_bytes(B, S, nnz), indices)
+    with _on_device(indices):
+        check(lib.spt_csr2csc(_p(indptr), _p(indices), _p(col_ptr), _p(row_idx), _p(perm), _p(ws), B, S, nnz,
+                              _stream(indices)))
+    return col_ptr, row_idx, perm
+
+
+def _check_spmm(indptr, indices, values, x):
+    _check_dim(x, 3, "x")
+    _check_dim(values, 2, "values")
+    B, S, d = x.shape
+    _check_csr(indptr, indices, S)
+    _check_type(values, torch.float32, "values")
+    if indices.size(0) != B or indices.shape != values.shape:
+        raise RuntimeError("indices / values / x shape mismatch")
+    return B, S, d, indices.size(-1), _float_code(x, "x")
+
+
+def spmm_csc(csc, values: torch.Tensor, x: torch.Tensor, out_dtype=None) -> torch.Tensor:
+    """y = A^T x using a CSC from csr2csc(); values stay in CSR order (gathered through perm)."""
+    col_ptr, row_idx, perm = csc
+    _check_dim(x, 3, "x")
+    _check_dim(values, 2, "values")
+    _check_type(values, torch.float32, "values")
+    B, S, d = x.shape
+    nnz = values.size(-1)
+    code = _float_code(x, "x")
+    if out_dtype is None:
+        out_dtype = x.dtype
+    y = torch.empty((B, S, d), dtype=out_dtype, device=x.device)
+    with _on_device(x):
+        check(lib.spt_spmm_t_fwd(_p(col_ptr), _p(row_idx), _p(perm), _p(values), _p(x), _p(y), B, S, d, nnz,
+                                 code, _DTYPES[out_dtype], _stream(x)))
+    return y
+
+
+def spmm_forward_cuda(trans_lhs, trans_rhs, indptr, indices, values, x) -> torch.Tensor:
+    """y = op(A) x, A = batched CSR with shared indptr (extension/spmm.cpp:3-72).  trans_lhs=True is
+    the transposed product of the backward passes; it builds the CSC on the fly (callers that need
+    it twice should use csr2csc() + spmm_csc(), as spt_proto_b200.kernels does)."""
+    if _flag(trans_rhs):
+        raise RuntimeError("spmm_forward_cuda: trans_rhs=True is not supported")
+    B, S, d, nnz, code = _check_spmm(indptr, indices, values, x)
+    if _flag(trans_lhs):
+        return spmm_csc(csr2csc(indptr, indices), values, x, out_dtype=x.dtype)
+    y = torch.empty_like(x)
+    with _on_device(x):
+        check(lib.spt_spmm_fwd(_p(indptr), _p(indices), _p(values), _p(x), _p(y), B, S, d, nnz, code, code,
+                               _stream(x)))
+    return y
+
+
+# ---- (4) softmax -------------------------------------------------------------------------------------
+def softmax_forward_cuda(indptr, indices, values) -> torch.Tensor:
+    """Causal CSR row softmax (extension/softmax.cu:84-114)."""
+    _check_dim(values, 2, "values")
+    _check_csr(indptr, indices, indptr.size(-1) - 1)
+    _check_type(values, torch.float32, "values")
+    if indices.shape != values.shape:
+        raise RuntimeError("indices and values must have the same shape")
+    B, nnz = indices.shape
+    S = indptr.size(-1) - 1
+    output = torch.empty_like(values)
+    with _on_device(values):
+        check(lib.spt_softmax_fwd(_p(indptr), _p(indices), _p(values), _p(output), B, S, nnz, _stream(values)))
+    return output
+
+
+def softmax_backward_cuda(indptr, indices, output, grad_output) -> torch.Tensor:
+    """True softmax gradient on the kept entries (extension/softmax.cu:116-148 without its clamp bug)."""
+    _check_dim(output, 2, "output")
+    _check_dim(grad_output, 2, "grad_output")
+    _check_csr(indptr, indices, indptr.size(-1) - 1)
+    _check_type(output, torch.float32, "output")
+    _check_type(grad_output, torch.float32, "grad_output")
+    if grad_output.shape != output.shape or indices.shape != output.shape:
+        raise RuntimeError("indices / output / grad_output shape mismatch")
+    B, nnz = indices.shape
+    S = indptr.size(-1) - 1
+    grad_values = torch.empty_like(output)
+    with _on_device(output):
+        check(lib.spt_softmax_bwd(_p(indptr), _p(indices), _p(output), _p(grad_output), _p(grad_values), B, S, nnz,
+                                  _stream(output)))
+    return grad_values
+
+
+def launch_count() -> int:
+    """Kernel launches issued through libspt_b200 by this process so far."""
+    return int(lib.spt_launch_count())

@@ -1,0 +1,9 @@
+"""torch.autograd Functions of the hot path — same names and call signatures as the reference's
+`naive_gpt.kernels` (naive_gpt/kernels/__init__.py:1-14)."""
+from .cdist import cdist
+from .lookup import lookup
+from .softmax import softmax
+from .sddmm import sddmm
+from .spmm import spmm
+
+__all__ = ["cdist", "lookup", "softmax", "sddmm", "spmm"]

@@ -1,0 +1,176 @@
+"""Dense building blocks the sparse layers derive from.  These mirror the *interface* of the
+reference's naive_gpt/layers/basic/{attention,position,feedforward,quantizer}.py (constructor
+arguments, attribute / parameter names — so reference checkpoints load — and forward contracts);
+they are plain PyTorch and out of the hot path except for PQ 'encode', which is one fused kernel."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .. import ext, kernels
+
+
+class RotaryEmbedding(nn.Module):
+    """RoPE with cached cos/sin tables (reference basic/position.py:5-48).  x: [N, S, H, E]."""
+
+    def __init__(self, n_embeddings: int, d_model: int, base: float = 10000.0):
+        super().__init__()
+        if d_model % 2:
+            raise ValueError("d_model must be even")
+        inv_freq = base ** (-torch.arange(0, d_model, 2) / d_model)
+        angles = torch.outer(torch.arange(n_embeddings), inv_freq).repeat(1, 2)   # [S, E]
+        self.register_buffer("cos_cached", angles.cos())
+        self.register_buffer("sin_cached", angles.sin())
+
+    @staticmethod
+    def rotate_half(x: torch.Tensor) -> torch.Tensor:
+        lo, hi = x.chunk(2, dim=-1)
+        return torch.cat((-hi, lo), dim=-1)
+
+    def forward(self, x: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+        assert x.dim() == 4 and ids.dim() == 1
+        cos = self.cos_cached[ids].view(1, -1, 1, x.size(-1))
+        sin = self.sin_cached[ids].view(1, -1, 1, x.size(-1))
+        return x * cos + self.rotate_half(x) * sin
+
+
+class VanillaAttention(nn.Module):
+    """Dense softmax attention on [N, S, H, E] tensors (reference basic/attention.py:6-57).
+    Sub-classes override _get_attn / _apply_attn."""
+
+    def __init__(self, d_head: int, p_dropout: float):
+        super().__init__()
+        self.d_head = d_head
+        self.p_dropout = p_dropout
+        self.scaling = float(d_head) ** -0.5
+        self.dropout = nn.Dropout(p_dropout)
+
+    def _get_attn(self, q, k, attn_mask):
+        scores = torch.einsum("niae,njae->naij", q, k)
+        if attn_mask is not None:
+            scores = scores + attn_mask
+        return self.dropout(torch.softmax(self.scaling * scores, dim=-1))
+
+    def _apply_attn(self, attn, v):
+        return torch.einsum("naij,njae->niae", attn, v).contiguous()
+
+    def forward(self, q, k, v, attn_mask=None):
+        assert q.dim() == 4 and k.dim() == 4 and v.dim() == 4
+        assert q.size(0) == k.size(0) == v.size(0)
+        return self._apply_attn(self._get_attn(q, k, attn_mask), v)
+
+
+class RotaryAttention(VanillaAttention):
+    """VanillaAttention with RoPE applied to q and k (reference basic/attention.py:60-92)."""
+
+    def __init__(self, d_head: int, p_dropout: float, max_length: int = 2048):
+        super().__init__(d_head=d_head, p_dropout=p_dropout)
+        self.max_length = max_length
+        self.embedding = RotaryEmbedding(n_embeddings=max_length, d_model=d_head)
+        self.register_buffer("cached_ids", torch.arange(max_length))
+
+    def _rotate(self, x):
+        return self.embedding(x, ids=self.cached_ids[: x.size(1)])
+
+    def _get_attn(self, q, k, attn_mask):
+        return VanillaAttention._get_attn(self, self._rotate(q), self._rotate(k), attn_mask)
+
+
+class Feedforward(nn.Module):
+    """fc2(act(dropout(fc1(x)))) (reference basic/feedforward.py:5-34)."""
+
+    def __init__(self, d_model: int, d_feedforward: int, p_dropout: float, activation: nn.Module):
+        super().__init__()
+        self.d_model, self.d_feedforward = d_model, d_feedforward
+        self.p_dropout = p_dropout
+        self.fc1 = nn.Linear(d_model, d_feedforward)
+        self.fc2 = nn.Linear(d_feedforward, d_model)
+        self.dropout = nn.Dropout(p_dropout)
+        self.activation = activation
+
+    def forward(self, x):
+        return self.fc2(self.activation(self.dropout(self.fc1(x))))
+
+
+class LLaMaFeedforward(nn.Module):
+    """down(act(gate(x)) * side(x)) (reference basic/feedforward.py:37-62)."""
+
+    def __init__(self, d_model: int, d_feedforward: int, activation: nn.Module):
+        super().__init__()
+        self.d_model, self.d_feedforward = d_model, d_feedforward
+        self.gate = nn.Linear(d_model, d_feedforward, bias=False)
+        self.side = nn.Linear(d_model, d_feedforward, bias=False)
+        self.down = nn.Linear(d_feedforward, d_model, bias=False)
+        self.activation = activation
+
+    def forward(self, x):
+        return self.down(self.activation(self.gate(x)) * self.side(x))
+
+
+class PQBase(nn.Module):
+    """Product quantizer with one codebook weight[m, c, dc] shared by all heads of a layer
+    (reference basic/quantizer.py:6-111).  forward(mode, z), mode in
+    {'encode', 'decode', 'quantize', 'train'}:
+        encode   z [..., m*dc]  -> codes [..., m]   (int64 for v1 like torch.argmin, int32 for v2)
+        decode   codes [..., m] -> centroids [..., m*dc]
+        quantize z -> nearest centroids
+        train    z -> (nearest centroids, soft/hard centroid MSE loss)
+    method 'v1' = torch.cdist(p=1)+argmin (the reference's torch oracle), 'v2' = CUDA kernels."""
+
+    def __init__(self, d_codeword: int, n_codewords: int, n_subspaces: int, method: str):
+        super().__init__()
+        self.method = method
+        self.d_codeword, self.n_codewords, self.n_subspaces = d_codeword, n_codewords, n_subspaces
+        self.weight = nn.Parameter(torch.randn(n_subspaces, n_codewords, d_codeword))
+        self.loss_fn = nn.MSELoss()
+
+    def _distance_and_codes(self, z_flat):
+        if self.method == "v1":
+            dist = torch.cdist(z_flat.float(), self.weight.float(), p=1.0).to(z_flat.dtype)
+            return dist, dist.argmin(dim=-1, keepdim=True)
+        if self.method == "v2":
+            dist, codes = kernels.cdist(z_flat, self.weight)
+            return dist, codes.unsqueeze(-1)
+        raise RuntimeError(f"unknown PQ method {self.method}")
+
+    def forward(self, mode: str, z: torch.Tensor):
+        if mode not in ("train", "encode", "decode", "quantize"):
+            raise AssertionError(mode)
+        assert z.dim() > 1
+        m, dc = self.n_subspaces, self.d_codeword
+        assert z.size(-1) == (m if mode == "decode" else m * dc)
+        out_shape = list(z.shape[:-1]) + [-1]
+
+        if mode == "encode" and self.method == "v2" and z.is_cuda:
+            # fused fast path: no [m, n, dc] copy, no distance tensor
+            return ext.pq_encode(z.contiguous(), self.weight)
+
+        z_flat = z.flatten(end_dim=-2).view(-1, m, z.size(-1) // m).transpose(0, 1).contiguous()
+        if mode == "decode":
+            distance, codes = None, z_flat
+        else:
+            distance, codes = self._distance_and_codes(z_flat)
+        if mode == "encode":
+            return codes.transpose(0, 1).reshape(out_shape).contiguous()
+
+        codes = codes.long()
+        z_q_flat = torch.gather(self.weight, 1, codes.expand(-1, -1, dc))
+        z_q = z_q_flat.transpose(0, 1).reshape(out_shape)
+        if mode in ("decode", "quantize"):
+            return z_q
+
+        # 'train': soft centroids from inverse distances vs the hard centroid, plus commitment term
+        weights = torch.softmax(-torch.log(torch.clamp(distance, min=1e-5)), dim=-1)
+        z_w = torch.matmul(weights, self.weight)
+        loss = self.loss_fn(z_w, z_q_flat) + self.loss_fn(z_flat, z_q_flat)
+        return z_q, loss
+
+
+class PQV1(PQBase):
+    def __init__(self, d_codeword: int, n_codewords: int, n_subspaces: int):
+        super().__init__(d_codeword, n_codewords, n_subspaces, method="v1")
+
+
+class PQV2(PQBase):
+    def __init__(self, d_codeword: int, n_codewords: int, n_subspaces: int):
+        super().__init__(d_codeword, n_codewords, n_subspaces, method="v2")

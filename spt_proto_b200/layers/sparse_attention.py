@@ -1,0 +1,134 @@
+"""PQ sparse attention layers (reference naive_gpt/layers/sparse/attention.py).
+
+V1 = dense attention + PQ training loss (how the codebooks are learned); V2 = the sparse hot path:
+    q, k -> PQ codes -> lookup (top S/sparse_coeff keys per query, fixed-stride CSR)
+         -> sddmm -> clamp(scaling * ., -10, 10) -> causal CSR softmax -> spmm with v.
+Constructors, buffers (`trigger`, `loss`) and `from_pretrained` match the reference; `sparse_coeff`
+(hard-wired to 8 in the reference, attention.py:110,115) is an attribute here."""
+from __future__ import annotations
+
+import torch
+
+from .. import kernels
+from .basic import PQV1, PQV2, RotaryAttention, VanillaAttention
+
+
+class _PQTrainMixin:
+    """V1 behaviour: dense attention, PQ loss recorded on every forward (attention.py:34-44,181-193)."""
+
+    def _init_pq(self, d_codeword, n_codewords, n_subspaces):
+        self.d_codeword, self.n_codewords, self.n_subspaces = d_codeword, n_codewords, n_subspaces
+        self.quantizer = PQV1(d_codeword=d_codeword, n_codewords=n_codewords, n_subspaces=n_subspaces)
+        self.register_buffer("trigger", torch.scalar_tensor(False, dtype=torch.bool))
+
+    def _record_loss(self, q, k):
+        loss = self.quantizer("train", z=q)[-1] + self.quantizer("train", z=k)[-1]
+        self.register_buffer("loss", loss, persistent=False)
+
+
+class SparseVanillaAttentionV1(_PQTrainMixin, VanillaAttention):
+    def __init__(self, d_head: int, p_dropout: float, d_codeword: int, n_codewords: int, n_subspaces: int):
+        VanillaAttention.__init__(self, d_head=d_head, p_dropout=p_dropout)
+        self._init_pq(d_codeword, n_codewords, n_subspaces)
+
+    def _get_attn(self, q, k, attn_mask):
+        self._record_loss(q, k)
+        return VanillaAttention._get_attn(self, q, k, attn_mask)
+
+
+class SparseRotaryAttentionV1(_PQTrainMixin, RotaryAttention):
+    def __init__(self, d_head: int, p_dropout: float, d_codeword: int, n_codewords: int, n_subspaces: int):
+        RotaryAttention.__init__(self, d_head=d_head, p_dropout=p_dropout)
+        # the reference ignores n_subspaces here and derives it (attention.py:165-169)
+        self._init_pq(d_codeword, n_codewords, d_head // d_codeword)
+        self.n_subspaces = n_subspaces
+
+    def _get_attn(self, q, k, attn_mask):
+        q, k = self._rotate(q), self._rotate(k)
+        self._record_loss(q, k)
+        return VanillaAttention._get_attn(self, q, k, attn_mask)
+
+
+class _SparseV2Mixin:
+    """The hot path shared by the vanilla and rotary V2 layers (attention.py:84-142, 233-299)."""
+
+    sparse_coeff: int = 8
+
+    def _init_v2(self, d_head, d_codeword, n_codewords):
+        self.quantizer = PQV2(d_codeword=d_codeword, n_codewords=n_codewords, n_subspaces=d_head // d_codeword)
+        self.register_buffer("trigger", torch.scalar_tensor(False, dtype=torch.bool))
+        self._indptr_cache = {}
+
+    @classmethod
+    def _from_v1(cls, source, v1_type):
+        assert isinstance(source, v1_type)
+        model = cls(d_head=source.d_head, d_codeword=source.d_codeword,
+                    n_codewords=source.n_codewords, p_dropout=0.0)
+        result = model.load_state_dict(source.state_dict(), strict=False)
+        if len(result.missing_keys) != 0:
+            raise RuntimeError
+        return model
+
+    def _fixed_indptr(self, seq_length: int, top_k: int, device) -> torch.Tensor:
+        key = (seq_length, top_k, str(device))
+        hit = self._indptr_cache.get(key)
+        if hit is None:  # the reference rebuilds this arange on every call (attention.py:116-119)
+            hit = torch.arange(0, top_k * seq_length + 1, step=top_k, dtype=torch.int32, device=device)
+            self._indptr_cache[key] = hit
+        return hit
+
+    @staticmethod
+    def _to_heads(x: torch.Tensor) -> torch.Tensor:  # [N, S, H, E] -> [N*H, S, E]
+        x = x.transpose(1, 2).contiguous()
+        return x.view(-1, x.size(-2), x.size(-1))
+
+    def _sparse_get_attn(self, q, k):
+        assert q.size() == k.size()
+        seq_length = q.size(1)
+        q, k = self._to_heads(q), self._to_heads(k)
+        if self.trigger.is_nonzero():  # one-shot PQ training loss, armed by the training loop
+            self.trigger.logical_not_()
+            loss = self.quantizer("train", z=q)[-1] + self.quantizer("train", z=k)[-1]
+            self.register_buffer("loss", loss, persistent=False)
+        q_c = self.quantizer("encode", z=q)
+        k_c = self.quantizer("encode", z=k)
+        topk = kernels.lookup(q_c, k_c, sparse_coeff=self.sparse_coeff)
+        csr_indices = topk.flatten(start_dim=1)
+        indptr = self._fixed_indptr(seq_length, seq_length // self.sparse_coeff, q.device)
+        values = kernels.sddmm(indptr, csr_indices, query=q, key=k)
+        values = torch.clamp_(self.scaling * values, min=-10.0, max=10.0)
+        values = kernels.softmax(indptr, csr_indices, values=values)
+        return indptr, csr_indices, values
+
+    def _apply_attn(self, attn, v):
+        v_size = v.size()
+        indptr, indices, values = attn
+        y = kernels.spmm(indptr, indices, values, self._to_heads(v))
+        y = y.view(v_size[0], v_size[2], v_size[1], v_size[3]).transpose(1, 2).contiguous()
+        return y.view(v_size)
+
+
+class SparseVanillaAttentionV2(_SparseV2Mixin, VanillaAttention):
+    def __init__(self, d_head: int, d_codeword: int, n_codewords: int, p_dropout: float):
+        VanillaAttention.__init__(self, d_head=d_head, p_dropout=p_dropout)
+        self._init_v2(d_head, d_codeword, n_codewords)
+
+    @staticmethod
+    def from_pretrained(source: SparseVanillaAttentionV1):
+        return SparseVanillaAttentionV2._from_v1(source, SparseVanillaAttentionV1)
+
+    def _get_attn(self, q, k, attn_mask):  # attn_mask is ignored: the path is always causal
+        return self._sparse_get_attn(q, k)
+
+
+class SparseRotaryAttentionV2(_SparseV2Mixin, RotaryAttention):
+    def __init__(self, d_head: int, p_dropout: float, d_codeword: int, n_codewords: int):
+        RotaryAttention.__init__(self, d_head=d_head, p_dropout=p_dropout)
+        self._init_v2(d_head, d_codeword, n_codewords)
+
+    @staticmethod
+    def from_pretrained(source: SparseRotaryAttentionV1):
+        return SparseRotaryAttentionV2._from_v1(source, SparseRotaryAttentionV1)
+
+    def _get_attn(self, q, k, attn_mask):
+        return self._sparse_get_attn(self._rotate(q), self._rotate(k))
