@@ -335,9 +335,16 @@ def sparse_attention_values(indptr, indices, q, k, v, scaling: float):
     return y, p
 
 
-def sparse_mha_layer(q4, k4, v4, weight, sparse_coeff: int = 8):
+def sparse_mha_layer(q4, k4, v4, weight, sparse_coeff: int = 8, reference_output_layout: bool = False):
     """SparseVanillaAttentionV2.forward on [N,S,H,E] tensors (attention.py:84-142 via
-    basic/attention.py:41-57): transposes to [N*H,S,E], builds the CSR, applies it, transposes back."""
+    basic/attention.py:41-57): transposes to [N*H,S,E], builds the CSR, applies it, transposes back.
+
+    reference_output_layout=True reproduces a quirk of the shipped layer: _apply_attn un-transposes
+    the 3-D result [N*H, S, E] with `y.transpose(1, 2).contiguous().view(v_size)`
+    (attention.py:139-142), which swaps S and E instead of S and H, so the returned [N,S,H,E] tensor
+    is a re-interpretation of [N*H, E, S] memory.  The reference's only layer test feeds all-ones
+    (test_sparse_mha.py:7-43) and cannot see it.  The default (False) returns the mathematically
+    intended layout, i.e. what the reference's dense VanillaAttention returns on the same pattern."""
     N, S, H, E = q4.shape
     q = q4.transpose(1, 2).reshape(N * H, S, E)
     k = k4.transpose(1, 2).reshape(N * H, S, E)
@@ -345,6 +352,8 @@ def sparse_mha_layer(q4, k4, v4, weight, sparse_coeff: int = 8):
     with torch.no_grad():
         indptr, indices = sparse_attention_indices(q.detach(), k.detach(), weight.detach(), sparse_coeff)
     y, _ = sparse_attention_values(indptr, indices, q.float(), k.float(), v.float(), float(E) ** -0.5)
+    if reference_output_layout:
+        return y.transpose(1, 2).contiguous().view(N, S, H, E)
     return y.reshape(N, H, S, E).transpose(1, 2).contiguous()
 
 

@@ -53,6 +53,12 @@ class _SparseV2Mixin:
     """The hot path shared by the vanilla and rotary V2 layers (attention.py:84-142, 233-299)."""
 
     sparse_coeff: int = 8
+    # The shipped reference un-transposes the 3-D result with `y.transpose(1, 2).contiguous()
+    # .view(v_size)` (attention.py:139-142), which swaps S and E instead of S and H: its output is
+    # a re-interpretation of [N*H, E, S] memory as [N, S, H, E] (invisible to its all-ones layer
+    # test).  False (default) returns the intended layout — identical to the reference's dense
+    # VanillaAttention on the same pattern; True reproduces the shipped layer bit for bit.
+    reference_output_layout: bool = False
 
     def _init_v2(self, d_head, d_codeword, n_codewords):
         self.quantizer = PQV2(d_codeword=d_codeword, n_codewords=n_codewords, n_subspaces=d_head // d_codeword)
@@ -104,6 +110,8 @@ class _SparseV2Mixin:
         v_size = v.size()
         indptr, indices, values = attn
         y = kernels.spmm(indptr, indices, values, self._to_heads(v))
+        if self.reference_output_layout:
+            return y.transpose(1, 2).contiguous().view(v_size)
         y = y.view(v_size[0], v_size[2], v_size[1], v_size[3]).transpose(1, 2).contiguous()
         return y.view(v_size)
 

@@ -143,8 +143,12 @@ def test_lookup_recall_reference_test():
     for b in range(B):
         for r in range(0, S, 7):
             kk = min(r + 1, S // 8)
-            gt = set(torch.topk(score[b, r, : r + 1], k=kk).indices.tolist())
-            rec.append(len(gt & set(got[b, r, :kk].tolist())) / len(gt))
+            # tie-aware recall: a prediction is a hit when its match count reaches the k-th best
+            # count (torch.topk breaks the many ties arbitrarily, so raw set overlap is not a
+            # property of the algorithm; the reference test's 0.8 threshold is kept)
+            sc = score[b, r, : r + 1]
+            thr = torch.topk(sc, k=kk).values.min()
+            rec.append((sc[got[b, r, :kk].long()] >= thr).float().mean().item())
     assert sum(rec) / len(rec) > 0.8
 
 
