@@ -174,8 +174,10 @@ def lookup_spec(query: torch.Tensor, key: torch.Tensor, sparse_coeff: int) -> to
     bucket(j) = min(3, matches(r,j) // (m // 4)).  Lane t fills output positions t, t+4, ...
     (< min(r+1, k)) with its keys ordered (bucket descending, j ascending).  A (lane,bucket)
     list keeps at most cap_t = k/4 (t<2) or k/4-1 (t>=2) entries; later entries of lanes 2/3
-    land on lane 1/0's LAST slot of that bucket (position k-3 / k-4), the latest writer in
-    scan (= ascending j) order wins; later entries of lanes 0/1 are dropped.
+    land on lane 1/0's LAST slot of that bucket (position k-3 / k-4); the latest writer in scan
+    order wins, where scan order is the group-of-4 index j // 4 (one warp instruction handles keys
+    4g..4g+3) and, inside one instruction, the LOWEST lane wins (measured on B200 against the
+    compiled reference kernel); later entries of lanes 0/1 are dropped.
     """
     q = query.detach().cpu().numpy().astype(np.int64) & 0xFFFF
     kk = key.detach().cpu().numpy().astype(np.int64) & 0xFFFF
@@ -202,7 +204,8 @@ def lookup_spec(query: torch.Tensor, key: torch.Tensor, sparse_coeff: int) -> to
                     if t < 2 and len(own) >= quarter:
                         partner = lists[3 - t][s]
                         if len(partner) >= quarter:           # partner overflowed into our last slot
-                            stored[quarter - 1] = max(stored[quarter - 1], partner[-1])
+                            if partner[-1] // 4 > stored[quarter - 1] // 4:   # same instruction: owner wins
+                                stored[quarter - 1] = partner[-1]
                     chain.extend(stored)
                 n_t = len(range(t, lim, 4))
                 chain = chain[:n_t]

@@ -34,10 +34,13 @@ static inline int imin(int a, int b) { return a < b ? a : b; }
  * __syncthreads(), every shared array is indexed by the row's own ty, so rows can be
  * emulated independently.  Lanes tx=0..3 of a row sit in the same warp and run the
  * `for local_x = tx; ...; local_x += WORKER_SIZE` loop (lookup.cu:48) in lock-step:
- * iteration `step` of all four lanes is one instruction.  We serialise each instruction
- * as tx = 0,1,2,3, i.e. the only hardware-undefined case (two lanes storing to the same
- * shared address in the same instruction) is resolved as "higher lane wins"
- * (SURVEY.md section 8 a-2 / appendix C).
+ * iteration `step` of all four lanes is one instruction.  The only hardware-undefined case is
+ * two lanes storing to the same shared address in the same instruction (lane 3 / 2 overflowing
+ * onto lane 0 / 1's last slot while that lane writes it).  MEASURED on B200 (sm_100a) against
+ * the compiled reference kernel (oracle/_ref/ext_ref.so, tests/test_kernels_gpu.py::
+ * test_lookup_vs_reference_kernel): the LOWEST lane's store survives, run after run.  We
+ * therefore serialise each instruction as tx = 3,2,1,0 (last writer = lowest lane).  SURVEY.md
+ * section 8 a-2 guessed "higher lane wins" without a GPU; the measurement overrides it.
  */
 static void lookup_row(const int32_t *lhs_row, const int32_t *rhs, int32_t *out_row,
                        int seq_length, int n_spaces, int nnz, int gy, uint16_t *ind /* [N_SLOTS][nnz] */) {
@@ -49,7 +52,7 @@ static void lookup_row(const int32_t *lhs_row, const int32_t *rhs, int32_t *out_
     for (int offset_x = 0; offset_x < seq_length; offset_x += BLOCK_SIZE) {
         if (offset_x > block_row0) break;                      /* lookup.cu:36-38 */
         for (int step = 0; step < BLOCK_SIZE / WORKER_SIZE; ++step) {
-            for (int tx = 0; tx < WORKER_SIZE; ++tx) {
+            for (int tx = WORKER_SIZE - 1; tx >= 0; --tx) {
                 int local_x = tx + step * WORKER_SIZE;
                 int j = offset_x + local_x;
                 if (j > gy) continue;                          /* tril, lookup.cu:50-52 (break == continue: j only grows) */

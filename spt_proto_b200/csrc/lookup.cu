@@ -5,8 +5,8 @@
 //   row r, lane t in 0..3 owns keys j = t (mod 4), j <= r (ascending); bucket(j) = min(3, matches /
 //   (m/4)); lane t fills output positions t, t+4, ... < min(r+1, nnz) with its keys ordered (bucket
 //   desc, j asc); a (lane, bucket) list holds cap_t = nnz/4 (t < 2) or nnz/4 - 1 (t >= 2) entries;
-//   overflow of lanes 2/3 lands on lane 1/0's last slot of that bucket (latest j wins); unfilled
-//   positions are 0.
+//   overflow of lanes 2/3 lands on lane 1/0's last slot of that bucket (latest warp instruction
+//   wins, the owner lane wins inside one instruction); unfilled positions are 0.
 //
 // B200 design (not a port of the reference's 64-thread, serial-per-lane kernel):
 //   * Bit-sliced matching.  A pre-pass turns the key codes of a head into bitmaps
@@ -230,8 +230,11 @@ __device__ __forceinline__ void place_word(LaneState &st, const uint32_t (&mask)
 __device__ __forceinline__ void fix_clobber(const LaneState &st, int t, int quarter, uint16_t *row_img) {
     const int recv = __shfl_xor_sync(FULL, st.track >= 0 ? st.last_j : -1, 3);
     if (st.s_need >= 0 && recv >= 0) {
+        // The partner's overflow store lands after ours only if it belongs to a later warp
+        // instruction of the reference kernel (keys 4g..4g+3 are one instruction); inside the same
+        // instruction the lower lane (ours) survives — measured on B200, see oracle/spt_oracle_c.c.
         const int p = t + 4 * (quarter - 1);
-        if (recv > (int)row_img[p]) row_img[p] = (uint16_t)recv;
+        if ((recv >> 2) > ((int)row_img[p] >> 2)) row_img[p] = (uint16_t)recv;
     }
 }
 

@@ -156,18 +156,18 @@ def test_lookup_vs_reference_kernel(ref_ext):
     if ref_ext is None:
         pytest.skip("oracle/_ref/ext_ref.so not built")
     g = torch.Generator().manual_seed(11)
-    for (B, S, m, c) in [(4, 256, 8, 16), (2, 512, 8, 3), (2, 1024, 16, 16), (2, 512, 10, 4), (2, 256, 8, 1)]:
+    for (B, S, m, c) in [(4, 256, 8, 16), (2, 512, 8, 3), (2, 1024, 16, 16), (2, 512, 10, 4), (2, 256, 8, 1),
+                         (8, 512, 8, 16), (4, 1024, 8, 2)]:
         q = torch.randint(0, c, (B, S, m), generator=g, dtype=torch.int32).to(DEV)
         k = torch.randint(0, c, (B, S, m), generator=g, dtype=torch.int32).to(DEV)
         ref = ref_ext.lookup_forward_cuda(torch.empty([8]), q, k)
         torch.cuda.synchronize()
         got = _kernels().lookup(q, k, sparse_coeff=8)
         emu = O.lookup_forward(q.cpu(), k.cpu(), 8)
-        mism_emu = (ref.cpu() != emu).sum().item()
-        # the only hardware-undefined case (same-instruction shared-memory store conflict) is rare:
-        # the emulator and the real kernel may differ in a handful of slots at most
-        assert mism_emu <= max(2, emu.numel() // 20000), f"emulator vs reference kernel: {mism_emu} mismatches"
-        assert torch.equal(got.cpu(), emu)
+        # the emulator resolves the one hardware-undefined case (same-instruction shared-memory store
+        # conflict) as "lowest lane wins", which is what B200 does: all three must agree bit for bit
+        assert torch.equal(ref.cpu(), emu), f"emulator vs reference kernel: {(ref.cpu() != emu).sum().item()} mismatches"
+        assert torch.equal(got.cpu(), ref.cpu())
 
 
 # ---------------------------------------------------------------------------------- sddmm / softmax / spmm

@@ -60,6 +60,16 @@ def test_lookup_literal_equals_spec(B, S, m, c, coeff):
     assert torch.equal(O.lookup_forward(q, k, coeff), O.lookup_spec(q, k, coeff))
 
 
+def test_lookup_oracle_matches_reference_kernel_on_b200():
+    """Golden vectors = outputs of the UNMODIFIED reference CUDA kernel run on a B200
+    (tests/golden/make_lookup_golden_gpu.py).  Pins both restatements bit-exactly, including the
+    same-instruction store conflict (lowest lane wins on this hardware)."""
+    for case in gold("lookup_ref_kernel_b200"):
+        q, k, ref = case["q"].int(), case["k"].int(), case["ref"].int()
+        assert torch.equal(O.lookup_forward(q, k, case["sparse_coeff"]), ref)
+        assert torch.equal(O.lookup_spec(q[:1], k[:1], case["sparse_coeff"]), ref[:1])
+
+
 def test_lookup_structure_properties():
     g = torch.Generator().manual_seed(2)
     B, S, m = 2, 256, 8
