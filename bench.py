@@ -163,7 +163,11 @@ def _time_cuda(fn, iters=5, warm=2):
     return statistics.median(ts)
 
 
-def stage_roofline(n_seq: int, dev, hbm_gbs: float):
+FUSED_PATH = ["pq_encode", "lookup_mask", "attn_fwd", "attn_bwd"]
+STAGE_PATH = ["pq_encode", "lookup", "sddmm", "softmax_fwd", "spmm", "softmax_bwd", "csr2csc", "spmm_t"]
+
+
+def stage_roofline(n_seq: int, dev, hbm_gbs: float, tensor_tflops: float):
     """Times every stage kernel of the step on the bench shapes (inputs >> L2: B = n_seq*32 heads) and
     reports algorithmic bytes (SURVEY.md section 8d formulas; e = 2 for bf16) / time."""
     from spt_proto_b200 import ext
@@ -195,7 +199,22 @@ def stage_roofline(n_seq: int, dev, hbm_gbs: float):
         "csr2csc": (lambda: ext.csr2csc(indptr, idx), 4 * Sk + S * 4),
         "spmm_t": (lambda: ext.spmm_csc(csc, p, dy), 3 * Sk + 2 * Sd),
     }
+    from spt_proto_b200 import kernels
+    mask, extra0, _ = ext.lookup_mask(qc, kc, COEFF)
+    y_f, z_f = ext.sparse_attn_fwd(q, kk, v, mask, extra0, d ** -0.5)
+    stages["lookup_mask"] = (lambda: ext.lookup_mask(qc, kc, COEFF), 2 * S * m * 4 + S * S // 8 + S * 4)
     out = {}
+    T = S // 64
+    tile_flops = (T * (T + 1) // 2) * 2 * 64 * 64 * 64          # one causal dense GEMM over a head
+    sparse_flops = 2 * S * k * d                                 # one selected-pair product over a head
+    for name, fn, n_gemm in (("attn_fwd", lambda: ext.sparse_attn_fwd(q, kk, v, mask, extra0, d ** -0.5), 2),
+                             ("attn_bwd", lambda: ext.sparse_attn_bwd(q, kk, v, y_f, dy, mask, extra0, z_f, d ** -0.5), 7)):
+        t = _time_cuda(fn)
+        tf = n_gemm * tile_flops * B / t / 1e12
+        n_sparse = 2 if name == "attn_fwd" else 6
+        out[name] = {"ms": t * 1e3, "executed_dense_GFLOP": n_gemm * tile_flops * B / 1e9, "achieved_TFLOPs": tf,
+                     "frac_tensor": tf / tensor_tflops,
+                     "algorithmic_sparse_TFLOPs": n_sparse * sparse_flops * B / t / 1e12}
     for name, (fn, bytes_per_head) in stages.items():
         t = _time_cuda(fn)
         gbs = bytes_per_head * B / t / 1e9
@@ -220,12 +239,13 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    hbm_gbs, _, peak_kind = _peaks()
+    hbm_gbs, tensor_tflops, peak_kind = _peaks()
 
     n_seq = args.seqs
     torch.manual_seed(1234 + rank)
     attn = layers.SparseVanillaAttentionV2(d_head=D_HEAD, d_codeword=D_CODE, n_codewords=N_CODE, p_dropout=0.0).to(dev)
     attn.sparse_coeff = COEFF
+    attn.use_fused = not args.stage_path
     shape = (n_seq, SEQ, HEADS, D_HEAD)
     q = torch.randn(shape, device=dev).bfloat16().requires_grad_()
     k = torch.randn(shape, device=dev).bfloat16().requires_grad_()
@@ -297,10 +317,18 @@ def run_ours(args):
     tensor_bytes = n_seq * SEQ * HEADS * D_HEAD * 2
 
     if rank == 0:
-        stages = stage_roofline(n_seq, dev, hbm_gbs)
-        dom = max(stages, key=lambda s: stages[s]["ms"])
-        roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_GBps"], "peak": hbm_gbs,
-                "unit": "GB/s", "frac": stages[dom]["frac_hbm"], "traffic": None, "peak_source": peak_kind}
+        stages = stage_roofline(n_seq, dev, hbm_gbs, tensor_tflops)
+        on_path = FUSED_PATH if attn.use_fused else STAGE_PATH
+        dom = max(on_path, key=lambda s: stages[s]["ms"])
+        if "achieved_TFLOPs" in stages[dom]:
+            roof = {"bound": "tensor", "kernel": dom, "achieved": stages[dom]["achieved_TFLOPs"],
+                    "peak": tensor_tflops, "unit": "TFLOP/s", "frac": stages[dom]["frac_tensor"], "traffic": None,
+                    "peak_source": peak_kind,
+                    "note": "executed dense-causal-tile MMA flops (the kernel computes masked dense tiles); "
+                            "the selected-pair (algorithmic sparse) flops are 1/4 of these"}
+        else:
+            roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_GBps"], "peak": hbm_gbs,
+                    "unit": "GB/s", "frac": stages[dom]["frac_hbm"], "traffic": None, "peak_source": peak_kind}
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -315,7 +343,9 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "seqs_per_gpu": n_seq, "global_tokens_per_step": tokens_per_step,
                        "l2": "inputs+intermediates per step exceed L2 (>1 GB vs 126 MB); no explicit flush",
-                       "path": "stage kernels (pq_encode, lookup, sddmm, softmax, spmm, csr2csc, spmm_t)",
+                       "path": ("fused: pq_encode x2 -> lookup(bitmask) -> masked-dense-tile attention fwd/bwd "
+                                "(mma.sync bf16)" if attn.use_fused else
+                                "stage kernels (pq_encode, lookup, sddmm, softmax, spmm, csr2csc, spmm_t)"),
                        "parallelism": f"dp{world} (batch x head sharded, no collective)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * tensor_bytes,
@@ -339,6 +369,7 @@ def main():
     ap.add_argument("--seqs", type=int, default=4, help="sequences per GPU per step")
     ap.add_argument("--ref-heads", type=int, default=8, help="heads in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-path", action="store_true", help="run the reference-style stage kernels, not the fused path")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -138,21 +138,31 @@ int spt_softmax_bwd(const int32_t *indptr, const int32_t *indices, const float *
                     spt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Fused sparse attention on the fixed-stride CSR the layer produces (attention.py:115-141):
- * every row has exactly `k` entries (indices [B, S, k]).  One pass computes
- *   p = softmax_causal(clamp(scale * q.K[idx], -10, 10)),  y = p . V[idx]
- * probs [B, S, k] fp32 is written for the backward pass.  q, k, v, y [B, S, d] (dtype).
- * Backward: grad_y [B,S,d] (dtype) -> grad_q, grad_k, grad_v [B,S,d] fp32 or dtype (out_dtype).
- * grad_k / grad_v are accumulated through the CSC (deterministic).
+ * Fused sparse attention (fast path of SparseVanillaAttentionV2 / SparseRotaryAttentionV2,
+ * naive_gpt/layers/sparse/attention.py:105-141) as masked dense tiles on the tensor cores.
+ *
+ * spt_lookup_mask_fwd: same selection as spt_lookup_fwd, emitted as a per-row bitmask
+ *   mask [B, S, S/32] uint32 (bit i of word w <=> key 32 w + i selected) and
+ *   extra0 [B, S] int32 = number of zero-padding slots of the row (multiplicity of key 0 beyond its
+ *   own bit).  `output` (the int32 index tensor) may be NULL on this path.  Needs S % 32 == 0.
+ *
+ * spt_sparse_attn_fwd: q, k, v [B, S, d] bf16 ->
+ *   y [B, S, d] bf16 = sum_j p_rj v_j,  p = w * exp(clamp(scale * q.k, -clamp, clamp)) / Z,
+ *   zsum [B, S] fp32 = Z (row sums, >= 1e-9) saved for the backward.  d = 64, S % 64 == 0.
+ * spt_sparse_attn_bwd: grad_y -> grad_q, grad_k, grad_v [B, S, d] bf16.  Recomputes p from q, k
+ *   (nothing of size S x k is read or written); deterministic (no atomics).
+ *   workspace: spt_sparse_attn_bwd_workspace_bytes(B, S).
  * ------------------------------------------------------------------------------------------ */
-int spt_sparse_attn_fwd(const int32_t *indices, const void *q, const void *k, const void *v,
-                        float *probs, void *y, int B, int S, int d, int topk, float scale,
+int spt_lookup_mask_fwd(const int32_t *query_codes, const int32_t *key_codes, int32_t *output,
+                        uint32_t *mask, int32_t *extra0, void *workspace, int B, int S, int m, int nnz,
+                        spt_stream_t stream);
+int spt_sparse_attn_fwd(const void *q, const void *k, const void *v, const uint32_t *mask,
+                        const int32_t *extra0, void *y, float *zsum, int B, int S, int d, float scale,
                         float clamp, int dtype, spt_stream_t stream);
-size_t spt_sparse_attn_bwd_workspace_bytes(int B, int S, int d, int topk);
-int spt_sparse_attn_bwd(const int32_t *indices, const int32_t *col_ptr, const int32_t *row_idx,
-                        const int32_t *perm, const void *q, const void *k, const void *v,
-                        const float *probs, const void *grad_y, void *grad_q, void *grad_k,
-                        void *grad_v, void *workspace, int B, int S, int d, int topk, float scale,
+size_t spt_sparse_attn_bwd_workspace_bytes(int B, int S);
+int spt_sparse_attn_bwd(const void *q, const void *k, const void *v, const void *y, const void *grad_y,
+                        const uint32_t *mask, const int32_t *extra0, const float *zsum, void *grad_q,
+                        void *grad_k, void *grad_v, void *workspace, int B, int S, int d, float scale,
                         float clamp, int dtype, spt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

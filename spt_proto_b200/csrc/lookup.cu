@@ -213,7 +213,7 @@ __device__ __forceinline__ void plan_lane(LaneState &st, int t, int n_t, int qua
 }
 
 __device__ __forceinline__ void place_word(LaneState &st, const uint32_t (&mask)[4], int w, int t,
-                                           uint16_t *row_img) {
+                                           uint16_t *row_img, uint32_t *row_bits) {
 #pragma unroll
     for (int s = 3; s >= 0; --s) {
         uint32_t mk = mask[s];
@@ -221,24 +221,52 @@ __device__ __forceinline__ void place_word(LaneState &st, const uint32_t (&mask)
         while (mk && st.done[s] < st.take[s]) {
             const int i = __ffs(mk) - 1;
             mk &= mk - 1;
-            row_img[t + 4 * (st.start[s] + st.done[s])] = (uint16_t)(4 * (32 * w + i) + t);
+            const int j = 4 * (32 * w + i) + t;
+            row_img[t + 4 * (st.start[s] + st.done[s])] = (uint16_t)j;
+            if (row_bits) atomicOr(&row_bits[j >> 5], 1u << (j & 31));
             st.done[s] += 1;
         }
     }
 }
 
-__device__ __forceinline__ void fix_clobber(const LaneState &st, int t, int quarter, uint16_t *row_img) {
+__device__ __forceinline__ void fix_clobber(const LaneState &st, int t, int quarter, uint16_t *row_img,
+                                            uint32_t *row_bits) {
     const int recv = __shfl_xor_sync(FULL, st.track >= 0 ? st.last_j : -1, 3);
     if (st.s_need >= 0 && recv >= 0) {
         // The partner's overflow store lands after ours only if it belongs to a later warp
         // instruction of the reference kernel (keys 4g..4g+3 are one instruction); inside the same
         // instruction the lower lane (ours) survives — measured on B200, see oracle/spt_oracle_c.c.
         const int p = t + 4 * (quarter - 1);
-        if ((recv >> 2) > ((int)row_img[p] >> 2)) row_img[p] = (uint16_t)recv;
+        const int old = (int)row_img[p];
+        if ((recv >> 2) > (old >> 2)) {
+            row_img[p] = (uint16_t)recv;
+            if (row_bits) {
+                atomicAnd(&row_bits[old >> 5], ~(1u << (old & 31)));
+                atomicOr(&row_bits[recv >> 5], 1u << (recv & 31));
+            }
+        }
     }
 }
 
+// bitmask image [LK_ROWS][S/32] -> mask_out[b][r][:]; extra0[b][r] = nnz - (#filled positions) is the
+// number of zero-padding slots of the row, i.e. the extra multiplicity of key 0 in the CSR row.
+__device__ __forceinline__ void flush_mask(const uint32_t *s_bits, uint32_t *mask_out, int b, int r0, int S) {
+    const int words = S / 32;
+    const int rows = min(LK_ROWS, S - r0);
+    uint32_t *dst = mask_out + ((size_t)b * S + r0) * words;
+    for (int i = threadIdx.x; i < rows * words; i += blockDim.x) dst[i] = s_bits[i];
+}
+
+__device__ __forceinline__ void store_extra0(const LaneState &st, int32_t *extra0_out, int b, int r, int S, int nnz,
+                                             bool live, int t) {
+    int filled = st.take[0] + st.take[1] + st.take[2] + st.take[3];
+    filled += __shfl_xor_sync(FULL, filled, 1);
+    filled += __shfl_xor_sync(FULL, filled, 2);
+    if (extra0_out && live && t == 0) extra0_out[(size_t)b * S + r] = nnz - filled;
+}
+
 __device__ __forceinline__ void flush_rows(const uint16_t *s_out, int32_t *out, int b, int r0, int S, int nnz) {
+    if (!out) return;
     const int per_row = nnz / 4;
     for (int idx = threadIdx.x; idx < LK_ROWS * per_row; idx += blockDim.x) {
         const int rl = idx / per_row, c4 = idx % per_row;
@@ -256,11 +284,15 @@ __device__ __forceinline__ void flush_rows(const uint16_t *s_out, int32_t *out, 
 template <int M>
 __global__ void __launch_bounds__(LK_THREADS)
 lookup_bitmap_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__restrict__ kb,
-                     const int *__restrict__ flag, int32_t *__restrict__ out, int S, int nnz, int W, int chunk_words) {
+                     const int *__restrict__ flag, int32_t *__restrict__ out, uint32_t *__restrict__ mask_out,
+                     int32_t *__restrict__ extra0_out, int S, int nnz, int W, int chunk_words) {
     if (*flag) return;  // some key code >= 16: the generic kernel handles this call
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t *s_out = reinterpret_cast<uint16_t *>(smem_raw);
-    uint32_t *s_kb = reinterpret_cast<uint32_t *>(smem_raw + (((size_t)LK_ROWS * nnz * 2 + 15) & ~(size_t)15));
+    const size_t img_bytes = ((size_t)LK_ROWS * nnz * 2 + 15) & ~(size_t)15;
+    const size_t bits_bytes = mask_out ? (size_t)LK_ROWS * (S / 32) * 4 : 0;
+    uint32_t *s_bits = mask_out ? reinterpret_cast<uint32_t *>(smem_raw + img_bytes) : nullptr;
+    uint32_t *s_kb = reinterpret_cast<uint32_t *>(smem_raw + img_bytes + bits_bytes);
     const int b = blockIdx.y;
     const int tile = gridDim.x - 1 - blockIdx.x;  // heaviest (last) rows first
     const int r0 = tile * LK_ROWS;
@@ -274,6 +306,9 @@ lookup_bitmap_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__
     const int tile_words = min(W, (min(S, r0 + LK_ROWS) + 127) / 128);  // words any row of the tile needs
 
     for (int i = threadIdx.x; i < LK_ROWS * nnz / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(s_out)[i] = 0;
+    if (s_bits)
+        for (int i = threadIdx.x; i < LK_ROWS * (S / 32); i += blockDim.x) s_bits[i] = 0;
+    uint32_t *row_bits = s_bits ? s_bits + rl * (S / 32) : nullptr;
 
     BitmapMatcher<M> mt;
     mt.s_kb = s_kb;
@@ -311,26 +346,32 @@ lookup_bitmap_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__
 #pragma unroll
                     for (int s = 0; s < 4; ++s) st.len[s] += __popc(mask[s]);
                 } else {
-                    place_word(st, mask, w, t, s_out + rl * nnz);
+                    place_word(st, mask, w, t, s_out + rl * nnz, row_bits);
                 }
             }
         }
         if (pass == 0) plan_lane(st, t, n_t, quarter);
     }
-    fix_clobber(st, t, quarter, s_out + rl * nnz);
+    fix_clobber(st, t, quarter, s_out + rl * nnz, row_bits);
+    store_extra0(st, extra0_out, b, r, S, nnz, live, t);
     __syncthreads();
     flush_rows(s_out, out, b, r0, S, nnz);
+    if (s_bits) flush_mask(s_bits, mask_out, b, r0, S);
 }
 
 // ---- generic path ----------------------------------------------------------------------------
 // smem: [ out image ][ query codes LK_ROWS * m u16 ]
 __global__ void __launch_bounds__(LK_THREADS)
 lookup_generic_kernel(const int32_t *__restrict__ query_codes, const int32_t *__restrict__ key_codes,
-                      const int *__restrict__ flag, int flag_expect, int32_t *__restrict__ out, int S, int m, int nnz) {
+                      const int *__restrict__ flag, int flag_expect, int32_t *__restrict__ out,
+                      uint32_t *__restrict__ mask_out, int32_t *__restrict__ extra0_out, int S, int m, int nnz) {
     if (flag && (*flag != 0) != (flag_expect != 0)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t *s_out = reinterpret_cast<uint16_t *>(smem_raw);
-    uint16_t *s_q = reinterpret_cast<uint16_t *>(smem_raw + (((size_t)LK_ROWS * nnz * 2 + 15) & ~(size_t)15));
+    const size_t img_bytes = ((size_t)LK_ROWS * nnz * 2 + 15) & ~(size_t)15;
+    const size_t bits_bytes = mask_out ? (size_t)LK_ROWS * (S / 32) * 4 : 0;
+    uint32_t *s_bits = mask_out ? reinterpret_cast<uint32_t *>(smem_raw + img_bytes) : nullptr;
+    uint16_t *s_q = reinterpret_cast<uint16_t *>(smem_raw + img_bytes + bits_bytes);
     const int b = blockIdx.y;
     const int tile = gridDim.x - 1 - blockIdx.x;
     const int r0 = tile * LK_ROWS;
@@ -343,6 +384,9 @@ lookup_generic_kernel(const int32_t *__restrict__ query_codes, const int32_t *__
     const int n_t = lim > t ? (lim - t + 3) / 4 : 0;
 
     for (int i = threadIdx.x; i < LK_ROWS * nnz / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(s_out)[i] = 0;
+    if (s_bits)
+        for (int i = threadIdx.x; i < LK_ROWS * (S / 32); i += blockDim.x) s_bits[i] = 0;
+    uint32_t *row_bits = s_bits ? s_bits + rl * (S / 32) : nullptr;
     for (int i = threadIdx.x; i < LK_ROWS * m; i += blockDim.x) {
         const int rr = r0 + i / m;
         s_q[i] = rr < S ? (uint16_t)((unsigned)query_codes[((size_t)b * S + rr) * m + i % m] & 0xffffu) : 0;
@@ -369,11 +413,13 @@ lookup_generic_kernel(const int32_t *__restrict__ query_codes, const int32_t *__
     for (int w = 0; w < my_words; ++w) {
         uint32_t mask[4];
         mt.buckets(w, valid_mask(w, nkeys), mask);
-        place_word(st, mask, w, t, s_out + rl * nnz);
+        place_word(st, mask, w, t, s_out + rl * nnz, row_bits);
     }
-    fix_clobber(st, t, quarter, s_out + rl * nnz);
+    fix_clobber(st, t, quarter, s_out + rl * nnz, row_bits);
+    store_extra0(st, extra0_out, b, r, S, nnz, live, t);
     __syncthreads();
     flush_rows(s_out, out, b, r0, S, nnz);
+    if (s_bits) flush_mask(s_bits, mask_out, b, r0, S);
 }
 
 static bool bitmap_m_supported(int m) { return m == 4 || m == 8 || m == 10 || m == 12 || m == 16 || m == 32; }
@@ -393,24 +439,26 @@ extern "C" size_t spt_lookup_workspace_bytes(int B, int S, int m, int nnz) {
     return 16 + (size_t)B * m * W * LK_WORD_U32 * sizeof(uint32_t);
 }
 
-extern "C" int spt_lookup_fwd(const int32_t *query_codes, const int32_t *key_codes, int32_t *output, void *workspace,
-                              int B, int S, int m, int nnz, spt_stream_t stream) {
-    SPT_REQUIRE(query_codes && key_codes && output, "lookup_fwd: null pointer");
+static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int32_t *output, uint32_t *mask_out,
+                       int32_t *extra0_out, void *workspace, int B, int S, int m, int nnz, spt_stream_t stream) {
+    SPT_REQUIRE(query_codes && key_codes && (output || mask_out), "lookup_fwd: null pointer");
     SPT_REQUIRE(B >= 1 && S >= 1 && S <= 65536, "lookup_fwd: bad batch/seq (B=%d, S=%d; S must be <= 65536)", B, S);
     SPT_REQUIRE(B <= 65535, "lookup_fwd: batch %d exceeds grid limit", B);
     SPT_REQUIRE(m >= 4, "lookup_fwd: n_subspaces must be >= 4 (got %d)", m);
     SPT_REQUIRE(nnz >= 8 && nnz % 4 == 0 && nnz <= S, "lookup_fwd: nonzeros per row must be a multiple of 4 in [8, S] (got %d)", nnz);
+    SPT_REQUIRE(!mask_out || (S % 32 == 0 && extra0_out), "lookup_fwd: bitmask output needs S %% 32 == 0 and extra0");
     cudaStream_t st = as_stream(stream);
     const int tiles = (S + LK_ROWS - 1) / LK_ROWS;
     dim3 grid(tiles, B);
-    const size_t img = out_image_bytes(nnz);
+    const size_t img = out_image_bytes(nnz) + (mask_out ? (size_t)LK_ROWS * (S / 32) * 4 : 0);
     const size_t gen_smem = img + (size_t)LK_ROWS * m * 2;
-    SPT_REQUIRE(gen_smem <= 200 * 1024, "lookup_fwd: nnz=%d too large for the shared-memory row image", nnz);
+    SPT_REQUIRE(gen_smem <= 200 * 1024, "lookup_fwd: nnz=%d / S=%d too large for the shared-memory row images", nnz, S);
     if (gen_smem > 48 * 1024)
         cudaFuncSetAttribute(lookup_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem);
 
     if (!bitmap_m_supported(m)) {
-        lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, nullptr, 0, output, S, m, nnz);
+        lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, nullptr, 0, output, mask_out,
+                                                                  extra0_out, S, m, nnz);
         SPT_LAUNCH_CHECK("lookup_generic_kernel");
         return SPT_OK;
     }
@@ -423,17 +471,18 @@ extern "C" int spt_lookup_fwd(const int32_t *query_codes, const int32_t *key_cod
     lookup_pack_kernel<<<dim3(W, B), 128, 0, st>>>(key_codes, kb, flag, S, m, W);
     SPT_LAUNCH_CHECK("lookup_pack_kernel");
 
-    // bitmaps per 128-key word: m * 256 B; pick the chunk so that image + chunk fits the budget
+    // bitmaps per 128-key word: m * 256 B; pick the chunk so that images + chunk fit the budget
     const size_t per_word = (size_t)m * LK_WORD_U32 * 4;
+    SPT_REQUIRE(img + per_word <= LK_SMEM_BUDGET, "lookup_fwd: nnz=%d / S=%d too large", nnz, S);
     int chunk_words = (int)((LK_SMEM_BUDGET - img) / per_word);
-    SPT_REQUIRE(img < LK_SMEM_BUDGET && chunk_words >= 1, "lookup_fwd: nnz=%d too large", nnz);
     if (chunk_words > W) chunk_words = W;
     const size_t smem = img + per_word * chunk_words;
 #define SPT_LK_CASE(MM)                                                                                          \
     case MM:                                                                                                     \
         if (smem > 48 * 1024)                                                                                    \
             cudaFuncSetAttribute(lookup_bitmap_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        lookup_bitmap_kernel<MM><<<grid, LK_THREADS, smem, st>>>(query_codes, kb, flag, output, S, nnz, W, chunk_words); \
+        lookup_bitmap_kernel<MM><<<grid, LK_THREADS, smem, st>>>(query_codes, kb, flag, output, mask_out, extra0_out, S, \
+                                                                 nnz, W, chunk_words);                           \
         break;
     switch (m) {
         SPT_LK_CASE(4)
@@ -447,7 +496,21 @@ extern "C" int spt_lookup_fwd(const int32_t *query_codes, const int32_t *key_cod
     }
 #undef SPT_LK_CASE
     SPT_LAUNCH_CHECK("lookup_bitmap_kernel");
-    lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, S, m, nnz);
+    lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, mask_out,
+                                                              extra0_out, S, m, nnz);
     SPT_LAUNCH_CHECK("lookup_generic_kernel(fallback)");
     return SPT_OK;
+}
+
+extern "C" int spt_lookup_fwd(const int32_t *query_codes, const int32_t *key_codes, int32_t *output, void *workspace,
+                              int B, int S, int m, int nnz, spt_stream_t stream) {
+    SPT_REQUIRE(output, "lookup_fwd: null output");
+    return lookup_impl(query_codes, key_codes, output, nullptr, nullptr, workspace, B, S, m, nnz, stream);
+}
+
+extern "C" int spt_lookup_mask_fwd(const int32_t *query_codes, const int32_t *key_codes, int32_t *output,
+                                   uint32_t *mask, int32_t *extra0, void *workspace, int B, int S, int m, int nnz,
+                                   spt_stream_t stream) {
+    SPT_REQUIRE(mask && extra0, "lookup_mask_fwd: null mask / extra0");
+    return lookup_impl(query_codes, key_codes, output, mask, extra0, workspace, B, S, m, nnz, stream);
 }

@@ -299,3 +299,62 @@ def softmax_backward_cuda(indptr, indices, output, grad_output) -> torch.Tensor:
 def launch_count() -> int:
     """Kernel launches issued through libspt_b200 by this process so far."""
     return int(lib.spt_launch_count())
+
+
+# ---- fused sparse attention (masked dense tiles on the tensor cores) ------------------------------------
+def lookup_mask(query: torch.Tensor, key: torch.Tensor, sparse_coeff: int, want_indices: bool = False):
+    """Same selection as lookup_forward_cuda, emitted as (mask [B,S,S/32] int32 bit-words,
+    extra0 [B,S] int32 zero-padding multiplicity of key 0, indices [B,S,nnz] or None)."""
+    _check_dim(key, 3, "key")
+    _check_dim(query, 3, "query")
+    _check_type(key, torch.int32, "key")
+    _check_type(query, torch.int32, "query")
+    if query.shape != key.shape:
+        raise RuntimeError("query and key must have the same shape")
+    B, S, m = query.shape
+    if sparse_coeff <= 0 or S % sparse_coeff != 0 or S % 32 != 0:
+        raise RuntimeError("seq_length must be divisible by sparse_coeff and by 32")
+    nnz = S // sparse_coeff
+    dev = query.device
+    mask = torch.empty((B, S, S // 32), dtype=torch.int32, device=dev)
+    extra0 = torch.empty((B, S), dtype=torch.int32, device=dev)
+    indices = torch.empty((B, S, nnz), dtype=torch.int32, device=dev) if want_indices else None
+    ws = _workspace(lib.spt_lookup_workspace_bytes(B, S, m, nnz), query)
+    with _on_device(query):
+        check(lib.spt_lookup_mask_fwd(_p(query), _p(key), _p(indices), _p(mask), _p(extra0), _p(ws), B, S, m, nnz,
+                                      _stream(query)))
+    return mask, extra0, indices
+
+
+def _check_attn(q, k, v):
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        _check_dim(t, 3, name)
+        _check_type(t, torch.bfloat16, name)
+    if q.shape != k.shape or q.shape != v.shape:
+        raise RuntimeError("q, k, v must have the same shape")
+    return q.shape
+
+
+def sparse_attn_fwd(q, k, v, mask, extra0, scale: float, clamp: float = 10.0):
+    """-> (y [B,S,d] bf16, zsum [B,S] fp32).  See include/spt_b200.h."""
+    B, S, d = _check_attn(q, k, v)
+    y = torch.empty_like(q)
+    zsum = torch.empty((B, S), dtype=torch.float32, device=q.device)
+    with _on_device(q):
+        check(lib.spt_sparse_attn_fwd(_p(q), _p(k), _p(v), _p(mask), _p(extra0), _p(y), _p(zsum), B, S, d,
+                                      float(scale), float(clamp), SPT_BF16, _stream(q)))
+    return y, zsum
+
+
+def sparse_attn_bwd(q, k, v, y, grad_y, mask, extra0, zsum, scale: float, clamp: float = 10.0):
+    """-> (grad_q, grad_k, grad_v) bf16."""
+    B, S, d = _check_attn(q, k, v)
+    _check_dim(grad_y, 3, "grad_y")
+    _check_type(grad_y, torch.bfloat16, "grad_y")
+    gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ws = _workspace(lib.spt_sparse_attn_bwd_workspace_bytes(B, S), q)
+    with _on_device(q):
+        check(lib.spt_sparse_attn_bwd(_p(q), _p(k), _p(v), _p(y), _p(grad_y), _p(mask), _p(extra0), _p(zsum),
+                                      _p(gq), _p(gk), _p(gv), _p(ws), B, S, d, float(scale), float(clamp), SPT_BF16,
+                                      _stream(q)))
+    return gq, gk, gv

@@ -5,5 +5,6 @@ from .lookup import lookup
 from .softmax import softmax
 from .sddmm import sddmm
 from .spmm import spmm
+from .fused import sparse_attention
 
-__all__ = ["cdist", "lookup", "softmax", "sddmm", "spmm"]
+__all__ = ["cdist", "lookup", "softmax", "sddmm", "spmm", "sparse_attention"]

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import torch
 
-from .. import kernels
+from .. import ext, kernels
 from .basic import PQV1, PQV2, RotaryAttention, VanillaAttention
 
 
@@ -59,6 +59,9 @@ class _SparseV2Mixin:
     # test).  False (default) returns the intended layout — identical to the reference's dense
     # VanillaAttention on the same pattern; True reproduces the shipped layer bit for bit.
     reference_output_layout: bool = False
+    # bf16, d_head 64, S % 64 == 0 on CUDA: run lookup -> bitmask -> fused masked-dense attention on
+    # the tensor cores instead of the stage chain (same result up to bf16 rounding).
+    use_fused: bool = True
 
     def _init_v2(self, d_head, d_codeword, n_codewords):
         self.quantizer = PQV2(d_codeword=d_codeword, n_codewords=n_codewords, n_subspaces=d_head // d_codeword)
@@ -88,14 +91,35 @@ class _SparseV2Mixin:
         x = x.transpose(1, 2).contiguous()
         return x.view(-1, x.size(-2), x.size(-1))
 
-    def _sparse_get_attn(self, q, k):
-        assert q.size() == k.size()
-        seq_length = q.size(1)
-        q, k = self._to_heads(q), self._to_heads(k)
+    def _fused_ok(self, q) -> bool:
+        return (self.use_fused and q.is_cuda and q.dtype == torch.bfloat16 and q.size(-1) == 64
+                and q.size(1) % 64 == 0 and q.size(1) % self.sparse_coeff == 0
+                and (q.size(1) // self.sparse_coeff) % 4 == 0 and q.size(1) // self.sparse_coeff >= 8)
+
+    def _maybe_train_loss(self, q, k):
         if self.trigger.is_nonzero():  # one-shot PQ training loss, armed by the training loop
             self.trigger.logical_not_()
             loss = self.quantizer("train", z=q)[-1] + self.quantizer("train", z=k)[-1]
             self.register_buffer("loss", loss, persistent=False)
+
+    def _fused_forward(self, q, k, v):
+        v_size = v.size()
+        q, k, v = self._to_heads(q), self._to_heads(k), self._to_heads(v)
+        self._maybe_train_loss(q, k)
+        q_c = self.quantizer("encode", z=q)
+        k_c = self.quantizer("encode", z=k)
+        mask, extra0, _ = ext.lookup_mask(q_c, k_c, self.sparse_coeff)
+        y = kernels.sparse_attention(q, k, v, mask, extra0, self.scaling)
+        if self.reference_output_layout:
+            return y.transpose(1, 2).contiguous().view(v_size)
+        y = y.view(v_size[0], v_size[2], v_size[1], v_size[3]).transpose(1, 2).contiguous()
+        return y.view(v_size)
+
+    def _sparse_get_attn(self, q, k):
+        assert q.size() == k.size()
+        seq_length = q.size(1)
+        q, k = self._to_heads(q), self._to_heads(k)
+        self._maybe_train_loss(q, k)
         q_c = self.quantizer("encode", z=q)
         k_c = self.quantizer("encode", z=k)
         topk = kernels.lookup(q_c, k_c, sparse_coeff=self.sparse_coeff)
@@ -128,6 +152,11 @@ class SparseVanillaAttentionV2(_SparseV2Mixin, VanillaAttention):
     def _get_attn(self, q, k, attn_mask):  # attn_mask is ignored: the path is always causal
         return self._sparse_get_attn(q, k)
 
+    def forward(self, q, k, v, attn_mask=None):
+        if self._fused_ok(q):
+            return self._fused_forward(q, k, v)
+        return VanillaAttention.forward(self, q, k, v, attn_mask)
+
 
 class SparseRotaryAttentionV2(_SparseV2Mixin, RotaryAttention):
     def __init__(self, d_head: int, p_dropout: float, d_codeword: int, n_codewords: int):
@@ -140,3 +169,8 @@ class SparseRotaryAttentionV2(_SparseV2Mixin, RotaryAttention):
 
     def _get_attn(self, q, k, attn_mask):
         return self._sparse_get_attn(self._rotate(q), self._rotate(k))
+
+    def forward(self, q, k, v, attn_mask=None):
+        if self._fused_ok(q):
+            return self._fused_forward(self._rotate(q), self._rotate(k), v)
+        return VanillaAttention.forward(self, q, k, v, attn_mask)

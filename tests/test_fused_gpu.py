@@ -1,0 +1,117 @@
+"""GPU parity of the fused (masked dense tile) attention path against the oracle and against the
+stage-kernel path.  bf16 operands: y / grads are bf16, compared with atol 2e-2 + rtol 2e-2 to the fp32
+oracle evaluated on the same bf16-rounded inputs (bf16 has 8 mantissa bits; P is rounded to bf16 before
+the PV product).  The selection (bitmask + key-0 multiplicity) must be bit-exact."""
+import pytest
+import torch
+
+from oracle import spt_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _mask_from_indices(indices, S):
+    B, nnz_total = indices.shape[0], indices.shape[1] * indices.shape[2]
+    dense = torch.zeros(B, S, S, dtype=torch.int32)
+    dense.scatter_add_(2, indices.long(), torch.ones_like(indices))
+    bits = (dense > 0).view(B, S, S // 32, 32).long()
+    words = (bits << torch.arange(32)).sum(-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+    extra0 = dense[:, :, 0] - (dense[:, :, 0] > 0).int()
+    assert ((dense[:, :, 1:] <= 1).all())        # only key 0 is ever duplicated (zero padding)
+    return words, extra0
+
+
+@pytest.mark.parametrize("B,S,m,c,coeff", [(3, 256, 8, 16, 8), (2, 512, 8, 2, 8), (2, 128, 8, 1, 8), (1, 2048, 8, 16, 8),
+                                            (2, 256, 8, 40, 8), (2, 192, 6, 3, 4)])
+def test_lookup_mask_matches_index_output(B, S, m, c, coeff):
+    from spt_proto_b200 import ext
+    g = torch.Generator().manual_seed(S + c)
+    q = torch.randint(0, c, (B, S, m), generator=g, dtype=torch.int32)
+    k = torch.randint(0, c, (B, S, m), generator=g, dtype=torch.int32)
+    want_idx = O.lookup_forward(q, k, coeff)
+    want_words, want_extra = _mask_from_indices(want_idx, S)
+    mask, extra0, idx = ext.lookup_mask(q.to(DEV), k.to(DEV), coeff, want_indices=True)
+    assert torch.equal(idx.cpu(), want_idx)
+    assert torch.equal(mask.cpu(), want_words)
+    assert torch.equal(extra0.cpu(), want_extra)
+    mask2, extra2, none = ext.lookup_mask(q.to(DEV), k.to(DEV), coeff)
+    assert none is None and torch.equal(mask2, mask) and torch.equal(extra2, extra0)
+
+
+@pytest.mark.parametrize("B,S,scale_mul", [(2, 128, 1.0), (3, 256, 1.0), (1, 1024, 1.0), (2, 256, 6.0)])
+def test_fused_attention_matches_oracle(B, S, scale_mul):
+    """scale_mul = 6 drives scores beyond +-10 so that the clamp (and its zero gradient) is exercised."""
+    from spt_proto_b200 import ext, kernels
+    d = 64
+    g = torch.Generator().manual_seed(S + B)
+    q = (torch.randn(B, S, d, generator=g) * scale_mul ** 0.5).bfloat16()
+    k = (torch.randn(B, S, d, generator=g) * scale_mul ** 0.5).bfloat16()
+    v = torch.randn(B, S, d, generator=g).bfloat16()
+    dy = torch.randn(B, S, d, generator=g).bfloat16()
+    w = torch.randn(8, 16, 8, generator=g)
+    indptr, indices = O.sparse_attention_indices(q.float(), k.float(), w, 8)
+    qf, kf, vf = (t.float().requires_grad_() for t in (q, k, v))
+    y_ref, _ = O.sparse_attention_values(indptr, indices, qf, kf, vf, d ** -0.5)
+    y_ref.backward(dy.float())
+
+    qd, kd, vd = (t.to(DEV).requires_grad_() for t in (q, k, v))
+    q_c, k_c = ext.pq_encode(qd.detach(), w.to(DEV)), ext.pq_encode(kd.detach(), w.to(DEV))
+    mask, extra0, idx = ext.lookup_mask(q_c, k_c, 8, want_indices=True)
+    assert torch.equal(idx.flatten(1).cpu(), indices)
+    y = kernels.sparse_attention(qd, kd, vd, mask, extra0, d ** -0.5)
+    y.backward(dy.to(DEV))
+    tol = dict(atol=2e-2, rtol=2e-2)
+    assert torch.allclose(y.float().cpu(), y_ref.detach(), **tol)
+    assert torch.allclose(vd.grad.float().cpu(), vf.grad, atol=4e-2, rtol=3e-2)
+    assert torch.allclose(qd.grad.float().cpu(), qf.grad, atol=4e-2, rtol=3e-2)
+    assert torch.allclose(kd.grad.float().cpu(), kf.grad, atol=4e-2, rtol=3e-2)
+    # tighter, scale-free check: relative Frobenius error
+    for got, want in ((y, y_ref.detach()), (qd.grad, qf.grad), (kd.grad, kf.grad), (vd.grad, vf.grad)):
+        err = (got.float().cpu() - want).norm() / want.norm()
+        assert err < 1e-2, err
+
+
+def test_fused_layer_matches_stage_layer():
+    from spt_proto_b200 import layers
+    torch.manual_seed(0)
+    N, S, H, E = 2, 256, 4, 64
+    attn = layers.SparseVanillaAttentionV2(d_head=E, d_codeword=8, n_codewords=16, p_dropout=0.0).to(DEV)
+    q, k, v = (torch.randn(N, S, H, E, device=DEV).bfloat16().requires_grad_() for _ in range(3))
+    dy = torch.randn(N, S, H, E, device=DEV).bfloat16()
+    out = {}
+    for fused in (True, False):
+        attn.use_fused = fused
+        q.grad = k.grad = v.grad = None
+        y = attn(q, k, v)
+        y.backward(dy)
+        out[fused] = [t.detach().float().clone() for t in (y, q.grad, k.grad, v.grad)]
+    for a, b in zip(out[True], out[False]):
+        assert (a - b).norm() / b.norm() < 1.5e-2
+    # determinism of the fused path (no atomics)
+    attn.use_fused = True
+    q.grad = k.grad = v.grad = None
+    y = attn(q, k, v)
+    y.backward(dy)
+    for a, t in zip(out[True], (y, q.grad, k.grad, v.grad)):
+        assert torch.equal(a, t.detach().float())
+
+
+def test_fused_full_size_properties():
+    """BASELINE size (32 heads, S 2048): size-independent properties — rows of P sum to 1 (y of an
+    all-ones V is all ones), dV of an all-ones dO is the column sum of P (non-negative, sums to S per head)."""
+    from spt_proto_b200 import ext, kernels
+    B, S, d = 32, 2048, 64
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(B, S, d, generator=g).bfloat16().to(DEV)
+    k = torch.randn(B, S, d, generator=g).bfloat16().to(DEV)
+    w = torch.randn(8, 16, 8, generator=g).to(DEV)
+    mask, extra0, _ = ext.lookup_mask(ext.pq_encode(q, w), ext.pq_encode(k, w), 8)
+    v = torch.ones(B, S, d, device=DEV, dtype=torch.bfloat16).requires_grad_()
+    y = kernels.sparse_attention(q, k, v, mask, extra0, d ** -0.5)
+    assert torch.allclose(y.float(), torch.ones_like(y, dtype=torch.float32), atol=1e-2)
+    y.backward(torch.ones_like(y))
+    col_mass = v.grad.float()[:, :, 0]
+    assert (col_mass >= 0).all()
+    assert torch.allclose(col_mass.sum(1), torch.full((B,), float(S), device=DEV), rtol=1e-2)
