@@ -184,19 +184,25 @@ int spt_route_bucket(const float *prob, int32_t *bucket_ptr, int32_t *bucket_tok
 int spt_gather_rows_bf16(const void *src, const int32_t *index, void *dst, int64_t n_rows, int cols,
                          spt_stream_t stream);
 
-/* Grouped GEMM on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM):
- *   for every group g and row i in [group_ptr[g], group_ptr[g+1]):
- *       C[i, :] = epilogue( A[i, :] . B_g^T + bias_g )          A [M_total, K] bf16 (row-major)
- *   B_g = B + g * b_group_stride, [N, K] bf16 with row stride ldb (K-major), bias_g = bias + g*N
- *   epilogue: act = 0 none, 1 relu, 2 silu;  optional per-row scale row_scale[i];
- *   C [M_total, N] bf16 or fp32 (c_dtype) with row stride ldc.
- * Used for fc1 (A = bucketed tokens, B_g = W1 block g) and fc2 (A = bucketed hidden, B_g = W2
- * column block g) of the routed FFN, and for the backward products after operand transposes. */
-size_t spt_grouped_gemm_workspace_bytes(int n_groups);
-int spt_grouped_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t ldb, int64_t b_group_stride,
-                          const float *bias, const float *row_scale, void *C, int64_t ldc,
-                          const int32_t *group_ptr, int n_groups, int64_t M_total, int N, int K,
-                          int act, int c_dtype, void *workspace, spt_stream_t stream);
+/* Grouped GEMM on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM, TMA-fed).
+ * Operands are described as STORED: a row-major matrix [rows, cols] with leading dimension ld.
+ *   K-major operand  (x_mn_major = 0): stored [MN, K]  (reduction dim contiguous)
+ *   MN-major operand (x_mn_major = 1): stored [K, MN]  (consumed in place through an MN-major UMMA
+ *                                      descriptor, no transposed copy)
+ * mode 0 (M-grouped; fc1, fc2, dH, dX): C[i, 0:N] = epi(A[i, :] . op(B_g)), i over 128-row tiles,
+ *   g = tile_group[i / 128] (-1: skip).  B_g is addressed by the per-group coordinate offsets
+ *   b_k_off (along K) and b_mn_off (along N), both multiplied by g.  A must be K-major.
+ *   epi: + bias[g * bias_stride + n], activation (0 none, 1 relu, 2 silu), * row_scale[i].
+ * mode 1 (K-grouped; weight gradients): for every group g, C_g[0:M, 0:N] = A_g . B_g^T reduced over
+ *   rows group_ptr[g] .. group_ptr[g+1] (multiples of 64); C_g origin = (g*c_row_off, g*c_col_off).
+ * C is fp32 or bf16 with leading dimension ldc. */
+int spt_grouped_gemm_bf16(int mode, const void *A, long long a_rows, long long a_cols, long long lda,
+                          int a_mn_major, const void *B, long long b_rows, long long b_cols,
+                          long long ldb, int b_mn_major, const int32_t *tile_group, int n_m_tiles,
+                          const int32_t *group_ptr, int n_groups, int M, int N, int K, int a_k_off,
+                          int a_mn_off, int b_k_off, int b_mn_off, long long c_row_off,
+                          long long c_col_off, void *C, long long ldc, int c_dtype, const float *bias,
+                          int bias_stride, const float *row_scale, int act, spt_stream_t stream);
 
 /* Deterministic combine: y[t, :] = bias + sum_j partial[token_slots[t, j], :] in ascending block
  * order (the accumulation order of feedforward.py:66-81).  partial [T*k_active, d] fp32 or bf16. */

@@ -47,6 +47,9 @@ def _load() -> ctypes.CDLL:
         "spt_sparse_attn_bwd_workspace_bytes": (sz, [i32, i32]),
         "spt_sparse_attn_bwd": (i32, [vp] * 12 + [i32, i32, i32, f32, f32, i32, vp]),
     }
+    ll = c.c_longlong
+    sig["spt_grouped_gemm_bf16"] = (i32, [i32, vp, ll, ll, ll, i32, vp, ll, ll, ll, i32, vp, i32, vp, i32, i32, i32, i32,
+                                          i32, i32, i32, i32, ll, ll, vp, ll, i32, vp, i32, vp, i32, vp])
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError => header/library mismatch, fail loudly
         fn.restype = res

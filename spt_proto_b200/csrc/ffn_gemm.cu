@@ -1,0 +1,372 @@
+// (6) Routed-FFN grouped GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), bf16 in,
+// fp32 accumulate.
+//
+// The reference ships the routed FFN as a Python loop over weight blocks — boolean mask, gather,
+// addmm, activation, matmul, scatter-add per block (naive_gpt/layers/sparse/feedforward.py:47-85);
+// its native attempt (legacy/routed.cpp:10-68) was never finished.  Here tokens are bucketed by
+// activated block once (ffn_route.cu), every bucket is padded to a multiple of 128 rows, and all
+// blocks run in ONE launch per product:
+//
+//   mode 0 "M-grouped":  C[i, :] = epi( A[i, :] . B_g^T ),  g = group of the 128-row tile of row i
+//       fc1 : A = bucketed tokens  [R, d]  (K-major)   B_g = W1[g*bs:(g+1)*bs, :]        (K-major)
+//       fc2 : A = bucketed hidden  [R, bs] (K-major)   B_g = W2[:, g*bs:(g+1)*bs]        (K-major, ld F)
+//       dH  : A = dY bucketed      [R, d]  (K-major)   B_g = W2[:, g*bs:(g+1)*bs]^T      (MN-major)
+//       dX  : A = dU               [R, bs] (K-major)   B_g = W1[g*bs:(g+1)*bs, :]^T      (MN-major)
+//   mode 1 "K-grouped":  C_g = A_g^T-style products over the group's rows (weight gradients)
+//       dW1_g = dU_g^T X_g : A = dU [R, bs] (MN-major, M = bs), B = X [R, d] (MN-major, N = d)
+//       dW2_g = dY_g^T H_g : A = dY [R, d]  (MN-major, M = d),  B = H [R, bs] (MN-major, N = bs)
+//   MN-major operands are consumed straight from their row-major home through MN-major UMMA shared
+//   memory descriptors — no transposed copies of weights or activations are ever made (the
+//   reference materialises a permuted copy of W2 on every call, feedforward.py:94-102).
+//
+// Kernel anatomy (one 128x128 output tile per CTA, 2 CTAs per SM so one tile's epilogue overlaps the
+// other's main loop):
+//   warp 0   : TMA producer  — cp.async.bulk.tensor.2d into a 3-stage ring of 128B-swizzled tiles
+//   warp 1   : TMEM allocator + MMA issuer — one thread issues tcgen05.mma (M128 N128 K16, kind::f16)
+//   warps 2-5: epilogue — tcgen05.ld TMEM -> registers, bias / activation / row scale, global stores
+//   smem full/empty mbarriers between TMA and MMA, one TMEM-full mbarrier between MMA and epilogue.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace spt {
+namespace gemm {
+
+constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16, STAGES = 3;
+constexpr int THREADS = 192;
+constexpr int TILE_BYTES = BM * BK * 2;                 // 16 KB per operand per stage
+constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 128;
+
+struct Params {
+    int mode;                      // 0 = M-grouped, 1 = K-grouped
+    const int32_t *tile_group;     // mode 0: group of every 128-row tile (-1 = unused tail tile)
+    const int32_t *group_ptr;      // mode 1: padded row offsets [G+1] (K range of group g)
+    int K;                         // mode 0: reduction extent
+    int M, N;                      // mode 1: output tile extents per group; mode 0: N only
+    int a_mn_major, b_mn_major;
+    // per-group coordinate offsets (elements): *_k along the reduction dim, *_mn along M / N
+    int a_k_off, a_mn_off, b_k_off, b_mn_off;
+    long long c_row_off, c_col_off;  // mode 1: C_g origin = (g * c_row_off, g * c_col_off)
+    void *C;
+    long long ldc;
+    int c_dtype;                   // SPT_F32 / SPT_BF16
+    const float *bias;             // optional, bias[g * bias_stride + n]
+    int bias_stride;
+    const float *row_scale;        // optional, one factor per C row (mode 0)
+    int act;                       // 0 none, 1 relu, 2 silu
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {  // try_wait suspends the thread in hardware up to a time limit, so this is not a hot spin
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 UMMA): start address, leading / stride byte offsets (all
+// >> 4), descriptor version 1, 128-byte swizzle.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;   // version = 1
+    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    return d;
+}
+// Operand tile of one stage -> descriptor of its k-th K16 slice.
+//   K-major  : [128 rows][64 k] rows of 128 B, 8-row swizzle atoms: SBO = 1024, slice k = +32 B
+//   MN-major : two [64 k][64 mn] halves (8 KB each): SBO = 1024 (8 k-rows), LBO = 8192 (next 64 mn),
+//              slice k = +16 rows = +2048 B
+__device__ __forceinline__ uint64_t operand_desc(uint32_t tile_addr, int mn_major, int k) {
+    return mn_major ? make_desc(tile_addr + k * (UMMA_K * 128), BK * 128, 1024)
+                    : make_desc(tile_addr + k * (UMMA_K * 2), 0, 1024);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.0f);
+    if (act == 2) return v / (1.0f + __expf(-v));
+    return v;
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
+grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023) & ~1023u;                 // 128B swizzle needs 1024-byte alignment
+    unsigned char *smem = smem_raw + (base - raw);
+    const uint32_t s_a = base, s_b = base + STAGES * TILE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * 2 * TILE_BYTES);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + s * 8; };
+    auto empty_bar = [&](int s) { return bar0 + (STAGES + s) * 8; };
+    const uint32_t tmem_full_bar = bar0 + 2 * STAGES * 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- which tile? -----------------------------------------------------------------------------
+    int g, m0, n0 = blockIdx.y * BN, k_begin, k_end;
+    long long c_row0, c_col0;
+    if (p.mode == 0) {
+        g = p.tile_group[blockIdx.x];
+        if (g < 0) return;                                       // tail tile beyond the bucketed rows
+        m0 = blockIdx.x * BM;
+        k_begin = 0;
+        k_end = p.K;
+        c_row0 = m0;
+        c_col0 = n0;
+    } else {
+        g = blockIdx.z;
+        m0 = blockIdx.x * BM;
+        k_begin = p.group_ptr[g];
+        k_end = p.group_ptr[g + 1];
+        c_row0 = (long long)g * p.c_row_off + m0;
+        c_col0 = (long long)g * p.c_col_off + n0;
+    }
+    const int n_kblk = (k_end - k_begin + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const int a_k = g * p.a_k_off, a_mn = (p.mode == 0 ? m0 : g * p.a_mn_off + m0);
+            const int b_k = g * p.b_k_off, b_mn = g * p.b_mn_off + n0;
+            for (int kb = 0; kb < n_kblk; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_expect_tx(full_bar(s), 2 * TILE_BYTES);
+                const int k0 = k_begin + kb * BK;
+                const uint32_t da = s_a + s * TILE_BYTES, db = s_b + s * TILE_BYTES;
+                if (p.a_mn_major) {   // tensor map dims: (mn contiguous, k rows); two 64-wide halves
+                    tma_load_2d(da, &map_a, full_bar(s), a_mn, a_k + k0);
+                    tma_load_2d(da + TILE_BYTES / 2, &map_a, full_bar(s), a_mn + 64, a_k + k0);
+                } else {              // tensor map dims: (k contiguous, mn rows)
+                    tma_load_2d(da, &map_a, full_bar(s), a_k + k0, a_mn);
+                }
+                if (p.b_mn_major) {
+                    tma_load_2d(db, &map_b, full_bar(s), b_mn, b_k + k0);
+                    tma_load_2d(db + TILE_BYTES / 2, &map_b, full_bar(s), b_mn + 64, b_k + k0);
+                } else {
+                    tma_load_2d(db, &map_b, full_bar(s), b_k + k0, b_mn);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1),
+            // a_major bit 15, b_major bit 16, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn_major << 15) |
+                                   ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < n_kblk; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    umma_bf16(tmem_base, operand_desc(s_a + s * TILE_BYTES, p.a_mn_major, k),
+                              operand_desc(s_b + s * TILE_BYTES, p.b_mn_major, k), idesc, (kb | k) != 0);
+                }
+                umma_commit(empty_bar(s));                      // frees the smem stage when the MMAs retire
+            }
+            umma_commit(tmem_full_bar);                         // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const bool row_ok = p.mode == 0 ? true : (m0 + row_in_tile) < p.M;
+        const long long c_row = c_row0 + row_in_tile;
+        const float rs = (p.row_scale && p.mode == 0) ? p.row_scale[c_row] : 1.0f;
+        const int n_valid = min(BN, p.N - n0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            __syncwarp();
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
+            if (n_kblk == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = 0;           // empty group: no MMA ever wrote TMEM
+            }
+            if (row_ok && c0 < n_valid) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float x = __uint_as_float(r[i]);
+                if (p.bias) x += (c0 + i < n_valid) ? p.bias[(long long)g * p.bias_stride + n0 + c0 + i] : 0.0f;
+                v[i] = apply_act(x, p.act) * rs;
+            }
+            const bool full = c0 + 32 <= n_valid;
+            if (p.c_dtype == SPT_BF16) {
+                __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.C) + c_row * p.ldc + c_col0 + c0;
+                if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        float t[8] = {v[i], v[i + 1], v[i + 2], v[i + 3], v[i + 4], v[i + 5], v[i + 6], v[i + 7]};
+                        Vec16<__nv_bfloat16>::store(dst + i, t);
+                    }
+                } else {
+                    for (int i = 0; i < 32 && c0 + i < n_valid; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+                }
+            } else {
+                float *dst = reinterpret_cast<float *>(p.C) + c_row * p.ldc + c_col0 + c0;
+                if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4 *>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+                    for (int i = 0; i < 32 && c0 + i < n_valid; ++i) dst[i] = v[i];
+                }
+            }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+// ---- host: tensor maps ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows of `ld` elements; box = (64, box_outer)
+static int make_map(CUtensorMap *map, const void *base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(SPT_ERR_CUDA, "grouped_gemm: cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SPT_ERR_CUDA, "grouped_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SPT_OK;
+}
+
+}  // namespace gemm
+}  // namespace spt
+
+using namespace spt;
+
+// See include/spt_b200.h.  A: rows x cols as stored (row-major, leading dim lda); for a K-major operand
+// the stored matrix is [MN, K], for an MN-major operand it is [K, MN].
+extern "C" int spt_grouped_gemm_bf16(int mode, const void *A, long long a_rows, long long a_cols, long long lda,
+                                     int a_mn_major, const void *B, long long b_rows, long long b_cols, long long ldb,
+                                     int b_mn_major, const int32_t *tile_group, int n_m_tiles,
+                                     const int32_t *group_ptr, int n_groups, int M, int N, int K, int a_k_off,
+                                     int a_mn_off, int b_k_off, int b_mn_off, long long c_row_off, long long c_col_off,
+                                     void *C, long long ldc, int c_dtype, const float *bias, int bias_stride,
+                                     const float *row_scale, int act, spt_stream_t stream) {
+    SPT_REQUIRE(A && B && C, "grouped_gemm: null pointer");
+    SPT_REQUIRE(mode == 0 || mode == 1, "grouped_gemm: bad mode %d", mode);
+    SPT_REQUIRE(mode == 1 || (tile_group && n_m_tiles >= 1 && K >= 1 && !a_mn_major),
+                "grouped_gemm: mode 0 needs tile_group, K and a K-major A");
+    SPT_REQUIRE(mode == 0 || (group_ptr && n_groups >= 1 && M >= 1), "grouped_gemm: mode 1 needs group_ptr and M");
+    SPT_REQUIRE(N >= 1, "grouped_gemm: bad N");
+    SPT_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0),
+                "grouped_gemm: operands must be 16-byte aligned with leading dims multiple of 8");
+    SPT_REQUIRE(c_dtype == SPT_F32 || c_dtype == SPT_BF16, "grouped_gemm: bad c_dtype");
+    CUtensorMap map_a, map_b;
+    int rc = gemm::make_map(&map_a, A, (uint64_t)a_cols, (uint64_t)a_rows, (uint64_t)lda, a_mn_major ? 64 : 128);
+    if (rc != SPT_OK) return rc;
+    rc = gemm::make_map(&map_b, B, (uint64_t)b_cols, (uint64_t)b_rows, (uint64_t)ldb, b_mn_major ? 64 : 128);
+    if (rc != SPT_OK) return rc;
+    gemm::Params p;
+    p.mode = mode; p.tile_group = tile_group; p.group_ptr = group_ptr; p.K = K; p.M = M; p.N = N;
+    p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major;
+    p.a_k_off = a_k_off; p.a_mn_off = a_mn_off; p.b_k_off = b_k_off; p.b_mn_off = b_mn_off;
+    p.c_row_off = c_row_off; p.c_col_off = c_col_off; p.C = C; p.ldc = ldc; p.c_dtype = c_dtype;
+    p.bias = bias; p.bias_stride = bias_stride; p.row_scale = row_scale; p.act = act;
+    dim3 grid;
+    if (mode == 0) grid = dim3(n_m_tiles, (N + gemm::BN - 1) / gemm::BN, 1);
+    else grid = dim3((M + gemm::BM - 1) / gemm::BM, (N + gemm::BN - 1) / gemm::BN, n_groups);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(gemm::grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
+        attr_set = true;
+    }
+    gemm::grouped_gemm_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, as_stream(stream)>>>(map_a, map_b, p);
+    return after_launch("grouped_gemm_kernel");
+}

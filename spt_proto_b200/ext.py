@@ -358,3 +358,27 @@ def sparse_attn_bwd(q, k, v, y, grad_y, mask, extra0, zsum, scale: float, clamp:
                                       _p(gq), _p(gk), _p(gv), _p(ws), B, S, d, float(scale), float(clamp), SPT_BF16,
                                       _stream(q)))
     return gq, gk, gv
+
+
+# ---- (6) routed FFN: grouped GEMM on tcgen05 ------------------------------------------------------------
+def grouped_gemm(mode: int, A: torch.Tensor, a_mn_major: bool, B: torch.Tensor, b_mn_major: bool, *,
+                 tile_group=None, group_ptr=None, M: int = 0, N: int, K: int = 0,
+                 a_k_off: int = 0, a_mn_off: int = 0, b_k_off: int = 0, b_mn_off: int = 0,
+                 c_row_off: int = 0, c_col_off: int = 0, out: torch.Tensor, bias=None, bias_stride: int = 0,
+                 row_scale=None, act: int = 0) -> torch.Tensor:
+    """Thin binding of spt_grouped_gemm_bf16 (see include/spt_b200.h).  A, B: 2-D bf16 tensors as
+    stored (row-major, possibly with a row stride); `out`: 2-D fp32/bf16 tensor written in place."""
+    for name, t in (("A", A), ("B", B)):
+        if not (t.is_cuda and t.dim() == 2 and t.dtype == torch.bfloat16 and t.stride(1) == 1):
+            raise RuntimeError(f"{name} must be a 2-D bf16 CUDA tensor with unit inner stride")
+    if not (out.is_cuda and out.dim() == 2 and out.stride(1) == 1 and out.dtype in _DTYPES):
+        raise RuntimeError("out must be a 2-D fp32/bf16 CUDA tensor with unit inner stride")
+    n_groups = 0 if group_ptr is None else group_ptr.numel() - 1
+    n_m_tiles = 0 if tile_group is None else tile_group.numel()
+    with _on_device(A):
+        check(lib.spt_grouped_gemm_bf16(
+            mode, _p(A), A.size(0), A.size(1), A.stride(0), int(a_mn_major), _p(B), B.size(0), B.size(1), B.stride(0),
+            int(b_mn_major), _p(tile_group), n_m_tiles, _p(group_ptr), n_groups, M, N, K, a_k_off, a_mn_off, b_k_off,
+            b_mn_off, c_row_off, c_col_off, _p(out), out.stride(0), _DTYPES[out.dtype], _p(bias), bias_stride,
+            _p(row_scale), act, _stream(A)))
+    return out
