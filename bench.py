@@ -223,6 +223,32 @@ def stage_roofline(n_seq: int, dev, hbm_gbs: float, tensor_tflops: float):
     return out
 
 
+def ffn_bench(dev, tensor_tflops: float):
+    """BASELINE configs[2]: OPT-1.3B-shape routed FFN (d 2048, ffn 8192, half the blocks active) fwd+bwd
+    with weight gradients, T = 8192 tokens, bf16, grouped GEMM on tcgen05.  Reported beside the headline."""
+    from spt_proto_b200 import layers
+    out = {}
+    for bs in (1024, 2048):
+        torch.manual_seed(4321)
+        d, F, T = 2048, 8192, 8192
+        ffn = layers.RoutedFFN(d_model=d, d_feedforward=F, block_size=bs, activation=torch.nn.ReLU()).to(dev).bfloat16()
+        x = torch.randn(16, T // 16, d, device=dev).bfloat16().requires_grad_()
+        dy = torch.randn(16, T // 16, d, device=dev).bfloat16()
+
+        def step():
+            x.grad = None
+            for p in ffn.parameters():
+                p.grad = None
+            ffn(x).backward(dy)
+
+        t = _time_cuda(step, iters=5, warm=3)
+        flops = 12 * T * 0.5 * F * d          # fwd 4 T rho F d, bwd dX 4 ..., bwd dW 4 ... (SURVEY.md 8d)
+        out[f"block_{bs}"] = {"ms": t * 1e3, "tokens_per_s": T / t, "algorithmic_TFLOPs": flops / t / 1e12,
+                              "frac_tensor": flops / t / 1e12 / tensor_tflops, "T": T, "d": d, "ffn": F,
+                              "n_blocks": F // bs, "active": (F // bs) // 2}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 # main arm
 # ---------------------------------------------------------------------------------------------------
@@ -353,6 +379,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": roof,
             "stages": stages,
+            "routed_ffn": ffn_bench(dev, tensor_tflops),
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

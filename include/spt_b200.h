@@ -169,20 +169,33 @@ int spt_sparse_attn_bwd(const void *q, const void *k, const void *v, const void 
  * (6) routed FFN — the grouped GEMM the reference only sketches (legacy/routed.cpp:10-68,
  * legacy/test_routed.py:9-26) and ships as a Python loop (layers/sparse/feedforward.py:47-85).
  *
- * spt_route_bucket: prob [T, nb] fp32 (router output) -> top-`k_active` blocks per token
- * (ties: lowest block index) bucketed by block:
- *   bucket_ptr [nb+1] int32, bucket_tokens [T*k_active] int32 (token ids, ascending per block),
- *   token_slots [T, k_active] int32 (position of the token's j-th active block, blocks ascending,
- *   inside bucket_tokens; used for the deterministic block-ordered combine).
+ * spt_route_bucket: prob [T, nb] fp32 (router output) -> top-`k_active` blocks per token (ties:
+ * lowest block index; only set membership matters, feedforward.py:67-70) bucketed by block, every
+ * bucket padded to a multiple of 128 rows:
+ *   bucket_ptr [nb+1], bucket_rows [nb] (real row counts), tile_group [R/128] (block of each 128-row
+ *   tile, -1 past the end), row_token [R] (token of each bucket row, ascending per bucket, -1 =
+ *   padding), row_prob [R] (prob[token, block], 0 = padding), token_rows [T, k_active] (bucket rows
+ *   of the token's active blocks, blocks ascending — the accumulation order of feedforward.py:66-81).
+ * R: caller's upper bound, multiple of 128, >= T*k_active + 127*nb.  nb <= 64.
  * ------------------------------------------------------------------------------------------ */
 size_t spt_route_bucket_workspace_bytes(int64_t T, int nb);
-int spt_route_bucket(const float *prob, int32_t *bucket_ptr, int32_t *bucket_tokens,
-                     int32_t *token_slots, void *workspace, int64_t T, int nb, int k_active,
-                     spt_stream_t stream);
+int spt_route_bucket(const float *prob, int32_t *bucket_ptr, int32_t *bucket_rows, int32_t *tile_group,
+                     int32_t *row_token, float *row_prob, int32_t *token_rows, void *workspace,
+                     int64_t T, int nb, int k_active, int64_t R, spt_stream_t stream);
 
-/* Gather rows: dst[i, :] = src[index[i], :] (bf16, `cols` elements per row, cols % 8 == 0). */
-int spt_gather_rows_bf16(const void *src, const int32_t *index, void *dst, int64_t n_rows, int cols,
+/* dst[r, :] = src[row_token[r], :] for r < R, zeros where row_token[r] < 0 (bf16, C % 8 == 0). */
+int spt_gather_rows_bf16(const void *src, const int32_t *row_token, void *dst, int64_t R, int C,
                          spt_stream_t stream);
+
+/* Deterministic combine: y[t, :] = bias + sum_j partial[token_rows[t, j], :], j ascending (= block
+ * order); fp32 accumulation; partial / y are fp32 or bf16; bias may be NULL. */
+int spt_ffn_combine(const void *partial, const int32_t *token_rows, const float *bias, void *y, int64_t T,
+                    int C, int k_active, int partial_dtype, int y_dtype, spt_stream_t stream);
+
+/* out[g, c] = sum of x[row, c] over the (padded) rows of bucket g — bias gradients; x bf16 [R, C]. */
+size_t spt_group_colsum_workspace_bytes(int n_groups, int C);
+int spt_group_colsum_bf16(const void *x, const int32_t *bucket_ptr, float *out, void *workspace,
+                          int n_groups, int C, spt_stream_t stream);
 
 /* Grouped GEMM on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM, TMA-fed).
  * Operands are described as STORED: a row-major matrix [rows, cols] with leading dimension ld.
@@ -203,11 +216,6 @@ int spt_grouped_gemm_bf16(int mode, const void *A, long long a_rows, long long a
                           int a_mn_off, int b_k_off, int b_mn_off, long long c_row_off,
                           long long c_col_off, void *C, long long ldc, int c_dtype, const float *bias,
                           int bias_stride, const float *row_scale, int act, spt_stream_t stream);
-
-/* Deterministic combine: y[t, :] = bias + sum_j partial[token_slots[t, j], :] in ascending block
- * order (the accumulation order of feedforward.py:66-81).  partial [T*k_active, d] fp32 or bf16. */
-int spt_ffn_combine(const void *partial, const int32_t *token_slots, const float *bias, void *y,
-                    int64_t T, int d, int k_active, int partial_dtype, int y_dtype, spt_stream_t stream);
 
 #ifdef __cplusplus
 }

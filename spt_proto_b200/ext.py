@@ -382,3 +382,68 @@ def grouped_gemm(mode: int, A: torch.Tensor, a_mn_major: bool, B: torch.Tensor, 
             b_mn_off, c_row_off, c_col_off, _p(out), out.stride(0), _DTYPES[out.dtype], _p(bias), bias_stride,
             _p(row_scale), act, _stream(A)))
     return out
+
+
+class Bucket:
+    """Device-side token -> block bucketing produced by route_bucket() (see include/spt_b200.h)."""
+    __slots__ = ("T", "nb", "k", "R", "bucket_ptr", "bucket_rows", "tile_group", "row_token", "row_prob", "token_rows")
+
+
+def route_bucket(prob: torch.Tensor, k_active: int) -> Bucket:
+    """prob [T, nb] fp32 router probabilities -> padded bucket layout.  No host synchronisation: the
+    row capacity R is the static upper bound round_up(T*k + 127*nb, 128)."""
+    _check_dim(prob, 2, "prob")
+    _check_type(prob, torch.float32, "prob")
+    T, nb = prob.shape
+    dev = prob.device
+    b = Bucket()
+    b.T, b.nb, b.k = T, nb, k_active
+    b.R = (T * k_active + 127 * nb + 127) // 128 * 128
+    i32 = dict(dtype=torch.int32, device=dev)
+    b.bucket_ptr = torch.empty(nb + 1, **i32)
+    b.bucket_rows = torch.empty(nb, **i32)
+    b.tile_group = torch.empty(b.R // 128, **i32)
+    b.row_token = torch.empty(b.R, **i32)
+    b.row_prob = torch.empty(b.R, dtype=torch.float32, device=dev)
+    b.token_rows = torch.empty(T, k_active, **i32)
+    ws = _workspace(lib.spt_route_bucket_workspace_bytes(T, nb), prob)
+    with _on_device(prob):
+        check(lib.spt_route_bucket(_p(prob), _p(b.bucket_ptr), _p(b.bucket_rows), _p(b.tile_group), _p(b.row_token),
+                                   _p(b.row_prob), _p(b.token_rows), _p(ws), T, nb, k_active, b.R, _stream(prob)))
+    return b
+
+
+def gather_rows(src: torch.Tensor, row_token: torch.Tensor) -> torch.Tensor:
+    """dst[r] = src[row_token[r]] (zeros for padding rows); src [T, C] bf16."""
+    _check_dim(src, 2, "src")
+    _check_type(src, torch.bfloat16, "src")
+    R, C = row_token.numel(), src.size(1)
+    dst = torch.empty(R, C, dtype=torch.bfloat16, device=src.device)
+    with _on_device(src):
+        check(lib.spt_gather_rows_bf16(_p(src), _p(row_token), _p(dst), R, C, _stream(src)))
+    return dst
+
+
+def ffn_combine(partial: torch.Tensor, token_rows: torch.Tensor, bias, out_dtype) -> torch.Tensor:
+    """y[t] = bias + sum_j partial[token_rows[t, j]] in ascending block order (fp32 accumulation)."""
+    _check_dim(partial, 2, "partial")
+    T, k = token_rows.shape
+    C = partial.size(1)
+    y = torch.empty(T, C, dtype=out_dtype, device=partial.device)
+    bias32 = None if bias is None else bias.float().contiguous()
+    with _on_device(partial):
+        check(lib.spt_ffn_combine(_p(partial), _p(token_rows), _p(bias32), _p(y), T, C, k, _DTYPES[partial.dtype],
+                                  _DTYPES[out_dtype], _stream(partial)))
+    return y
+
+
+def group_colsum(x: torch.Tensor, bucket_ptr: torch.Tensor) -> torch.Tensor:
+    """out[g, c] = sum of x[row, c] over bucket g's rows; x [R, C] bf16 -> [G, C] fp32."""
+    _check_dim(x, 2, "x")
+    _check_type(x, torch.bfloat16, "x")
+    G, C = bucket_ptr.numel() - 1, x.size(1)
+    out = torch.empty(G, C, dtype=torch.float32, device=x.device)
+    ws = _workspace(lib.spt_group_colsum_workspace_bytes(G, C), x)
+    with _on_device(x):
+        check(lib.spt_group_colsum_bf16(_p(x), _p(bucket_ptr), _p(out), _p(ws), G, C, _stream(x)))
+    return out

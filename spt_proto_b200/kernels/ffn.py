@@ -1,0 +1,127 @@
+"""Autograd building blocks of the routed FFN (reference naive_gpt/layers/sparse/feedforward.py:47-85
+and its torch-autograd backward), on the tcgen05 grouped GEMM:
+
+    bucket   = route(prob)                              tokens bucketed by active block (no grad)
+    Xp       = gather(x, bucket)                        [R, d]    backward: block-ordered combine
+    H        = blocked_linear_rows(Xp, W1, b1, act)     [R, bs]   block g uses W1[g*bs:(g+1)*bs, :]
+    Yp       = blocked_linear_cols(H, W2)               [R, d]    block g uses W2[:, g*bs:(g+1)*bs]
+    y        = combine(Yp, bucket, b2)                  [T, d]    backward: gather
+
+All GEMM operands are bf16 (fp32 accumulation); weight gradients come out in fp32."""
+import torch
+from torch import autograd
+
+from .. import ext
+
+ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
+
+
+class GatherRows(autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bucket):
+        ctx.bucket = bucket
+        return ext.gather_rows(x, bucket.row_token)
+
+    @staticmethod
+    def backward(ctx, grad):
+        b = ctx.bucket
+        return ext.ffn_combine(grad.contiguous(), b.token_rows, None, grad.dtype), None
+
+
+class CombineRows(autograd.Function):
+    @staticmethod
+    def forward(ctx, partial, bucket, bias, out_dtype):
+        ctx.bucket, ctx.has_bias, ctx.p_dtype = bucket, bias is not None, partial.dtype
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        return ext.ffn_combine(partial, bucket.token_rows, bias, out_dtype)
+
+    @staticmethod
+    def backward(ctx, grad):
+        g16 = grad.contiguous().to(torch.bfloat16)
+        d_partial = ext.gather_rows(g16, ctx.bucket.row_token).to(ctx.p_dtype)
+        d_bias = grad.float().sum(0).to(ctx.bias_dtype) if ctx.has_bias else None
+        return d_partial, None, d_bias, None
+
+
+class BlockedLinearRows(autograd.Function):
+    """y[i, :] = act(x[i, :] @ W[g*bs:(g+1)*bs, :].T + b[g*bs:(g+1)*bs]) * row_scale[i],  g = block of row i.
+    W [F, K] (fc1 / gate / side layout).  act in {none, relu}; other activations are applied by the caller."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, bucket, bs, act):
+        w16 = weight if weight.dtype == torch.bfloat16 else weight.to(torch.bfloat16)
+        y = torch.empty(x.size(0), bs, dtype=torch.bfloat16, device=x.device)
+        b32 = None if bias is None else bias.float().contiguous()
+        ext.grouped_gemm(0, x, False, w16, False, tile_group=bucket.tile_group, N=bs, K=x.size(1), b_mn_off=bs,
+                         out=y, bias=b32, bias_stride=bs, act=act)
+        ctx.save_for_backward(x, w16, y if act == ACT_RELU else None)
+        ctx.bucket, ctx.bs, ctx.act = bucket, bs, act
+        ctx.w_dtype, ctx.w_shape = weight.dtype, weight.shape
+        ctx.b_dtype = None if bias is None else bias.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, w16, y = ctx.saved_tensors
+        b, bs = ctx.bucket, ctx.bs
+        grad = grad.contiguous()
+        if ctx.act == ACT_RELU:
+            grad = grad * (y > 0)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:   # dx[i, :] = grad[i, :] @ W_g : W consumed MN-major, K offset g*bs
+            dx = torch.empty_like(x)
+            ext.grouped_gemm(0, grad, False, w16, True, tile_group=b.tile_group, N=x.size(1), K=bs, b_k_off=bs, out=dx)
+        if ctx.needs_input_grad[1]:   # dW_g = grad_g^T x_g over the bucket's rows
+            dw32 = torch.empty(ctx.w_shape, dtype=torch.float32, device=x.device)
+            ext.grouped_gemm(1, grad, True, x, True, group_ptr=b.bucket_ptr, M=bs, N=x.size(1), c_row_off=bs, out=dw32)
+            dw = dw32.to(ctx.w_dtype)
+        if ctx.b_dtype is not None and ctx.needs_input_grad[2]:
+            db = ext.group_colsum(grad, b.bucket_ptr).reshape(-1).to(ctx.b_dtype)
+        return dx, dw, db, None, None, None
+
+
+class BlockedLinearCols(autograd.Function):
+    """y[i, :] = (x[i, :] @ W[:, g*bs:(g+1)*bs].T) * row_scale[i],  W [d, F] (fc2 / down layout)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bucket, bs):
+        w16 = weight if weight.dtype == torch.bfloat16 else weight.to(torch.bfloat16)
+        d = weight.size(0)
+        y = torch.empty(x.size(0), d, dtype=torch.bfloat16, device=x.device)
+        ext.grouped_gemm(0, x, False, w16, False, tile_group=bucket.tile_group, N=d, K=bs, b_k_off=bs, out=y)
+        ctx.save_for_backward(x, w16)
+        ctx.bucket, ctx.bs, ctx.w_dtype, ctx.w_shape = bucket, bs, weight.dtype, weight.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, w16 = ctx.saved_tensors
+        b, bs = ctx.bucket, ctx.bs
+        grad = grad.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:   # dx[i, f] = sum_n grad[i, n] W[n, g*bs + f] : W MN-major, N offset g*bs
+            dx = torch.empty_like(x)
+            ext.grouped_gemm(0, grad, False, w16, True, tile_group=b.tile_group, N=bs, K=grad.size(1), b_mn_off=bs,
+                             out=dx)
+        if ctx.needs_input_grad[1]:   # dW[:, g*bs:(g+1)*bs] = grad_g^T x_g
+            dw32 = torch.empty(ctx.w_shape, dtype=torch.float32, device=x.device)
+            ext.grouped_gemm(1, grad, True, x, True, group_ptr=b.bucket_ptr, M=grad.size(1), N=bs, c_col_off=bs,
+                             out=dw32)
+            dw = dw32.to(ctx.w_dtype)
+        return dx, dw, None, None
+
+
+def gather(x, bucket):
+    return GatherRows.apply(x, bucket)
+
+
+def combine(partial, bucket, bias, out_dtype):
+    return CombineRows.apply(partial, bucket, bias, out_dtype)
+
+
+def blocked_linear_rows(x, weight, bias, bucket, bs, act=ACT_NONE):
+    return BlockedLinearRows.apply(x, weight, bias, bucket, bs, act)
+
+
+def blocked_linear_cols(x, weight, bucket, bs):
+    return BlockedLinearCols.apply(x, weight, bucket, bs)

@@ -96,3 +96,129 @@ def test_grouped_gemm_mode1_weight_grad(sizes, M, N):
     ext.grouped_gemm(1, dU.to(DEV), True, X.to(DEV), True, group_ptr=torch.tensor(ptr, dtype=torch.int32).to(DEV),
                      M=M, N=N, c_col_off=N, out=out2)
     assert torch.allclose(out2.cpu().view(M, G, N).transpose(0, 1), want, atol=5e-2, rtol=1e-2)
+
+
+# ---------------------------------------------------------------------------------- routing / bucketing
+@pytest.mark.parametrize("T,nb,k", [(1000, 8, 4), (8192, 4, 2), (77, 16, 4), (513, 8, 2)])
+def test_route_bucket_matches_oracle(T, nb, k):
+    from oracle import spt_oracle as O
+    from spt_proto_b200 import ext
+    g = torch.Generator().manual_seed(T + nb)
+    prob = torch.sigmoid(torch.randn(T, nb, generator=g))
+    prob[::7, 1] = prob[::7, 0]                       # exact ties: lowest block index must win
+    prob[::11] = 0.5
+    mask = O.route_topk_mask(prob, k)
+    b = ext.route_bucket(prob.to(DEV), k)
+    ptr, rows = b.bucket_ptr.cpu(), b.bucket_rows.cpu()
+    assert torch.equal(rows, mask.sum(0).int())
+    row_token, row_prob, token_rows, tile_group = b.row_token.cpu(), b.row_prob.cpu(), b.token_rows.cpu(), b.tile_group.cpu()
+    for gi in range(nb):
+        assert ptr[gi] % 128 == 0
+        want = torch.nonzero(mask[:, gi]).flatten().int()
+        assert torch.equal(row_token[ptr[gi]: ptr[gi] + rows[gi]], want)          # ascending token order
+        assert (row_token[ptr[gi] + rows[gi]: ptr[gi + 1]] == -1).all()           # padding
+        assert torch.equal(row_prob[ptr[gi]: ptr[gi] + rows[gi]], prob[want.long(), gi])
+        assert (tile_group[ptr[gi] // 128: ptr[gi + 1] // 128] == gi).all()
+    assert (tile_group[ptr[nb] // 128:] == -1).all()
+    # token_rows: the token's active blocks in ascending order
+    for t in range(0, T, 13):
+        blocks = torch.nonzero(mask[t]).flatten().tolist()
+        for j, gi in enumerate(blocks):
+            r = token_rows[t, j].item()
+            assert ptr[gi] <= r < ptr[gi + 1] and row_token[r] == t
+
+
+# ---------------------------------------------------------------------------------- layers vs oracle / golden
+def _bf(t):
+    return t.bfloat16().float()
+
+
+@pytest.mark.parametrize("T,d,Fdim,bs", [(512, 128, 1024, 128), (300, 256, 1024, 256), (2048, 256, 2048, 256)])
+def test_routed_ffn_layer_matches_oracle(T, d, Fdim, bs):
+    """RoutedFFN fwd+bwd vs the masked-dense oracle (the reference test's own formulation,
+    test_sparse_ffn.py:8-38) on bf16-rounded weights/inputs.  Tolerances: bf16 GEMM operands and bf16
+    intermediates (h, per-block partial outputs) => relative Frobenius error < 1e-2."""
+    from oracle import spt_oracle as O
+    from spt_proto_b200 import layers
+    torch.manual_seed(T + d)
+    ffn = layers.RoutedFFN(d_model=d, d_feedforward=Fdim, block_size=bs, activation=torch.nn.ReLU()).to(DEV)
+    with torch.no_grad():
+        for p in ffn.parameters():
+            p.copy_(_bf(p))
+    x = _bf(torch.randn(4, T // 4, d)).to(DEV).requires_grad_()
+    y = ffn(x)
+    dy = _bf(torch.randn_like(y))
+    y.backward(dy)
+    sd = {k: v.detach().cpu() for k, v in ffn.state_dict().items()}
+    xc = x.detach().cpu().requires_grad_()
+    ps = {n: sd[n].clone().requires_grad_() for n in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")}
+    y_ref = O.routed_ffn(xc, sd["router.0.weight"], sd["router.0.bias"], ps["fc1.weight"], ps["fc1.bias"],
+                         ps["fc2.weight"], ps["fc2.bias"], bs, (Fdim // bs) // 2)
+    y_ref.backward(dy.cpu())
+
+    def rel(a, b):
+        return ((a.float().cpu() - b).norm() / b.norm()).item()
+
+    assert rel(y, y_ref.detach()) < 1e-2
+    assert rel(x.grad, xc.grad) < 1e-2
+    got = dict(ffn.named_parameters())
+    for n, p in ps.items():
+        assert rel(got[n].grad, p.grad) < 1e-2, n
+    assert got["router.0.weight"].grad is None          # plain RoutedFFN: the router gets no gradient
+
+
+def test_routed_ffn_matches_reference_golden():
+    """Golden vectors from the reference's own RoutedFFN / RoutedLLaMaFFN modules (tests/golden/make_golden.py).
+    d_model 32, block 16 are far below tensor-core tile sizes: exercises the padding / masking paths."""
+    import os
+    from spt_proto_b200 import layers
+    gd = torch.load(os.path.join(os.path.dirname(__file__), "golden", "routed_ffn.pt"), weights_only=False)
+    for key, cls, act in (("routed_ffn", layers.RoutedFFN, torch.nn.ReLU()),
+                          ("routed_llama_ffn", layers.RoutedLLaMaFFN, torch.nn.SiLU())):
+        case = gd[key]
+        cfg = case["cfg"]
+        ffn = cls(d_model=cfg["d_model"], d_feedforward=cfg["d_feedforward"], block_size=cfg["block_size"],
+                  activation=act).to(DEV)
+        ffn.load_state_dict(case["state"])
+        x = case["x"].to(DEV).requires_grad_()
+        y = ffn(x)
+        y.sum().backward()
+        # fp32 reference vs bf16 tensor-core path: absolute tolerance scaled to the output magnitude
+        scale = case["y"].abs().max().item()
+        assert (y.detach().cpu() - case["y"]).abs().max().item() < 3e-2 * max(scale, 1.0), key
+        # gradients: a bf16 rounding can flip a ReLU gate that sits at ~0 in fp32, which moves single
+        # elements by a whole term — compare in the Frobenius norm, like the weight gradients below
+        # (measured: 4e-2 vs this fp32 golden, 3e-3 vs the oracle on bf16-rounded weights, see
+        # test_routed_ffn_layer_matches_oracle which is the tight check)
+        assert (x.grad.cpu() - case["grads"]["x"]).norm() / case["grads"]["x"].norm() < 6e-2, key
+        for n, p in ffn.named_parameters():
+            if n in case["grads"] and case["grads"][n] is not None:
+                ref = case["grads"][n]
+                assert (p.grad.cpu() - ref).norm() / ref.norm() < 6e-2, (key, n)
+
+
+def test_routed_llama_ffn_layer_matches_oracle():
+    from oracle import spt_oracle as O
+    from spt_proto_b200 import layers
+    torch.manual_seed(3)
+    d, Fdim, bs, T = 256, 2048, 256, 1024
+    ffn = layers.RoutedLLaMaFFN(d_model=d, d_feedforward=Fdim, block_size=bs, activation=torch.nn.SiLU()).to(DEV)
+    with torch.no_grad():
+        for p in ffn.parameters():
+            p.copy_(_bf(p))
+    x = _bf(torch.randn(T, d)).to(DEV).requires_grad_()
+    y = ffn(x)
+    dy = _bf(torch.randn_like(y))
+    y.backward(dy)
+    sd = {k: v.detach().cpu() for k, v in ffn.state_dict().items()}
+    xc = x.detach().cpu().requires_grad_()
+    ps = {n: sd[n].clone().requires_grad_() for n in ("gate.weight", "side.weight", "down.weight")}
+    y_ref = O.routed_llama_ffn(xc, sd["router.0.weight"], sd["router.0.bias"], ps["gate.weight"], ps["side.weight"],
+                               ps["down.weight"], bs, (Fdim // bs) // 4)
+    y_ref.backward(dy.cpu())
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    assert rel(y, y_ref.detach()) < 1.5e-2
+    assert rel(x.grad, xc.grad) < 1.5e-2
+    got = dict(ffn.named_parameters())
+    for n, p in ps.items():
+        assert rel(got[n].grad, p.grad) < 1.5e-2, n
