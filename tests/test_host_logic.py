@@ -1,0 +1,108 @@
+"""Host-side logic that needs no GPU: layer constructors / state-dict layout / from_pretrained match
+the reference's names, the drop-in registration, the loud failure without CUDA, sharding helpers."""
+import sys
+
+import pytest
+import torch
+from torch import nn
+
+
+def test_layer_constructors_and_state_dict_keys():
+    from spt_proto_b200 import layers
+    v1 = layers.SparseVanillaAttentionV1(d_head=64, p_dropout=0.0, d_codeword=8, n_codewords=16, n_subspaces=8)
+    assert set(v1.state_dict()) == {"trigger", "quantizer.weight"}
+    assert v1.quantizer.weight.shape == (8, 16, 8)
+    v2 = layers.SparseVanillaAttentionV2.from_pretrained(v1)
+    assert torch.equal(v2.quantizer.weight, v1.quantizer.weight) and v2.sparse_coeff == 8
+    r1 = layers.SparseRotaryAttentionV1(d_head=64, p_dropout=0.0, d_codeword=8, n_codewords=16, n_subspaces=8)
+    r2 = layers.SparseRotaryAttentionV2.from_pretrained(r1)
+    assert {"trigger", "quantizer.weight", "cached_ids", "embedding.cos_cached", "embedding.sin_cached"} <= set(r2.state_dict())
+    with pytest.raises(AssertionError):
+        layers.SparseVanillaAttentionV2.from_pretrained(r1)
+
+    ff = layers.Feedforward(32, 128, 0.0, nn.ReLU())
+    routed = layers.RoutedFFN.from_pretrained(16, ff)
+    assert set(routed.state_dict()) == {"fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "router.0.weight", "router.0.bias"}
+    assert routed.n_blocks == 8 and routed.k_active == 4
+    lf = layers.LLaMaFeedforward(32, 128, nn.SiLU())
+    lrouted = layers.RoutedLLaMaFFN.from_pretrained(16, lf)
+    assert lrouted.k_active == 2 and "router.0.weight" in lrouted.state_dict()
+
+
+def test_v1_layers_are_dense_attention_plus_pq_loss():
+    from spt_proto_b200 import layers
+    torch.manual_seed(0)
+    v1 = layers.SparseVanillaAttentionV1(d_head=32, p_dropout=0.0, d_codeword=8, n_codewords=16, n_subspaces=4)
+    dense = layers.VanillaAttention(d_head=32, p_dropout=0.0)
+    q, k, v = (torch.randn(2, 16, 3, 32) for _ in range(3))
+    mask = torch.full([16, 16], float("-inf")).triu(1)
+    assert torch.allclose(v1(q, k, v, attn_mask=mask), dense(q, k, v, attn_mask=mask))
+    assert v1.loss.dim() == 0 and v1.loss.item() > 0
+
+
+def test_pq_modes_v1():
+    from spt_proto_b200 import layers
+    torch.manual_seed(1)
+    pq = layers.PQV1(d_codeword=4, n_codewords=8, n_subspaces=6)
+    z = torch.randn(5, 7, 24)
+    codes = pq("encode", z=z)
+    assert codes.shape == (5, 7, 6)
+    zq = pq("decode", z=codes)
+    assert zq.shape == z.shape and torch.allclose(zq, pq("quantize", z=z))
+    z_q, loss = pq("train", z=z)
+    assert torch.allclose(z_q, zq) and loss.requires_grad
+
+
+def test_no_cpu_fallback():
+    from spt_proto_b200 import ext, layers
+    q = torch.zeros(8, 64, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ext.cdist_forward_cuda(q, torch.zeros(8, 16, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ext.lookup_forward_cuda(torch.empty([8]), torch.zeros(1, 64, 8, dtype=torch.int32), torch.zeros(1, 64, 8, dtype=torch.int32))
+    ffn = layers.RoutedFFN(32, 128, 16, nn.ReLU())
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ffn(torch.zeros(2, 4, 32))
+    attn = layers.SparseVanillaAttentionV2(d_head=64, d_codeword=8, n_codewords=16, p_dropout=0.0)
+    with pytest.raises(RuntimeError):
+        attn(torch.zeros(1, 64, 2, 64), torch.zeros(1, 64, 2, 64), torch.zeros(1, 64, 2, 64))
+
+
+def test_product_never_imports_the_oracle():
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spt_proto_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "spt_oracle" not in text.replace(
+                    "oracle/spt_oracle", ""), f
+
+
+def test_dropin_install():
+    import spt_proto_b200.dropin as dropin
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "naive_gpt" or k.startswith("naive_gpt.")}
+    try:
+        dropin.install()
+        from naive_gpt import ext, kernels, layers  # noqa: F401
+        assert {"cdist", "lookup", "softmax", "sddmm", "spmm"} <= set(dir(kernels))
+        for name in ("cdist_forward_cuda", "cdist_backward_cuda", "lookup_forward_cuda", "spmm_forward_cuda",
+                     "sddmm_forward_cuda", "softmax_forward_cuda", "softmax_backward_cuda"):
+            assert callable(getattr(ext, name))           # extension/entry.cpp:43-56
+        assert layers.SparseVanillaAttentionV2 and layers.RoutedFFN
+    finally:
+        for k in list(sys.modules):
+            if k == "naive_gpt" or k.startswith("naive_gpt."):
+                del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_shard_range_partitions_exactly():
+    from spt_proto_b200.distributed import shard_range
+    for n in (0, 1, 7, 32, 256, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,55 @@
+"""world_size-2 gloo tests of the N > 1 host logic (run on CPU): unit sharding is exact and disjoint,
+and the fine-tuning step's gradient all-reduce of the trainable parameters averages across ranks."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spt_proto_b200.distributed import allreduce_grads, shard_range
+
+    # (1) batch x head sharding: every head owned exactly once
+    begin, end = shard_range(32 * 3, rank, world)
+    owned = torch.zeros(96)
+    owned[begin:end] = 1
+    dist.all_reduce(owned)
+    ok_shard = bool((owned == 1).all())
+
+    # (2) gradient all-reduce of trainable parameters only (frozen base weights are skipped)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 4))
+    for p in model[0].parameters():
+        p.requires_grad = False
+    x = torch.full((2, 8), float(rank + 1))
+    model(x).sum().backward()
+    local = [p.grad.clone() for p in model[1].parameters()]
+    n_calls = allreduce_grads(model.parameters(), bucket_bytes=64)
+    gathered = [torch.zeros_like(local[0]) for _ in range(world)]
+    dist.all_gather(gathered, local[0])
+    want = sum(gathered) / world
+    ok_grad = torch.allclose(model[1].weight.grad, want) and model[0].weight.grad is None
+    ret[rank] = (ok_shard, ok_grad, n_calls)
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_grad_allreduce():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for rank in range(world):
+        ok_shard, ok_grad, n_calls = ret[rank]
+        assert ok_shard and ok_grad and n_calls >= 1
