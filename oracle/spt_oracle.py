@@ -422,3 +422,25 @@ def lora_routed_ffn(x, router_w, router_b, w1, b1, w2, b2, l1_left, l1_right, l2
         y = y + m_i * (coeff * (h @ w2[:, sl].t()) + (h @ l2_left[sl]) @ l2_right.t())
     y = y + b2
     return y.reshape(shape)
+
+
+def lora_routed_llama_ffn(x, router_w, router_b, w_gate, w_side, w_down, lg_left, lg_right, ls_left, ls_right,
+                          ld_left, ld_right, block_size: int, k_active: int, activation=torch.nn.functional.silu):
+    """LoRARoutedLLaMaFFN.forward (tuning/lora_ffn.py:164-225) in masked-dense form:
+       g = coeff (x Wg_i^T) + (x Lg) Rg_i^T;  s = coeff (x Ws_i^T) + (x Ls) Rs_i^T;  h = act(g) * s;
+       y += coeff (h Wd_i) + (h Ld_i) Rd^T.   *_left [in, r], *_right [out, r]."""
+    shape = x.shape
+    x2 = x.reshape(-1, shape[-1])
+    nb = w_gate.shape[0] // block_size
+    prob = torch.sigmoid(x2 @ router_w.t() + router_b)
+    mask = route_topk_mask(prob.detach(), k_active)
+    y = torch.zeros_like(x2)
+    for i in range(nb):
+        sl = slice(i * block_size, (i + 1) * block_size)
+        m_i = mask[:, i].to(x2.dtype).unsqueeze(-1)
+        coeff = 2.0 * prob[:, i: i + 1]
+        g = coeff * (x2 @ w_gate[sl].t()) + (x2 @ lg_left) @ lg_right[sl].t()
+        s = coeff * (x2 @ w_side[sl].t()) + (x2 @ ls_left) @ ls_right[sl].t()
+        h = activation(g) * s
+        y = y + m_i * (coeff * (h @ w_down[:, sl].t()) + (h @ ld_left[sl]) @ ld_right.t())
+    return y.reshape(shape)

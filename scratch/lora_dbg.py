@@ -1,0 +1,22 @@
+import sys; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import torch
+from oracle import spt_oracle as O
+from spt_proto_b200 import layers
+import test_ffn_gpu as T
+d, Fdim, bs, r, Tn = 256, 1024, 256, 16, 1024
+ffn, x = T._lora_setup(layers.LoRARoutedFFN, torch.nn.ReLU(), d, Fdim, bs, r, Tn, 11)
+y = ffn(x); dy = T._bf(torch.randn_like(y)); y.backward(dy)
+sd = {k: v.detach().cpu() for k, v in ffn.state_dict().items()}
+names = [n for n, p in ffn.named_parameters() if p.requires_grad]
+p = {n: sd[n].clone().requires_grad_() for n in names}
+xc = x.detach().cpu().requires_grad_()
+y_ref = O.lora_routed_ffn(xc, p["router.0.weight"], p["router.0.bias"], sd["fc1.weight"], sd["fc1.bias"], sd["fc2.weight"], sd["fc2.bias"], p["fc1.lora.left.weight"], p["fc1.lora.right.weight"], p["fc2.lora.left.weight"], p["fc2.lora.right.weight"], bs, (Fdim // bs) // 2)
+y_ref.backward(dy.cpu())
+rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+print('y', rel(y, y_ref.detach()), 'dx', rel(x.grad, xc.grad))
+got = dict(ffn.named_parameters())
+for n in names: print(n, rel(got[n].grad, p[n].grad), p[n].grad.norm().item())
+# router-free comparison: detach router influence by comparing dx with router grads removed
+xc2 = x.detach().cpu().requires_grad_()
+with torch.no_grad():
+    prob = torch.sigmoid(xc2 @ sd["router.0.weight"].t() + sd["router.0.bias"])

@@ -152,7 +152,17 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     long long c_row0, c_col0;
     if (p.mode == 0) {
         g = p.tile_group[blockIdx.x];
-        if (g < 0) return;                                       // tail tile beyond the bucketed rows
+        if (g < 0) {
+            // tail tile beyond the bucketed rows: define its output (zeros) so that elementwise
+            // consumers of the whole [R, N] buffer never see uninitialised memory
+            const int n_valid = min(BN, p.N - n0);
+            for (int i = threadIdx.x; i < BM * n_valid; i += THREADS) {
+                const long long off = ((long long)blockIdx.x * BM + i / n_valid) * p.ldc + n0 + i % n_valid;
+                if (p.c_dtype == SPT_BF16) reinterpret_cast<__nv_bfloat16 *>(p.C)[off] = __float2bfloat16_rn(0.0f);
+                else reinterpret_cast<float *>(p.C)[off] = 0.0f;
+            }
+            return;
+        }
         m0 = blockIdx.x * BM;
         k_begin = 0;
         k_end = p.K;

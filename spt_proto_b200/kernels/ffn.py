@@ -48,9 +48,9 @@ class BlockedLinearRows(autograd.Function):
     W [F, K] (fc1 / gate / side layout).  act in {none, relu}; other activations are applied by the caller."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, bucket, bs, act):
+    def forward(ctx, x, weight, bias, bucket, bs, act, out_dtype):
         w16 = weight if weight.dtype == torch.bfloat16 else weight.to(torch.bfloat16)
-        y = torch.empty(x.size(0), bs, dtype=torch.bfloat16, device=x.device)
+        y = torch.empty(x.size(0), bs, dtype=out_dtype, device=x.device)
         b32 = None if bias is None else bias.float().contiguous()
         ext.grouped_gemm(0, x, False, w16, False, tile_group=bucket.tile_group, N=bs, K=x.size(1), b_mn_off=bs,
                          out=y, bias=b32, bias_stride=bs, act=act)
@@ -67,6 +67,8 @@ class BlockedLinearRows(autograd.Function):
         grad = grad.contiguous()
         if ctx.act == ACT_RELU:
             grad = grad * (y > 0)
+        if grad.dtype != torch.bfloat16:
+            grad = grad.to(torch.bfloat16)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:   # dx[i, :] = grad[i, :] @ W_g : W consumed MN-major, K offset g*bs
             dx = torch.empty_like(x)
@@ -77,7 +79,7 @@ class BlockedLinearRows(autograd.Function):
             dw = dw32.to(ctx.w_dtype)
         if ctx.b_dtype is not None and ctx.needs_input_grad[2]:
             db = ext.group_colsum(grad, b.bucket_ptr).reshape(-1).to(ctx.b_dtype)
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 class BlockedLinearCols(autograd.Function):
@@ -119,9 +121,47 @@ def combine(partial, bucket, bias, out_dtype):
     return CombineRows.apply(partial, bucket, bias, out_dtype)
 
 
-def blocked_linear_rows(x, weight, bias, bucket, bs, act=ACT_NONE):
-    return BlockedLinearRows.apply(x, weight, bias, bucket, bs, act)
+def blocked_linear_rows(x, weight, bias, bucket, bs, act=ACT_NONE, out_dtype=torch.bfloat16):
+    """out_dtype=torch.float32 keeps the fp32 accumulator (used where the result feeds an activation gate
+    after further additions, so that gates are decided in fp32 like in the reference)."""
+    return BlockedLinearRows.apply(x, weight, bias, bucket, bs, act, out_dtype)
 
 
 def blocked_linear_cols(x, weight, bucket, bs):
     return BlockedLinearCols.apply(x, weight, bucket, bs)
+
+
+class BlockedLinearColsT(autograd.Function):
+    """y[i, :] = x[i, :] @ W[g*bs:(g+1)*bs, :],  W [F, n] row-blocked, reduction over the block's rows
+    (h L2_i of the LoRA FFN: W = fc2.lora.left.weight [F, r]).  W is consumed MN-major in place."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bucket, bs):
+        w16 = weight if weight.dtype == torch.bfloat16 else weight.to(torch.bfloat16)
+        n = weight.size(1)
+        y = torch.empty(x.size(0), n, dtype=torch.bfloat16, device=x.device)
+        ext.grouped_gemm(0, x, False, w16, True, tile_group=bucket.tile_group, N=n, K=bs, b_k_off=bs, out=y)
+        ctx.save_for_backward(x, w16)
+        ctx.bucket, ctx.bs, ctx.w_dtype, ctx.w_shape = bucket, bs, weight.dtype, weight.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, w16 = ctx.saved_tensors
+        b, bs = ctx.bucket, ctx.bs
+        grad = grad.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:   # dx[i, f] = sum_n grad[i, n] W[g*bs + f, n] : W K-major, N offset g*bs
+            dx = torch.empty_like(x)
+            ext.grouped_gemm(0, grad, False, w16, False, tile_group=b.tile_group, N=bs, K=grad.size(1), b_mn_off=bs,
+                             out=dx)
+        if ctx.needs_input_grad[1]:   # dW[g*bs:(g+1)*bs, :] = x_g^T grad_g
+            dw32 = torch.empty(ctx.w_shape, dtype=torch.float32, device=x.device)
+            ext.grouped_gemm(1, x, True, grad, True, group_ptr=b.bucket_ptr, M=bs, N=grad.size(1), c_row_off=bs,
+                             out=dw32)
+            dw = dw32.to(ctx.w_dtype)
+        return dx, dw, None, None
+
+
+def blocked_linear_cols_t(x, weight, bucket, bs):
+    return BlockedLinearColsT.apply(x, weight, bucket, bs)

@@ -50,7 +50,7 @@ def test_grouped_gemm_mode0(b_mn, sizes, N, K):
                          b_mn_off=N, out=out, bias=bias.to(DEV), bias_stride=N, row_scale=torch.cat(
                              [scale, torch.ones(256)]).to(DEV), act=1)
     got = out.cpu()
-    assert torch.isnan(got[R:]).all()                              # tail tiles (-1) are not touched
+    assert (got[R:] == 0).all()                                    # tail tiles (-1) are defined: zeros
     assert torch.allclose(got[:R], want, atol=2e-2, rtol=1e-2)
 
 
@@ -222,3 +222,89 @@ def test_routed_llama_ffn_layer_matches_oracle():
     got = dict(ffn.named_parameters())
     for n, p in ps.items():
         assert rel(got[n].grad, p.grad) < 1.5e-2, n
+
+
+# ---------------------------------------------------------------------------------- LoRA routed FFN (a-10)
+def _lora_setup(cls, act, d, Fdim, bs, r, T, seed):
+    torch.manual_seed(seed)
+    ffn = cls(d_lora=r, block_size=bs, d_model=d, d_feedforward=Fdim, activation=act).to(DEV)
+    with torch.no_grad():
+        for n, p in ffn.named_parameters():
+            if "lora.right" in n:
+                torch.nn.init.normal_(p, std=0.05)
+            p.copy_(_bf(p))
+    x = _bf(torch.randn(T, d)).to(DEV).requires_grad_()
+    return ffn, x
+
+
+def test_lora_routed_ffn_layer_matches_oracle():
+    from oracle import spt_oracle as O
+    from spt_proto_b200 import layers
+    d, Fdim, bs, r, T = 256, 1024, 256, 16, 1024
+    ffn, x = _lora_setup(layers.LoRARoutedFFN, torch.nn.ReLU(), d, Fdim, bs, r, T, 11)
+    y = ffn(x)
+    dy = _bf(torch.randn_like(y))
+    y.backward(dy)
+    sd = {k: v.detach().cpu() for k, v in ffn.state_dict().items()}
+    names = [n for n, p in ffn.named_parameters() if p.requires_grad]
+    assert set(names) == {"router.0.weight", "router.0.bias", "fc1.lora.left.weight", "fc1.lora.right.weight",
+                          "fc2.lora.left.weight", "fc2.lora.right.weight"}          # frozen base (lora.py:43-44)
+    p = {n: sd[n].clone().requires_grad_() for n in names}
+    xc = x.detach().cpu().requires_grad_()
+    y_ref = O.lora_routed_ffn(xc, p["router.0.weight"], p["router.0.bias"], sd["fc1.weight"], sd["fc1.bias"],
+                              sd["fc2.weight"], sd["fc2.bias"], p["fc1.lora.left.weight"], p["fc1.lora.right.weight"],
+                              p["fc2.lora.left.weight"], p["fc2.lora.right.weight"], bs, (Fdim // bs) // 2)
+    y_ref.backward(dy.cpu())
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    assert rel(y, y_ref.detach()) < 1.5e-2
+    assert rel(x.grad, xc.grad) < 2e-2
+    got = dict(ffn.named_parameters())
+    for n in names:
+        assert rel(got[n].grad, p[n].grad) < 3e-2, (n, rel(got[n].grad, p[n].grad))
+    assert got["fc1.weight"].grad is None and got["fc2.weight"].grad is None
+
+
+def test_lora_routed_llama_ffn_layer_matches_oracle():
+    from oracle import spt_oracle as O
+    from spt_proto_b200 import layers
+    d, Fdim, bs, r, T = 256, 1024, 256, 16, 768
+    ffn, x = _lora_setup(layers.LoRARoutedLLaMaFFN, torch.nn.SiLU(), d, Fdim, bs, r, T, 12)
+    y = ffn(x)
+    dy = _bf(torch.randn_like(y))
+    y.backward(dy)
+    sd = {k: v.detach().cpu() for k, v in ffn.state_dict().items()}
+    names = [n for n, p in ffn.named_parameters() if p.requires_grad]
+    p = {n: sd[n].clone().requires_grad_() for n in names}
+    xc = x.detach().cpu().requires_grad_()
+    y_ref = O.lora_routed_llama_ffn(
+        xc, p["router.0.weight"], p["router.0.bias"], sd["gate.weight"], sd["side.weight"], sd["down.weight"],
+        p["gate.lora.left.weight"], p["gate.lora.right.weight"], p["side.lora.left.weight"],
+        p["side.lora.right.weight"], p["down.lora.left.weight"], p["down.lora.right.weight"], bs, (Fdim // bs) // 2)
+    y_ref.backward(dy.cpu())
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    assert rel(y, y_ref.detach()) < 1.5e-2
+    assert rel(x.grad, xc.grad) < 2e-2
+    got = dict(ffn.named_parameters())
+    for n in names:
+        assert rel(got[n].grad, p[n].grad) < 3e-2, (n, rel(got[n].grad, p[n].grad))
+
+
+def test_lora_routed_ffn_matches_reference_golden():
+    import os
+    from spt_proto_b200 import layers
+    gd = torch.load(os.path.join(os.path.dirname(__file__), "golden", "routed_ffn.pt"), weights_only=False)
+    for key, cls, act in (("lora_routed_ffn", layers.LoRARoutedFFN, torch.nn.ReLU()),
+                          ("lora_routed_llama_ffn", layers.LoRARoutedLLaMaFFN, torch.nn.SiLU())):
+        case, cfg = gd[key], gd[key]["cfg"]
+        ffn = cls(d_lora=cfg["d_lora"], block_size=cfg["block_size"], d_model=cfg["d_model"],
+                  d_feedforward=cfg["d_feedforward"], activation=act).to(DEV)
+        ffn.load_state_dict(case["state"])
+        x = case["x"].to(DEV).requires_grad_()
+        y = ffn(x)
+        y.sum().backward()
+        rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+        assert rel(y.detach(), case["y"]) < 2e-2, key                     # fp32 golden vs bf16 tensor-core path
+        assert rel(x.grad, case["grads"]["x"]) < 8e-2, key
+        for n, p in ffn.named_parameters():
+            if p.requires_grad:
+                assert rel(p.grad, case["grads"][n]) < 8e-2, (key, n, rel(p.grad, case["grads"][n]))

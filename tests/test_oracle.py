@@ -249,3 +249,22 @@ def test_lora_routed_ffn_matches_reference_module():
     assert torch.allclose(x.grad, gd["grads"]["x"], atol=1e-5)
     for n in names:
         assert torch.allclose(p[n].grad, gd["grads"][n], atol=1e-4), n
+
+
+def test_lora_routed_llama_ffn_matches_reference_module():
+    gd = gold("routed_ffn")["lora_routed_llama_ffn"]
+    st, cfg = gd["state"], gd["cfg"]
+    x = gd["x"].clone().requires_grad_()
+    names = ["router.0.weight", "router.0.bias"] + [f"{l}.lora.{s}.weight" for l in ("gate", "side", "down")
+                                                    for s in ("left", "right")]
+    p = {n: st[n].clone().requires_grad_() for n in names}
+    y = O.lora_routed_llama_ffn(
+        x, p["router.0.weight"], p["router.0.bias"], st["gate.weight"], st["side.weight"], st["down.weight"],
+        p["gate.lora.left.weight"], p["gate.lora.right.weight"], p["side.lora.left.weight"],
+        p["side.lora.right.weight"], p["down.lora.left.weight"], p["down.lora.right.weight"],
+        cfg["block_size"], cfg["k_active"])
+    y.sum().backward()
+    assert torch.allclose(y, gd["y"], atol=1e-5)
+    assert torch.allclose(x.grad, gd["grads"]["x"], atol=1e-5)
+    for n in names:
+        assert torch.allclose(p[n].grad, gd["grads"][n], atol=1e-4), n
