@@ -152,18 +152,23 @@ int spt_softmax_bwd(const int32_t *indptr, const int32_t *indices, const float *
  * spt_sparse_attn_bwd: grad_y -> grad_q, grad_k, grad_v [B, S, d] bf16.  Recomputes p from q, k
  *   (nothing of size S x k is read or written); deterministic (no atomics).
  *   workspace: spt_sparse_attn_bwd_workspace_bytes(B, S).
+ * Layout: H = 1 means head-major [B, S, *] operands (the reference's layout after its transposes);
+ * H > 1 means the layer's native [N, S, H, *] layout with B = N*H heads interleaved (codes
+ * [N, S, H, m]; q/k/v/y and their gradients [N, S, H, d]) — the kernels stride over it directly, so
+ * the reference's transpose(1,2).contiguous() copies (attention.py:92-95,138-142) disappear.
+ * mask / extra0 / zsum are always head-major [B, S, ...].
  * ------------------------------------------------------------------------------------------ */
 int spt_lookup_mask_fwd(const int32_t *query_codes, const int32_t *key_codes, int32_t *output,
                         uint32_t *mask, int32_t *extra0, void *workspace, int B, int S, int m, int nnz,
-                        spt_stream_t stream);
+                        int H, spt_stream_t stream);
 int spt_sparse_attn_fwd(const void *q, const void *k, const void *v, const uint32_t *mask,
-                        const int32_t *extra0, void *y, float *zsum, int B, int S, int d, float scale,
-                        float clamp, int dtype, spt_stream_t stream);
+                        const int32_t *extra0, void *y, float *zsum, int B, int S, int d, int H,
+                        float scale, float clamp, int dtype, spt_stream_t stream);
 size_t spt_sparse_attn_bwd_workspace_bytes(int B, int S);
 int spt_sparse_attn_bwd(const void *q, const void *k, const void *v, const void *y, const void *grad_y,
                         const uint32_t *mask, const int32_t *extra0, const float *zsum, void *grad_q,
-                        void *grad_k, void *grad_v, void *workspace, int B, int S, int d, float scale,
-                        float clamp, int dtype, spt_stream_t stream);
+                        void *grad_k, void *grad_v, void *workspace, int B, int S, int d, int H,
+                        float scale, float clamp, int dtype, spt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (6) routed FFN — the grouped GEMM the reference only sketches (legacy/routed.cpp:10-68,

@@ -42,10 +42,10 @@ def _load() -> ctypes.CDLL:
         "spt_csr2csc": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp]),
         "spt_softmax_fwd": (i32, [vp, vp, vp, vp, i32, i32, i64, vp]),
         "spt_softmax_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i64, vp]),
-        "spt_lookup_mask_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
-        "spt_sparse_attn_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]),
+        "spt_lookup_mask_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        "spt_sparse_attn_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, i32, vp]),
         "spt_sparse_attn_bwd_workspace_bytes": (sz, [i32, i32]),
-        "spt_sparse_attn_bwd": (i32, [vp] * 12 + [i32, i32, i32, f32, f32, i32, vp]),
+        "spt_sparse_attn_bwd": (i32, [vp] * 12 + [i32, i32, i32, i32, f32, f32, i32, vp]),
     }
     ll = c.c_longlong
     sig["spt_grouped_gemm_bf16"] = (i32, [i32, vp, ll, ll, ll, i32, vp, ll, ll, ll, i32, vp, i32, vp, i32, i32, i32, i32,

@@ -79,13 +79,13 @@ __device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk)
 
 // cp.async a [64][64] tile (rows row0.. of a [S][64] matrix); rows >= S are zero-filled by the caller's
 // guarantee S % 64 == 0, so no predicate is needed.
-__device__ __forceinline__ void load_tile_async(uint32_t s_base, const __nv_bfloat16 *g, int row0) {
+__device__ __forceinline__ void load_tile_async(uint32_t s_base, const __nv_bfloat16 *g, int row0, int rs) {
     // 64 rows * 8 chunks = 512 chunks, 128 threads -> 4 each
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int idx = threadIdx.x + i * THREADS;
         const int r = idx >> 3, c = idx & 7;
-        cp_async16(tile_addr(s_base, r, c), g + (size_t)(row0 + r) * D + c * 8);
+        cp_async16(tile_addr(s_base, r, c), g + (size_t)(row0 + r) * rs + c * 8);
     }
 }
 
@@ -146,7 +146,7 @@ __device__ __forceinline__ void zero_acc(float (&acc)[8][4]) {
 // warp's own 16-row slab of a shared tile so that global stores are 16-byte coalesced.
 __device__ __forceinline__ void store_slab_bf16(const float (&acc)[8][4], float s_lo, float s_hi, uint32_t s_base,
                                                 unsigned char *s_ptr, int slab_row0, __nv_bfloat16 *g, int g_row0,
-                                                int lane) {
+                                                int lane, int rs) {
     const int g4 = lane >> 2, t4 = lane & 3;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
@@ -163,7 +163,7 @@ __device__ __forceinline__ void store_slab_bf16(const float (&acc)[8][4], float 
         const int idx = lane + i * 32;
         const int r = slab_row0 + (idx >> 3), c = idx & 7;
         const uint4 v = *reinterpret_cast<const uint4 *>(s_ptr + r * (D * 2) + ((c ^ (r & 7)) << 4));
-        *reinterpret_cast<uint4 *>(g + (size_t)(g_row0 + (idx >> 3)) * D + c * 8) = v;
+        *reinterpret_cast<uint4 *>(g + (size_t)(g_row0 + (idx >> 3)) * rs + c * 8) = v;
     }
     (void)s_base;
 }
@@ -174,7 +174,7 @@ __device__ __forceinline__ void store_slab_bf16(const float (&acc)[8][4], float 
 __global__ void __launch_bounds__(THREADS)
 attn_fwd_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__restrict__ k,
                 const __nv_bfloat16 *__restrict__ v, const uint32_t *__restrict__ mask,
-                const int32_t *__restrict__ extra0, __nv_bfloat16 *__restrict__ y, float *__restrict__ zsum, int S,
+                const int32_t *__restrict__ extra0, __nv_bfloat16 *__restrict__ y, float *__restrict__ zsum, int S, int H,
                 float scale_log2, float clamp_log2) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *s_q = smem;                       // 8 KB
@@ -186,13 +186,15 @@ attn_fwd_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__rest
     const int b = blockIdx.y;
     const int m0 = tile * BM;
     const size_t head = (size_t)b * S;
-    const __nv_bfloat16 *qh = q + head * D, *kh = k + head * D, *vh = v + head * D;
+    const int rs = H * D;                              // row stride: [N, S, H, D] interleaved heads (H = 1: [B, S, D])
+    const size_t hoff = ((size_t)(b / H) * S * H + (b % H)) * D;
+    const __nv_bfloat16 *qh = q + hoff, *kh = k + hoff, *vh = v + hoff;
     const int words = S / 32;
     const int n_tiles = tile + 1;                    // key tiles 0..tile (causal)
 
-    load_tile_async(smem_u32(s_q), qh, m0);
-    load_tile_async(smem_u32(s_k), kh, 0);
-    load_tile_async(smem_u32(s_v), vh, 0);
+    load_tile_async(smem_u32(s_q), qh, m0, rs);
+    load_tile_async(smem_u32(s_k), kh, 0, rs);
+    load_tile_async(smem_u32(s_v), vh, 0, rs);
     cp_async_commit();
 
     const int row_lo = m0 + warp * 16 + g4, row_hi = row_lo + 8;
@@ -207,8 +209,8 @@ attn_fwd_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__rest
     for (int jt = 0; jt < n_tiles; ++jt) {
         const int buf = jt & 1;
         if (jt + 1 < n_tiles) {
-            load_tile_async(smem_u32(s_k + (buf ^ 1) * 8192), kh, (jt + 1) * BN);
-            load_tile_async(smem_u32(s_v + (buf ^ 1) * 8192), vh, (jt + 1) * BN);
+            load_tile_async(smem_u32(s_k + (buf ^ 1) * 8192), kh, (jt + 1) * BN, rs);
+            load_tile_async(smem_u32(s_v + (buf ^ 1) * 8192), vh, (jt + 1) * BN, rs);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -255,19 +257,21 @@ attn_fwd_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__rest
         zsum[head + row_hi] = sum_hi;
     }
     // s_q is free (fragments are in registers): reuse it as the store staging tile
-    store_slab_bf16(o, 1.0f / sum_lo, 1.0f / sum_hi, smem_u32(s_q), s_q, warp * 16, y + head * D, m0 + warp * 16, lane);
+    store_slab_bf16(o, 1.0f / sum_lo, 1.0f / sum_hi, smem_u32(s_q), s_q, warp * 16, y + hoff, m0 + warp * 16, lane, rs);
 }
 
 // D_r = dO_r . y_r  (one warp per row pair; bf16 inputs, fp32 out)
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__restrict__ y,
-                  float *__restrict__ delta, int64_t rows) {
+                  float *__restrict__ delta, int64_t rows, int S, int H) {
     const int64_t row = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);  // 8 lanes per row (8 x 16 B = 128 B)
     if (row >= rows) return;
     const int sub = threadIdx.x & 7;
+    const int64_t b = row / S, r = row % S;                              // delta is head-major [B, S]
+    const int64_t off = (((b / H) * S + r) * H + (b % H)) * D;
     float a[8], c[8];
-    Vec16<__nv_bfloat16>::load(dy + row * D + sub * 8, a);
-    Vec16<__nv_bfloat16>::load(y + row * D + sub * 8, c);
+    Vec16<__nv_bfloat16>::load(dy + off + sub * 8, a);
+    Vec16<__nv_bfloat16>::load(y + off + sub * 8, c);
     float acc = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc = fmaf(a[i], c[i], acc);
@@ -296,7 +300,7 @@ attn_bwd_kv_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__r
                    const __nv_bfloat16 *__restrict__ v, const __nv_bfloat16 *__restrict__ dy,
                    const uint32_t *__restrict__ mask, const int32_t *__restrict__ extra0,
                    const float *__restrict__ zsum, const float *__restrict__ delta, __nv_bfloat16 *__restrict__ dk,
-                   __nv_bfloat16 *__restrict__ dv, int S, float scale, float scale_log2, float clamp_log2) {
+                   __nv_bfloat16 *__restrict__ dv, int S, int H, float scale, float scale_log2, float clamp_log2) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *s_k = smem;                  // 8 KB (also store staging)
     unsigned char *s_v = smem + 8192;           // 8 KB (also store staging)
@@ -312,13 +316,15 @@ attn_bwd_kv_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__r
     const int b = blockIdx.y;
     const int n0 = jt * BN;
     const size_t head = (size_t)b * S;
-    const __nv_bfloat16 *qh = q + head * D, *kh = k + head * D, *vh = v + head * D, *dyh = dy + head * D;
+    const int rs = H * D;
+    const size_t hoff = ((size_t)(b / H) * S * H + (b % H)) * D;
+    const __nv_bfloat16 *qh = q + hoff, *kh = k + hoff, *vh = v + hoff, *dyh = dy + hoff;
     const int words = S / 32;
     const int n_q_tiles = S / BM;
 
     auto load_row_tile = [&](int it, int buf) {
-        load_tile_async(smem_u32(s_q + buf * 8192), qh, it * BM);
-        load_tile_async(smem_u32(s_dy + buf * 8192), dyh, it * BM);
+        load_tile_async(smem_u32(s_q + buf * 8192), qh, it * BM, rs);
+        load_tile_async(smem_u32(s_dy + buf * 8192), dyh, it * BM, rs);
         if (threadIdx.x < BM) {
             const size_t r = head + it * BM + threadIdx.x;
             s_invz[buf * BM + threadIdx.x] = 1.0f / zsum[r];
@@ -329,8 +335,8 @@ attn_bwd_kv_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__r
         }
     };
 
-    load_tile_async(smem_u32(s_k), kh, n0);
-    load_tile_async(smem_u32(s_v), vh, n0);
+    load_tile_async(smem_u32(s_k), kh, n0, rs);
+    load_tile_async(smem_u32(s_v), vh, n0, rs);
     load_row_tile(jt, 0);
     cp_async_commit();
 
@@ -386,8 +392,8 @@ attn_bwd_kv_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__r
         gemm_nn(acc_dk, pa, smem_u32(s_q + buf * 8192), lane);   // dK += dS^T Q
         __syncthreads();
     }
-    store_slab_bf16(acc_dv, 1.0f, 1.0f, smem_u32(s_v), s_v, warp * 16, dv + head * D, n0 + warp * 16, lane);
-    store_slab_bf16(acc_dk, scale, scale, smem_u32(s_k), s_k, warp * 16, dk + head * D, n0 + warp * 16, lane);
+    store_slab_bf16(acc_dv, 1.0f, 1.0f, smem_u32(s_v), s_v, warp * 16, dv + hoff, n0 + warp * 16, lane, rs);
+    store_slab_bf16(acc_dk, scale, scale, smem_u32(s_k), s_k, warp * 16, dk + hoff, n0 + warp * 16, lane, rs);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -398,7 +404,7 @@ attn_bwd_q_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__re
                   const __nv_bfloat16 *__restrict__ v, const __nv_bfloat16 *__restrict__ dy,
                   const uint32_t *__restrict__ mask, const int32_t *__restrict__ extra0,
                   const float *__restrict__ zsum, const float *__restrict__ delta, __nv_bfloat16 *__restrict__ dq,
-                  int S, float scale, float scale_log2, float clamp_log2) {
+                  int S, int H, float scale, float scale_log2, float clamp_log2) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *s_q = smem;               // 8 KB (also store staging)
     unsigned char *s_dy = smem + 8192;       // 8 KB
@@ -410,14 +416,16 @@ attn_bwd_q_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__re
     const int b = blockIdx.y;
     const int m0 = tile * BM;
     const size_t head = (size_t)b * S;
-    const __nv_bfloat16 *qh = q + head * D, *kh = k + head * D, *vh = v + head * D, *dyh = dy + head * D;
+    const int rs = H * D;
+    const size_t hoff = ((size_t)(b / H) * S * H + (b % H)) * D;
+    const __nv_bfloat16 *qh = q + hoff, *kh = k + hoff, *vh = v + hoff, *dyh = dy + hoff;
     const int words = S / 32;
     const int n_tiles = tile + 1;
 
-    load_tile_async(smem_u32(s_q), qh, m0);
-    load_tile_async(smem_u32(s_dy), dyh, m0);
-    load_tile_async(smem_u32(s_k), kh, 0);
-    load_tile_async(smem_u32(s_v), vh, 0);
+    load_tile_async(smem_u32(s_q), qh, m0, rs);
+    load_tile_async(smem_u32(s_dy), dyh, m0, rs);
+    load_tile_async(smem_u32(s_k), kh, 0, rs);
+    load_tile_async(smem_u32(s_v), vh, 0, rs);
     cp_async_commit();
 
     const int row_lo = m0 + warp * 16 + g4, row_hi = row_lo + 8;
@@ -432,8 +440,8 @@ attn_bwd_q_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__re
     for (int jt = 0; jt < n_tiles; ++jt) {
         const int buf = jt & 1;
         if (jt + 1 < n_tiles) {
-            load_tile_async(smem_u32(s_k + (buf ^ 1) * 8192), kh, (jt + 1) * BN);
-            load_tile_async(smem_u32(s_v + (buf ^ 1) * 8192), vh, (jt + 1) * BN);
+            load_tile_async(smem_u32(s_k + (buf ^ 1) * 8192), kh, (jt + 1) * BN, rs);
+            load_tile_async(smem_u32(s_v + (buf ^ 1) * 8192), vh, (jt + 1) * BN, rs);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -471,7 +479,7 @@ attn_bwd_q_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__re
         gemm_nn(acc, pa, smem_u32(s_k + buf * 8192), lane);   // dQ += dS K
         __syncthreads();
     }
-    store_slab_bf16(acc, scale, scale, smem_u32(s_q), s_q, warp * 16, dq + head * D, m0 + warp * 16, lane);
+    store_slab_bf16(acc, scale, scale, smem_u32(s_q), s_q, warp * 16, dq + hoff, m0 + warp * 16, lane, rs);
 }
 
 constexpr int FWD_SMEM = 8192 * 5;
@@ -492,15 +500,16 @@ static int check_attn_args(const char *what, int B, int S, int d, int dtype) {
 }
 
 extern "C" int spt_sparse_attn_fwd(const void *q, const void *k, const void *v, const uint32_t *mask,
-                                   const int32_t *extra0, void *y, float *zsum, int B, int S, int d, float scale,
-                                   float clamp, int dtype, spt_stream_t stream) {
+                                   const int32_t *extra0, void *y, float *zsum, int B, int S, int d, int H,
+                                   float scale, float clamp, int dtype, spt_stream_t stream) {
     SPT_REQUIRE(q && k && v && mask && extra0 && y && zsum, "sparse_attn_fwd: null pointer");
+    SPT_REQUIRE(H >= 1 && B % H == 0, "sparse_attn_fwd: B=%d must be a multiple of the interleaved head count H=%d", B, H);
     int rc = check_attn_args("sparse_attn_fwd", B, S, d, dtype);
     if (rc != SPT_OK) return rc;
     using bf = __nv_bfloat16;
     cudaFuncSetAttribute(attn::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::FWD_SMEM);
     attn::attn_fwd_kernel<<<dim3(S / attn::BM, B), attn::THREADS, attn::FWD_SMEM, as_stream(stream)>>>(
-        (const bf *)q, (const bf *)k, (const bf *)v, mask, extra0, (bf *)y, zsum, S, scale * attn::LOG2E,
+        (const bf *)q, (const bf *)k, (const bf *)v, mask, extra0, (bf *)y, zsum, S, H, scale * attn::LOG2E,
         clamp * attn::LOG2E);
     return after_launch("attn_fwd_kernel");
 }
@@ -509,26 +518,27 @@ extern "C" size_t spt_sparse_attn_bwd_workspace_bytes(int B, int S) { return (si
 
 extern "C" int spt_sparse_attn_bwd(const void *q, const void *k, const void *v, const void *y, const void *grad_y,
                                    const uint32_t *mask, const int32_t *extra0, const float *zsum, void *grad_q,
-                                   void *grad_k, void *grad_v, void *workspace, int B, int S, int d, float scale,
-                                   float clamp, int dtype, spt_stream_t stream) {
+                                   void *grad_k, void *grad_v, void *workspace, int B, int S, int d, int H,
+                                   float scale, float clamp, int dtype, spt_stream_t stream) {
     SPT_REQUIRE(q && k && v && y && grad_y && mask && extra0 && zsum && grad_q && grad_k && grad_v && workspace,
                 "sparse_attn_bwd: null pointer");
     int rc = check_attn_args("sparse_attn_bwd", B, S, d, dtype);
     if (rc != SPT_OK) return rc;
+    SPT_REQUIRE(H >= 1 && B % H == 0, "sparse_attn_bwd: B=%d must be a multiple of H=%d", B, H);
     using bf = __nv_bfloat16;
     cudaStream_t st = as_stream(stream);
     float *delta = (float *)workspace;
     const int64_t rows = (int64_t)B * S;
-    attn::attn_delta_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>((const bf *)grad_y, (const bf *)y, delta, rows);
+    attn::attn_delta_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>((const bf *)grad_y, (const bf *)y, delta, rows, S, H);
     SPT_LAUNCH_CHECK("attn_delta_kernel");
     cudaFuncSetAttribute(attn::attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::BWD_KV_SMEM);
     attn::attn_bwd_kv_kernel<<<dim3(S / attn::BN, B), attn::THREADS, attn::BWD_KV_SMEM, st>>>(
         (const bf *)q, (const bf *)k, (const bf *)v, (const bf *)grad_y, mask, extra0, zsum, delta, (bf *)grad_k,
-        (bf *)grad_v, S, scale, scale * attn::LOG2E, clamp * attn::LOG2E);
+        (bf *)grad_v, S, H, scale, scale * attn::LOG2E, clamp * attn::LOG2E);
     SPT_LAUNCH_CHECK("attn_bwd_kv_kernel");
     cudaFuncSetAttribute(attn::attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::BWD_Q_SMEM);
     attn::attn_bwd_q_kernel<<<dim3(S / attn::BM, B), attn::THREADS, attn::BWD_Q_SMEM, st>>>(
-        (const bf *)q, (const bf *)k, (const bf *)v, (const bf *)grad_y, mask, extra0, zsum, delta, (bf *)grad_q, S,
+        (const bf *)q, (const bf *)k, (const bf *)v, (const bf *)grad_y, mask, extra0, zsum, delta, (bf *)grad_q, S, H,
         scale, scale * attn::LOG2E, clamp * attn::LOG2E);
     SPT_LAUNCH_CHECK("attn_bwd_q_kernel");
     return SPT_OK;

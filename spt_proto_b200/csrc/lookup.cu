@@ -37,11 +37,12 @@ constexpr int LK_WORD_U32 = LK_CV * 4;       // u32 per (subspace, 128-key word)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 lookup_pack_kernel(const int32_t *__restrict__ key_codes, uint32_t *__restrict__ kb, int *__restrict__ flag,
-                   int S, int m, int W) {
+                   int S, int m, int W, int H) {
     const int w = blockIdx.x, b = blockIdx.y;
     const int t = threadIdx.x >> 5, i = threadIdx.x & 31;
     const int j = 128 * w + 4 * i + t;
-    const int32_t *kp = key_codes + ((size_t)b * S + j) * m;
+    // codes are [N, S, H, m] (heads interleaved; H = 1: [B, S, m])
+    const int32_t *kp = key_codes + (((size_t)(b / H) * S + j) * H + (b % H)) * m;
     bool overflow = false;
     for (int s = 0; s < m; ++s) {
         const unsigned code = (j < S) ? ((unsigned)kp[s] & 0xffffu) : 0xffffu;
@@ -157,9 +158,9 @@ struct BitmapMatcher {
 };
 
 struct GenericMatcher {
-    const int32_t *kc;     // key codes of this head [S][m]
+    const int32_t *kc;     // key codes of this head, row j at kc + j * kstride
     const uint16_t *s_q;   // shared: this row's query codes [m]
-    int m, div, t;
+    int m, div, t, kstride;
     __device__ __forceinline__ void buckets(int w, uint32_t valid, uint32_t (&mask)[4]) const {
         mask[0] = mask[1] = mask[2] = mask[3] = 0;
         uint32_t v = valid;
@@ -167,7 +168,7 @@ struct GenericMatcher {
             const int i = __ffs(v) - 1;
             v &= v - 1;
             const int j = 4 * (32 * w + i) + t;
-            const int32_t *kp = kc + (size_t)j * m;
+            const int32_t *kp = kc + (size_t)j * kstride;
             int cnt = 0;
             for (int s = 0; s < m; ++s) cnt += ((unsigned)s_q[s] == ((unsigned)kp[s] & 0xffffu));
             const int bucket = min(3, cnt / div);
@@ -285,7 +286,7 @@ template <int M>
 __global__ void __launch_bounds__(LK_THREADS)
 lookup_bitmap_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__restrict__ kb,
                      const int *__restrict__ flag, int32_t *__restrict__ out, uint32_t *__restrict__ mask_out,
-                     int32_t *__restrict__ extra0_out, int S, int nnz, int W, int chunk_words) {
+                     int32_t *__restrict__ extra0_out, int S, int nnz, int W, int chunk_words, int H) {
     if (*flag) return;  // some key code >= 16: the generic kernel handles this call
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t *s_out = reinterpret_cast<uint16_t *>(smem_raw);
@@ -315,7 +316,7 @@ lookup_bitmap_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__
     mt.t = t;
 #pragma unroll
     for (int s = 0; s < M; ++s)
-        mt.q[s] = live ? ((unsigned)query_codes[((size_t)b * S + r) * M + s] & 0xffffu) : 0xffffu;
+        mt.q[s] = live ? ((unsigned)query_codes[(((size_t)(b / H) * S + r) * H + (b % H)) * M + s] & 0xffffu) : 0xffffu;
 
     LaneState st;
 #pragma unroll
@@ -364,7 +365,7 @@ lookup_bitmap_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__
 __global__ void __launch_bounds__(LK_THREADS)
 lookup_generic_kernel(const int32_t *__restrict__ query_codes, const int32_t *__restrict__ key_codes,
                       const int *__restrict__ flag, int flag_expect, int32_t *__restrict__ out,
-                      uint32_t *__restrict__ mask_out, int32_t *__restrict__ extra0_out, int S, int m, int nnz) {
+                      uint32_t *__restrict__ mask_out, int32_t *__restrict__ extra0_out, int S, int m, int nnz, int H) {
     if (flag && (*flag != 0) != (flag_expect != 0)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t *s_out = reinterpret_cast<uint16_t *>(smem_raw);
@@ -389,12 +390,13 @@ lookup_generic_kernel(const int32_t *__restrict__ query_codes, const int32_t *__
     uint32_t *row_bits = s_bits ? s_bits + rl * (S / 32) : nullptr;
     for (int i = threadIdx.x; i < LK_ROWS * m; i += blockDim.x) {
         const int rr = r0 + i / m;
-        s_q[i] = rr < S ? (uint16_t)((unsigned)query_codes[((size_t)b * S + rr) * m + i % m] & 0xffffu) : 0;
+        s_q[i] = rr < S ? (uint16_t)((unsigned)query_codes[(((size_t)(b / H) * S + rr) * H + (b % H)) * m + i % m] & 0xffffu) : 0;
     }
     __syncthreads();
 
     GenericMatcher mt;
-    mt.kc = key_codes + (size_t)b * S * m;
+    mt.kc = key_codes + ((size_t)(b / H) * S * H + (b % H)) * m;
+    mt.kstride = H * m;
     mt.s_q = s_q + rl * m;
     mt.m = m;
     mt.div = m / 4;
@@ -440,8 +442,9 @@ extern "C" size_t spt_lookup_workspace_bytes(int B, int S, int m, int nnz) {
 }
 
 static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int32_t *output, uint32_t *mask_out,
-                       int32_t *extra0_out, void *workspace, int B, int S, int m, int nnz, spt_stream_t stream) {
+                       int32_t *extra0_out, void *workspace, int B, int S, int m, int nnz, int H, spt_stream_t stream) {
     SPT_REQUIRE(query_codes && key_codes && (output || mask_out), "lookup_fwd: null pointer");
+    SPT_REQUIRE(H >= 1 && B % H == 0, "lookup_fwd: B=%d must be a multiple of the interleaved head count H=%d", B, H);
     SPT_REQUIRE(B >= 1 && S >= 1 && S <= 65536, "lookup_fwd: bad batch/seq (B=%d, S=%d; S must be <= 65536)", B, S);
     SPT_REQUIRE(B <= 65535, "lookup_fwd: batch %d exceeds grid limit", B);
     SPT_REQUIRE(m >= 4, "lookup_fwd: n_subspaces must be >= 4 (got %d)", m);
@@ -458,7 +461,7 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
 
     if (!bitmap_m_supported(m)) {
         lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, nullptr, 0, output, mask_out,
-                                                                  extra0_out, S, m, nnz);
+                                                                  extra0_out, S, m, nnz, H);
         SPT_LAUNCH_CHECK("lookup_generic_kernel");
         return SPT_OK;
     }
@@ -468,7 +471,7 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
     const int W = (S + 127) / 128;
     cudaError_t e = cudaMemsetAsync(flag, 0, 16, st);
     if (e != cudaSuccess) return fail(SPT_ERR_CUDA, "lookup_fwd: memset: %s", cudaGetErrorString(e));
-    lookup_pack_kernel<<<dim3(W, B), 128, 0, st>>>(key_codes, kb, flag, S, m, W);
+    lookup_pack_kernel<<<dim3(W, B), 128, 0, st>>>(key_codes, kb, flag, S, m, W, H);
     SPT_LAUNCH_CHECK("lookup_pack_kernel");
 
     // bitmaps per 128-key word: m * 256 B; pick the chunk so that images + chunk fit the budget
@@ -482,7 +485,7 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
         if (smem > 48 * 1024)                                                                                    \
             cudaFuncSetAttribute(lookup_bitmap_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         lookup_bitmap_kernel<MM><<<grid, LK_THREADS, smem, st>>>(query_codes, kb, flag, output, mask_out, extra0_out, S, \
-                                                                 nnz, W, chunk_words);                           \
+                                                                 nnz, W, chunk_words, H);                        \
         break;
     switch (m) {
         SPT_LK_CASE(4)
@@ -497,7 +500,7 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
 #undef SPT_LK_CASE
     SPT_LAUNCH_CHECK("lookup_bitmap_kernel");
     lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, mask_out,
-                                                              extra0_out, S, m, nnz);
+                                                              extra0_out, S, m, nnz, H);
     SPT_LAUNCH_CHECK("lookup_generic_kernel(fallback)");
     return SPT_OK;
 }
@@ -505,12 +508,12 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
 extern "C" int spt_lookup_fwd(const int32_t *query_codes, const int32_t *key_codes, int32_t *output, void *workspace,
                               int B, int S, int m, int nnz, spt_stream_t stream) {
     SPT_REQUIRE(output, "lookup_fwd: null output");
-    return lookup_impl(query_codes, key_codes, output, nullptr, nullptr, workspace, B, S, m, nnz, stream);
+    return lookup_impl(query_codes, key_codes, output, nullptr, nullptr, workspace, B, S, m, nnz, 1, stream);
 }
 
 extern "C" int spt_lookup_mask_fwd(const int32_t *query_codes, const int32_t *key_codes, int32_t *output,
                                    uint32_t *mask, int32_t *extra0, void *workspace, int B, int S, int m, int nnz,
-                                   spt_stream_t stream) {
+                                   int H, spt_stream_t stream) {
     SPT_REQUIRE(mask && extra0, "lookup_mask_fwd: null mask / extra0");
-    return lookup_impl(query_codes, key_codes, output, mask, extra0, workspace, B, S, m, nnz, stream);
+    return lookup_impl(query_codes, key_codes, output, mask, extra0, workspace, B, S, m, nnz, H, stream);
 }

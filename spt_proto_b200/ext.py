@@ -302,16 +302,26 @@ def launch_count() -> int:
 
 
 # ---- fused sparse attention (masked dense tiles on the tensor cores) ------------------------------------
+def _heads(t: torch.Tensor, name: str):
+    """(B, S, H): 3-D [B, S, *] is head-major (H = 1); 4-D [N, S, H, *] has the heads interleaved."""
+    if t.dim() == 3:
+        return t.size(0), t.size(1), 1
+    if t.dim() == 4:
+        return t.size(0) * t.size(2), t.size(1), t.size(2)
+    raise RuntimeError(f"{name} must be of dim 3 ([B,S,*]) or 4 ([N,S,H,*])")
+
+
 def lookup_mask(query: torch.Tensor, key: torch.Tensor, sparse_coeff: int, want_indices: bool = False):
     """Same selection as lookup_forward_cuda, emitted as (mask [B,S,S/32] int32 bit-words,
-    extra0 [B,S] int32 zero-padding multiplicity of key 0, indices [B,S,nnz] or None)."""
-    _check_dim(key, 3, "key")
-    _check_dim(query, 3, "query")
+    extra0 [B,S] int32 zero-padding multiplicity of key 0, indices [B,S,nnz] or None).
+    Codes: [B,S,m] head-major or [N,S,H,m] (heads interleaved, B = N*H)."""
+    _check_dim(key, query.dim(), "key")
     _check_type(key, torch.int32, "key")
     _check_type(query, torch.int32, "query")
-    if query.shape != key.shape:
-        raise RuntimeError("query and key must have the same shape")
-    B, S, m = query.shape
+    if query.shape != key.shape or not query.is_cuda or not query.is_contiguous():
+        raise RuntimeError("query and key must be contiguous CUDA tensors of the same shape")
+    B, S, H = _heads(query, "query")
+    m = query.size(-1)
     if sparse_coeff <= 0 or S % sparse_coeff != 0 or S % 32 != 0:
         raise RuntimeError("seq_length must be divisible by sparse_coeff and by 32")
     nnz = S // sparse_coeff
@@ -321,41 +331,43 @@ def lookup_mask(query: torch.Tensor, key: torch.Tensor, sparse_coeff: int, want_
     indices = torch.empty((B, S, nnz), dtype=torch.int32, device=dev) if want_indices else None
     ws = _workspace(lib.spt_lookup_workspace_bytes(B, S, m, nnz), query)
     with _on_device(query):
-        check(lib.spt_lookup_mask_fwd(_p(query), _p(key), _p(indices), _p(mask), _p(extra0), _p(ws), B, S, m, nnz,
+        check(lib.spt_lookup_mask_fwd(_p(query), _p(key), _p(indices), _p(mask), _p(extra0), _p(ws), B, S, m, nnz, H,
                                       _stream(query)))
     return mask, extra0, indices
 
 
 def _check_attn(q, k, v):
     for name, t in (("q", q), ("k", k), ("v", v)):
-        _check_dim(t, 3, name)
+        _check_dim(t, q.dim(), name)
         _check_type(t, torch.bfloat16, name)
     if q.shape != k.shape or q.shape != v.shape:
         raise RuntimeError("q, k, v must have the same shape")
-    return q.shape
+    B, S, H = _heads(q, "q")
+    return B, S, q.size(-1), H
 
 
 def sparse_attn_fwd(q, k, v, mask, extra0, scale: float, clamp: float = 10.0):
-    """-> (y [B,S,d] bf16, zsum [B,S] fp32).  See include/spt_b200.h."""
-    B, S, d = _check_attn(q, k, v)
+    """q, k, v: [B,S,d] head-major or [N,S,H,d] (native layer layout, no transposes) bf16
+    -> (y, same layout as q; zsum [B,S] fp32).  See include/spt_b200.h."""
+    B, S, d, H = _check_attn(q, k, v)
     y = torch.empty_like(q)
     zsum = torch.empty((B, S), dtype=torch.float32, device=q.device)
     with _on_device(q):
-        check(lib.spt_sparse_attn_fwd(_p(q), _p(k), _p(v), _p(mask), _p(extra0), _p(y), _p(zsum), B, S, d,
+        check(lib.spt_sparse_attn_fwd(_p(q), _p(k), _p(v), _p(mask), _p(extra0), _p(y), _p(zsum), B, S, d, H,
                                       float(scale), float(clamp), SPT_BF16, _stream(q)))
     return y, zsum
 
 
 def sparse_attn_bwd(q, k, v, y, grad_y, mask, extra0, zsum, scale: float, clamp: float = 10.0):
     """-> (grad_q, grad_k, grad_v) bf16."""
-    B, S, d = _check_attn(q, k, v)
-    _check_dim(grad_y, 3, "grad_y")
+    B, S, d, H = _check_attn(q, k, v)
+    _check_dim(grad_y, q.dim(), "grad_y")
     _check_type(grad_y, torch.bfloat16, "grad_y")
     gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
     ws = _workspace(lib.spt_sparse_attn_bwd_workspace_bytes(B, S), q)
     with _on_device(q):
         check(lib.spt_sparse_attn_bwd(_p(q), _p(k), _p(v), _p(y), _p(grad_y), _p(mask), _p(extra0), _p(zsum),
-                                      _p(gq), _p(gk), _p(gv), _p(ws), B, S, d, float(scale), float(clamp), SPT_BF16,
+                                      _p(gq), _p(gk), _p(gv), _p(ws), B, S, d, H, float(scale), float(clamp), SPT_BF16,
                                       _stream(q)))
     return gq, gk, gv
 

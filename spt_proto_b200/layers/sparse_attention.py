@@ -103,17 +103,18 @@ class _SparseV2Mixin:
             self.register_buffer("loss", loss, persistent=False)
 
     def _fused_forward(self, q, k, v):
-        v_size = v.size()
-        q, k, v = self._to_heads(q), self._to_heads(k), self._to_heads(v)
-        self._maybe_train_loss(q, k)
-        q_c = self.quantizer("encode", z=q)
+        # everything runs on the layer's native [N, S, H, E] layout: PQ encode is row-wise, lookup and
+        # the attention kernels stride over the interleaved heads, so none of the reference's
+        # transpose(1, 2).contiguous() copies (attention.py:92-95,138-142) is made
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        self._maybe_train_loss(q, k)           # PQ loss is a mean over rows: layout-invariant
+        q_c = self.quantizer("encode", z=q)    # [N, S, H, m]
         k_c = self.quantizer("encode", z=k)
         mask, extra0, _ = ext.lookup_mask(q_c, k_c, self.sparse_coeff)
-        y = kernels.sparse_attention(q, k, v, mask, extra0, self.scaling)
-        if self.reference_output_layout:
-            return y.transpose(1, 2).contiguous().view(v_size)
-        y = y.view(v_size[0], v_size[2], v_size[1], v_size[3]).transpose(1, 2).contiguous()
-        return y.view(v_size)
+        y = kernels.sparse_attention(q, k, v, mask, extra0, self.scaling)      # [N, S, H, E]
+        if self.reference_output_layout:   # the shipped layer's re-interpretation of [N*H, E, S] memory
+            return y.permute(0, 2, 3, 1).contiguous().view(v.size())
+        return y
 
     def _sparse_get_attn(self, q, k):
         assert q.size() == k.size()
