@@ -142,13 +142,13 @@ int spt_softmax_bwd(const int32_t *indptr, const int32_t *indices, const float *
  * naive_gpt/layers/sparse/attention.py:105-141) as masked dense tiles on the tensor cores.
  *
  * spt_lookup_mask_fwd: same selection as spt_lookup_fwd, emitted as a per-row bitmask
- *   mask [B, S, S/32] uint32 (bit i of word w <=> key 32 w + i selected) and
+ *   mask [B, S, S/32] uint32, lane-major: bit i of word 4 g + t <=> key 128 g + 4 i + t selected, and
  *   extra0 [B, S] int32 = number of zero-padding slots of the row (multiplicity of key 0 beyond its
- *   own bit).  `output` (the int32 index tensor) may be NULL on this path.  Needs S % 32 == 0.
+ *   own bit).  `output` (the int32 index tensor) may be NULL on this path.  Needs S % 128 == 0.
  *
  * spt_sparse_attn_fwd: q, k, v [B, S, d] bf16 ->
  *   y [B, S, d] bf16 = sum_j p_rj v_j,  p = w * exp(clamp(scale * q.k, -clamp, clamp)) / Z,
- *   zsum [B, S] fp32 = Z (row sums, >= 1e-9) saved for the backward.  d = 64, S % 64 == 0.
+ *   zsum [B, S] fp32 = Z (row sums, >= 1e-9) saved for the backward.  d = 64, S % 128 == 0.
  * spt_sparse_attn_bwd: grad_y -> grad_q, grad_k, grad_v [B, S, d] bf16.  Recomputes p from q, k
  *   (nothing of size S x k is read or written); deterministic (no atomics).
  *   workspace: spt_sparse_attn_bwd_workspace_bytes(B, S).

@@ -10,8 +10,9 @@
 // and needs a CSR->CSC transpose for dK/dV.  On B200 the tensor pipe makes the *dense causal* tile
 // product cheaper than that gather even though only 1/4 of the causal entries are selected
 // (hard part 4 "decide by measurement": stage path measured at 4.1 ms per
-// 2048-token sequence, see profiles/).  The selection enters as a per-row bitmask
-//     mask[b][r][w] bit i  <=>  key 32 w + i is one of row r's lookup candidates
+// 2048-token sequence, see profiles/).  The selection enters as a per-row bitmask in the lookup
+// kernel's native "lane-major" layout (S % 128 == 0):
+//     mask[b][r][4 g + t] bit i  <=>  key 128 g + 4 i + t is one of row r's lookup candidates
 // plus extra0[b][r] = number of zero-padding slots of the row (they all alias key 0 and, like in the
 // reference, take part in the softmax).  Both are emitted by the lookup kernel directly, so the
 // int32 index tensor (64 MB per sequence) is never materialised on this path.
@@ -223,15 +224,17 @@ attn_fwd_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__rest
         zero_acc(s);
         gemm_nt(s, aq, smem_u32(s_k + buf * 8192), lane);
 
-        const uint32_t w_lo0 = __ldg(mrow_lo + jt * 2), w_lo1 = __ldg(mrow_lo + jt * 2 + 1);
-        const uint32_t w_hi0 = __ldg(mrow_hi + jt * 2), w_hi1 = __ldg(mrow_hi + jt * 2 + 1);
+        // tile column c = 8 n + 2 t4 + i is key 64 jt + c: lane t = 2 (t4 & 1) + i, bit 16 (jt & 1) + 2 n + (t4 >> 1)
+        const int wbase = (jt >> 1) * 4 + 2 * (t4 & 1), bbase = 16 * (jt & 1) + (t4 >> 1);
+        const uint32_t w_lo0 = __ldg(mrow_lo + wbase), w_lo1 = __ldg(mrow_lo + wbase + 1);
+        const uint32_t w_hi0 = __ldg(mrow_hi + wbase), w_hi1 = __ldg(mrow_hi + wbase + 1);
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            const uint32_t wl = n < 4 ? w_lo0 : w_lo1, wh = n < 4 ? w_hi0 : w_hi1;
-            const int bit = (n & 3) * 8 + t4 * 2;
+            const int bit = bbase + 2 * n;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                float wgt_lo = (float)((wl >> (bit + i)) & 1u), wgt_hi = (float)((wh >> (bit + i)) & 1u);
+                const uint32_t wl = i ? w_lo1 : w_lo0, wh = i ? w_hi1 : w_hi0;
+                float wgt_lo = (float)((wl >> bit) & 1u), wgt_hi = (float)((wh >> bit) & 1u);
                 if (jt == 0 && n == 0 && t4 == 0 && i == 0) { wgt_lo += ex_lo; wgt_hi += ex_hi; }  // key 0
                 const float e_lo = wgt_lo * ex2(fminf(fmaxf(s[n][i] * scale_log2, -clamp_log2), clamp_log2));
                 const float e_hi = wgt_hi * ex2(fminf(fmaxf(s[n][2 + i] * scale_log2, -clamp_log2), clamp_log2));
@@ -309,7 +312,7 @@ attn_bwd_kv_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__r
     float *s_invz = reinterpret_cast<float *>(smem + 8192 * 6);       // 2 x 64
     float *s_delta = s_invz + 2 * BM;                                  // 2 x 64
     float *s_ex0 = s_delta + 2 * BM;                                   // 2 x 64
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_ex0 + 2 * BM);   // 2 x 64 x 2 words
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_ex0 + 2 * BM);   // 2 x 64 x 4 words (lane t = 0..3)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g4 = lane >> 2, t4 = lane & 3;
     const int jt = blockIdx.x;                   // key tile (early key tiles are the heaviest)
@@ -330,8 +333,8 @@ attn_bwd_kv_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__r
             s_invz[buf * BM + threadIdx.x] = 1.0f / zsum[r];
             s_delta[buf * BM + threadIdx.x] = delta[r];
             s_ex0[buf * BM + threadIdx.x] = (float)extra0[r];
-            s_mask[(buf * BM + threadIdx.x) * 2] = mask[r * words + jt * 2];
-            s_mask[(buf * BM + threadIdx.x) * 2 + 1] = mask[r * words + jt * 2 + 1];
+            *reinterpret_cast<uint4 *>(s_mask + (buf * BM + threadIdx.x) * 4) =
+                *reinterpret_cast<const uint4 *>(mask + r * words + (jt >> 1) * 4);
         }
     };
 
@@ -367,14 +370,16 @@ attn_bwd_kv_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__r
         gemm_nt(st, ak, smem_u32(s_q + buf * 8192), lane);     // S^T  [16 keys x 64 rows]
         gemm_nt(dpt, av, smem_u32(s_dy + buf * 8192), lane);   // dP^T [16 keys x 64 rows]
         const float *invz = s_invz + buf * BM, *dl = s_delta + buf * BM, *ex0 = s_ex0 + buf * BM;
-        const uint32_t *mk = s_mask + buf * BM * 2;
+        const uint32_t *mk = s_mask + buf * BM * 4;
+        // key (in tile) -> lane t = key & 3 (same for key_lo and key_hi = key_lo + 8), bit 16 (jt & 1) + (key >> 2)
+        const int kt = key_lo & 3, kb_lo = 16 * (jt & 1) + (key_lo >> 2), kb_hi = kb_lo + 2;
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int r = n * 8 + t4 * 2 + i;           // query row inside the tile
-                const uint32_t w_lo = mk[r * 2 + (key_lo >> 5)], w_hi = mk[r * 2 + (key_hi >> 5)];
-                float wgt_lo = (float)((w_lo >> (key_lo & 31)) & 1u), wgt_hi = (float)((w_hi >> (key_hi & 31)) & 1u);
+                const uint32_t wd = mk[r * 4 + kt];
+                float wgt_lo = (float)((wd >> kb_lo) & 1u), wgt_hi = (float)((wd >> kb_hi) & 1u);
                 if (jt == 0 && key_lo == 0) wgt_lo += ex0[r];  // key 0 carries the zero-padding multiplicity
                 float p_lo, ds_lo, p_hi, ds_hi;
                 bwd_elem(st[n][i], dpt[n][i], wgt_lo, invz[r], dl[r], scale_log2, clamp_log2, p_lo, ds_lo);
@@ -457,15 +462,17 @@ attn_bwd_q_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__re
         zero_acc(dp);
         gemm_nt(s, aq, smem_u32(s_k + buf * 8192), lane);
         gemm_nt(dp, ady, smem_u32(s_v + buf * 8192), lane);
-        const uint32_t w_lo0 = __ldg(mrow_lo + jt * 2), w_lo1 = __ldg(mrow_lo + jt * 2 + 1);
-        const uint32_t w_hi0 = __ldg(mrow_hi + jt * 2), w_hi1 = __ldg(mrow_hi + jt * 2 + 1);
+        // tile column c = 8 n + 2 t4 + i is key 64 jt + c: lane t = 2 (t4 & 1) + i, bit 16 (jt & 1) + 2 n + (t4 >> 1)
+        const int wbase = (jt >> 1) * 4 + 2 * (t4 & 1), bbase = 16 * (jt & 1) + (t4 >> 1);
+        const uint32_t w_lo0 = __ldg(mrow_lo + wbase), w_lo1 = __ldg(mrow_lo + wbase + 1);
+        const uint32_t w_hi0 = __ldg(mrow_hi + wbase), w_hi1 = __ldg(mrow_hi + wbase + 1);
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            const uint32_t wl = n < 4 ? w_lo0 : w_lo1, wh = n < 4 ? w_hi0 : w_hi1;
-            const int bit = (n & 3) * 8 + t4 * 2;
+            const int bit = bbase + 2 * n;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                float wgt_lo = (float)((wl >> (bit + i)) & 1u), wgt_hi = (float)((wh >> (bit + i)) & 1u);
+                const uint32_t wl = i ? w_lo1 : w_lo0, wh = i ? w_hi1 : w_hi0;
+                float wgt_lo = (float)((wl >> bit) & 1u), wgt_hi = (float)((wh >> bit) & 1u);
                 if (jt == 0 && n == 0 && t4 == 0 && i == 0) { wgt_lo += ex_lo; wgt_hi += ex_hi; }
                 float p_lo, ds_lo, p_hi, ds_hi;
                 bwd_elem(s[n][i], dp[n][i], wgt_lo, iz_lo, dl_lo, scale_log2, clamp_log2, p_lo, ds_lo);
@@ -483,7 +490,7 @@ attn_bwd_q_kernel(const __nv_bfloat16 *__restrict__ q, const __nv_bfloat16 *__re
 }
 
 constexpr int FWD_SMEM = 8192 * 5;
-constexpr int BWD_KV_SMEM = 8192 * 6 + (3 * 2 * BM) * 4 + 2 * BM * 2 * 4;
+constexpr int BWD_KV_SMEM = 8192 * 6 + (3 * 2 * BM) * 4 + 2 * BM * 4 * 4;
 constexpr int BWD_Q_SMEM = 8192 * 6;
 
 }  // namespace attn
@@ -494,8 +501,8 @@ using namespace spt;
 static int check_attn_args(const char *what, int B, int S, int d, int dtype) {
     if (dtype != SPT_BF16) return fail(SPT_ERR_UNSUPPORTED, "%s: only bf16 is supported on the fused path", what);
     if (d != attn::D) return fail(SPT_ERR_UNSUPPORTED, "%s: head dim %d not supported (64 only)", what, d);
-    if (B < 1 || B > 65535 || S < 64 || S % 64 != 0)
-        return fail(SPT_ERR_INVALID_ARGUMENT, "%s: need 1 <= B <= 65535 and S a positive multiple of 64 (B=%d S=%d)", what, B, S);
+    if (B < 1 || B > 65535 || S < 128 || S % 128 != 0)
+        return fail(SPT_ERR_INVALID_ARGUMENT, "%s: need 1 <= B <= 65535 and S a positive multiple of 128 (B=%d S=%d)", what, B, S);
     return SPT_OK;
 }
 

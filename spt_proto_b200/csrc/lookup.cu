@@ -185,6 +185,11 @@ struct LaneState {
     int s_need, track, last_j;
 };
 
+// Bitmask output layout ("lane-major", S % 128 == 0): word 4 g + t of a row holds the keys
+// 128 g + 4 i + t at bit i — exactly the words the (row, lane t) threads of this kernel work on.
+__device__ __forceinline__ int mask_word(int j) { return ((j >> 7) << 2) | (j & 3); }
+__device__ __forceinline__ int mask_bit(int j) { return (j & 127) >> 2; }
+
 __device__ __forceinline__ uint32_t valid_mask(int w, int nkeys) {
     const int rem = nkeys - 32 * w;
     return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
@@ -224,7 +229,7 @@ __device__ __forceinline__ void place_word(LaneState &st, const uint32_t (&mask)
             mk &= mk - 1;
             const int j = 4 * (32 * w + i) + t;
             row_img[t + 4 * (st.start[s] + st.done[s])] = (uint16_t)j;
-            if (row_bits) atomicOr(&row_bits[j >> 5], 1u << (j & 31));
+            if (row_bits) atomicOr(&row_bits[mask_word(j)], 1u << mask_bit(j));
             st.done[s] += 1;
         }
     }
@@ -242,8 +247,8 @@ __device__ __forceinline__ void fix_clobber(const LaneState &st, int t, int quar
         if ((recv >> 2) > (old >> 2)) {
             row_img[p] = (uint16_t)recv;
             if (row_bits) {
-                atomicAnd(&row_bits[old >> 5], ~(1u << (old & 31)));
-                atomicOr(&row_bits[recv >> 5], 1u << (recv & 31));
+                atomicAnd(&row_bits[mask_word(old)], ~(1u << mask_bit(old)));
+                atomicOr(&row_bits[mask_word(recv)], 1u << mask_bit(recv));
             }
         }
     }
@@ -360,6 +365,147 @@ lookup_bitmap_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__
     if (s_bits) flush_mask(s_bits, mask_out, b, r0, S);
 }
 
+// ---- mask-only path (fused attention) -------------------------------------------------------------
+// Same selection, but only the SET of selected keys is needed (bitmask + extra0), not their output
+// positions.  Each (row, lane t) thread evaluates the adder tree ONCE per 32-key word, keeps the
+// bucket masks of its <= MAXW words in registers, and after the plan (bucket sizes -> quotas) selects
+// whole words: a bucket that is taken completely is OR-ed in, only the single partially taken bucket
+// needs a "lowest q bits" trim.  The thread's words ARE the lane-major mask words, so they are stored
+// directly — no per-key loop, no shared-memory image, no atomics.
+template <int MAXW>
+__device__ __forceinline__ uint32_t bucket_word(int s, int w, const uint32_t (&m1)[MAXW], const uint32_t (&m2)[MAXW],
+                                                const uint32_t (&m3)[MAXW], int nkeys) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < MAXW; ++i) {
+        if (i == w) {
+            const uint32_t m0 = valid_mask(i, nkeys) & ~(m1[i] | m2[i] | m3[i]);
+            r = s == 3 ? m3[i] : (s == 2 ? m2[i] : (s == 1 ? m1[i] : m0));
+        }
+    }
+    return r;
+}
+
+__device__ __forceinline__ uint32_t pick_lowest(uint32_t mask, int &quota) {
+    if (quota <= 0 || mask == 0) return 0;
+    const int c = __popc(mask);
+    if (c <= quota) {
+        quota -= c;
+        return mask;
+    }
+    uint32_t r = 0, x = mask;
+    for (int k = 0; k < quota; ++k) {
+        r |= x & (0u - x);
+        x &= x - 1;
+    }
+    quota = 0;
+    return r;
+}
+
+template <int M, int MAXW>
+__global__ void __launch_bounds__(LK_THREADS)
+lookup_maskonly_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__restrict__ kb,
+                       const int *__restrict__ flag, uint32_t *__restrict__ mask_out,
+                       int32_t *__restrict__ extra0_out, int S, int nnz, int W, int H) {
+    if (*flag) return;  // some key code >= 16: the generic kernel handles this call
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *s_kb = reinterpret_cast<uint32_t *>(smem_raw);
+    const int b = blockIdx.y;
+    const int tile = gridDim.x - 1 - blockIdx.x;  // heaviest (last) rows first
+    const int r0 = tile * LK_ROWS;
+    const int rl = threadIdx.x >> 2, t = threadIdx.x & 3;
+    const int r = r0 + rl;
+    const bool live = r < S;
+    const int quarter = nnz / 4;
+    const int nkeys = (live && r >= t) ? (r - t) / 4 + 1 : 0;
+    const int lim = live ? min(r + 1, nnz) : 0;
+    const int n_t = lim > t ? (lim - t + 3) / 4 : 0;
+    const int tile_words = min(W, (min(S, r0 + LK_ROWS) + 127) / 128);
+
+    const uint32_t *kb_head = kb + (size_t)b * M * W * LK_WORD_U32;
+    {
+        const int per_s = tile_words * LK_WORD_U32 / 4;  // uint4 per subspace
+        for (int i = threadIdx.x; i < M * per_s; i += blockDim.x) {
+            const int s = i / per_s, o = i % per_s;
+            reinterpret_cast<uint4 *>(s_kb)[s * per_s + o] =
+                reinterpret_cast<const uint4 *>(kb_head + (size_t)s * W * LK_WORD_U32)[o];
+        }
+    }
+    __syncthreads();
+
+    BitmapMatcher<M> mt;
+    mt.s_kb = s_kb;
+    mt.t = t;
+    mt.cw = tile_words;
+    mt.w0 = 0;
+#pragma unroll
+    for (int s = 0; s < M; ++s)
+        mt.q[s] = live ? ((unsigned)query_codes[(((size_t)(b / H) * S + r) * H + (b % H)) * M + s] & 0xffffu) : 0xffffu;
+
+    uint32_t m1[MAXW], m2[MAXW], m3[MAXW];
+    LaneState st;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) st.len[s] = 0;
+#pragma unroll
+    for (int w = 0; w < MAXW; ++w) {
+        uint32_t mask[4] = {0, 0, 0, 0};
+        const uint32_t valid = w < tile_words ? valid_mask(w, nkeys) : 0u;
+        if (valid) mt.buckets(w, valid, mask);
+        m1[w] = mask[1];
+        m2[w] = mask[2];
+        m3[w] = mask[3];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) st.len[s] += __popc(mask[s]);
+    }
+    plan_lane(st, t, n_t, quarter);
+
+    uint32_t sel[MAXW];
+    {
+        int q3 = st.take[3], q2 = st.take[2], q1 = st.take[1], q0 = st.take[0];
+#pragma unroll
+        for (int w = 0; w < MAXW; ++w) {
+            const uint32_t m0 = valid_mask(w, nkeys) & ~(m1[w] | m2[w] | m3[w]);
+            sel[w] = pick_lowest(m3[w], q3) | pick_lowest(m2[w], q2) | pick_lowest(m1[w], q1) | pick_lowest(m0, q0);
+        }
+    }
+
+    // clobbered last slot (see fix_clobber): lanes 2/3 report the last key of the tracked bucket, the
+    // owner (lane 0/1) swaps it for its own last taken key of that bucket if a later warp instruction
+    // of the reference kernel would have overwritten the slot.
+    int last_j = -1;
+    if (st.track >= 0) {
+        for (int w = MAXW - 1; w >= 0 && last_j < 0; --w) {
+            const uint32_t mk = bucket_word<MAXW>(st.track, w, m1, m2, m3, nkeys);
+            if (mk) last_j = 4 * (32 * w + 31 - __clz(mk)) + t;
+        }
+    }
+    const int recv = __shfl_xor_sync(FULL, last_j, 3);
+    int swap_old = -1;
+    if (st.s_need >= 0 && recv >= 0) {
+        int quota = quarter, j_old = -1;
+        for (int w = 0; w < MAXW && quota > 0; ++w) {
+            const uint32_t mk = bucket_word<MAXW>(st.s_need, w, m1, m2, m3, nkeys);
+            const uint32_t got = pick_lowest(mk, quota);
+            if (got) j_old = 4 * (32 * w + 31 - __clz(got)) + t;
+        }
+        if (j_old >= 0 && (recv >> 2) > (j_old >> 2)) swap_old = j_old;
+    }
+    const int partner_swapped = __shfl_xor_sync(FULL, swap_old >= 0 ? 1 : 0, 3);
+#pragma unroll
+    for (int w = 0; w < MAXW; ++w) {
+        if (swap_old >= 0 && (swap_old >> 7) == w) sel[w] &= ~(1u << mask_bit(swap_old));
+        if (partner_swapped && last_j >= 0 && (last_j >> 7) == w) sel[w] |= 1u << mask_bit(last_j);
+    }
+
+    store_extra0(st, extra0_out, b, r, S, nnz, live, t);
+    if (live) {
+        uint32_t *dst = mask_out + ((size_t)b * S + r) * (S / 32) + t;
+#pragma unroll
+        for (int w = 0; w < MAXW; ++w)
+            if (w < W) dst[4 * w] = sel[w];
+    }
+}
+
 // ---- generic path ----------------------------------------------------------------------------
 // smem: [ out image ][ query codes LK_ROWS * m u16 ]
 __global__ void __launch_bounds__(LK_THREADS)
@@ -449,7 +595,7 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
     SPT_REQUIRE(B <= 65535, "lookup_fwd: batch %d exceeds grid limit", B);
     SPT_REQUIRE(m >= 4, "lookup_fwd: n_subspaces must be >= 4 (got %d)", m);
     SPT_REQUIRE(nnz >= 8 && nnz % 4 == 0 && nnz <= S, "lookup_fwd: nonzeros per row must be a multiple of 4 in [8, S] (got %d)", nnz);
-    SPT_REQUIRE(!mask_out || (S % 32 == 0 && extra0_out), "lookup_fwd: bitmask output needs S %% 32 == 0 and extra0");
+    SPT_REQUIRE(!mask_out || (S % 128 == 0 && extra0_out), "lookup_fwd: bitmask output needs S %% 128 == 0 and extra0");
     cudaStream_t st = as_stream(stream);
     const int tiles = (S + LK_ROWS - 1) / LK_ROWS;
     dim3 grid(tiles, B);
@@ -480,6 +626,35 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
     int chunk_words = (int)((LK_SMEM_BUDGET - img) / per_word);
     if (chunk_words > W) chunk_words = W;
     const size_t smem = img + per_word * chunk_words;
+    const bool mask_only = mask_out && !output && W <= 32;
+    if (mask_only) {
+        const size_t msmem = per_word * W;
+#define SPT_LKM_CASE(MM)                                                                                          \
+    case MM:                                                                                                      \
+        if (W <= 16) {                                                                                            \
+            if (msmem > 48 * 1024)                                                                                \
+                cudaFuncSetAttribute(lookup_maskonly_kernel<MM, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem); \
+            lookup_maskonly_kernel<MM, 16><<<grid, LK_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H); \
+        } else {                                                                                                  \
+            if (msmem > 48 * 1024)                                                                                \
+                cudaFuncSetAttribute(lookup_maskonly_kernel<MM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem); \
+            lookup_maskonly_kernel<MM, 32><<<grid, LK_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H); \
+        }                                                                                                         \
+        break;
+        switch (m) {
+            SPT_LKM_CASE(8)
+            SPT_LKM_CASE(16)
+            default:
+                goto general_path;
+        }
+#undef SPT_LKM_CASE
+        SPT_LAUNCH_CHECK("lookup_maskonly_kernel");
+        lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, mask_out,
+                                                                  extra0_out, S, m, nnz, H);
+        SPT_LAUNCH_CHECK("lookup_generic_kernel(fallback)");
+        return SPT_OK;
+    }
+general_path:
 #define SPT_LK_CASE(MM)                                                                                          \
     case MM:                                                                                                     \
         if (smem > 48 * 1024)                                                                                    \

@@ -312,8 +312,9 @@ def _heads(t: torch.Tensor, name: str):
 
 
 def lookup_mask(query: torch.Tensor, key: torch.Tensor, sparse_coeff: int, want_indices: bool = False):
-    """Same selection as lookup_forward_cuda, emitted as (mask [B,S,S/32] int32 bit-words,
-    extra0 [B,S] int32 zero-padding multiplicity of key 0, indices [B,S,nnz] or None).
+    """Same selection as lookup_forward_cuda, emitted as (mask [B,S,S/32] int32 bit-words in the
+    lane-major layout: word 4g+t bit i <=> key 128g+4i+t, extra0 [B,S] int32 zero-padding multiplicity
+    of key 0, indices [B,S,nnz] or None).
     Codes: [B,S,m] head-major or [N,S,H,m] (heads interleaved, B = N*H)."""
     _check_dim(key, query.dim(), "key")
     _check_type(key, torch.int32, "key")
@@ -322,8 +323,8 @@ def lookup_mask(query: torch.Tensor, key: torch.Tensor, sparse_coeff: int, want_
         raise RuntimeError("query and key must be contiguous CUDA tensors of the same shape")
     B, S, H = _heads(query, "query")
     m = query.size(-1)
-    if sparse_coeff <= 0 or S % sparse_coeff != 0 or S % 32 != 0:
-        raise RuntimeError("seq_length must be divisible by sparse_coeff and by 32")
+    if sparse_coeff <= 0 or S % sparse_coeff != 0 or S % 128 != 0:
+        raise RuntimeError("seq_length must be divisible by sparse_coeff and by 128")
     nnz = S // sparse_coeff
     dev = query.device
     mask = torch.empty((B, S, S // 32), dtype=torch.int32, device=dev)

@@ -15,7 +15,8 @@ def _mask_from_indices(indices, S):
     B, nnz_total = indices.shape[0], indices.shape[1] * indices.shape[2]
     dense = torch.zeros(B, S, S, dtype=torch.int32)
     dense.scatter_add_(2, indices.long(), torch.ones_like(indices))
-    bits = (dense > 0).view(B, S, S // 32, 32).long()
+    # lane-major layout: word 4 g + t, bit i  <=>  key 128 g + 4 i + t
+    bits = (dense > 0).view(B, S, S // 128, 32, 4).permute(0, 1, 2, 4, 3).reshape(B, S, S // 32, 32).long()
     words = (bits << torch.arange(32)).sum(-1)
     words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
     extra0 = dense[:, :, 0] - (dense[:, :, 0] > 0).int()
@@ -24,7 +25,8 @@ def _mask_from_indices(indices, S):
 
 
 @pytest.mark.parametrize("B,S,m,c,coeff", [(3, 256, 8, 16, 8), (2, 512, 8, 2, 8), (2, 128, 8, 1, 8), (1, 2048, 8, 16, 8),
-                                            (2, 256, 8, 40, 8), (2, 192, 6, 3, 4)])
+                                            (2, 256, 8, 40, 8), (2, 256, 6, 3, 4), (2, 4096, 8, 16, 8),
+                                            (2, 384, 16, 4, 8), (1, 128, 8, 16, 4)])
 def test_lookup_mask_matches_index_output(B, S, m, c, coeff):
     from spt_proto_b200 import ext
     g = torch.Generator().manual_seed(S + c)
