@@ -36,6 +36,8 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+_REAL_STDOUT = sys.stdout
+
 HEADS, D_HEAD, SEQ, M_SUB, N_CODE, D_CODE, COEFF = 32, 64, 2048, 8, 16, 8, 8
 METRIC = "sparse_mha_fwd_bwd_tokens_per_s"
 UNIT = "tokens/s"
@@ -142,7 +144,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -310,15 +312,11 @@ def run_ours(args):
     hq, hk, hv, hdy = (t.detach().cpu().pin_memory() for t in (q, k, v, dy))
     outs = [torch.empty(shape, dtype=torch.bfloat16).pin_memory() for _ in range(4)]
 
+    from spt_proto_b200.host_io import HostPipeline
+    pipe = HostPipeline(attn, dev, chunk=1)     # per-sequence chunks: H2D / kernels / D2H overlap
+
     def step_e2e():
-        dq = hq.to(dev, non_blocking=True).requires_grad_()
-        dk = hk.to(dev, non_blocking=True).requires_grad_()
-        dv = hv.to(dev, non_blocking=True).requires_grad_()
-        ddy = hdy.to(dev, non_blocking=True)
-        y = attn(dq, dk, dv)
-        y.backward(ddy)
-        for dst, src in zip(outs, (y.detach(), dq.grad, dk.grad, dv.grad)):
-            dst.copy_(src, non_blocking=True)
+        pipe.run((hq, hk, hv, hdy), outs)
 
     for _ in range(2):
         step_e2e()
@@ -382,12 +380,18 @@ def run_ours(args):
             "routed_ffn": ffn_bench(dev, tensor_tflops),
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version banner there) get
+    # stderr, the line goes to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
