@@ -274,6 +274,7 @@ def run_ours(args):
     attn = layers.SparseVanillaAttentionV2(d_head=D_HEAD, d_codeword=D_CODE, n_codewords=N_CODE, p_dropout=0.0).to(dev)
     attn.sparse_coeff = COEFF
     attn.use_fused = not args.stage_path
+    attn.host_trigger = False    # inference-style call: PQ loss not armed, decided on the host (no D2H sync)
     shape = (n_seq, SEQ, HEADS, D_HEAD)
     q = torch.randn(shape, device=dev).bfloat16().requires_grad_()
     k = torch.randn(shape, device=dev).bfloat16().requires_grad_()

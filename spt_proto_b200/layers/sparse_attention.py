@@ -62,6 +62,12 @@ class _SparseV2Mixin:
     # bf16, d_head 64, S % 128 == 0 on CUDA: run lookup -> bitmask -> fused masked-dense attention on
     # the tensor cores instead of the stage chain (same result up to bf16 rounding).
     use_fused: bool = True
+    # The reference reads its device-side `trigger` buffer with `is_nonzero()` on every forward
+    # (attention.py:98) — a device->host synchronisation per layer call.  None (default) keeps that
+    # behaviour (a training loop arms the layer with `trigger.fill_(True)`, script/4-sparse-tuning-0.py:
+    # 71-78).  Setting host_trigger to a bool makes the decision on the host, with no synchronisation:
+    # True = compute the PQ loss on the next forward (then resets to False), False = skip it.
+    host_trigger = None
 
     def _init_v2(self, d_head, d_codeword, n_codewords):
         self.quantizer = PQV2(d_codeword=d_codeword, n_codewords=n_codewords, n_subspaces=d_head // d_codeword)
@@ -97,8 +103,13 @@ class _SparseV2Mixin:
                 and (q.size(1) // self.sparse_coeff) % 4 == 0 and q.size(1) // self.sparse_coeff >= 8)
 
     def _maybe_train_loss(self, q, k):
-        if self.trigger.is_nonzero():  # one-shot PQ training loss, armed by the training loop
-            self.trigger.logical_not_()
+        if self.host_trigger is not None:
+            armed, self.host_trigger = bool(self.host_trigger), False
+        else:
+            armed = self.trigger.is_nonzero()  # one-shot PQ training loss, armed by the training loop
+            if armed:
+                self.trigger.logical_not_()
+        if armed:
             loss = self.quantizer("train", z=q)[-1] + self.quantizer("train", z=k)[-1]
             self.register_buffer("loss", loss, persistent=False)
 

@@ -148,3 +148,26 @@ def test_fused_interleaved_layout_equals_head_major():
     g3 = ext.sparse_attn_bwd(to_heads(q4), to_heads(k4), to_heads(v4), y3, to_heads(dy4), m3, e3, z3, E ** -0.5)
     for a, b in zip(g4, g3):
         assert torch.equal(to_heads(a), b)
+
+
+def test_host_pipeline_equals_direct_call():
+    """HostPipeline (pinned host buffers, chunked, 3 streams) returns exactly what the direct layer call does."""
+    from spt_proto_b200 import layers
+    from spt_proto_b200.host_io import HostPipeline
+    torch.manual_seed(3)
+    N, S, H, E = 5, 256, 4, 64
+    attn = layers.SparseVanillaAttentionV2(d_head=E, d_codeword=8, n_codewords=16, p_dropout=0.0).to(DEV)
+    attn.host_trigger = False
+    host_in = [torch.randn(N, S, H, E).bfloat16().pin_memory() for _ in range(4)]
+    q, k, v = (t.to(DEV).requires_grad_() for t in host_in[:3])
+    y = attn(q, k, v)
+    y.backward(host_in[3].to(DEV))
+    want = [t.detach().cpu() for t in (y, q.grad, k.grad, v.grad)]
+    for chunk in (1, 2):
+        pipe = HostPipeline(attn, torch.device(DEV), chunk=chunk, depth=2)
+        for _ in range(2):   # second run reuses the staging slots
+            host_out = [torch.zeros(N, S, H, E, dtype=torch.bfloat16).pin_memory() for _ in range(4)]
+            pipe.run(host_in, host_out)
+            torch.cuda.synchronize()
+            for a, b in zip(host_out, want):
+                assert torch.equal(a, b)
