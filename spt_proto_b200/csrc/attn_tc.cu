@@ -25,12 +25,15 @@
 // Deterministic: no atomics anywhere.
 //
 // Kernel anatomy (all three kernels): a CTA owns one 128-row "owner" tile (queries for fwd / dQ, keys
-// for dK/dV) and loops over 64-row "other" tiles.  192 threads:
-//   warps 0-3 : one thread per owner row = one TMEM lane; tcgen05.ld the score row, mask/exp math,
-//               tcgen05.st the bf16 probability row back to TMEM
-//   warp  4   : TMA producer (cp.async.bulk.tensor 4-D straight from the [N, S, H, d] layout)
-//   warp  5   : TMEM allocator + tcgen05.mma issuer (one thread)
-// Two CTAs per SM (256 TMEM columns each) so one CTA's MMAs run under the other's exp math.
+// for dK/dV) and loops over 64-row "other" tiles.  320 threads:
+//   warps 0-7 : two warpgroups; thread = (owner row = TMEM lane, column half): tcgen05.ld its 32 score
+//               columns, mask/exp math, tcgen05.st the bf16 probability columns back to TMEM
+//   warp  8   : TMA producer (cp.async.bulk.tensor 4-D straight from the [N, S, H, d] layout)
+//   warp  9   : TMEM allocator + tcgen05.mma issuer (one thread)
+// Two CTAs per SM (256 TMEM columns each): 16 math warps per SM keep the XU/FMA pipes fed while the
+// other CTA's MMAs and barrier round trips are in flight.  Score tiles of the next iteration are
+// issued while the current one is still in the math phase (double-buffered S in the forward; in the
+// dQ kernel the score columns are released as soon as they are in registers).
 #include "tc.cuh"
 
 namespace spt {
@@ -42,7 +45,8 @@ constexpr int D = 64;          // head dim
 constexpr int BM = 128;        // owner tile rows  (= TMEM lanes)
 constexpr int BN = 64;         // other tile rows per iteration
 constexpr int STAGES = 3;
-constexpr int THREADS = 192;
+constexpr int N_MATH = 256;      // warps 0-7
+constexpr int THREADS = 320;
 constexpr int OWN_BYTES = BM * D * 2;   // 16 KB
 constexpr int T_BYTES = BN * D * 2;     // 8 KB
 constexpr int TMEM_COLS = 256;
@@ -57,6 +61,121 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&h);
 }
+// The element math is written for pipe balance: per element the XU pipe (ex2) is the floor, so
+// everything else is pushed onto the FMA pipe and kept off the half-rate ALU pipe.
+//   clamp:  u = sat(s * a + 0.5) with a = scale / (2 clamp)  (FFMA.SAT), arg = u * 2L - L  (FFMA)
+//           replaces FMUL + 2 FMNMX (ALU);  |scale s| <= clamp  <=>  the unsaturated value equals u
+//   mask :  bit test straight into a predicate (one LOP3), then a predicated multiply by zero (FMA
+//           pipe) instead of shift + and + int->float + FSEL
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float d;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float sat01(float v) {
+    float d;
+    asm("add.sat.f32 %0, %1, 0f00000000;" : "=f"(d) : "f"(v));
+    return d;
+}
+__device__ __forceinline__ float keep_if_bit(float e, uint32_t w, uint32_t bitmask) {   // e if w & bitmask, else 0
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.eq.u32 p, t, 0;\n\t"
+        "@p mul.f32 %0, %0, 0f00000000;\n\t"
+        "}" : "+f"(e) : "r"(w), "r"(bitmask));
+    return e;
+}
+__device__ __forceinline__ float zero_if_ne(float g, float u, float v) {   // g if u == v, else 0
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.neu.f32 p, %1, %2;\n\t"
+        "@p mul.f32 %0, %0, 0f00000000;\n\t"
+        "}" : "+f"(g) : "f"(u), "f"(v));
+    return g;
+}
+
+
+struct ClampK {     // constants of the FMA-pipe clamp: u = sat(s * a + 0.5), arg = u * two_l + neg_l
+    float a, two_l, neg_l;
+};
+__device__ __forceinline__ ClampK make_clamp(float scale_log2, float clamp_log2) {
+    return {scale_log2 / (2.0f * clamp_log2), 2.0f * clamp_log2, -clamp_log2};
+}
+
+// Forward: 32 score columns of one row -> 16 packed bf16 pairs of e = w * exp(clamp(scale s)), row sum.
+// w[t] = lane-major mask word t shifted so that column i tests bit i >> 2.  FIRST: column 0 is key 0.
+template <bool FIRST>
+__device__ __forceinline__ void fwd_chunk32(const uint32_t (&r)[32], const uint32_t (&w)[4], const ClampK ck, float ex0,
+                                            float &sum, uint32_t (&pk)[16]) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+        float e0 = ex2(fmaf(fma_sat(__uint_as_float(r[i]), ck.a, 0.5f), ck.two_l, ck.neg_l));
+        float e1 = ex2(fmaf(fma_sat(__uint_as_float(r[i + 1]), ck.a, 0.5f), ck.two_l, ck.neg_l));
+        if (FIRST && i == 0) e0 *= (float)(w[0] & 1u) + ex0;     // key 0 carries the zero-padding multiplicity
+        else e0 = keep_if_bit(e0, w[i & 3], 1u << (i >> 2));
+        e1 = keep_if_bit(e1, w[(i + 1) & 3], 1u << (i >> 2));
+        sum += e0 + e1;
+        pk[i >> 1] = pack_bf16(e0, e1);
+    }
+}
+
+// Backward element: s = q.k, dp = dO'.v, masked weight applied by the caller through `e`.
+//   e_raw = exp(clamp(scale s));   ds = e * (dp - delta') * [|scale s| <= clamp]
+__device__ __forceinline__ float bwd_exp(float s_raw, const ClampK ck, float &u, float &v) {
+    v = fmaf(s_raw, ck.a, 0.5f);
+    u = sat01(v);
+    return ex2(fmaf(u, ck.two_l, ck.neg_l));
+}
+__device__ __forceinline__ float bwd_ds(float e, float dp, float delta, float u, float v) {
+    return zero_if_ne(e * (dp - delta), u, v);
+}
+
+// dQ kernel: 32 columns (keys) of one query row.  w[t] as in fwd_chunk32.
+template <bool FIRST>
+__device__ __forceinline__ void bwdq_chunk32(const uint32_t (&r)[32], const uint32_t (&g)[32], const uint32_t (&w)[4],
+                                             const ClampK ck, float delta, float ex0, uint32_t (&pk)[16]) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+        float u0, v0, u1, v1;
+        float e0 = bwd_exp(__uint_as_float(r[i]), ck, u0, v0);
+        float e1 = bwd_exp(__uint_as_float(r[i + 1]), ck, u1, v1);
+        if (FIRST && i == 0) e0 *= (float)(w[0] & 1u) + ex0;
+        else e0 = keep_if_bit(e0, w[i & 3], 1u << (i >> 2));
+        e1 = keep_if_bit(e1, w[(i + 1) & 3], 1u << (i >> 2));
+        pk[i >> 1] = pack_bf16(bwd_ds(e0, __uint_as_float(g[i]), delta, u0, v0),
+                               bwd_ds(e1, __uint_as_float(g[i + 1]), delta, u1, v1));
+    }
+}
+
+// dK/dV kernel: 16 columns (query rows c0 .. c0+15) of one key.  mrow = this key's lane-major word of every
+// row, [64] in shared memory; bitmask selects the key's bit.  KEY0: this thread is key 0 (adds extra0[row]).
+template <bool KEY0>
+__device__ __forceinline__ void bwdkv_chunk16(const uint32_t (&r)[16], const uint32_t (&g)[16], const uint32_t *mrow,
+                                              const float *s_delta, const float *s_ex0, int c0, uint32_t bitmask,
+                                              const ClampK ck, uint32_t (&pe)[8], uint32_t (&pd)[8]) {
+#pragma unroll
+    for (int q4 = 0; q4 < 16; q4 += 4) {
+        const uint4 mw = *reinterpret_cast<const uint4 *>(mrow + c0 + q4);
+        const float4 dl = *reinterpret_cast<const float4 *>(s_delta + c0 + q4);
+        const uint32_t mwv[4] = {mw.x, mw.y, mw.z, mw.w};
+        const float dlv[4] = {dl.x, dl.y, dl.z, dl.w};
+        float e[4], d[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float u, v;
+            e[t] = bwd_exp(__uint_as_float(r[q4 + t]), ck, u, v);
+            if (KEY0) e[t] *= (float)((mwv[t] & bitmask) != 0u) + s_ex0[c0 + q4 + t];
+            else e[t] = keep_if_bit(e[t], mwv[t], bitmask);
+            d[t] = bwd_ds(e[t], __uint_as_float(g[q4 + t]), dlv[t], u, v);
+        }
+        pe[(q4 >> 1)] = pack_bf16(e[0], e[1]);
+        pe[(q4 >> 1) + 1] = pack_bf16(e[2], e[3]);
+        pd[(q4 >> 1)] = pack_bf16(d[0], d[1]);
+        pd[(q4 >> 1) + 1] = pack_bf16(d[2], d[3]);
+    }
+}
 
 struct Smem {
     uint32_t base;            // 1024-aligned shared address
@@ -67,6 +186,7 @@ __device__ __forceinline__ Smem align_smem(unsigned char *raw) {
     const uint32_t base = (a + 1023) & ~1023u;
     return {base, raw + (base - a)};
 }
+__device__ __forceinline__ void math_warps_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_MATH) : "memory"); }
 
 // store 32 fp32 accumulator values (scaled) as 32 bf16 = 64 contiguous bytes
 __device__ __forceinline__ void store_row32(__nv_bfloat16 *dst, const uint32_t (&r)[32], float s) {
@@ -82,7 +202,7 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16 *dst, const uint32_t (
 // ---------------------------------------------------------------------------------------------------
 // Forward.  TMEM columns: S[2] 0/64 (fp32 128x64), P[2] 128/160 (bf16 pairs, 32 cols), O 192 (128x64).
 // ---------------------------------------------------------------------------------------------------
-constexpr int FWD_SMEM = OWN_BYTES + 2 * STAGES * T_BYTES + 1024 + 256;
+constexpr int FWD_SMEM = OWN_BYTES + 2 * STAGES * T_BYTES + 1024 /*row sums*/ + 1024 /*align*/ + 256 /*barriers*/;
 
 __global__ void __launch_bounds__(THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -92,7 +212,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     extern __shared__ unsigned char smem_raw[];
     const Smem sm = align_smem(smem_raw);
     const uint32_t s_q = sm.base, s_k = s_q + OWN_BYTES, s_v = s_k + STAGES * T_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm.ptr + OWN_BYTES + 2 * STAGES * T_BYTES);
+    float *s_part = reinterpret_cast<float *>(sm.ptr + OWN_BYTES + 2 * STAGES * T_BYTES);   // [2][128] partial row sums
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm.ptr + OWN_BYTES + 2 * STAGES * T_BYTES + 1024);
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t q_full = bar0, o_full = bar0 + 8;
     auto k_full = [&](int s) { return bar0 + 16 + s * 8; };
@@ -121,18 +242,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(s_full(i), 1);
-            mbar_init(p_full(i), 128);
+            mbar_init(p_full(i), N_MATH);
         }
         mbar_fence_init();
     }
-    if (warp == 5) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    if (warp == 9) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===== TMA producer =====
         if (lane == 0) {
             mbar_expect_tx(q_full, OWN_BYTES);
@@ -149,100 +270,89 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 tma_load_4d(s_v + st * T_BYTES, &map_v, v_full(st), 0, hh, j * BN, hn);
             }
         }
-    } else if (warp == 5) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t id_s = idesc_bf16(BM, BN, 0, 0);   // S = Q K^T   (both K-major)
-            constexpr uint32_t id_o = idesc_bf16(BM, D, 0, 1);    // O += P V    (A from TMEM, V MN-major)
-            auto issue_s = [&](int j) {
-                const int st = j % STAGES;
-                mbar_wait(k_full(st), (j / STAGES) & 1);
-                fence_after_sync();
+    } else if (warp == 9) {
+        // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues =====
+        constexpr uint32_t id_s = idesc_bf16(BM, BN, 0, 0);   // S = Q K^T   (both K-major)
+        constexpr uint32_t id_o = idesc_bf16(BM, D, 0, 1);    // O += P V    (A from TMEM, V MN-major)
+        const uint64_t dq0 = desc_kmajor(s_q, 0), dk0 = desc_kmajor(s_k, 0), dv0 = desc_mnmajor(s_v, 0, T_BYTES);
+        auto issue_s = [&](int j) {
+            const int st = j % STAGES;
+            mbar_wait(k_full(st), (j / STAGES) & 1);
+            fence_after_sync();
+            if (elect_one()) {
+                const uint64_t dk = dk0 + (uint64_t)(st * (T_BYTES >> 4));
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + COL_S + (j & 1) * BN, desc_kmajor(s_q, k), desc_kmajor(s_k + st * T_BYTES, k),
-                              id_s, k != 0);
+                    umma_bf16(tmem_base + COL_S + (j & 1) * BN, dq0 + k * KMAJOR_K16, dk + k * KMAJOR_K16, id_s, k != 0);
                 umma_commit(s_full(j & 1));
                 umma_commit(k_empty(st));
-            };
-            mbar_wait(q_full, 0);
-            issue_s(0);
-            for (int j = 0; j < n_tiles; ++j) {
-                if (j + 1 < n_tiles) issue_s(j + 1);   // S buffer (j+1)&1 was released by p_full of tile j-1
-                mbar_wait(p_full(j & 1), (j >> 1) & 1);
-                const int st = j % STAGES;
-                mbar_wait(v_full(st), (j / STAGES) & 1);
-                fence_after_sync();
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        issue_s(0);
+        for (int j = 0; j < n_tiles; ++j) {
+            if (j + 1 < n_tiles) issue_s(j + 1);   // S buffer (j+1)&1 was released by p_full of tile j-1
+            mbar_wait(p_full(j & 1), (j >> 1) & 1);
+            const int st = j % STAGES;
+            mbar_wait(v_full(st), (j / STAGES) & 1);
+            fence_after_sync();
+            if (elect_one()) {
+                const uint64_t dv = dv0 + (uint64_t)(st * (T_BYTES >> 4));
 #pragma unroll
                 for (int k = 0; k < BN / 16; ++k)
-                    umma_bf16_ts(tmem_base + COL_O, tmem_base + COL_P + (j & 1) * 32 + k * 8,
-                                 desc_mnmajor(s_v + st * T_BYTES, k, T_BYTES), id_o, (j | k) != 0);
+                    umma_bf16_ts(tmem_base + COL_O, tmem_base + COL_P + (j & 1) * 32 + k * 8, dv + k * MNMAJOR_K16, id_o,
+                                 (j | k) != 0);
                 umma_commit(v_empty(st));
+                if (j + 1 == n_tiles) umma_commit(o_full);
             }
-            umma_commit(o_full);
+            __syncwarp();
         }
     } else {
-        // ===== softmax warps: thread = query row = TMEM lane =====
-        const int row = m0 + warp * 32 + lane;
+        // ===== softmax warps: thread = (query row = TMEM lane, column half) =====
+        const int quarter = warp & 3, half = warp >> 2;
+        const int rt = quarter * 32 + lane;               // row inside the tile
+        const int row = m0 + rt;
         const size_t grow = (size_t)b * S + row;
         const uint4 *mrow = reinterpret_cast<const uint4 *>(mask + grow * (S / 32));
         const float ex0 = (float)extra0[grow];
-        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         float sum = 0.0f;
+        const ClampK ck = make_clamp(scale_log2, clamp_log2);
         uint4 mw = __ldg(mrow), mw_next = mw;
         for (int j = 0; j < n_tiles; ++j) {
             const int bsel = j & 1;
             if (bsel == 0 && j + 2 < n_tiles) mw_next = __ldg(mrow + (j >> 1) + 1);
             mbar_wait(s_full(bsel), (j >> 1) & 1);
             fence_after_sync();
-#pragma unroll
-            for (int c32 = 0; c32 < 2; ++c32) {
-                uint32_t r[32];
-                tmem_ld32(lane_base + COL_S + bsel * BN + c32 * 32, r);
-                // tile column c = 32 c32 + i is key 64 j + c of group j >> 1: word c & 3, bit 16 (j & 1) + (c >> 2)
-                const int b0 = 16 * bsel + 8 * c32;
-                const uint32_t w[4] = {mw.x >> b0, mw.y >> b0, mw.z >> b0, mw.w >> b0};
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float t0 = fminf(fmaxf(__uint_as_float(r[i]) * scale_log2, -clamp_log2), clamp_log2);
-                    const float t1 = fminf(fmaxf(__uint_as_float(r[i + 1]) * scale_log2, -clamp_log2), clamp_log2);
-                    float e0 = ex2(t0), e1 = ex2(t1);
-                    const uint32_t wa = w[i & 3], wb = w[(i + 1) & 3];
-                    if (i == 0) {
-                        float wgt = (float)(wa & 1u);
-                        if (j == 0 && c32 == 0) wgt += ex0;      // key 0 carries the zero-padding multiplicity
-                        e0 *= wgt;
-                    } else {
-                        e0 = ((wa >> (i >> 2)) & 1u) ? e0 : 0.0f;
-                    }
-                    e1 = ((wb >> (i >> 2)) & 1u) ? e1 : 0.0f;
-                    sum += e0 + e1;
-                    pk[i >> 1] = pack_bf16(e0, e1);
-                }
-                tmem_st16(lane_base + COL_P + bsel * 32 + c32 * 16, pk);
-            }
+            uint32_t r[32];
+            tmem_ld32(lane_base + COL_S + bsel * BN + half * 32, r);
+            // tile column c = 32 half + i is key 64 j + c of group j >> 1: word c & 3, bit 16 (j & 1) + (c >> 2)
+            const int b0 = 16 * bsel + 8 * half;
+            const uint32_t w[4] = {mw.x >> b0, mw.y >> b0, mw.z >> b0, mw.w >> b0};
+            uint32_t pk[16];
+            if (j == 0 && half == 0) fwd_chunk32<true>(r, w, ck, ex0, sum, pk);
+            else fwd_chunk32<false>(r, w, ck, ex0, sum, pk);
+            tmem_st16(lane_base + COL_P + bsel * 32 + half * 16, pk);
             tmem_st_wait();
             fence_before_sync();
             mbar_arrive(p_full(bsel));
             if (bsel == 1) mw = mw_next;
         }
-        sum = fmaxf(sum, 1e-9f);
-        zsum[grow] = sum;
+        s_part[half * BM + rt] = sum;
+        math_warps_sync();
+        sum = fmaxf(s_part[rt] + s_part[BM + rt], 1e-9f);
+        if (half == 0) zsum[grow] = sum;
         const float inv = 1.0f / sum;
         mbar_wait(o_full, 0);
         fence_after_sync();
-        __nv_bfloat16 *dst = y + (((size_t)hn * S + row) * H + hh) * D;
-#pragma unroll
-        for (int c32 = 0; c32 < 2; ++c32) {
-            uint32_t r[32];
-            tmem_ld32(lane_base + COL_O + c32 * 32, r);
-            store_row32(dst + c32 * 32, r, inv);
-        }
+        uint32_t r[32];
+        tmem_ld32(lane_base + COL_O + half * 32, r);
+        store_row32(y + (((size_t)hn * S + row) * H + hh) * D + half * 32, r, inv);
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -272,19 +382,11 @@ attn_bwd_prep_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *
     if (sub == 0) delta[row] = acc * inv;
 }
 
-// shared element math of the two backward kernels
-//   s_raw = q.k, dp = dO'.v, wgt = mask weight  ->  e = wgt * exp(clamp(scale s)), ds = e * (dp - delta') * inside
-__device__ __forceinline__ void bwd_elem(float s_raw, float dp, float wgt, float delta, float scale_log2,
-                                         float clamp_log2, float &e, float &ds) {
-    const float t = s_raw * scale_log2;
-    e = wgt * ex2(fminf(fmaxf(t, -clamp_log2), clamp_log2));
-    const float g = e * (dp - delta);
-    ds = (fabsf(t) <= clamp_log2) ? g : 0.0f;
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Backward, dQ: owner = 128 query rows (Q, dO'), loop over 64-key tiles (K_j, V_j).
-// TMEM columns: S 0 (128x64 fp32; dS bf16 pairs are written back over columns 0..31), dP' 64, dQ 128.
+// TMEM columns: S 0, dP' 64 (128x64 fp32 each), dS[2] 128/160 (bf16 pairs), dQ 192.
+// The score columns are released (s_read) as soon as every math thread holds its 32+32 values in
+// registers, so the tensor core computes the next tile's scores under this tile's exp math.
 // ---------------------------------------------------------------------------------------------------
 constexpr int BWD_SMEM = 2 * OWN_BYTES + 2 * STAGES * T_BYTES + STAGES * (BN * 16 + BN * 4 + BN * 4) + 1024 + 256;
 
@@ -299,10 +401,11 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t s_q = sm.base, s_dy = s_q + OWN_BYTES, s_k = s_dy + OWN_BYTES, s_v = s_k + STAGES * T_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm.ptr + 2 * OWN_BYTES + 2 * STAGES * T_BYTES);
     const uint32_t bar0 = smem_u32(bars);
-    const uint32_t own_full = bar0, acc_full = bar0 + 8, sc_full = bar0 + 16, p_full = bar0 + 24;
-    auto kv_full = [&](int s) { return bar0 + 32 + s * 8; };
-    auto kv_empty = [&](int s) { return bar0 + 32 + (STAGES + s) * 8; };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 + 2 * STAGES);
+    const uint32_t own_full = bar0, acc_full = bar0 + 8, sc_full = bar0 + 16, s_read = bar0 + 24;
+    auto p_full = [&](int i) { return bar0 + 32 + i * 8; };
+    auto kv_full = [&](int s) { return bar0 + 48 + s * 8; };
+    auto kv_empty = [&](int s) { return bar0 + 48 + (STAGES + s) * 8; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6 + 2 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = gridDim.x - 1 - blockIdx.x;
@@ -315,21 +418,23 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         mbar_init(own_full, 1);
         mbar_init(acc_full, 1);
         mbar_init(sc_full, 1);
-        mbar_init(p_full, 128);
+        mbar_init(s_read, N_MATH);
+        mbar_init(p_full(0), N_MATH);
+        mbar_init(p_full(1), N_MATH);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(kv_full(s), 1);
             mbar_init(kv_empty(s), 1);
         }
         mbar_fence_init();
     }
-    if (warp == 5) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    if (warp == 9) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t COL_S = 0, COL_DP = 64, COL_DQ = 128;
+    constexpr uint32_t COL_S = 0, COL_DP = 64, COL_DS = 128, COL_DQ = 192;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             mbar_expect_tx(own_full, 2 * OWN_BYTES);
             tma_load_4d(s_q, &map_q, own_full, 0, hh, m0, hn);
@@ -344,84 +449,87 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 tma_load_4d(s_v + st * T_BYTES, &map_v, kv_full(st), 0, hh, j * BN, hn);
             }
         }
-    } else if (warp == 5) {
-        if (lane == 0) {
-            constexpr uint32_t id_s = idesc_bf16(BM, BN, 0, 0);   // S = Q K^T, dP' = dO' V^T
-            constexpr uint32_t id_a = idesc_bf16(BM, D, 0, 1);    // dQ += dS K   (A from TMEM, K MN-major)
-            mbar_wait(own_full, 0);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int st = j % STAGES;
-                mbar_wait(kv_full(st), (j / STAGES) & 1);
-                fence_after_sync();
-#pragma unroll
-                for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + COL_S, desc_kmajor(s_q, k), desc_kmajor(s_k + st * T_BYTES, k), id_s, k != 0);
-#pragma unroll
-                for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + COL_DP, desc_kmajor(s_dy, k), desc_kmajor(s_v + st * T_BYTES, k), id_s, k != 0);
-                umma_commit(sc_full);
-                mbar_wait(p_full, j & 1);
-                fence_after_sync();
+    } else if (warp == 9) {
+        constexpr uint32_t id_s = idesc_bf16(BM, BN, 0, 0);   // S = Q K^T, dP' = dO' V^T
+        constexpr uint32_t id_a = idesc_bf16(BM, D, 0, 1);    // dQ += dS K   (A from TMEM, K MN-major)
+        const uint64_t dq0 = desc_kmajor(s_q, 0), ddy0 = desc_kmajor(s_dy, 0), dk0 = desc_kmajor(s_k, 0),
+                       dv0 = desc_kmajor(s_v, 0), dkt0 = desc_mnmajor(s_k, 0, T_BYTES);
+        auto issue_acc = [&](int j, bool last) {                  // dQ += dS_j K_j
+            const int st = j % STAGES;
+            mbar_wait(p_full(j & 1), (j >> 1) & 1);
+            fence_after_sync();
+            if (elect_one()) {
+                const uint64_t dkt = dkt0 + (uint64_t)(st * (T_BYTES >> 4));
 #pragma unroll
                 for (int k = 0; k < BN / 16; ++k)
-                    umma_bf16_ts(tmem_base + COL_DQ, tmem_base + COL_S + k * 8,
-                                 desc_mnmajor(s_k + st * T_BYTES, k, T_BYTES), id_a, (j | k) != 0);
+                    umma_bf16_ts(tmem_base + COL_DQ, tmem_base + COL_DS + (j & 1) * 32 + k * 8, dkt + k * MNMAJOR_K16, id_a,
+                                 (j | k) != 0);
                 umma_commit(kv_empty(st));
+                if (last) umma_commit(acc_full);
             }
-            umma_commit(acc_full);
+            __syncwarp();
+        };
+        mbar_wait(own_full, 0);
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j % STAGES;
+            mbar_wait(kv_full(st), (j / STAGES) & 1);
+            if (j > 0) mbar_wait(s_read, (j - 1) & 1);        // tile j-1's scores are in registers
+            fence_after_sync();
+            if (elect_one()) {
+                const uint64_t off = (uint64_t)(st * (T_BYTES >> 4));
+#pragma unroll
+                for (int k = 0; k < D / 16; ++k)
+                    umma_bf16(tmem_base + COL_S, dq0 + k * KMAJOR_K16, dk0 + off + k * KMAJOR_K16, id_s, k != 0);
+#pragma unroll
+                for (int k = 0; k < D / 16; ++k)
+                    umma_bf16(tmem_base + COL_DP, ddy0 + k * KMAJOR_K16, dv0 + off + k * KMAJOR_K16, id_s, k != 0);
+                umma_commit(sc_full);
+            }
+            __syncwarp();
+            if (j > 0) issue_acc(j - 1, false);
         }
+        issue_acc(n_tiles - 1, true);
     } else {
-        const int row = m0 + warp * 32 + lane;
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = m0 + quarter * 32 + lane;
         const size_t grow = (size_t)b * S + row;
         const uint4 *mrow = reinterpret_cast<const uint4 *>(mask + grow * (S / 32));
         const float ex0 = (float)extra0[grow];
         const float dl = delta[grow];
-        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const ClampK ck = make_clamp(scale_log2, clamp_log2);
         uint4 mw = __ldg(mrow), mw_next = mw;
         for (int j = 0; j < n_tiles; ++j) {
             const int bsel = j & 1;
             if (bsel == 0 && j + 2 < n_tiles) mw_next = __ldg(mrow + (j >> 1) + 1);
             mbar_wait(sc_full, j & 1);
             fence_after_sync();
-#pragma unroll
-            for (int c32 = 0; c32 < 2; ++c32) {
-                uint32_t r[32], g[32];
-                tmem_ld32_nowait(lane_base + COL_S + c32 * 32, r);
-                tmem_ld32_nowait(lane_base + COL_DP + c32 * 32, g);
-                tmem_ld_wait();
-                const int b0 = 16 * bsel + 8 * c32;
-                const uint32_t w[4] = {mw.x >> b0, mw.y >> b0, mw.z >> b0, mw.w >> b0};
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float wg0 = (float)((w[i & 3] >> (i >> 2)) & 1u);
-                    const float wg1 = (float)((w[(i + 1) & 3] >> (i >> 2)) & 1u);
-                    if (i == 0 && j == 0 && c32 == 0) wg0 += ex0;
-                    float e0, e1, d0, d1;
-                    bwd_elem(__uint_as_float(r[i]), __uint_as_float(g[i]), wg0, dl, scale_log2, clamp_log2, e0, d0);
-                    bwd_elem(__uint_as_float(r[i + 1]), __uint_as_float(g[i + 1]), wg1, dl, scale_log2, clamp_log2, e1, d1);
-                    pk[i >> 1] = pack_bf16(d0, d1);
-                }
-                tmem_st16(lane_base + COL_S + c32 * 16, pk);   // dS over the consumed score columns
-            }
+            uint32_t r[32], g[32];
+            tmem_ld32_nowait(lane_base + COL_S + half * 32, r);
+            tmem_ld32_nowait(lane_base + COL_DP + half * 32, g);
+            tmem_ld_wait();
+            fence_before_sync();
+            mbar_arrive(s_read);
+            const int b0 = 16 * bsel + 8 * half;
+            const uint32_t w[4] = {mw.x >> b0, mw.y >> b0, mw.z >> b0, mw.w >> b0};
+            uint32_t pk[16];
+            if (j == 0 && half == 0) bwdq_chunk32<true>(r, g, w, ck, dl, ex0, pk);
+            else bwdq_chunk32<false>(r, g, w, ck, dl, ex0, pk);
+            tmem_st16(lane_base + COL_DS + bsel * 32 + half * 16, pk);
             tmem_st_wait();
             fence_before_sync();
-            mbar_arrive(p_full);
+            mbar_arrive(p_full(bsel));
             if (bsel == 1) mw = mw_next;
         }
         mbar_wait(acc_full, 0);
         fence_after_sync();
-        __nv_bfloat16 *dst = dq + (((size_t)hn * S + row) * H + hh) * D;
-#pragma unroll
-        for (int c32 = 0; c32 < 2; ++c32) {
-            uint32_t r[32];
-            tmem_ld32(lane_base + COL_DQ + c32 * 32, r);
-            store_row32(dst + c32 * 32, r, scale);
-        }
+        uint32_t r[32];
+        tmem_ld32(lane_base + COL_DQ + half * 32, r);
+        store_row32(dq + (((size_t)hn * S + row) * H + hh) * D + half * 32, r, scale);
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -429,7 +537,8 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 // (Q_j, dO'_j) at and below the diagonal.  Works on the transposed tiles S^T = K Q^T, dP'^T = V dO'^T
 // so that E^T and dS^T come out with keys on the TMEM lanes, ready to be the A operands of
 //   dV += E^T dO'_j   and   dK += dS^T Q_j.
-// TMEM columns: S^T 0 (E^T bf16 written back over 0..31), dP'^T 64 (dS^T over 64..95), dV 128, dK 192.
+// TMEM columns: S^T 0, dP'^T 64, dV 128, dK 192.  E^T / dS^T (bf16 pairs) are written back over score
+// columns the same thread has already consumed: column half h (query rows 32h..32h+31) -> 32h..32h+15.
 // Per-row quantities of the 64 query rows (mask words of this key group, delta', extra0) are staged in
 // shared memory by the producer warp, one slot per pipeline stage.
 // ---------------------------------------------------------------------------------------------------
@@ -442,7 +551,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     extern __shared__ unsigned char smem_raw[];
     const Smem sm = align_smem(smem_raw);
     const uint32_t s_k = sm.base, s_v = s_k + OWN_BYTES, s_q = s_v + OWN_BYTES, s_dy = s_q + STAGES * T_BYTES;
-    unsigned char *rowq = sm.ptr + 2 * OWN_BYTES + 2 * STAGES * T_BYTES;   // per stage: mask uint4[64], delta[64], ex0[64]
+    unsigned char *rowq = sm.ptr + 2 * OWN_BYTES + 2 * STAGES * T_BYTES;   // per stage: mask^T [4][64], delta[64], ex0[64]
     constexpr int ROWQ_BYTES = BN * 16 + BN * 4 + BN * 4;
     uint64_t *bars = reinterpret_cast<uint64_t *>(rowq + STAGES * ROWQ_BYTES);
     const uint32_t bar0 = smem_u32(bars);
@@ -465,21 +574,21 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         mbar_init(own_full, 1);
         mbar_init(acc_full, 1);
         mbar_init(sc_full, 1);
-        mbar_init(p_full, 128);
+        mbar_init(p_full, N_MATH);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(qd_full(s), 1 + 32);             // expect_tx arrive + the 32 producer lanes' row data
             mbar_init(qd_empty(s), 1);
         }
         mbar_fence_init();
     }
-    if (warp == 5) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    if (warp == 9) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     constexpr uint32_t COL_S = 0, COL_DP = 64, COL_DV = 128, COL_DK = 192;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             mbar_expect_tx(own_full, 2 * OWN_BYTES);
             tma_load_4d(s_k, &map_k, own_full, 0, hh, n0, hn);
@@ -501,82 +610,86 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             for (int u = 0; u < 2; ++u) {
                 const int rr = lane + 32 * u;
                 const size_t gr = head + r0 + rr;
-                reinterpret_cast<uint4 *>(slot)[rr] = __ldg(reinterpret_cast<const uint4 *>(mask + gr * words) + kt);
+                const uint4 mw = __ldg(reinterpret_cast<const uint4 *>(mask + gr * words) + kt);
+                uint32_t *mt = reinterpret_cast<uint32_t *>(slot);        // transposed: [word t][row]
+                mt[rr] = mw.x;
+                mt[BN + rr] = mw.y;
+                mt[2 * BN + rr] = mw.z;
+                mt[3 * BN + rr] = mw.w;
                 reinterpret_cast<float *>(slot + BN * 16)[rr] = delta[gr];
                 reinterpret_cast<float *>(slot + BN * 16 + BN * 4)[rr] = (float)extra0[gr];
             }
             mbar_arrive(qd_full(st));
         }
-    } else if (warp == 5) {
-        if (lane == 0) {
-            constexpr uint32_t id_s = idesc_bf16(BM, BN, 0, 0);   // S^T = K Q^T, dP'^T = V dO'^T
-            constexpr uint32_t id_a = idesc_bf16(BM, D, 0, 1);    // dV += E^T dO', dK += dS^T Q (B MN-major)
-            mbar_wait(own_full, 0);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int st = j % STAGES;
-                mbar_wait(qd_full(st), (j / STAGES) & 1);
-                fence_after_sync();
+    } else if (warp == 9) {
+        constexpr uint32_t id_s = idesc_bf16(BM, BN, 0, 0);   // S^T = K Q^T, dP'^T = V dO'^T
+        constexpr uint32_t id_a = idesc_bf16(BM, D, 0, 1);    // dV += E^T dO', dK += dS^T Q (B MN-major)
+        const uint64_t dk0 = desc_kmajor(s_k, 0), dv0 = desc_kmajor(s_v, 0), dq0 = desc_kmajor(s_q, 0),
+                       ddy0 = desc_kmajor(s_dy, 0), dqt0 = desc_mnmajor(s_q, 0, T_BYTES),
+                       ddyt0 = desc_mnmajor(s_dy, 0, T_BYTES);
+        mbar_wait(own_full, 0);
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j % STAGES;
+            const uint64_t off = (uint64_t)(st * (T_BYTES >> 4));
+            mbar_wait(qd_full(st), (j / STAGES) & 1);
+            fence_after_sync();
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + COL_S, desc_kmajor(s_k, k), desc_kmajor(s_q + st * T_BYTES, k), id_s, k != 0);
+                    umma_bf16(tmem_base + COL_S, dk0 + k * KMAJOR_K16, dq0 + off + k * KMAJOR_K16, id_s, k != 0);
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + COL_DP, desc_kmajor(s_v, k), desc_kmajor(s_dy + st * T_BYTES, k), id_s, k != 0);
+                    umma_bf16(tmem_base + COL_DP, dv0 + k * KMAJOR_K16, ddy0 + off + k * KMAJOR_K16, id_s, k != 0);
                 umma_commit(sc_full);
-                mbar_wait(p_full, j & 1);
-                fence_after_sync();
-#pragma unroll
-                for (int k = 0; k < BN / 16; ++k)
-                    umma_bf16_ts(tmem_base + COL_DV, tmem_base + COL_S + k * 8,
-                                 desc_mnmajor(s_dy + st * T_BYTES, k, T_BYTES), id_a, (j | k) != 0);
-#pragma unroll
-                for (int k = 0; k < BN / 16; ++k)
-                    umma_bf16_ts(tmem_base + COL_DK, tmem_base + COL_DP + k * 8,
-                                 desc_mnmajor(s_q + st * T_BYTES, k, T_BYTES), id_a, (j | k) != 0);
-                umma_commit(qd_empty(st));
             }
-            umma_commit(acc_full);
+            __syncwarp();
+            mbar_wait(p_full, j & 1);
+            fence_after_sync();
+            if (elect_one()) {
+                // query rows 16 k .. 16 k + 15 of the tile sit in columns 32 (k >> 1) + 8 (k & 1) .. + 7
+#pragma unroll
+                for (int k = 0; k < BN / 16; ++k)
+                    umma_bf16_ts(tmem_base + COL_DV, tmem_base + COL_S + (k >> 1) * 32 + (k & 1) * 8,
+                                 ddyt0 + off + k * MNMAJOR_K16, id_a, (j | k) != 0);
+#pragma unroll
+                for (int k = 0; k < BN / 16; ++k)
+                    umma_bf16_ts(tmem_base + COL_DK, tmem_base + COL_DP + (k >> 1) * 32 + (k & 1) * 8,
+                                 dqt0 + off + k * MNMAJOR_K16, id_a, (j | k) != 0);
+                umma_commit(qd_empty(st));
+                if (j + 1 == n_tiles) umma_commit(acc_full);
+            }
+            __syncwarp();
         }
     } else {
-        // thread = key n0 + kk = TMEM lane kk: lane-major word kk & 3 of the row's group kt, bit kk >> 2
-        const int kk = warp * 32 + lane;
-        const int wsel = kk & 3, bit = kk >> 2;
+        // thread = (key n0 + kk = TMEM lane kk, column half): lane-major word kk & 3 of the row's group kt, bit kk >> 2
+        const int quarter = warp & 3, half = warp >> 2;
+        const int kk = quarter * 32 + lane;
+        const int wsel = kk & 3;
+        const uint32_t bitmask = 1u << (kk >> 2);
         const bool key0 = (n0 + kk) == 0;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const ClampK ck = make_clamp(scale_log2, clamp_log2);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j % STAGES;
             const unsigned char *slot = rowq + st * ROWQ_BYTES;
-            const uint32_t *s_mask = reinterpret_cast<const uint32_t *>(slot);
+            const uint32_t *mrow = reinterpret_cast<const uint32_t *>(slot) + wsel * BN;   // this key's word of every row
             const float *s_delta = reinterpret_cast<const float *>(slot + BN * 16);
             const float *s_ex0 = s_delta + BN;
             mbar_wait(qd_full(st), (j / STAGES) & 1);   // the producer lanes' row data of this stage
             mbar_wait(sc_full, j & 1);
             fence_after_sync();
 #pragma unroll
-            for (int c32 = 0; c32 < 2; ++c32) {
-                uint32_t r[32], g[32];
-                tmem_ld32_nowait(lane_base + COL_S + c32 * 32, r);
-                tmem_ld32_nowait(lane_base + COL_DP + c32 * 32, g);
+            for (int c16 = 0; c16 < 2; ++c16) {
+                const int c0 = half * 32 + c16 * 16;          // first query row (tile column) of this chunk
+                uint32_t r[16], g[16];
+                tmem_ld16_nowait(lane_base + COL_S + c0, r);
+                tmem_ld16_nowait(lane_base + COL_DP + c0, g);
                 tmem_ld_wait();
-                uint32_t pe[16], pd[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const int c = c32 * 32 + i;                      // query row inside the tile
-                    float wg0 = (float)((s_mask[c * 4 + wsel] >> bit) & 1u);
-                    float wg1 = (float)((s_mask[(c + 1) * 4 + wsel] >> bit) & 1u);
-                    if (key0) {
-                        wg0 += s_ex0[c];
-                        wg1 += s_ex0[c + 1];
-                    }
-                    float e0, e1, d0, d1;
-                    bwd_elem(__uint_as_float(r[i]), __uint_as_float(g[i]), wg0, s_delta[c], scale_log2, clamp_log2, e0, d0);
-                    bwd_elem(__uint_as_float(r[i + 1]), __uint_as_float(g[i + 1]), wg1, s_delta[c + 1], scale_log2,
-                             clamp_log2, e1, d1);
-                    pe[i >> 1] = pack_bf16(e0, e1);
-                    pd[i >> 1] = pack_bf16(d0, d1);
-                }
-                tmem_st16(lane_base + COL_S + c32 * 16, pe);    // E^T over the consumed S^T columns
-                tmem_st16(lane_base + COL_DP + c32 * 16, pd);   // dS^T over the consumed dP'^T columns
+                uint32_t pe[8], pd[8];
+                if (key0) bwdkv_chunk16<true>(r, g, mrow, s_delta, s_ex0, c0, bitmask, ck, pe, pd);
+                else bwdkv_chunk16<false>(r, g, mrow, s_delta, s_ex0, c0, bitmask, ck, pe, pd);
+                tmem_st8(lane_base + COL_S + half * 32 + c16 * 8, pe);    // E^T over consumed S^T columns
+                tmem_st8(lane_base + COL_DP + half * 32 + c16 * 8, pd);   // dS^T over consumed dP'^T columns
             }
             tmem_st_wait();
             fence_before_sync();
@@ -584,19 +697,16 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         }
         mbar_wait(acc_full, 0);
         fence_after_sync();
-        const size_t off = (((size_t)hn * S + n0 + kk) * H + hh) * D;
-#pragma unroll
-        for (int c32 = 0; c32 < 2; ++c32) {
-            uint32_t r[32];
-            tmem_ld32(lane_base + COL_DV + c32 * 32, r);
-            store_row32(dv + off + c32 * 32, r, 1.0f);
-            tmem_ld32(lane_base + COL_DK + c32 * 32, r);
-            store_row32(dk + off + c32 * 32, r, scale);
-        }
+        const size_t off = (((size_t)hn * S + n0 + kk) * H + hh) * D + half * 32;
+        uint32_t r[32];
+        tmem_ld32(lane_base + COL_DV + half * 32, r);
+        store_row32(dv + off, r, 1.0f);
+        tmem_ld32(lane_base + COL_DK + half * 32, r);
+        store_row32(dk + off, r, scale);
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ---- host -----------------------------------------------------------------------------------------

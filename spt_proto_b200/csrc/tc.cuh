@@ -46,6 +46,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// One lane of a converged warp (warp-uniform control flow around it keeps operands in uniform registers).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------------
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem_addr) {  // one full warp
@@ -105,6 +117,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA descriptors ------------------------------------------------------------------------------
@@ -125,6 +151,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 //   K-major  (rows = M/N index, the 64 columns = K): SBO = 1024, slice k = +32 B
 //   MN-major (rows = K index, the 64 columns = M/N): SBO = 1024 (8 k-rows), LBO = bytes to the next
 //             64-wide MN chunk, slice k = +16 rows = +2048 B
+// The address field (bits 0-13, 16-byte units) never carries for shared-memory offsets, so a slice /
+// stage offset is a plain add on a precomputed descriptor: KMAJOR_K16 per K16 slice of a K-major tile,
+// MNMAJOR_K16 per K16 slice of an MN-major tile, bytes >> 4 for a stage offset.
+constexpr uint64_t KMAJOR_K16 = 32 >> 4, MNMAJOR_K16 = 2048 >> 4;
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int k) { return make_desc(tile_addr + k * 32, 0, 1024); }
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int k, uint32_t lbo_bytes) {
     return make_desc(tile_addr + k * 2048, lbo_bytes, 1024);
