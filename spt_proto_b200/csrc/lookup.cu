@@ -367,24 +367,17 @@ lookup_bitmap_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__
 
 // ---- mask-only path (fused attention) -------------------------------------------------------------
 // Same selection, but only the SET of selected keys is needed (bitmask + extra0), not their output
-// positions.  Each (row, lane t) thread evaluates the adder tree ONCE per 32-key word, keeps the
-// bucket masks of its <= MAXW words in registers, and after the plan (bucket sizes -> quotas) selects
-// whole words: a bucket that is taken completely is OR-ed in, only the single partially taken bucket
-// needs a "lowest q bits" trim.  The thread's words ARE the lane-major mask words, so they are stored
-// directly — no per-key loop, no shared-memory image, no atomics.
-template <int MAXW>
-__device__ __forceinline__ uint32_t bucket_word(int s, int w, const uint32_t (&m1)[MAXW], const uint32_t (&m2)[MAXW],
-                                                const uint32_t (&m3)[MAXW], int nkeys) {
-    uint32_t r = 0;
-#pragma unroll
-    for (int i = 0; i < MAXW; ++i) {
-        if (i == w) {
-            const uint32_t m0 = valid_mask(i, nkeys) & ~(m1[i] | m2[i] | m3[i]);
-            r = s == 3 ? m3[i] : (s == 2 ? m2[i] : (s == 1 ? m1[i] : m0));
-        }
-    }
-    return r;
-}
+// positions.  A block owns one lane-major group of 128 query rows (512 threads, thread = (row, lane
+// t)); every row of the group has the same number of 128-key words, so the block is perfectly
+// balanced.  Pass 1 evaluates the adder tree ONCE per 32-key word and parks the bucket id of every
+// key as two bit-planes in shared memory (bucket = 2 hi + lo) while popcounting the bucket sizes;
+// after the plan (sizes -> quotas) pass 2 re-reads the planes and selects whole words: a bucket that
+// is taken completely is OR-ed in, only the single partially taken bucket needs a "lowest q bits"
+// trim.  The thread's words ARE the lane-major mask words — no per-key loop, no atomics.  Both passes
+// are rolled loops (a few hundred instructions in total: the fully unrolled register version of this
+// kernel spent 70 % of its issue slots waiting on instruction fetch).
+constexpr int LKM_ROWS = 128;
+constexpr int LKM_THREADS = LKM_ROWS * 4;
 
 __device__ __forceinline__ uint32_t pick_lowest(uint32_t mask, int &quota) {
     if (quota <= 0 || mask == 0) return 0;
@@ -402,107 +395,104 @@ __device__ __forceinline__ uint32_t pick_lowest(uint32_t mask, int &quota) {
     return r;
 }
 
-template <int M, int MAXW>
-__global__ void __launch_bounds__(LK_THREADS)
+template <int M>
+__global__ void __launch_bounds__(LKM_THREADS)
 lookup_maskonly_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__restrict__ kb,
                        const int *__restrict__ flag, uint32_t *__restrict__ mask_out,
                        int32_t *__restrict__ extra0_out, int S, int nnz, int W, int H) {
     if (*flag) return;  // some key code >= 16: the generic kernel handles this call
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *s_kb = reinterpret_cast<uint32_t *>(smem_raw);
     const int b = blockIdx.y;
     const int tile = gridDim.x - 1 - blockIdx.x;  // heaviest (last) rows first
-    const int r0 = tile * LK_ROWS;
-    const int rl = threadIdx.x >> 2, t = threadIdx.x & 3;
-    const int r = r0 + rl;
-    const bool live = r < S;
+    const int tw = tile + 1;                       // 128-key words a row of this group can see
+    uint32_t *s_kb = reinterpret_cast<uint32_t *>(smem_raw);                 // [M][tw][16][4]
+    uint32_t *s_pl = s_kb + (size_t)M * tw * LK_WORD_U32;                    // [2 tw][LKM_THREADS]
+    const int tid = threadIdx.x;
+    const int rl = tid >> 2, t = tid & 3;
+    const int r = tile * LKM_ROWS + rl;            // S % 128 == 0: every row is live
     const int quarter = nnz / 4;
-    const int nkeys = (live && r >= t) ? (r - t) / 4 + 1 : 0;
-    const int lim = live ? min(r + 1, nnz) : 0;
+    const int nkeys = r >= t ? (r - t) / 4 + 1 : 0;
+    const int lim = min(r + 1, nnz);
     const int n_t = lim > t ? (lim - t + 3) / 4 : 0;
-    const int tile_words = min(W, (min(S, r0 + LK_ROWS) + 127) / 128);
 
-    const uint32_t *kb_head = kb + (size_t)b * M * W * LK_WORD_U32;
     {
-        const int per_s = tile_words * LK_WORD_U32 / 4;  // uint4 per subspace
-        for (int i = threadIdx.x; i < M * per_s; i += blockDim.x) {
-            const int s = i / per_s, o = i % per_s;
-            reinterpret_cast<uint4 *>(s_kb)[s * per_s + o] =
-                reinterpret_cast<const uint4 *>(kb_head + (size_t)s * W * LK_WORD_U32)[o];
+        const uint32_t *kb_head = kb + (size_t)b * M * W * LK_WORD_U32;
+        const int per_s = tw * LK_WORD_U32 / 4;  // uint4 per subspace
+        for (int i = tid; i < M * per_s; i += LKM_THREADS) {
+            const int s = i / per_s, o = i - s * per_s;
+            reinterpret_cast<uint4 *>(s_kb)[i] = reinterpret_cast<const uint4 *>(kb_head + (size_t)s * W * LK_WORD_U32)[o];
+        }
+    }
+    // this row's bitmap column of every subspace: s_kb[s][w][q_s][t] = kcol[s][w * 64]; a query code the
+    // bitmaps do not cover (>= 16) matches no key
+    const uint32_t *kcol[M];
+    uint32_t qok = 0;
+    {
+        const int32_t *qp = query_codes + (((size_t)(b / H) * S + r) * H + (b % H)) * M;
+#pragma unroll
+        for (int s = 0; s < M; ++s) {
+            const unsigned q = (unsigned)qp[s] & 0xffffu;
+            if (q < (unsigned)LK_CV) qok |= 1u << s;
+            kcol[s] = s_kb + ((size_t)s * tw * LK_CV + (q & (LK_CV - 1))) * 4 + t;
         }
     }
     __syncthreads();
 
-    BitmapMatcher<M> mt;
-    mt.s_kb = s_kb;
-    mt.t = t;
-    mt.cw = tile_words;
-    mt.w0 = 0;
-#pragma unroll
-    for (int s = 0; s < M; ++s)
-        mt.q[s] = live ? ((unsigned)query_codes[(((size_t)(b / H) * S + r) * H + (b % H)) * M + s] & 0xffffu) : 0xffffu;
-
-    uint32_t m1[MAXW], m2[MAXW], m3[MAXW];
+    constexpr int DIV = M / 4;
     LaneState st;
 #pragma unroll
     for (int s = 0; s < 4; ++s) st.len[s] = 0;
+#pragma unroll 1
+    for (int w = 0; w < tw; ++w) {
+        const uint32_t valid = valid_mask(w, nkeys);
+        uint32_t x[M];
 #pragma unroll
-    for (int w = 0; w < MAXW; ++w) {
-        uint32_t mask[4] = {0, 0, 0, 0};
-        const uint32_t valid = w < tile_words ? valid_mask(w, nkeys) : 0u;
-        if (valid) mt.buckets(w, valid, mask);
-        m1[w] = mask[1];
-        m2[w] = mask[2];
-        m3[w] = mask[3];
-#pragma unroll
-        for (int s = 0; s < 4; ++s) st.len[s] += __popc(mask[s]);
+        for (int s = 0; s < M; ++s) x[s] = ((qok >> s) & 1u) ? kcol[s][w * LK_WORD_U32] : 0u;
+        uint32_t bits[BitCount<M>::NB];
+        BitCount<M>::run(x, bits);
+        const uint32_t g1 = ge_const(bits, DIV), g2 = ge_const(bits, 2 * DIV), g3 = ge_const(bits, 3 * DIV);
+        s_pl[(2 * w) * LKM_THREADS + tid] = g1 ^ g2 ^ g3;   // lo (g3 <= g2 <= g1 as sets)
+        s_pl[(2 * w + 1) * LKM_THREADS + tid] = g2;         // hi
+        st.len[3] += __popc(g3 & valid);
+        st.len[2] += __popc(g2 & ~g3 & valid);
+        st.len[1] += __popc(g1 & ~g2 & valid);
+        st.len[0] += __popc(~g1 & valid);
     }
     plan_lane(st, t, n_t, quarter);
 
-    uint32_t sel[MAXW];
-    {
-        int q3 = st.take[3], q2 = st.take[2], q1 = st.take[1], q0 = st.take[0];
-#pragma unroll
-        for (int w = 0; w < MAXW; ++w) {
-            const uint32_t m0 = valid_mask(w, nkeys) & ~(m1[w] | m2[w] | m3[w]);
-            sel[w] = pick_lowest(m3[w], q3) | pick_lowest(m2[w], q2) | pick_lowest(m1[w], q1) | pick_lowest(m0, q0);
-        }
+    int q3 = st.take[3], q2 = st.take[2], q1 = st.take[1], q0 = st.take[0];
+    int j_old = -1, last_j = -1;
+#pragma unroll 1
+    for (int w = 0; w < tw; ++w) {
+        const uint32_t valid = valid_mask(w, nkeys);
+        const uint32_t lo = s_pl[(2 * w) * LKM_THREADS + tid], hi = s_pl[(2 * w + 1) * LKM_THREADS + tid];
+        const uint32_t m3 = hi & lo & valid, m2 = hi & ~lo & valid, m1 = ~hi & lo & valid, m0 = ~hi & ~lo & valid;
+        const uint32_t g3 = pick_lowest(m3, q3), g2 = pick_lowest(m2, q2), g1 = pick_lowest(m1, q1), g0 = pick_lowest(m0, q0);
+        s_pl[(2 * w) * LKM_THREADS + tid] = g3 | g2 | g1 | g0;
+        // own last TAKEN key of the bucket whose last slot the partner lane may clobber (see fix_clobber)
+        const uint32_t gn = st.s_need == 3 ? g3 : st.s_need == 2 ? g2 : st.s_need == 1 ? g1 : st.s_need == 0 ? g0 : 0u;
+        if (gn) j_old = 4 * (32 * w + 31 - __clz(gn)) + t;
+        // own last key (taken or not) of the bucket the partner reads its clobbered slot from
+        const uint32_t mt = st.track == 3 ? m3 : st.track == 2 ? m2 : st.track == 1 ? m1 : st.track == 0 ? m0 : 0u;
+        if (mt) last_j = 4 * (32 * w + 31 - __clz(mt)) + t;
     }
-
-    // clobbered last slot (see fix_clobber): lanes 2/3 report the last key of the tracked bucket, the
-    // owner (lane 0/1) swaps it for its own last taken key of that bucket if a later warp instruction
-    // of the reference kernel would have overwritten the slot.
-    int last_j = -1;
-    if (st.track >= 0) {
-        for (int w = MAXW - 1; w >= 0 && last_j < 0; --w) {
-            const uint32_t mk = bucket_word<MAXW>(st.track, w, m1, m2, m3, nkeys);
-            if (mk) last_j = 4 * (32 * w + 31 - __clz(mk)) + t;
-        }
-    }
+    // lanes 2/3 report the last key of the tracked bucket; the owner (lane 1/0) swaps its own last taken key
+    // of that bucket for it if a later warp instruction of the reference kernel would have overwritten the slot
     const int recv = __shfl_xor_sync(FULL, last_j, 3);
-    int swap_old = -1;
-    if (st.s_need >= 0 && recv >= 0) {
-        int quota = quarter, j_old = -1;
-        for (int w = 0; w < MAXW && quota > 0; ++w) {
-            const uint32_t mk = bucket_word<MAXW>(st.s_need, w, m1, m2, m3, nkeys);
-            const uint32_t got = pick_lowest(mk, quota);
-            if (got) j_old = 4 * (32 * w + 31 - __clz(got)) + t;
-        }
-        if (j_old >= 0 && (recv >> 2) > (j_old >> 2)) swap_old = j_old;
-    }
+    const int swap_old = (st.s_need >= 0 && recv >= 0 && j_old >= 0 && (recv >> 2) > (j_old >> 2)) ? j_old : -1;
     const int partner_swapped = __shfl_xor_sync(FULL, swap_old >= 0 ? 1 : 0, 3);
-#pragma unroll
-    for (int w = 0; w < MAXW; ++w) {
-        if (swap_old >= 0 && (swap_old >> 7) == w) sel[w] &= ~(1u << mask_bit(swap_old));
-        if (partner_swapped && last_j >= 0 && (last_j >> 7) == w) sel[w] |= 1u << mask_bit(last_j);
-    }
+    if (swap_old >= 0) s_pl[(2 * (swap_old >> 7)) * LKM_THREADS + tid] &= ~(1u << mask_bit(swap_old));
+    if (partner_swapped && last_j >= 0) s_pl[(2 * (last_j >> 7)) * LKM_THREADS + tid] |= 1u << mask_bit(last_j);
+    store_extra0(st, extra0_out, b, r, S, nnz, true, t);
+    __syncthreads();
 
-    store_extra0(st, extra0_out, b, r, S, nnz, live, t);
-    if (live) {
-        uint32_t *dst = mask_out + ((size_t)b * S + r) * (S / 32) + t;
-#pragma unroll
-        for (int w = 0; w < MAXW; ++w)
-            if (w < W) dst[4 * w] = sel[w];
+    // flush: thread -> (row, word w): 16 B = the four lane words; words the group cannot see are zero
+    uint4 *dst = reinterpret_cast<uint4 *>(mask_out + ((size_t)b * S + (size_t)tile * LKM_ROWS) * (S / 32));
+    for (int i = tid; i < LKM_ROWS * W; i += LKM_THREADS) {
+        const int w = i / LKM_ROWS, row = i - w * LKM_ROWS;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (w < tw) v = *reinterpret_cast<const uint4 *>(s_pl + (size_t)(2 * w) * LKM_THREADS + row * 4);
+        dst[(size_t)row * W + w] = v;
     }
 }
 
@@ -626,35 +616,22 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
     int chunk_words = (int)((LK_SMEM_BUDGET - img) / per_word);
     if (chunk_words > W) chunk_words = W;
     const size_t smem = img + per_word * chunk_words;
-    const bool mask_only = mask_out && !output && W <= 32;
-    if (mask_only) {
-        const size_t msmem = per_word * W;
-#define SPT_LKM_CASE(MM)                                                                                          \
-    case MM:                                                                                                      \
-        if (W <= 16) {                                                                                            \
-            if (msmem > 48 * 1024)                                                                                \
-                cudaFuncSetAttribute(lookup_maskonly_kernel<MM, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem); \
-            lookup_maskonly_kernel<MM, 16><<<grid, LK_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H); \
-        } else {                                                                                                  \
-            if (msmem > 48 * 1024)                                                                                \
-                cudaFuncSetAttribute(lookup_maskonly_kernel<MM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem); \
-            lookup_maskonly_kernel<MM, 32><<<grid, LK_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H); \
-        }                                                                                                         \
-        break;
-        switch (m) {
-            SPT_LKM_CASE(8)
-            SPT_LKM_CASE(16)
-            default:
-                goto general_path;
+    const size_t msmem = (per_word + 2 * LKM_THREADS * 4) * (size_t)W;
+    if (mask_out && !output && (m == 8 || m == 16) && msmem <= 200 * 1024) {
+        const dim3 mgrid(S / LKM_ROWS, B);
+        if (m == 8) {
+            cudaFuncSetAttribute(lookup_maskonly_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+            lookup_maskonly_kernel<8><<<mgrid, LKM_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H);
+        } else {
+            cudaFuncSetAttribute(lookup_maskonly_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+            lookup_maskonly_kernel<16><<<mgrid, LKM_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H);
         }
-#undef SPT_LKM_CASE
         SPT_LAUNCH_CHECK("lookup_maskonly_kernel");
         lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, mask_out,
                                                                   extra0_out, S, m, nnz, H);
         SPT_LAUNCH_CHECK("lookup_generic_kernel(fallback)");
         return SPT_OK;
     }
-general_path:
 #define SPT_LK_CASE(MM)                                                                                          \
     case MM:                                                                                                     \
         if (smem > 48 * 1024)                                                                                    \
