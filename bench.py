@@ -192,7 +192,7 @@ def stage_roofline(n_seq: int, dev, hbm_gbs: float, tensor_tflops: float):
     Sd, Sk = S * d * e, S * k * 4
     stages = {
         # name: (callable, algorithmic bytes per head)
-        "pq_encode": (lambda: ext.pq_encode(q, w), Sd + S * m * 4),
+        "pq_encode": (lambda: ext.pq_encode_pair(q, kk, w), 2 * (Sd + S * m * 4)),     # q and k in one launch
         "lookup": (lambda: ext.lookup_forward_cuda(cfg, qc, kc), 2 * S * m * 4 + Sk),
         "sddmm": (lambda: ext.sddmm_forward_cuda(False, True, indptr, idx, q, kk), 2 * Sd + 2 * Sk),
         "softmax_fwd": (lambda: ext.softmax_forward_cuda(indptr, idx, sc), 3 * Sk),

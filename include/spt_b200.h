@@ -73,6 +73,10 @@ int spt_cdist_bwd(const float *query, const float *table, const float *grad_dist
  * distance tensor. */
 int spt_pq_encode(const void *z, const float *table, int32_t *codes,
                   int64_t rows, int m, int c, int dc, int dtype, spt_stream_t stream);
+/* The same for two tensors of identical shape that share the codebook — the q and k of one attention
+ * call (naive_gpt/layers/sparse/attention.py:105-106) — in a single launch. */
+int spt_pq_encode_pair(const void *z0, const void *z1, const float *table, int32_t *codes0, int32_t *codes1,
+                       int64_t rows, int m, int c, int dc, int dtype, spt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (2) lookup — replaces lookup_forward_cuda (extension/lookup.cu:87-174).

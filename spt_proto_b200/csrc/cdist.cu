@@ -67,19 +67,40 @@ cdist_fwd_kernel(const T *__restrict__ query, const float *__restrict__ table, f
 
 // ---- fused encode, layer layout: z [rows, m*dc] -> codes [rows, m] ----------------------------
 // Thread g handles (row = g / m, subspace = g % m): consecutive threads read consecutive dc-element
-// chunks (fully coalesced 16/32-byte loads) and write consecutive int32 codes.  The codebook is
-// staged in shared memory as [codeword][element][subspace] so that the lanes of a warp (which
-// differ in subspace) hit distinct banks and equal-subspace lanes broadcast.
+// chunks (fully coalesced 16/32-byte loads) and write consecutive int32 codes.  L1 distance is not a
+// GEMM; the kernel is bound by the fp32 add pipe (2 adds per (element, codeword)), so the adds are
+// issued as packed FADD2 (sm_100 add.f32x2) over PAIRS OF CODEWORDS: the two halves carry codewords
+// w and w+1, the element loop stays sequential in i, hence every distance is still the reference's
+// i-ascending fp32 sum and, with the strict `<`, the codes are bit-identical to the reference kernel
+// (extension/cdist.cu:42-54).  |x| is a LOP3 on the otherwise idle ALU pipe.  The codebook is staged in
+// shared memory as [codeword pair][element][subspace] float2 (lanes of a warp differ in subspace:
+// distinct banks, equal-subspace lanes broadcast).  blockIdx.y selects one of up to two tensors (q and
+// k of a layer share the codebook and are encoded by one launch).
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 template <typename T, int DC>
 __global__ void __launch_bounds__(CDIST_THREADS)
-pq_encode_kernel(const T *__restrict__ z, const float *__restrict__ table, int32_t *__restrict__ codes,
-                 int64_t total /* rows*m */, int m, int c) {
-    extern __shared__ float s_table[];  // [c][DC][m]
-    for (int i = threadIdx.x; i < m * c * DC; i += blockDim.x) {
-        int s = i / (c * DC), rem = i % (c * DC);  // table is [m][c][DC]
-        s_table[rem * m + s] = table[i];
+pq_encode_kernel(const T *__restrict__ z0, const T *__restrict__ z1, const float *__restrict__ table,
+                 int32_t *__restrict__ codes0, int32_t *__restrict__ codes1, int64_t total /* rows*m */, int m, int c) {
+    extern __shared__ __align__(16) float s_table[];  // [(c+1)/2][DC][m][2]; an odd last codeword is paired with +inf
+    const int cp = (c + 1) / 2;
+    for (int i = threadIdx.x; i < cp * DC * m * 2; i += blockDim.x) {
+        const int h = i & 1, s = (i >> 1) % m, e = ((i >> 1) / m) % DC, wp = (i >> 1) / (m * DC);
+        const int w = 2 * wp + h;
+        s_table[i] = w < c ? table[((size_t)s * c + w) * DC + e] : __int_as_float(0x7f800000);
     }
     __syncthreads();
+    const T *z = blockIdx.y ? z1 : z0;
+    int32_t *codes = blockIdx.y ? codes1 : codes0;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total) return;
     const int s = (int)(g % m);
@@ -97,16 +118,26 @@ pq_encode_kernel(const T *__restrict__ z, const float *__restrict__ table, int32
 #pragma unroll
         for (int i = 0; i < DC; ++i) qv[i] = to_f32(zp[i]);
     }
+    uint64_t q2[DC];   // (q_i, q_i)
+#pragma unroll
+    for (int i = 0; i < DC; ++i) q2[i] = ((uint64_t)__float_as_uint(qv[i]) << 32) | __float_as_uint(qv[i]);
     int min_index = 0;
     float min_distance = 1e13f;
-    for (int w = 0; w < c; ++w) {
-        const float *tp = s_table + (size_t)w * DC * m + s;
-        float reduced = 0.0f;
+    const uint64_t *tp = reinterpret_cast<const uint64_t *>(s_table) + s;
+#pragma unroll 2
+    for (int wp = 0; wp < cp; ++wp, tp += (size_t)DC * m) {
+        uint64_t acc = 0;   // (+0.0f, +0.0f)
 #pragma unroll
-        for (int i = 0; i < DC; ++i) reduced += fabsf(qv[i] - tp[i * m]);
-        if (reduced < min_distance) {
-            min_distance = reduced;
-            min_index = w;
+        for (int i = 0; i < DC; ++i)
+            acc = add_f32x2(acc, sub_f32x2(q2[i], tp[(size_t)i * m]) & 0x7fffffff7fffffffull);
+        const float d0 = __uint_as_float((uint32_t)acc), d1 = __uint_as_float((uint32_t)(acc >> 32));
+        if (d0 < min_distance) {
+            min_distance = d0;
+            min_index = 2 * wp;
+        }
+        if (d1 < min_distance) {   // an odd c pairs its last codeword with +inf: never selected
+            min_distance = d1;
+            min_index = 2 * wp + 1;
         }
     }
     codes[g] = min_index;
@@ -237,17 +268,17 @@ static int launch_cdist_fwd(const T *query, const float *table, float *distance,
 }
 
 template <typename T>
-static int launch_pq_encode(const T *z, const float *table, int32_t *codes, int64_t rows, int m, int c, int dc,
-                            cudaStream_t st) {
+static int launch_pq_encode(const T *z0, const T *z1, const float *table, int32_t *codes0, int32_t *codes1,
+                            int64_t rows, int m, int c, int dc, cudaStream_t st) {
     const int64_t total = rows * m;
-    dim3 grid((unsigned)((total + CDIST_THREADS - 1) / CDIST_THREADS));
-    size_t smem = (size_t)m * c * dc * sizeof(float);
+    dim3 grid((unsigned)((total + CDIST_THREADS - 1) / CDIST_THREADS), z1 ? 2 : 1);
+    size_t smem = (size_t)m * ((c + 1) / 2) * 2 * dc * sizeof(float);
 #define SPT_ENC_CASE(D)                                                                                 \
     case D:                                                                                             \
         if (smem > 48 * 1024)                                                                           \
             cudaFuncSetAttribute(pq_encode_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                  (int)smem);                                                            \
-        pq_encode_kernel<T, D><<<grid, CDIST_THREADS, smem, st>>>(z, table, codes, total, m, c);        \
+        pq_encode_kernel<T, D><<<grid, CDIST_THREADS, smem, st>>>(z0, z1, table, codes0, codes1, total, m, c); \
         break;
     switch (dc) {
         SPT_ENC_CASE(4)
@@ -280,16 +311,29 @@ extern "C" int spt_cdist_fwd(const void *query, const float *table, float *dista
     return fail(SPT_ERR_INVALID_ARGUMENT, "cdist_fwd: unknown dtype %d", dtype);
 }
 
-extern "C" int spt_pq_encode(const void *z, const float *table, int32_t *codes, int64_t rows, int m, int c, int dc,
-                             int dtype, spt_stream_t stream) {
-    SPT_REQUIRE(z && table && codes, "pq_encode: null pointer");
+static int pq_encode_impl(const void *z0, const void *z1, const float *table, int32_t *codes0, int32_t *codes1,
+                          int64_t rows, int m, int c, int dc, int dtype, spt_stream_t stream) {
+    SPT_REQUIRE(z0 && table && codes0 && (!z1 == !codes1), "pq_encode: null pointer");
     SPT_REQUIRE(m >= 1 && rows >= 0 && c >= 1 && dc >= 1, "pq_encode: bad sizes");
     SPT_REQUIRE((size_t)m * c * dc * 4 <= 200 * 1024, "pq_encode: codebook %d x %d x %d does not fit shared memory", m, c, dc);
     if (rows == 0) return SPT_OK;
-    if (dtype == SPT_F32) return launch_pq_encode((const float *)z, table, codes, rows, m, c, dc, as_stream(stream));
+    if (dtype == SPT_F32)
+        return launch_pq_encode((const float *)z0, (const float *)z1, table, codes0, codes1, rows, m, c, dc, as_stream(stream));
     if (dtype == SPT_BF16)
-        return launch_pq_encode((const __nv_bfloat16 *)z, table, codes, rows, m, c, dc, as_stream(stream));
+        return launch_pq_encode((const __nv_bfloat16 *)z0, (const __nv_bfloat16 *)z1, table, codes0, codes1, rows, m, c,
+                                dc, as_stream(stream));
     return fail(SPT_ERR_INVALID_ARGUMENT, "pq_encode: unknown dtype %d", dtype);
+}
+
+extern "C" int spt_pq_encode(const void *z, const float *table, int32_t *codes, int64_t rows, int m, int c, int dc,
+                             int dtype, spt_stream_t stream) {
+    return pq_encode_impl(z, nullptr, table, codes, nullptr, rows, m, c, dc, dtype, stream);
+}
+
+extern "C" int spt_pq_encode_pair(const void *z0, const void *z1, const float *table, int32_t *codes0, int32_t *codes1,
+                                  int64_t rows, int m, int c, int dc, int dtype, spt_stream_t stream) {
+    SPT_REQUIRE(z1 && codes1, "pq_encode_pair: null pointer");
+    return pq_encode_impl(z0, z1, table, codes0, codes1, rows, m, c, dc, dtype, stream);
 }
 
 extern "C" size_t spt_cdist_bwd_workspace_bytes(int m, int64_t n, int c, int dc) {

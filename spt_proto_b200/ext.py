@@ -138,6 +138,29 @@ def pq_encode(z: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     return codes
 
 
+def pq_encode_pair(z0: torch.Tensor, z1: torch.Tensor, table: torch.Tensor):
+    """pq_encode of two same-shaped tensors sharing the codebook (q and k of one attention call) in one
+    launch -> (codes0, codes1)."""
+    if not (z0.is_cuda and z1.is_cuda and z0.is_contiguous() and z1.is_contiguous()):
+        raise RuntimeError("z0 and z1 must be contiguous CUDA tensors")
+    if z0.shape != z1.shape or z0.dtype != z1.dtype:
+        raise RuntimeError("z0 and z1 must have the same shape and dtype")
+    _check_dim(table, 3, "table")
+    code = _float_code(z0, "z0")
+    m, c, dc = table.shape
+    if z0.size(-1) != m * dc:
+        raise RuntimeError("z last dim must equal n_subspaces * d_codeword")
+    table32 = table if table.dtype == torch.float32 else table.float()
+    rows = z0.numel() // (m * dc)
+    shape = list(z0.shape[:-1]) + [m]
+    codes0 = torch.empty(shape, dtype=torch.int32, device=z0.device)
+    codes1 = torch.empty(shape, dtype=torch.int32, device=z0.device)
+    with _on_device(z0):
+        check(lib.spt_pq_encode_pair(_p(z0), _p(z1), _p(table32), _p(codes0), _p(codes1), rows, m, c, dc, code,
+                                     _stream(z0)))
+    return codes0, codes1
+
+
 # ---- (2) lookup --------------------------------------------------------------------------------------
 def lookup_forward_cuda(config: torch.Tensor, query: torch.Tensor, key: torch.Tensor) -> torch.Tensor:
     """config carries sparse_coeff in its SHAPE (kernels/lookup.py:23, lookup.cu:99);

@@ -119,8 +119,7 @@ class _SparseV2Mixin:
         # transpose(1, 2).contiguous() copies (attention.py:92-95,138-142) is made
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         self._maybe_train_loss(q, k)           # PQ loss is a mean over rows: layout-invariant
-        q_c = self.quantizer("encode", z=q)    # [N, S, H, m]
-        k_c = self.quantizer("encode", z=k)
+        q_c, k_c = ext.pq_encode_pair(q, k, self.quantizer.weight)   # quantizer('encode') of both: [N, S, H, m]
         mask, extra0, _ = ext.lookup_mask(q_c, k_c, self.sparse_coeff)
         y = kernels.sparse_attention(q, k, v, mask, extra0, self.scaling)      # [N, S, H, E]
         if self.reference_output_layout:   # the shipped layer's re-interpretation of [N*H, E, S] memory

@@ -76,6 +76,9 @@ def test_pq_encode_fused(dtype, rows, m, c, dc):
     want = O.pq_encode(z.float(), w)                          # bf16 = upcast, then reference math
     got = _ext().pq_encode(z.to(DEV), w.to(DEV))
     assert got.dtype == torch.int32 and torch.equal(got.cpu(), want)
+    z2 = torch.randn(rows, m * dc, generator=g).to(dtype)       # the q/k pair launch gives the same codes
+    a, b = _ext().pq_encode_pair(z.to(DEV), z2.to(DEV), w.to(DEV))
+    assert torch.equal(a.cpu(), want) and torch.equal(b.cpu(), O.pq_encode(z2.float(), w))
 
 
 def test_pq_encode_ties_lowest_index():
