@@ -101,46 +101,47 @@ pq_encode_kernel(const T *__restrict__ z0, const T *__restrict__ z1, const float
     __syncthreads();
     const T *z = blockIdx.y ? z1 : z0;
     int32_t *codes = blockIdx.y ? codes1 : codes0;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total) return;
-    const int s = (int)(g % m);
-    float qv[DC];
-    const T *zp = z + (size_t)g * DC;
-    if constexpr (DC % Vec16<T>::N == 0) {
+    // grid-stride over (row, subspace) items: the codebook is staged once per resident block
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int s = (int)(g % m);
+        float qv[DC];
+        const T *zp = z + (size_t)g * DC;
+        if constexpr (DC % Vec16<T>::N == 0) {
 #pragma unroll
-        for (int i = 0; i < DC; i += Vec16<T>::N) {
-            float tmp[Vec16<T>::N];
-            Vec16<T>::load(zp + i, tmp);
+            for (int i = 0; i < DC; i += Vec16<T>::N) {
+                float tmp[Vec16<T>::N];
+                Vec16<T>::load(zp + i, tmp);
 #pragma unroll
-            for (int j = 0; j < Vec16<T>::N; ++j) qv[i + j] = tmp[j];
+                for (int j = 0; j < Vec16<T>::N; ++j) qv[i + j] = tmp[j];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < DC; ++i) qv[i] = to_f32(zp[i]);
         }
-    } else {
+        uint64_t q2[DC];   // (q_i, q_i)
 #pragma unroll
-        for (int i = 0; i < DC; ++i) qv[i] = to_f32(zp[i]);
-    }
-    uint64_t q2[DC];   // (q_i, q_i)
-#pragma unroll
-    for (int i = 0; i < DC; ++i) q2[i] = ((uint64_t)__float_as_uint(qv[i]) << 32) | __float_as_uint(qv[i]);
-    int min_index = 0;
-    float min_distance = 1e13f;
-    const uint64_t *tp = reinterpret_cast<const uint64_t *>(s_table) + s;
+        for (int i = 0; i < DC; ++i) q2[i] = ((uint64_t)__float_as_uint(qv[i]) << 32) | __float_as_uint(qv[i]);
+        int min_index = 0;
+        float min_distance = 1e13f;
+        const uint64_t *tp = reinterpret_cast<const uint64_t *>(s_table) + s;
 #pragma unroll 2
-    for (int wp = 0; wp < cp; ++wp, tp += (size_t)DC * m) {
-        uint64_t acc = 0;   // (+0.0f, +0.0f)
+        for (int wp = 0; wp < cp; ++wp, tp += (size_t)DC * m) {
+            uint64_t acc = 0;   // (+0.0f, +0.0f)
 #pragma unroll
-        for (int i = 0; i < DC; ++i)
-            acc = add_f32x2(acc, sub_f32x2(q2[i], tp[(size_t)i * m]) & 0x7fffffff7fffffffull);
-        const float d0 = __uint_as_float((uint32_t)acc), d1 = __uint_as_float((uint32_t)(acc >> 32));
-        if (d0 < min_distance) {
-            min_distance = d0;
-            min_index = 2 * wp;
+            for (int i = 0; i < DC; ++i)
+                acc = add_f32x2(acc, sub_f32x2(q2[i], tp[(size_t)i * m]) & 0x7fffffff7fffffffull);
+            const float d0 = __uint_as_float((uint32_t)acc), d1 = __uint_as_float((uint32_t)(acc >> 32));
+            if (d0 < min_distance) {
+                min_distance = d0;
+                min_index = 2 * wp;
+            }
+            if (d1 < min_distance) {   // an odd c pairs its last codeword with +inf: never selected
+                min_distance = d1;
+                min_index = 2 * wp + 1;
+            }
         }
-        if (d1 < min_distance) {   // an odd c pairs its last codeword with +inf: never selected
-            min_distance = d1;
-            min_index = 2 * wp + 1;
-        }
+        codes[g] = min_index;
     }
-    codes[g] = min_index;
 }
 
 // ---- backward wrt query: gq[s,n,i] = sum_c sgn(q_i - t_ci) * g[s,n,c]  (cdist.cu:72-131) --------
@@ -271,7 +272,9 @@ template <typename T>
 static int launch_pq_encode(const T *z0, const T *z1, const float *table, int32_t *codes0, int32_t *codes1,
                             int64_t rows, int m, int c, int dc, cudaStream_t st) {
     const int64_t total = rows * m;
-    dim3 grid((unsigned)((total + CDIST_THREADS - 1) / CDIST_THREADS), z1 ? 2 : 1);
+    const int64_t want = (total + CDIST_THREADS - 1) / CDIST_THREADS;
+    const int64_t cap = (int64_t)num_sms() * 8 / (z1 ? 2 : 1);      // resident blocks: one codebook staging each
+    dim3 grid((unsigned)(want < cap ? want : cap), z1 ? 2 : 1);
     size_t smem = (size_t)m * ((c + 1) / 2) * 2 * dc * sizeof(float);
 #define SPT_ENC_CASE(D)                                                                                 \
     case D:                                                                                             \

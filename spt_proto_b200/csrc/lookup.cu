@@ -423,41 +423,42 @@ lookup_maskonly_kernel(const int32_t *__restrict__ query_codes, const uint32_t *
             reinterpret_cast<uint4 *>(s_kb)[i] = reinterpret_cast<const uint4 *>(kb_head + (size_t)s * W * LK_WORD_U32)[o];
         }
     }
-    // this row's bitmap column of every subspace: s_kb[s][w][q_s][t] = kcol[s][w * 64]; a query code the
-    // bitmaps do not cover (>= 16) matches no key
-    const uint32_t *kcol[M];
-    uint32_t qok = 0;
+    // this row's bitmap column of every subspace: s_kb[s][w][q_s][t] = s_kb[koff[s] + 64 w]; a query code the
+    // bitmaps do not cover (>= 16) matches no key (qmask[s] = 0)
+    uint32_t koff[M], qmask[M];
     {
         const int32_t *qp = query_codes + (((size_t)(b / H) * S + r) * H + (b % H)) * M;
 #pragma unroll
         for (int s = 0; s < M; ++s) {
             const unsigned q = (unsigned)qp[s] & 0xffffu;
-            if (q < (unsigned)LK_CV) qok |= 1u << s;
-            kcol[s] = s_kb + ((size_t)s * tw * LK_CV + (q & (LK_CV - 1))) * 4 + t;
+            qmask[s] = q < (unsigned)LK_CV ? 0xffffffffu : 0u;
+            koff[s] = (uint32_t)((s * tw * LK_CV + (q & (LK_CV - 1))) * 4 + t);
         }
     }
     __syncthreads();
 
     constexpr int DIV = M / 4;
     LaneState st;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) st.len[s] = 0;
+    int len1 = 0, len2 = 0, len3 = 0;
 #pragma unroll 1
     for (int w = 0; w < tw; ++w) {
         const uint32_t valid = valid_mask(w, nkeys);
         uint32_t x[M];
 #pragma unroll
-        for (int s = 0; s < M; ++s) x[s] = ((qok >> s) & 1u) ? kcol[s][w * LK_WORD_U32] : 0u;
+        for (int s = 0; s < M; ++s) x[s] = s_kb[koff[s] + w * LK_WORD_U32] & qmask[s];
         uint32_t bits[BitCount<M>::NB];
         BitCount<M>::run(x, bits);
         const uint32_t g1 = ge_const(bits, DIV), g2 = ge_const(bits, 2 * DIV), g3 = ge_const(bits, 3 * DIV);
         s_pl[(2 * w) * LKM_THREADS + tid] = g1 ^ g2 ^ g3;   // lo (g3 <= g2 <= g1 as sets)
         s_pl[(2 * w + 1) * LKM_THREADS + tid] = g2;         // hi
-        st.len[3] += __popc(g3 & valid);
-        st.len[2] += __popc(g2 & ~g3 & valid);
-        st.len[1] += __popc(g1 & ~g2 & valid);
-        st.len[0] += __popc(~g1 & valid);
+        len3 += __popc(g3 & valid);
+        len2 += __popc(g2 & valid);
+        len1 += __popc(g1 & valid);
     }
+    st.len[3] = len3;
+    st.len[2] = len2 - len3;
+    st.len[1] = len1 - len2;
+    st.len[0] = nkeys - len1;
     plan_lane(st, t, n_t, quarter);
 
     int q3 = st.take[3], q2 = st.take[2], q1 = st.take[1], q0 = st.take[0];
