@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""BASELINE configs[3]: LLaMA-7B-shape 4-layer SPT fine-tuning step, batch-sharded over N GPUs.
+
+    python scripts/finetune_step.py --steps 5 --warmup 2 --seq 2048
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P scripts/finetune_step.py ...
+
+Each rank owns `--batch` sequences (weak scaling).  A step = forward + backward through 4 pre-norm blocks
+(d_model 4096, 32 heads x d_head 128, d_ff 11008) built the way the reference builds and upgrades them
+(script/0-profile.py:87-143,182-189 + utils/adapter.py:94-97,155-184): frozen base weights, rank-16 LoRA
+on q/k/v/o and gate/side/down, SparseRotaryAttentionV2 (PQ 16 subspaces x 16 codewords, top-k S/8,
+PQ training loss armed every step like script/4-sparse-tuning-0.py:71-91), LoRARoutedLLaMaFFN
+(block = d_ff/4, half the blocks active); then ONE bucketed NCCL all-reduce of the trainable gradients
+(spt_proto_b200.distributed.allreduce_grads), grad-clip 1.0 and AdamW.  Prints one JSON line (rank 0).
+
+d_head 128 is outside the fused attention kernels (d_head 64 only): the attention here runs the
+stage kernels (lookup -> sddmm -> softmax -> spmm, CSC transposed products in backward)."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+from torch import nn  # noqa: E402
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, d: int, eps: float = 1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(d))
+        self.eps = eps
+
+    def forward(self, x):
+        v = x.float()
+        return (v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + self.eps)).to(x.dtype) * self.weight
+
+
+class Block(nn.Module):
+    """Pre-norm block: x + o(attn(q(h), k(h), v(h))), x + ffn(h)  (reference basic/transformer.py:78-97)."""
+
+    def __init__(self, layers, d_model, n_heads, d_ff, d_lora):
+        super().__init__()
+        self.n_heads = n_heads
+        mk = lambda: layers.LoRALinear(d_lora=d_lora, in_features=d_model, out_features=d_model, bias=False)
+        self.linear_q, self.linear_k, self.linear_v, self.linear_o = mk(), mk(), mk(), mk()
+        self.attn_fn = layers.SparseRotaryAttentionV2(d_head=d_model // n_heads, p_dropout=0.0, d_codeword=8, n_codewords=16)
+        self.ffd = layers.LoRARoutedLLaMaFFN(d_lora=d_lora, block_size=d_ff // 4, d_model=d_model, d_feedforward=d_ff,
+                                             activation=nn.SiLU())
+        self.norm1, self.norm2 = RMSNorm(d_model), RMSNorm(d_model)
+        for n in (self.norm1, self.norm2):
+            n.weight.requires_grad = False
+
+    def forward(self, x):
+        h = self.norm1(x)
+        shape = (x.size(0), x.size(1), self.n_heads, -1)
+        y = self.attn_fn(self.linear_q(h).view(shape), self.linear_k(h).view(shape), self.linear_v(h).view(shape))
+        x = x + self.linear_o(y.reshape(x.size(0), x.size(1), -1))
+        return x + self.ffd(self.norm2(x))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--seq", type=int, default=2048)
+    ap.add_argument("--batch", type=int, default=1, help="sequences per GPU per step")
+    ap.add_argument("--layers", type=int, default=4)
+    ap.add_argument("--d-lora", type=int, default=16)
+    args = ap.parse_args()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    from spt_proto_b200 import ext, layers
+    from spt_proto_b200.distributed import allreduce_grads
+
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    d_model, n_heads, d_ff = 4096, 32, 11008
+    torch.manual_seed(1234)                       # same weights on every rank (DDP starts from a broadcast)
+    model = nn.Sequential(*[Block(layers, d_model, n_heads, d_ff, args.d_lora) for _ in range(args.layers)])
+    model = model.to(dev).bfloat16()
+    for blk in model:
+        nn.init.normal_(blk.linear_q.lora.right.weight, std=0.02)   # non-zero LoRA so that every gradient is exercised
+        nn.init.normal_(blk.ffd.down.lora.right.weight, std=0.02)
+    trainable = [p for p in model.parameters() if p.requires_grad]
+    n_train = sum(p.numel() for p in trainable)
+    opt = torch.optim.AdamW(trainable, lr=1e-4, weight_decay=1e-2)
+    torch.manual_seed(1234 + rank)
+    x = torch.randn(args.batch, args.seq, d_model, device=dev).bfloat16()
+    target = torch.randn(args.batch, args.seq, d_model, device=dev).bfloat16()
+
+    def step():
+        for blk in model:
+            blk.attn_fn.host_trigger = True           # arm the PQ loss (no device->host sync)
+        y = model(x)
+        loss = nn.functional.mse_loss(y.float(), target.float())
+        loss = loss + 1e-2 * sum(blk.attn_fn.loss for blk in model)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        n_coll = allreduce_grads(trainable)
+        nn.utils.clip_grad_norm_(trainable, 1.0)
+        opt.step()
+        return loss, n_coll
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        loss, n_coll = step()
+    barrier()
+    launches0 = ext.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        loss, n_coll = step()
+    b.record()
+    barrier()
+    elapsed = a.elapsed_time(b) * 1e-3
+    if world > 1:
+        t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = t.item()
+    if rank == 0:
+        tokens = args.batch * args.seq * world
+        line = {"metric": "spt_finetune_step_tokens_per_s", "value": tokens * args.steps / elapsed, "unit": "tokens/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"LLaMA-7B-shape {args.layers}-layer SPT fine-tuning step (sparse rotary MHA d_head 128 "
+                                       f"stage kernels + LoRA routed FFN), seq {args.seq}, {args.batch} seq/GPU",
+                           "d_model": d_model, "n_heads": n_heads, "d_ff": d_ff, "d_lora": args.d_lora,
+                           "trainable_params": n_train, "allreduce_calls_per_step": n_coll,
+                           "parallelism": f"dp{world} + NCCL all-reduce of trainable grads"},
+                "loss": float(loss), "gpu_launches": ext.launch_count() - launches0}
+        print(json.dumps(line), file=real_stdout, flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -160,9 +160,10 @@ class PQBase(nn.Module):
             return z_q
 
         # 'train': soft centroids from inverse distances vs the hard centroid, plus commitment term
-        weights = torch.softmax(-torch.log(torch.clamp(distance, min=1e-5)), dim=-1)
-        z_w = torch.matmul(weights, self.weight)
-        loss = self.loss_fn(z_w, z_q_flat) + self.loss_fn(z_flat, z_q_flat)
+        # (computed in fp32 whatever the module dtype: the reference path is fp32 throughout)
+        weights = torch.softmax(-torch.log(torch.clamp(distance.float(), min=1e-5)), dim=-1)
+        z_w = torch.matmul(weights, self.weight.float())
+        loss = self.loss_fn(z_w, z_q_flat.float()) + self.loss_fn(z_flat.float(), z_q_flat.float())
         return z_q, loss
 
 
