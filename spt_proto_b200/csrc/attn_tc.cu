@@ -41,15 +41,42 @@ namespace attn_tc {
 
 using namespace tc;
 
-constexpr int D = 64;          // head dim
 constexpr int BM = 128;        // owner tile rows  (= TMEM lanes)
 constexpr int BN = 64;         // other tile rows per iteration
 constexpr int STAGES = 3;
 constexpr int N_MATH = 256;      // warps 0-7
 constexpr int THREADS = 320;
-constexpr int OWN_BYTES = BM * D * 2;   // 16 KB
-constexpr int T_BYTES = BN * D * 2;     // 8 KB
-constexpr int TMEM_COLS = 256;
+// Head dim D in {64, 128}.  Operand tiles are stored as D / 64 sub-tiles of [rows][64] bf16 (one TMA box
+// each, 128-byte swizzled): an owner tile is [D/64][128 rows][64], an "other" tile [D/64][64 rows][64].
+// D = 64 needs 256 TMEM columns (two CTAs per SM), D = 128 takes the whole TMEM (one CTA per SM).
+template <int D>
+struct Dim {
+    static_assert(D == 64 || D == 128, "head dim must be 64 or 128");
+    static constexpr int NSUB = D / 64;
+    static constexpr int OWN_SUB = BM * 64 * 2, T_SUB = BN * 64 * 2;          // 16 KB, 8 KB
+    static constexpr int OWN_BYTES = NSUB * OWN_SUB, T_BYTES = NSUB * T_SUB;
+    static constexpr int TMEM_COLS = D == 64 ? 256 : 512;
+    static constexpr int CTAS = D == 64 ? 2 : 1;
+    static constexpr int FWD_SMEM = OWN_BYTES + 2 * STAGES * T_BYTES + 1024 /*row sums*/ + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int BWD_SMEM = 2 * OWN_BYTES + 2 * STAGES * T_BYTES + STAGES * (BN * 16 + BN * 4 + BN * 4) + 1024 + 256;
+};
+// descriptor offset (16-byte units) of K16 slice k of a K-major tile whose 64-wide sub-tiles are SUB bytes apart
+template <int SUB>
+__device__ constexpr uint64_t kslice(int k) { return (uint64_t)((k >> 2) * (SUB >> 4) + (k & 3) * 2); }
+// TMA: 128-row owner tile / 64-row other tile of head (hn, hh) starting at sequence row `row0`
+template <int D>
+__device__ __forceinline__ void tma_owner(uint32_t dst, const CUtensorMap *map, uint32_t bar, int hh, int row0, int hn) {
+#pragma unroll
+    for (int dh = 0; dh < Dim<D>::NSUB; ++dh) {
+        tma_load_4d(dst + dh * Dim<D>::OWN_SUB, map, bar, dh * 64, hh, row0, hn);
+        tma_load_4d(dst + dh * Dim<D>::OWN_SUB + Dim<D>::T_SUB, map, bar, dh * 64, hh, row0 + BN, hn);
+    }
+}
+template <int D>
+__device__ __forceinline__ void tma_other(uint32_t dst, const CUtensorMap *map, uint32_t bar, int hh, int row0, int hn) {
+#pragma unroll
+    for (int dh = 0; dh < Dim<D>::NSUB; ++dh) tma_load_4d(dst + dh * Dim<D>::T_SUB, map, bar, dh * 64, hh, row0, hn);
+}
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2(float x) {
@@ -202,13 +229,15 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16 *dst, const uint32_t (
 // ---------------------------------------------------------------------------------------------------
 // Forward.  TMEM columns: S[2] 0/64 (fp32 128x64), P[2] 128/160 (bf16 pairs, 32 cols), O 192 (128x64).
 // ---------------------------------------------------------------------------------------------------
-constexpr int FWD_SMEM = OWN_BYTES + 2 * STAGES * T_BYTES + 1024 /*row sums*/ + 1024 /*align*/ + 256 /*barriers*/;
 
-__global__ void __launch_bounds__(THREADS, 2)
+template <int D>
+__global__ void __launch_bounds__(THREADS, Dim<D>::CTAS)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, const uint32_t *__restrict__ mask,
                    const int32_t *__restrict__ extra0, __nv_bfloat16 *__restrict__ y, float *__restrict__ zsum, int S,
                    int H, float scale_log2, float clamp_log2) {
+    constexpr int OWN_BYTES = Dim<D>::OWN_BYTES, T_BYTES = Dim<D>::T_BYTES, OWN_SUB = Dim<D>::OWN_SUB, T_SUB = Dim<D>::T_SUB,
+                  TMEM_COLS = Dim<D>::TMEM_COLS;
     extern __shared__ unsigned char smem_raw[];
     const Smem sm = align_smem(smem_raw);
     const uint32_t s_q = sm.base, s_k = s_q + OWN_BYTES, s_v = s_k + STAGES * T_BYTES;
@@ -257,24 +286,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         // ===== TMA producer =====
         if (lane == 0) {
             mbar_expect_tx(q_full, OWN_BYTES);
-            tma_load_4d(s_q, &map_q, q_full, 0, hh, m0, hn);
-            tma_load_4d(s_q + T_BYTES, &map_q, q_full, 0, hh, m0 + BN, hn);
+            tma_owner<D>(s_q, &map_q, q_full, hh, m0, hn);
             for (int j = 0; j < n_tiles; ++j) {
                 const int st = j % STAGES;
                 const uint32_t ph = (j / STAGES) & 1;
                 mbar_wait(k_empty(st), ph ^ 1);
                 mbar_expect_tx(k_full(st), T_BYTES);
-                tma_load_4d(s_k + st * T_BYTES, &map_k, k_full(st), 0, hh, j * BN, hn);
+                tma_other<D>(s_k + st * T_BYTES, &map_k, k_full(st), hh, j * BN, hn);
                 mbar_wait(v_empty(st), ph ^ 1);
                 mbar_expect_tx(v_full(st), T_BYTES);
-                tma_load_4d(s_v + st * T_BYTES, &map_v, v_full(st), 0, hh, j * BN, hn);
+                tma_other<D>(s_v + st * T_BYTES, &map_v, v_full(st), hh, j * BN, hn);
             }
         }
     } else if (warp == 9) {
         // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues =====
         constexpr uint32_t id_s = idesc_bf16(BM, BN, 0, 0);   // S = Q K^T   (both K-major)
         constexpr uint32_t id_o = idesc_bf16(BM, D, 0, 1);    // O += P V    (A from TMEM, V MN-major)
-        const uint64_t dq0 = desc_kmajor(s_q, 0), dk0 = desc_kmajor(s_k, 0), dv0 = desc_mnmajor(s_v, 0, T_BYTES);
+        const uint64_t dq0 = desc_kmajor(s_q, 0), dk0 = desc_kmajor(s_k, 0), dv0 = desc_mnmajor(s_v, 0, T_SUB);
         auto issue_s = [&](int j) {
             const int st = j % STAGES;
             mbar_wait(k_full(st), (j / STAGES) & 1);
@@ -283,7 +311,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 const uint64_t dk = dk0 + (uint64_t)(st * (T_BYTES >> 4));
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + COL_S + (j & 1) * BN, dq0 + k * KMAJOR_K16, dk + k * KMAJOR_K16, id_s, k != 0);
+                    umma_bf16(tmem_base + COL_S + (j & 1) * BN, dq0 + kslice<OWN_SUB>(k), dk + kslice<T_SUB>(k), id_s, k != 0);
                 umma_commit(s_full(j & 1));
                 umma_commit(k_empty(st));
             }
@@ -346,9 +374,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const float inv = 1.0f / sum;
         mbar_wait(o_full, 0);
         fence_after_sync();
-        uint32_t r[32];
-        tmem_ld32(lane_base + COL_O + half * 32, r);
-        store_row32(y + (((size_t)hn * S + row) * H + hh) * D + half * 32, r, inv);
+        __nv_bfloat16 *dst = y + (((size_t)hn * S + row) * H + hh) * D + half * (D / 2);
+#pragma unroll
+        for (int c = 0; c < D / 64; ++c) {
+            uint32_t r[32];
+            tmem_ld32(lane_base + COL_O + half * (D / 2) + c * 32, r);
+            store_row32(dst + c * 32, r, inv);
+        }
     }
     fence_before_sync();
     __syncthreads();
@@ -359,13 +391,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 // Backward prologue: delta'_r = (dO_r . y_r) / Z_r  and  dO'_r = dO_r / Z_r (bf16, same layout as dO).
 // 8 lanes per row (8 x 16 B = one 128-byte row).
 // ---------------------------------------------------------------------------------------------------
+template <int D>
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__restrict__ y,
                      const float *__restrict__ zsum, float *__restrict__ delta, __nv_bfloat16 *__restrict__ dys,
                      int64_t rows, int S, int H) {
-    const int64_t row = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+    constexpr int LPR = D / 8;                                             // lanes per row (16 B each)
+    const int64_t row = (int64_t)blockIdx.x * (256 / LPR) + (threadIdx.x / LPR);
     if (row >= rows) return;
-    const int sub = threadIdx.x & 7;
+    const int sub = threadIdx.x % LPR;
     const int64_t b = row / S, r = row % S;                               // delta, zsum are head-major [B, S]
     const int64_t off = (((b / H) * S + r) * H + (b % H)) * D + sub * 8;
     float a[8], c[8];
@@ -374,7 +408,7 @@ attn_bwd_prep_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *
     float acc = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc = fmaf(a[i], c[i], acc);
-    acc = group_sum<8>(acc);
+    acc = group_sum<LPR>(acc);
     const float inv = 1.0f / zsum[row];
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] *= inv;
@@ -388,14 +422,16 @@ attn_bwd_prep_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *
 // The score columns are released (s_read) as soon as every math thread holds its 32+32 values in
 // registers, so the tensor core computes the next tile's scores under this tile's exp math.
 // ---------------------------------------------------------------------------------------------------
-constexpr int BWD_SMEM = 2 * OWN_BYTES + 2 * STAGES * T_BYTES + STAGES * (BN * 16 + BN * 4 + BN * 4) + 1024 + 256;
 
-__global__ void __launch_bounds__(THREADS, 2)
+template <int D>
+__global__ void __launch_bounds__(THREADS, Dim<D>::CTAS)
 attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_dys,
                      const uint32_t *__restrict__ mask, const int32_t *__restrict__ extra0,
                      const float *__restrict__ delta, __nv_bfloat16 *__restrict__ dq, int S, int H, float scale,
                      float scale_log2, float clamp_log2) {
+    constexpr int OWN_BYTES = Dim<D>::OWN_BYTES, T_BYTES = Dim<D>::T_BYTES, OWN_SUB = Dim<D>::OWN_SUB, T_SUB = Dim<D>::T_SUB,
+                  TMEM_COLS = Dim<D>::TMEM_COLS;
     extern __shared__ unsigned char smem_raw[];
     const Smem sm = align_smem(smem_raw);
     const uint32_t s_q = sm.base, s_dy = s_q + OWN_BYTES, s_k = s_dy + OWN_BYTES, s_v = s_k + STAGES * T_BYTES;
@@ -437,23 +473,21 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     if (warp == 8) {
         if (lane == 0) {
             mbar_expect_tx(own_full, 2 * OWN_BYTES);
-            tma_load_4d(s_q, &map_q, own_full, 0, hh, m0, hn);
-            tma_load_4d(s_q + T_BYTES, &map_q, own_full, 0, hh, m0 + BN, hn);
-            tma_load_4d(s_dy, &map_dys, own_full, 0, hh, m0, hn);
-            tma_load_4d(s_dy + T_BYTES, &map_dys, own_full, 0, hh, m0 + BN, hn);
+            tma_owner<D>(s_q, &map_q, own_full, hh, m0, hn);
+            tma_owner<D>(s_dy, &map_dys, own_full, hh, m0, hn);
             for (int j = 0; j < n_tiles; ++j) {
                 const int st = j % STAGES;
                 mbar_wait(kv_empty(st), ((j / STAGES) & 1) ^ 1);
                 mbar_expect_tx(kv_full(st), 2 * T_BYTES);
-                tma_load_4d(s_k + st * T_BYTES, &map_k, kv_full(st), 0, hh, j * BN, hn);
-                tma_load_4d(s_v + st * T_BYTES, &map_v, kv_full(st), 0, hh, j * BN, hn);
+                tma_other<D>(s_k + st * T_BYTES, &map_k, kv_full(st), hh, j * BN, hn);
+                tma_other<D>(s_v + st * T_BYTES, &map_v, kv_full(st), hh, j * BN, hn);
             }
         }
     } else if (warp == 9) {
         constexpr uint32_t id_s = idesc_bf16(BM, BN, 0, 0);   // S = Q K^T, dP' = dO' V^T
         constexpr uint32_t id_a = idesc_bf16(BM, D, 0, 1);    // dQ += dS K   (A from TMEM, K MN-major)
         const uint64_t dq0 = desc_kmajor(s_q, 0), ddy0 = desc_kmajor(s_dy, 0), dk0 = desc_kmajor(s_k, 0),
-                       dv0 = desc_kmajor(s_v, 0), dkt0 = desc_mnmajor(s_k, 0, T_BYTES);
+                       dv0 = desc_kmajor(s_v, 0), dkt0 = desc_mnmajor(s_k, 0, T_SUB);
         auto issue_acc = [&](int j, bool last) {                  // dQ += dS_j K_j
             const int st = j % STAGES;
             mbar_wait(p_full(j & 1), (j >> 1) & 1);
@@ -479,10 +513,10 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 const uint64_t off = (uint64_t)(st * (T_BYTES >> 4));
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + COL_S, dq0 + k * KMAJOR_K16, dk0 + off + k * KMAJOR_K16, id_s, k != 0);
+                    umma_bf16(tmem_base + COL_S, dq0 + kslice<OWN_SUB>(k), dk0 + off + kslice<T_SUB>(k), id_s, k != 0);
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + COL_DP, ddy0 + k * KMAJOR_K16, dv0 + off + k * KMAJOR_K16, id_s, k != 0);
+                    umma_bf16(tmem_base + COL_DP, ddy0 + kslice<OWN_SUB>(k), dv0 + off + kslice<T_SUB>(k), id_s, k != 0);
                 umma_commit(sc_full);
             }
             __syncwarp();
@@ -523,9 +557,13 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
         mbar_wait(acc_full, 0);
         fence_after_sync();
-        uint32_t r[32];
-        tmem_ld32(lane_base + COL_DQ + half * 32, r);
-        store_row32(dq + (((size_t)hn * S + row) * H + hh) * D + half * 32, r, scale);
+        __nv_bfloat16 *dst = dq + (((size_t)hn * S + row) * H + hh) * D + half * (D / 2);
+#pragma unroll
+        for (int c = 0; c < D / 64; ++c) {
+            uint32_t r[32];
+            tmem_ld32(lane_base + COL_DQ + half * (D / 2) + c * 32, r);
+            store_row32(dst + c * 32, r, scale);
+        }
     }
     fence_before_sync();
     __syncthreads();
@@ -542,12 +580,15 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 // Per-row quantities of the 64 query rows (mask words of this key group, delta', extra0) are staged in
 // shared memory by the producer warp, one slot per pipeline stage.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS, 2)
+template <int D>
+__global__ void __launch_bounds__(THREADS, Dim<D>::CTAS)
 attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                       const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_dys,
                       const uint32_t *__restrict__ mask, const int32_t *__restrict__ extra0,
                       const float *__restrict__ delta, __nv_bfloat16 *__restrict__ dk, __nv_bfloat16 *__restrict__ dv,
                       int S, int H, float scale, float scale_log2, float clamp_log2) {
+    constexpr int OWN_BYTES = Dim<D>::OWN_BYTES, T_BYTES = Dim<D>::T_BYTES, OWN_SUB = Dim<D>::OWN_SUB, T_SUB = Dim<D>::T_SUB,
+                  TMEM_COLS = Dim<D>::TMEM_COLS;
     extern __shared__ unsigned char smem_raw[];
     const Smem sm = align_smem(smem_raw);
     const uint32_t s_k = sm.base, s_v = s_k + OWN_BYTES, s_q = s_v + OWN_BYTES, s_dy = s_q + STAGES * T_BYTES;
@@ -586,15 +627,13 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t COL_S = 0, COL_DP = 64, COL_DV = 128, COL_DK = 192;
+    constexpr uint32_t COL_S = 0, COL_DP = 64, COL_DV = 128, COL_DK = 128 + D;
 
     if (warp == 8) {
         if (lane == 0) {
             mbar_expect_tx(own_full, 2 * OWN_BYTES);
-            tma_load_4d(s_k, &map_k, own_full, 0, hh, n0, hn);
-            tma_load_4d(s_k + T_BYTES, &map_k, own_full, 0, hh, n0 + BN, hn);
-            tma_load_4d(s_v, &map_v, own_full, 0, hh, n0, hn);
-            tma_load_4d(s_v + T_BYTES, &map_v, own_full, 0, hh, n0 + BN, hn);
+            tma_owner<D>(s_k, &map_k, own_full, hh, n0, hn);
+            tma_owner<D>(s_v, &map_v, own_full, hh, n0, hn);
         }
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j % STAGES;
@@ -602,8 +641,8 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             mbar_wait(qd_empty(st), ((j / STAGES) & 1) ^ 1);
             if (lane == 0) {
                 mbar_expect_tx(qd_full(st), 2 * T_BYTES);
-                tma_load_4d(s_q + st * T_BYTES, &map_q, qd_full(st), 0, hh, r0, hn);
-                tma_load_4d(s_dy + st * T_BYTES, &map_dys, qd_full(st), 0, hh, r0, hn);
+                tma_other<D>(s_q + st * T_BYTES, &map_q, qd_full(st), hh, r0, hn);
+                tma_other<D>(s_dy + st * T_BYTES, &map_dys, qd_full(st), hh, r0, hn);
             }
             unsigned char *slot = rowq + st * ROWQ_BYTES;
 #pragma unroll
@@ -625,8 +664,8 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         constexpr uint32_t id_s = idesc_bf16(BM, BN, 0, 0);   // S^T = K Q^T, dP'^T = V dO'^T
         constexpr uint32_t id_a = idesc_bf16(BM, D, 0, 1);    // dV += E^T dO', dK += dS^T Q (B MN-major)
         const uint64_t dk0 = desc_kmajor(s_k, 0), dv0 = desc_kmajor(s_v, 0), dq0 = desc_kmajor(s_q, 0),
-                       ddy0 = desc_kmajor(s_dy, 0), dqt0 = desc_mnmajor(s_q, 0, T_BYTES),
-                       ddyt0 = desc_mnmajor(s_dy, 0, T_BYTES);
+                       ddy0 = desc_kmajor(s_dy, 0), dqt0 = desc_mnmajor(s_q, 0, T_SUB),
+                       ddyt0 = desc_mnmajor(s_dy, 0, T_SUB);
         mbar_wait(own_full, 0);
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j % STAGES;
@@ -636,10 +675,10 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + COL_S, dk0 + k * KMAJOR_K16, dq0 + off + k * KMAJOR_K16, id_s, k != 0);
+                    umma_bf16(tmem_base + COL_S, dk0 + kslice<OWN_SUB>(k), dq0 + off + kslice<T_SUB>(k), id_s, k != 0);
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + COL_DP, dv0 + k * KMAJOR_K16, ddy0 + off + k * KMAJOR_K16, id_s, k != 0);
+                    umma_bf16(tmem_base + COL_DP, dv0 + kslice<OWN_SUB>(k), ddy0 + off + kslice<T_SUB>(k), id_s, k != 0);
                 umma_commit(sc_full);
             }
             __syncwarp();
@@ -697,12 +736,15 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         }
         mbar_wait(acc_full, 0);
         fence_after_sync();
-        const size_t off = (((size_t)hn * S + n0 + kk) * H + hh) * D + half * 32;
-        uint32_t r[32];
-        tmem_ld32(lane_base + COL_DV + half * 32, r);
-        store_row32(dv + off, r, 1.0f);
-        tmem_ld32(lane_base + COL_DK + half * 32, r);
-        store_row32(dk + off, r, scale);
+        const size_t off = (((size_t)hn * S + n0 + kk) * H + hh) * D + half * (D / 2);
+#pragma unroll
+        for (int c = 0; c < D / 64; ++c) {
+            uint32_t r[32];
+            tmem_ld32(lane_base + COL_DV + half * (D / 2) + c * 32, r);
+            store_row32(dv + off + c * 32, r, 1.0f);
+            tmem_ld32(lane_base + COL_DK + half * (D / 2) + c * 32, r);
+            store_row32(dk + off + c * 32, r, scale);
+        }
     }
     fence_before_sync();
     __syncthreads();
@@ -710,18 +752,52 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 }
 
 // ---- host -----------------------------------------------------------------------------------------
-// 4-D bf16 tensor map over a [N, S, H, D] tensor (H = 1: head-major [B, S, D]); box = 64 rows of one head
-static int make_map(CUtensorMap *map, const void *base, int N, int S, int H) {
+// 4-D bf16 tensor map over a [N, S, H, D] tensor (H = 1: head-major [B, S, D]); box = 64 rows x 64 elements of one head
+static int make_map(CUtensorMap *map, const void *base, int N, int S, int H, int D) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(SPT_ERR_CUDA, "sparse_attn: cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)H, (cuuint64_t)S, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)D * 2, (cuuint64_t)H * D * 2, (cuuint64_t)S * H * D * 2};
-    cuuint32_t box[4] = {(cuuint32_t)D, 1, (cuuint32_t)BN, 1};
+    cuuint32_t box[4] = {64, 1, (cuuint32_t)BN, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SPT_ERR_CUDA, "sparse_attn: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SPT_OK;
+}
+
+template <int D>
+static int launch_fwd(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const uint32_t *mask,
+                      const int32_t *extra0, __nv_bfloat16 *y, float *zsum, int B, int S, int H, float scale, float clamp,
+                      cudaStream_t st) {
+    cudaFuncSetAttribute(attn_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dim<D>::FWD_SMEM);
+    attn_fwd_tc_kernel<D><<<dim3(S / BM, B), THREADS, Dim<D>::FWD_SMEM, st>>>(mq, mk, mv, mask, extra0, y, zsum, S, H,
+                                                                              scale * LOG2E, clamp * LOG2E);
+    return after_launch("attn_fwd_tc_kernel");
+}
+
+template <int D>
+static int launch_prep(const __nv_bfloat16 *y, const __nv_bfloat16 *grad_y, const float *zsum, float *delta,
+                       __nv_bfloat16 *dys, int B, int S, int H, cudaStream_t st) {
+    const int64_t rows = (int64_t)B * S;
+    constexpr int RPB = 256 / (D / 8);
+    attn_bwd_prep_kernel<D><<<(unsigned)((rows + RPB - 1) / RPB), 256, 0, st>>>(grad_y, y, zsum, delta, dys, rows, S, H);
+    return after_launch("attn_bwd_prep_kernel");
+}
+
+template <int D>
+static int launch_bwd(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const CUtensorMap &md,
+                      const uint32_t *mask, const int32_t *extra0, const float *delta, __nv_bfloat16 *gq,
+                      __nv_bfloat16 *gk, __nv_bfloat16 *gv, int B, int S, int H, float scale, float clamp, cudaStream_t st) {
+    cudaFuncSetAttribute(attn_bwd_kv_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dim<D>::BWD_SMEM);
+    attn_bwd_kv_tc_kernel<D><<<dim3(S / BM, B), THREADS, Dim<D>::BWD_SMEM, st>>>(
+        mq, mk, mv, md, mask, extra0, delta, gk, gv, S, H, scale, scale * LOG2E, clamp * LOG2E);
+    SPT_LAUNCH_CHECK("attn_bwd_kv_tc_kernel");
+    cudaFuncSetAttribute(attn_bwd_q_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dim<D>::BWD_SMEM);
+    attn_bwd_q_tc_kernel<D><<<dim3(S / BM, B), THREADS, Dim<D>::BWD_SMEM, st>>>(
+        mq, mk, mv, md, mask, extra0, delta, gq, S, H, scale, scale * LOG2E, clamp * LOG2E);
+    SPT_LAUNCH_CHECK("attn_bwd_q_tc_kernel");
     return SPT_OK;
 }
 
@@ -732,7 +808,7 @@ using namespace spt;
 
 static int check_attn_args(const char *what, int B, int S, int d, int H, int dtype) {
     if (dtype != SPT_BF16) return fail(SPT_ERR_UNSUPPORTED, "%s: only bf16 is supported on the fused path", what);
-    if (d != attn_tc::D) return fail(SPT_ERR_UNSUPPORTED, "%s: head dim %d not supported (64 only)", what, d);
+    if (d != 64 && d != 128) return fail(SPT_ERR_UNSUPPORTED, "%s: head dim %d not supported (64 or 128)", what, d);
     if (B < 1 || B > 65535 || S < 128 || S % 128 != 0)
         return fail(SPT_ERR_INVALID_ARGUMENT, "%s: need 1 <= B <= 65535 and S a positive multiple of 128 (B=%d S=%d)", what, B, S);
     if (H < 1 || B % H != 0)
@@ -749,18 +825,16 @@ extern "C" int spt_sparse_attn_fwd(const void *q, const void *k, const void *v, 
     SPT_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)y) % 16 == 0, "sparse_attn_fwd: operands must be 16-byte aligned");
     using bf = __nv_bfloat16;
     CUtensorMap mq, mk, mv;
-    if ((rc = attn_tc::make_map(&mq, q, B / H, S, H)) != SPT_OK) return rc;
-    if ((rc = attn_tc::make_map(&mk, k, B / H, S, H)) != SPT_OK) return rc;
-    if ((rc = attn_tc::make_map(&mv, v, B / H, S, H)) != SPT_OK) return rc;
-    cudaFuncSetAttribute(attn_tc::attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc::FWD_SMEM);
-    attn_tc::attn_fwd_tc_kernel<<<dim3(S / attn_tc::BM, B), attn_tc::THREADS, attn_tc::FWD_SMEM, as_stream(stream)>>>(
-        mq, mk, mv, mask, extra0, (bf *)y, zsum, S, H, scale * attn_tc::LOG2E, clamp * attn_tc::LOG2E);
-    return after_launch("attn_fwd_tc_kernel");
+    if ((rc = attn_tc::make_map(&mq, q, B / H, S, H, d)) != SPT_OK) return rc;
+    if ((rc = attn_tc::make_map(&mk, k, B / H, S, H, d)) != SPT_OK) return rc;
+    if ((rc = attn_tc::make_map(&mv, v, B / H, S, H, d)) != SPT_OK) return rc;
+    if (d == 64) return attn_tc::launch_fwd<64>(mq, mk, mv, mask, extra0, (bf *)y, zsum, B, S, H, scale, clamp, as_stream(stream));
+    return attn_tc::launch_fwd<128>(mq, mk, mv, mask, extra0, (bf *)y, zsum, B, S, H, scale, clamp, as_stream(stream));
 }
 
-// workspace: delta' [B, S] fp32, then dO' (bf16, same shape as grad_y)
+// workspace: delta' [B, S] fp32, then dO' (bf16, same shape as grad_y; sized for the largest head dim)
 extern "C" size_t spt_sparse_attn_bwd_workspace_bytes(int B, int S) {
-    return (size_t)B * S * sizeof(float) + (size_t)B * S * attn_tc::D * 2;
+    return (size_t)B * S * sizeof(float) + (size_t)B * S * 128 * 2;
 }
 
 extern "C" int spt_sparse_attn_bwd(const void *q, const void *k, const void *v, const void *y, const void *grad_y,
@@ -774,26 +848,21 @@ extern "C" int spt_sparse_attn_bwd(const void *q, const void *k, const void *v, 
     SPT_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)grad_y | (uintptr_t)workspace) % 16 == 0,
                 "sparse_attn_bwd: operands must be 16-byte aligned");
     using bf = __nv_bfloat16;
-    cudaStream_t st = as_stream(stream);
     float *delta = (float *)workspace;
     bf *dys = (bf *)((char *)workspace + (size_t)B * S * sizeof(float));
-    const int64_t rows = (int64_t)B * S;
-    attn_tc::attn_bwd_prep_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>((const bf *)grad_y, (const bf *)y, zsum,
-                                                                                delta, dys, rows, S, H);
-    SPT_LAUNCH_CHECK("attn_bwd_prep_kernel");
+    // the row kernel goes first: besides producing dO' and delta' it is a runtime-API launch, which binds the
+    // device's primary context to this (autograd worker) thread before the driver-API tensor-map encoder runs
+    rc = d == 64 ? attn_tc::launch_prep<64>((const bf *)y, (const bf *)grad_y, zsum, delta, dys, B, S, H, as_stream(stream))
+                 : attn_tc::launch_prep<128>((const bf *)y, (const bf *)grad_y, zsum, delta, dys, B, S, H, as_stream(stream));
+    if (rc != SPT_OK) return rc;
     CUtensorMap mq, mk, mv, md;
-    if ((rc = attn_tc::make_map(&mq, q, B / H, S, H)) != SPT_OK) return rc;
-    if ((rc = attn_tc::make_map(&mk, k, B / H, S, H)) != SPT_OK) return rc;
-    if ((rc = attn_tc::make_map(&mv, v, B / H, S, H)) != SPT_OK) return rc;
-    if ((rc = attn_tc::make_map(&md, dys, B / H, S, H)) != SPT_OK) return rc;
-    cudaFuncSetAttribute(attn_tc::attn_bwd_kv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc::BWD_SMEM);
-    attn_tc::attn_bwd_kv_tc_kernel<<<dim3(S / attn_tc::BM, B), attn_tc::THREADS, attn_tc::BWD_SMEM, st>>>(
-        mq, mk, mv, md, mask, extra0, delta, (bf *)grad_k, (bf *)grad_v, S, H, scale, scale * attn_tc::LOG2E,
-        clamp * attn_tc::LOG2E);
-    SPT_LAUNCH_CHECK("attn_bwd_kv_tc_kernel");
-    cudaFuncSetAttribute(attn_tc::attn_bwd_q_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc::BWD_SMEM);
-    attn_tc::attn_bwd_q_tc_kernel<<<dim3(S / attn_tc::BM, B), attn_tc::THREADS, attn_tc::BWD_SMEM, st>>>(
-        mq, mk, mv, md, mask, extra0, delta, (bf *)grad_q, S, H, scale, scale * attn_tc::LOG2E, clamp * attn_tc::LOG2E);
-    SPT_LAUNCH_CHECK("attn_bwd_q_tc_kernel");
-    return SPT_OK;
+    if ((rc = attn_tc::make_map(&mq, q, B / H, S, H, d)) != SPT_OK) return rc;
+    if ((rc = attn_tc::make_map(&mk, k, B / H, S, H, d)) != SPT_OK) return rc;
+    if ((rc = attn_tc::make_map(&mv, v, B / H, S, H, d)) != SPT_OK) return rc;
+    if ((rc = attn_tc::make_map(&md, dys, B / H, S, H, d)) != SPT_OK) return rc;
+    if (d == 64)
+        return attn_tc::launch_bwd<64>(mq, mk, mv, md, mask, extra0, delta, (bf *)grad_q, (bf *)grad_k, (bf *)grad_v, B, S,
+                                       H, scale, clamp, as_stream(stream));
+    return attn_tc::launch_bwd<128>(mq, mk, mv, md, mask, extra0, delta, (bf *)grad_q, (bf *)grad_k, (bf *)grad_v, B, S, H,
+                                    scale, clamp, as_stream(stream));
 }

@@ -171,6 +171,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline EncodeTiledFn encode_fn() {
+    // cuTensorMapEncodeTiled is a driver-API call: it needs the device's primary context bound to the
+    // calling thread.  A thread whose first CUDA action is this call (an autograd worker entering a
+    // backward pass) has none yet (CUDA_ERROR_INVALID_CONTEXT); any runtime-API call binds it.
+    static thread_local bool bound = false;
+    if (!bound) {
+        cudaFree(nullptr);
+        bound = true;
+    }
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void *ptr = nullptr;

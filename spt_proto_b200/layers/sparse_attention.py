@@ -59,7 +59,7 @@ class _SparseV2Mixin:
     # test).  False (default) returns the intended layout — identical to the reference's dense
     # VanillaAttention on the same pattern; True reproduces the shipped layer bit for bit.
     reference_output_layout: bool = False
-    # bf16, d_head 64, S % 128 == 0 on CUDA: run lookup -> bitmask -> fused masked-dense attention on
+    # bf16, d_head 64 or 128, S % 128 == 0 on CUDA: run lookup -> bitmask -> fused masked-dense attention on
     # the tensor cores instead of the stage chain (same result up to bf16 rounding).
     use_fused: bool = True
     # The reference reads its device-side `trigger` buffer with `is_nonzero()` on every forward
@@ -98,7 +98,7 @@ class _SparseV2Mixin:
         return x.view(-1, x.size(-2), x.size(-1))
 
     def _fused_ok(self, q) -> bool:
-        return (self.use_fused and q.is_cuda and q.dtype == torch.bfloat16 and q.size(-1) == 64
+        return (self.use_fused and q.is_cuda and q.dtype == torch.bfloat16 and q.size(-1) in (64, 128)
                 and q.size(1) % 128 == 0 and q.size(1) % self.sparse_coeff == 0
                 and (q.size(1) // self.sparse_coeff) % 4 == 0 and q.size(1) // self.sparse_coeff >= 8)
 
