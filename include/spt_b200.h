@@ -78,6 +78,19 @@ int spt_pq_encode(const void *z, const float *table, int32_t *codes,
 int spt_pq_encode_pair(const void *z0, const void *z1, const float *table, int32_t *codes0, int32_t *codes1,
                        int64_t rows, int m, int c, int dc, int dtype, spt_stream_t stream);
 
+/* Fused PQBase.forward(mode='train') (quantizer.py:81-111): z [rows, m*dc] (dtype), table [m, c, dc] fp32.
+ *   fwd: zq_out [rows, m*dc] fp32 (hard centroids, may be NULL); partial [spt_pq_train_blocks(rows, m)] fp32 with
+ *        sum(partial) / (rows*m*dc) = mean((zw - zq)^2) + mean((z - zq)^2), zw = soft centroid (see cdist.cu).
+ *   bwd: grad_loss [1] fp32 (device), grad_zq [rows, m*dc] fp32 or NULL -> grad_z [rows, m*dc] (dtype) and
+ *        grad_table_partial [spt_pq_train_blocks(rows, m)][m][c][dc] fp32 (sum over the first axis = grad_table).
+ * Covers c = 16, dc = 8 (the reference's configuration, utils/adapter.py:94-97), m <= 64. */
+int spt_pq_train_blocks(int64_t rows, int m);
+int spt_pq_train_fwd(const void *z, const float *table, float *zq_out, float *partial,
+                     int64_t rows, int m, int c, int dc, int dtype, spt_stream_t stream);
+int spt_pq_train_bwd(const void *z, const float *table, const float *grad_zq, const float *grad_loss,
+                     void *grad_z, float *grad_table_partial,
+                     int64_t rows, int m, int c, int dc, int dtype, spt_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * (2) lookup — replaces lookup_forward_cuda (extension/lookup.cu:87-174).
  * query_codes, key_codes [B, S, m] int32 -> output [B, S, nnz] int32, nnz = S / sparse_coeff.

@@ -12,8 +12,8 @@ PQ training loss armed every step like script/4-sparse-tuning-0.py:71-91), LoRAR
 (block = d_ff/4, half the blocks active); then ONE bucketed NCCL all-reduce of the trainable gradients
 (spt_proto_b200.distributed.allreduce_grads), grad-clip 1.0 and AdamW.  Prints one JSON line (rank 0).
 
-d_head 128 is outside the fused attention kernels (d_head 64 only): the attention here runs the
-stage kernels (lookup -> sddmm -> softmax -> spmm, CSC transposed products in backward)."""
+The attention runs the fused tcgen05 kernels (head dim 128 instantiation), the PQ loss the fused
+pq_train kernels, the FFN the grouped GEMM."""
 from __future__ import annotations
 
 import argparse
@@ -137,11 +137,11 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
                 "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"LLaMA-7B-shape {args.layers}-layer SPT fine-tuning step (sparse rotary MHA d_head 128 "
-                                       f"stage kernels + LoRA routed FFN), seq {args.seq}, {args.batch} seq/GPU",
+                                       f"+ LoRA routed FFN), seq {args.seq}, {args.batch} seq/GPU",
                            "d_model": d_model, "n_heads": n_heads, "d_ff": d_ff, "d_lora": args.d_lora,
                            "trainable_params": n_train, "allreduce_calls_per_step": n_coll,
                            "parallelism": f"dp{world} + NCCL all-reduce of trainable grads"},
-                "loss": float(loss), "gpu_launches": ext.launch_count() - launches0}
+                "loss": float(loss.detach()), "gpu_launches": ext.launch_count() - launches0}
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()

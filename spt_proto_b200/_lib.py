@@ -34,6 +34,9 @@ def _load() -> ctypes.CDLL:
         "spt_cdist_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp]),
         "spt_pq_encode": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, vp]),
         "spt_pq_encode_pair": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+        "spt_pq_train_blocks": (i32, [i64, i32]),
+        "spt_pq_train_fwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+        "spt_pq_train_bwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
         "spt_lookup_workspace_bytes": (sz, [i32, i32, i32, i32]),
         "spt_lookup_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "spt_sddmm_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i64, f32, f32, i32, vp]),

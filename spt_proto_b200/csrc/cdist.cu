@@ -379,3 +379,255 @@ extern "C" int spt_cdist_bwd(const float *query, const float *table, const float
     }
     return SPT_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// PQ 'train' mode, fused (reference naive_gpt/layers/basic/quantizer.py:81-111):
+//   d_c  = sum_i |z_i - W_ci|                   (L1 distance to the c codewords of the row's subspace)
+//   idx  = argmin_c d_c (first minimum)          zq = W_idx                     (hard centroid)
+//   w_c  = softmax(-log(clamp(d_c, 1e-5)))_c = (1 / max(d_c, 1e-5)) / sum_k (1 / max(d_k, 1e-5))
+//   zw   = sum_c w_c W_c                          (soft centroid)
+//   loss = mean((zw - zq)^2) + mean((z - zq)^2)   (means over all rows * m * dc elements)
+// The reference runs ~10 torch ops over the materialised [m, rows, c] distance tensor, and its backward
+// scatter-adds rows * m * dc values into 16 codewords per subspace (serialised atomics: 4.8 ms per call
+// at the LLaMA-7B shape).  Here one thread owns (row, subspace) items of ONE subspace (grid stride is a
+// multiple of m), recomputes everything in registers, and in the backward keeps its subspace's
+// [c][dc] codebook gradient in registers across all its rows; threads are combined once per block
+// through shared memory and once per launch through per-block partials (summed by the caller).
+// sgn(x) = +1 if x > 0 else -1, the convention of the cdist backward (extension/cdist.cu:117,168).
+// ---------------------------------------------------------------------------------------------------
+namespace spt {
+
+constexpr int PQT_THREADS = 256;
+
+template <typename T, int DC>
+__device__ __forceinline__ void load_row(const T *zp, float (&zv)[DC]) {
+    if constexpr (DC % Vec16<T>::N == 0) {
+#pragma unroll
+        for (int i = 0; i < DC; i += Vec16<T>::N) {
+            float tmp[Vec16<T>::N];
+            Vec16<T>::load(zp + i, tmp);
+#pragma unroll
+            for (int j = 0; j < Vec16<T>::N; ++j) zv[i + j] = tmp[j];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < DC; ++i) zv[i] = to_f32(zp[i]);
+    }
+}
+
+// distances, argmin, soft weights of one (row, subspace) item; wt = this subspace's [C][DC] codebook in smem
+template <int DC, int C>
+__device__ __forceinline__ void pq_soft(const float (&zv)[DC], const float *wt, float (&dist)[C], float (&wgt)[C],
+                                        int &idx, float &inv_a) {
+    float best = 1e13f;
+    idx = 0;
+    float a_sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        float d = 0.0f;
+#pragma unroll
+        for (int i = 0; i < DC; ++i) d += fabsf(zv[i] - wt[c * DC + i]);
+        dist[c] = d;
+        if (d < best) {
+            best = d;
+            idx = c;
+        }
+        wgt[c] = 1.0f / fmaxf(d, 1e-5f);
+        a_sum += wgt[c];
+    }
+    inv_a = 1.0f / a_sum;
+#pragma unroll
+    for (int c = 0; c < C; ++c) wgt[c] *= inv_a;
+}
+
+template <typename T, int DC, int C>
+__global__ void __launch_bounds__(PQT_THREADS)
+pq_train_fwd_kernel(const T *__restrict__ z, const float *__restrict__ table, float *__restrict__ zq_out,
+                    float *__restrict__ partial, int64_t total, int m) {
+    extern __shared__ __align__(16) float s_w[];   // [m][C*DC + 4] (padded: lanes differ in subspace)
+    __shared__ float s_red[PQT_THREADS / 32];
+    constexpr int PAD = C * DC + 4;
+    for (int i = threadIdx.x; i < m * C * DC; i += blockDim.x) s_w[(i / (C * DC)) * PAD + i % (C * DC)] = table[i];
+    __syncthreads();
+    float local = 0.0f;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const float *wt = s_w + (size_t)(g % m) * PAD;
+        float zv[DC], dist[C], wgt[C], inv_a;
+        int idx;
+        load_row<T, DC>(z + (size_t)g * DC, zv);
+        pq_soft<DC, C>(zv, wt, dist, wgt, idx, inv_a);
+        float zw[DC];
+#pragma unroll
+        for (int i = 0; i < DC; ++i) zw[i] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int i = 0; i < DC; ++i) zw[i] = fmaf(wgt[c], wt[c * DC + i], zw[i]);
+#pragma unroll
+        for (int i = 0; i < DC; ++i) {
+            const float zq = wt[idx * DC + i];
+            const float e1 = zw[i] - zq, e2 = zv[i] - zq;
+            local = fmaf(e1, e1, fmaf(e2, e2, local));
+            if (zq_out) zq_out[(size_t)g * DC + i] = zq;
+        }
+    }
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int i = 0; i < PQT_THREADS / 32; ++i) t += s_red[i];
+        partial[blockIdx.x] = t;
+    }
+}
+
+// g_loss = dLoss * 2 / (rows * m * dc).  grad_zq (optional, fp32 [rows, m*dc]) is the gradient that reached the
+// hard-centroid output.  grad_z in z's dtype; grad_table partials [gridDim.x][m][C][DC] fp32.
+template <typename T, int DC, int C>
+__global__ void __launch_bounds__(PQT_THREADS)
+pq_train_bwd_kernel(const T *__restrict__ z, const float *__restrict__ table, const float *__restrict__ grad_zq,
+                    const float *__restrict__ grad_loss, float loss_scale, T *__restrict__ grad_z,
+                    float *__restrict__ grad_table_partial, int64_t total, int m) {
+    extern __shared__ __align__(16) float s_mem[];   // [m][PAD] codebook, then [m][C*DC] block gradient
+    constexpr int PAD = C * DC + 4;
+    float *s_w = s_mem, *s_g = s_mem + (size_t)m * PAD;
+    for (int i = threadIdx.x; i < m * C * DC; i += blockDim.x) {
+        s_w[(i / (C * DC)) * PAD + i % (C * DC)] = table[i];
+        s_g[i] = 0.0f;
+    }
+    __syncthreads();
+    const float gl = grad_loss[0] * loss_scale;
+    const int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = (int)(g0 % m);                    // the grid stride is a multiple of m: s is fixed per thread
+    const float *wt = s_w + (size_t)s * PAD;
+    float acc[C][DC];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int i = 0; i < DC; ++i) acc[c][i] = 0.0f;
+    for (int64_t g = g0; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        float zv[DC], dist[C], wgt[C], inv_a;
+        int idx;
+        load_row<T, DC>(z + (size_t)g * DC, zv);
+        pq_soft<DC, C>(zv, wt, dist, wgt, idx, inv_a);
+        float zw[DC];
+#pragma unroll
+        for (int i = 0; i < DC; ++i) zw[i] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int i = 0; i < DC; ++i) zw[i] = fmaf(wgt[c], wt[c * DC + i], zw[i]);
+        float e1[DC], gz[DC], gq[DC];    // gq: gradient into the hard centroid W_idx
+#pragma unroll
+        for (int i = 0; i < DC; ++i) {
+            const float zq = wt[idx * DC + i];
+            e1[i] = gl * (zw[i] - zq);
+            const float e2 = gl * (zv[i] - zq);
+            gz[i] = e2;
+            gq[i] = -e1[i] - e2 + (grad_zq ? grad_zq[(size_t)g * DC + i] : 0.0f);
+        }
+        // gw_c = e1 . W_c ;  t = sum_c gw_c w_c ;  dd_c = -(a_c)^2 (gw_c - t) / A  with a_c = w_c A
+        // (gw_c is recomputed in the second pass instead of being kept: registers are the scarce resource)
+        float t = 0.0f;
+        uint32_t live = 0;   // bit c: d_c > 1e-5 (the clamp passes gradient)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float v = 0.0f;
+#pragma unroll
+            for (int i = 0; i < DC; ++i) v = fmaf(e1[i], wt[c * DC + i], v);
+            t = fmaf(v, wgt[c], t);
+            live |= (dist[c] > 1e-5f ? 1u : 0u) << c;
+        }
+        const float a_sum = 1.0f / inv_a;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float v = 0.0f;
+#pragma unroll
+            for (int i = 0; i < DC; ++i) v = fmaf(e1[i], wt[c * DC + i], v);
+            const float dd = ((live >> c) & 1u) ? -(wgt[c] * wgt[c]) * a_sum * (v - t) : 0.0f;
+#pragma unroll
+            for (int i = 0; i < DC; ++i) {
+                const float sg = (zv[i] - wt[c * DC + i]) > 0.0f ? dd : -dd;
+                gz[i] += sg;
+                acc[c][i] += fmaf(wgt[c], e1[i], -sg);
+            }
+        }
+        // the hard centroid's gradient goes straight to the block accumulator (8 shared-memory adds per item)
+#pragma unroll
+        for (int i = 0; i < DC; ++i) atomicAdd(&s_g[(s * C + idx) * DC + i], gq[i]);
+        T *op = grad_z + (size_t)g * DC;
+        if constexpr (DC % Vec16<T>::N == 0) {
+#pragma unroll
+            for (int i = 0; i < DC; i += Vec16<T>::N) {
+                float tmp[Vec16<T>::N];
+#pragma unroll
+                for (int j = 0; j < Vec16<T>::N; ++j) tmp[j] = gz[i + j];
+                Vec16<T>::store(op + i, tmp);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < DC; ++i) op[i] = from_f32<T>(gz[i]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int i = 0; i < DC; ++i) atomicAdd(&s_g[(s * C + c) * DC + i], acc[c][i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < m * C * DC; i += blockDim.x)
+        grad_table_partial[(size_t)blockIdx.x * m * C * DC + i] = s_g[i];
+}
+
+static int pq_train_grid(int64_t total, int m) {
+    int64_t want = (total + PQT_THREADS - 1) / PQT_THREADS;
+    int64_t cap = (int64_t)num_sms() * 2;
+    int64_t g = want < cap ? want : cap;
+    // the grid stride (g * PQT_THREADS) must be a multiple of m so that a thread keeps its subspace
+    while ((g * PQT_THREADS) % m != 0) ++g;
+    return (int)g;
+}
+
+}  // namespace spt
+
+extern "C" int spt_pq_train_blocks(int64_t rows, int m) { return spt::pq_train_grid(rows * m, m); }
+
+extern "C" int spt_pq_train_fwd(const void *z, const float *table, float *zq_out, float *partial, int64_t rows, int m,
+                                int c, int dc, int dtype, spt_stream_t stream) {
+    SPT_REQUIRE(z && table && partial, "pq_train_fwd: null pointer");
+    SPT_REQUIRE(c == 16 && dc == 8 && m >= 1 && m <= 64, "pq_train_fwd: fused path covers c = 16, dc = 8, m <= 64 (got c=%d dc=%d m=%d)", c, dc, m);
+    SPT_REQUIRE(rows >= 1, "pq_train_fwd: no rows");
+    const int64_t total = rows * m;
+    const int grid = pq_train_grid(total, m);
+    const size_t smem = (size_t)m * (16 * 8 + 4) * sizeof(float);
+    if (dtype == SPT_F32)
+        pq_train_fwd_kernel<float, 8, 16><<<grid, PQT_THREADS, smem, as_stream(stream)>>>((const float *)z, table, zq_out, partial, total, m);
+    else if (dtype == SPT_BF16)
+        pq_train_fwd_kernel<__nv_bfloat16, 8, 16><<<grid, PQT_THREADS, smem, as_stream(stream)>>>((const __nv_bfloat16 *)z, table, zq_out, partial, total, m);
+    else
+        return fail(SPT_ERR_INVALID_ARGUMENT, "pq_train_fwd: unknown dtype %d", dtype);
+    return after_launch("pq_train_fwd_kernel");
+}
+
+extern "C" int spt_pq_train_bwd(const void *z, const float *table, const float *grad_zq, const float *grad_loss,
+                                void *grad_z, float *grad_table_partial, int64_t rows, int m, int c, int dc, int dtype,
+                                spt_stream_t stream) {
+    SPT_REQUIRE(z && table && grad_loss && grad_z && grad_table_partial, "pq_train_bwd: null pointer");
+    SPT_REQUIRE(c == 16 && dc == 8 && m >= 1 && m <= 64, "pq_train_bwd: fused path covers c = 16, dc = 8, m <= 64");
+    SPT_REQUIRE(rows >= 1, "pq_train_bwd: no rows");
+    const int64_t total = rows * m;
+    const int grid = pq_train_grid(total, m);
+    const float loss_scale = 2.0f / (float)((double)total * dc);
+    const size_t smem = (size_t)m * (16 * 8 + 4 + 16 * 8) * sizeof(float);
+    if (dtype == SPT_F32) {
+        cudaFuncSetAttribute(pq_train_bwd_kernel<float, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        pq_train_bwd_kernel<float, 8, 16><<<grid, PQT_THREADS, smem, as_stream(stream)>>>(
+            (const float *)z, table, grad_zq, grad_loss, loss_scale, (float *)grad_z, grad_table_partial, total, m);
+    } else if (dtype == SPT_BF16) {
+        cudaFuncSetAttribute(pq_train_bwd_kernel<__nv_bfloat16, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        pq_train_bwd_kernel<__nv_bfloat16, 8, 16><<<grid, PQT_THREADS, smem, as_stream(stream)>>>(
+            (const __nv_bfloat16 *)z, table, grad_zq, grad_loss, loss_scale, (__nv_bfloat16 *)grad_z, grad_table_partial, total, m);
+    } else {
+        return fail(SPT_ERR_INVALID_ARGUMENT, "pq_train_bwd: unknown dtype %d", dtype);
+    }
+    return after_launch("pq_train_bwd_kernel");
+}

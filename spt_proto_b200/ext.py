@@ -161,6 +161,35 @@ def pq_encode_pair(z0: torch.Tensor, z1: torch.Tensor, table: torch.Tensor):
     return codes0, codes1
 
 
+def pq_train_supported(z: torch.Tensor, table: torch.Tensor) -> bool:
+    return (z.is_cuda and z.dtype in _DTYPES and table.dim() == 3 and table.size(1) == 16 and table.size(2) == 8
+            and table.size(0) <= 64 and z.size(-1) == table.size(0) * 8 and z.numel() > 0)
+
+
+def pq_train_fwd(z: torch.Tensor, table32: torch.Tensor):
+    """Fused PQ 'train' forward: -> (zq [rows, m*dc] fp32 hard centroids, loss scalar fp32)."""
+    m, c, dc = table32.shape
+    rows = z.numel() // (m * dc)
+    zq = torch.empty((rows, m * dc), dtype=torch.float32, device=z.device)
+    partial = torch.empty((lib.spt_pq_train_blocks(rows, m),), dtype=torch.float32, device=z.device)
+    with _on_device(z):
+        check(lib.spt_pq_train_fwd(_p(z), _p(table32), _p(zq), _p(partial), rows, m, c, dc, _float_code(z, "z"), _stream(z)))
+    return zq, partial.sum() / float(rows * m * dc)
+
+
+def pq_train_bwd(z: torch.Tensor, table32: torch.Tensor, grad_zq, grad_loss: torch.Tensor):
+    """-> (grad_z like z, grad_table [m, c, dc] fp32)."""
+    m, c, dc = table32.shape
+    rows = z.numel() // (m * dc)
+    grad_z = torch.empty_like(z)
+    partial = torch.empty((lib.spt_pq_train_blocks(rows, m), m, c, dc), dtype=torch.float32, device=z.device)
+    gl = grad_loss.reshape(1).float().contiguous()
+    with _on_device(z):
+        check(lib.spt_pq_train_bwd(_p(z), _p(table32), _p(grad_zq), _p(gl), _p(grad_z), _p(partial), rows, m, c, dc,
+                                   _float_code(z, "z"), _stream(z)))
+    return grad_z, partial.sum(0)
+
+
 # ---- (2) lookup --------------------------------------------------------------------------------------
 def lookup_forward_cuda(config: torch.Tensor, query: torch.Tensor, key: torch.Tensor) -> torch.Tensor:
     """config carries sparse_coeff in its SHAPE (kernels/lookup.py:23, lookup.cu:99);

@@ -107,6 +107,27 @@ class LLaMaFeedforward(nn.Module):
         return self.down(self.activation(self.gate(x)) * self.side(x))
 
 
+class _PQTrainFused(torch.autograd.Function):
+    """PQ 'train' mode as one forward and one backward kernel (csrc/cdist.cu, pq_train_*)."""
+
+    @staticmethod
+    def forward(ctx, z, weight):
+        w32 = weight.detach().float().contiguous()
+        zq, loss = ext.pq_train_fwd(z, w32)
+        ctx.save_for_backward(z, w32)
+        ctx.w_dtype = weight.dtype
+        return zq.view(list(z.shape[:-1]) + [-1]), loss
+
+    @staticmethod
+    def backward(ctx, grad_zq, grad_loss):
+        z, w32 = ctx.saved_tensors
+        if grad_loss is None:
+            grad_loss = torch.zeros((), device=z.device)
+        gzq = None if grad_zq is None else grad_zq.reshape(-1, z.size(-1)).float().contiguous()
+        grad_z, grad_w = ext.pq_train_bwd(z, w32, gzq, grad_loss)
+        return grad_z, grad_w.to(ctx.w_dtype)
+
+
 class PQBase(nn.Module):
     """Product quantizer with one codebook weight[m, c, dc] shared by all heads of a layer
     (reference basic/quantizer.py:6-111).  forward(mode, z), mode in
@@ -123,6 +144,7 @@ class PQBase(nn.Module):
         self.d_codeword, self.n_codewords, self.n_subspaces = d_codeword, n_codewords, n_subspaces
         self.weight = nn.Parameter(torch.randn(n_subspaces, n_codewords, d_codeword))
         self.loss_fn = nn.MSELoss()
+        self.fused_train = True    # v2 on CUDA with 16 codewords x 8: one kernel each way instead of ~10 torch ops
 
     def _distance_and_codes(self, z_flat):
         if self.method == "v1":
@@ -144,6 +166,9 @@ class PQBase(nn.Module):
         if mode == "encode" and self.method == "v2" and z.is_cuda:
             # fused fast path: no [m, n, dc] copy, no distance tensor
             return ext.pq_encode(z.contiguous(), self.weight)
+
+        if mode == "train" and self.method == "v2" and self.fused_train and ext.pq_train_supported(z, self.weight):
+            return _PQTrainFused.apply(z.contiguous(), self.weight)
 
         z_flat = z.flatten(end_dim=-2).view(-1, m, z.size(-1) // m).transpose(0, 1).contiguous()
         if mode == "decode":
