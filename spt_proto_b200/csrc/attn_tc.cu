@@ -58,7 +58,7 @@ struct Dim {
     static constexpr int TMEM_COLS = D == 64 ? 256 : 512;
     static constexpr int CTAS = D == 64 ? 2 : 1;
     static constexpr int FWD_SMEM = OWN_BYTES + 2 * STAGES * T_BYTES + 1024 /*row sums*/ + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr int BWD_SMEM = 2 * OWN_BYTES + 2 * STAGES * T_BYTES + STAGES * (BN * 16 + BN * 4 + BN * 4) + 1024 + 256;
+    static constexpr int BWD_SMEM = 2 * OWN_BYTES + 2 * STAGES * T_BYTES + STAGES * ((BN + 4) * 16 + BN * 4 + BN * 4) + 1024 + 256;
 };
 // descriptor offset (16-byte units) of K16 slice k of a K-major tile whose 64-wide sub-tiles are SUB bytes apart
 template <int SUB>
@@ -575,8 +575,9 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 // (Q_j, dO'_j) at and below the diagonal.  Works on the transposed tiles S^T = K Q^T, dP'^T = V dO'^T
 // so that E^T and dS^T come out with keys on the TMEM lanes, ready to be the A operands of
 //   dV += E^T dO'_j   and   dK += dS^T Q_j.
-// TMEM columns: S^T 0, dP'^T 64, dV 128, dK 192.  E^T / dS^T (bf16 pairs) are written back over score
-// columns the same thread has already consumed: column half h (query rows 32h..32h+31) -> 32h..32h+15.
+// The 64-row tiles are consumed as two 32-row sub-tiles with two score buffers in TMEM (S^T 32 + dP'^T 32
+// columns each, then dV, dK): the tensor core computes the next sub-tile's scores under this one's exp math.
+// E^T / dS^T (bf16 pairs) are written back over score columns the same thread has already consumed.
 // Per-row quantities of the 64 query rows (mask words of this key group, delta', extra0) are staged in
 // shared memory by the producer warp, one slot per pipeline stage.
 // ---------------------------------------------------------------------------------------------------
@@ -592,14 +593,17 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     extern __shared__ unsigned char smem_raw[];
     const Smem sm = align_smem(smem_raw);
     const uint32_t s_k = sm.base, s_v = s_k + OWN_BYTES, s_q = s_v + OWN_BYTES, s_dy = s_q + STAGES * T_BYTES;
-    unsigned char *rowq = sm.ptr + 2 * OWN_BYTES + 2 * STAGES * T_BYTES;   // per stage: mask^T [4][64], delta[64], ex0[64]
-    constexpr int ROWQ_BYTES = BN * 16 + BN * 4 + BN * 4;
+    unsigned char *rowq = sm.ptr + 2 * OWN_BYTES + 2 * STAGES * T_BYTES;   // per stage: mask^T [4][64 + 4], delta[64], ex0[64]
+    constexpr int MT = BN + 4;                         // padded row of the transposed mask: the 4 words hit distinct banks
+    constexpr int ROWQ_BYTES = MT * 16 + BN * 4 + BN * 4;
     uint64_t *bars = reinterpret_cast<uint64_t *>(rowq + STAGES * ROWQ_BYTES);
     const uint32_t bar0 = smem_u32(bars);
-    const uint32_t own_full = bar0, acc_full = bar0 + 8, sc_full = bar0 + 16, p_full = bar0 + 24;
-    auto qd_full = [&](int s) { return bar0 + 32 + s * 8; };
-    auto qd_empty = [&](int s) { return bar0 + 32 + (STAGES + s) * 8; };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 + 2 * STAGES);
+    const uint32_t own_full = bar0, acc_full = bar0 + 8;
+    auto sc_full = [&](int i) { return bar0 + 16 + i * 8; };
+    auto p_full = [&](int i) { return bar0 + 32 + i * 8; };
+    auto qd_full = [&](int s) { return bar0 + 48 + s * 8; };
+    auto qd_empty = [&](int s) { return bar0 + 48 + (STAGES + s) * 8; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6 + 2 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kt = blockIdx.x;                         // key tile (early key tiles are the heaviest)
@@ -614,8 +618,10 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (threadIdx.x == 0) {
         mbar_init(own_full, 1);
         mbar_init(acc_full, 1);
-        mbar_init(sc_full, 1);
-        mbar_init(p_full, N_MATH);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(sc_full(i), 1);
+            mbar_init(p_full(i), N_MATH);
+        }
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(qd_full(s), 1 + 32);             // expect_tx arrive + the 32 producer lanes' row data
             mbar_init(qd_empty(s), 1);
@@ -627,7 +633,9 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t COL_S = 0, COL_DP = 64, COL_DV = 128, COL_DK = 128 + D;
+    // score buffers b = 0, 1 (one per 32-row sub-tile in flight): S^T at 64 b, dP'^T at 64 b + 32
+    constexpr uint32_t COL_SC = 0, COL_DV = 128, COL_DK = 128 + D;
+    constexpr int SUBN = 32;
 
     if (warp == 8) {
         if (lane == 0) {
@@ -650,52 +658,62 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 const int rr = lane + 32 * u;
                 const size_t gr = head + r0 + rr;
                 const uint4 mw = __ldg(reinterpret_cast<const uint4 *>(mask + gr * words) + kt);
-                uint32_t *mt = reinterpret_cast<uint32_t *>(slot);        // transposed: [word t][row]
+                uint32_t *mt = reinterpret_cast<uint32_t *>(slot);        // transposed: [word t][row], rows padded to MT
                 mt[rr] = mw.x;
-                mt[BN + rr] = mw.y;
-                mt[2 * BN + rr] = mw.z;
-                mt[3 * BN + rr] = mw.w;
-                reinterpret_cast<float *>(slot + BN * 16)[rr] = delta[gr];
-                reinterpret_cast<float *>(slot + BN * 16 + BN * 4)[rr] = (float)extra0[gr];
+                mt[MT + rr] = mw.y;
+                mt[2 * MT + rr] = mw.z;
+                mt[3 * MT + rr] = mw.w;
+                reinterpret_cast<float *>(slot + MT * 16)[rr] = delta[gr];
+                reinterpret_cast<float *>(slot + MT * 16 + BN * 4)[rr] = (float)extra0[gr];
             }
             mbar_arrive(qd_full(st));
         }
     } else if (warp == 9) {
-        constexpr uint32_t id_s = idesc_bf16(BM, BN, 0, 0);   // S^T = K Q^T, dP'^T = V dO'^T
-        constexpr uint32_t id_a = idesc_bf16(BM, D, 0, 1);    // dV += E^T dO', dK += dS^T Q (B MN-major)
+        // Sub-tiles t = 2 j + h of 32 query rows: scores of sub-tile t+1 are issued before the math warps have
+        // finished sub-tile t (two score buffers), the accumulating MMAs of t follow once its E^T / dS^T are written.
+        constexpr uint32_t id_s = idesc_bf16(BM, SUBN, 0, 0); // S^T = K Q^T, dP'^T = V dO'^T   (N = 32 query rows)
+        constexpr uint32_t id_a = idesc_bf16(BM, D, 0, 1);    // dV += E^T dO', dK += dS^T Q (B MN-major, K = 32)
         const uint64_t dk0 = desc_kmajor(s_k, 0), dv0 = desc_kmajor(s_v, 0), dq0 = desc_kmajor(s_q, 0),
                        ddy0 = desc_kmajor(s_dy, 0), dqt0 = desc_mnmajor(s_q, 0, T_SUB),
                        ddyt0 = desc_mnmajor(s_dy, 0, T_SUB);
-        mbar_wait(own_full, 0);
-        for (int j = 0; j < n_tiles; ++j) {
-            const int st = j % STAGES;
-            const uint64_t off = (uint64_t)(st * (T_BYTES >> 4));
-            mbar_wait(qd_full(st), (j / STAGES) & 1);
+        const int n_sub = 2 * n_tiles;
+        auto issue_scores = [&](int t) {
+            const int j = t >> 1, h = t & 1, st = j % STAGES;
+            if (h == 0) mbar_wait(qd_full(st), (j / STAGES) & 1);
             fence_after_sync();
             if (elect_one()) {
+                // rows 32 h .. 32 h + 31 of the stage's 64-row tiles: + 32 rows * 128 B inside every 64-wide sub-tile
+                const uint64_t off = (uint64_t)((st * T_BYTES + h * SUBN * 128) >> 4);
+                const uint32_t col = tmem_base + COL_SC + (t & 1) * 64;
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + COL_S, dk0 + kslice<OWN_SUB>(k), dq0 + off + kslice<T_SUB>(k), id_s, k != 0);
+                    umma_bf16(col, dk0 + kslice<OWN_SUB>(k), dq0 + off + kslice<T_SUB>(k), id_s, k != 0);
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + COL_DP, dv0 + kslice<OWN_SUB>(k), ddy0 + off + kslice<T_SUB>(k), id_s, k != 0);
-                umma_commit(sc_full);
+                    umma_bf16(col + 32, dv0 + kslice<OWN_SUB>(k), ddy0 + off + kslice<T_SUB>(k), id_s, k != 0);
+                umma_commit(sc_full(t & 1));
             }
             __syncwarp();
-            mbar_wait(p_full, j & 1);
+        };
+        mbar_wait(own_full, 0);
+        issue_scores(0);
+        for (int t = 0; t < n_sub; ++t) {
+            if (t + 1 < n_sub) issue_scores(t + 1);   // its buffer was last read by the accumulating MMAs of t - 1 (in order)
+            const int j = t >> 1, h = t & 1, st = j % STAGES;
+            mbar_wait(p_full(t & 1), (t >> 1) & 1);
             fence_after_sync();
             if (elect_one()) {
-                // query rows 16 k .. 16 k + 15 of the tile sit in columns 32 (k >> 1) + 8 (k & 1) .. + 7
+                const uint64_t off = (uint64_t)((st * T_BYTES) >> 4);
+                const uint32_t col = tmem_base + COL_SC + (t & 1) * 64;
+                // query rows 16 k .. 16 k + 15 of the sub-tile sit in columns 16 k .. 16 k + 7 (the writer's own half)
 #pragma unroll
-                for (int k = 0; k < BN / 16; ++k)
-                    umma_bf16_ts(tmem_base + COL_DV, tmem_base + COL_S + (k >> 1) * 32 + (k & 1) * 8,
-                                 ddyt0 + off + k * MNMAJOR_K16, id_a, (j | k) != 0);
+                for (int k = 0; k < SUBN / 16; ++k)
+                    umma_bf16_ts(tmem_base + COL_DV, col + k * 16, ddyt0 + off + (2 * h + k) * MNMAJOR_K16, id_a, (t | k) != 0);
 #pragma unroll
-                for (int k = 0; k < BN / 16; ++k)
-                    umma_bf16_ts(tmem_base + COL_DK, tmem_base + COL_DP + (k >> 1) * 32 + (k & 1) * 8,
-                                 dqt0 + off + k * MNMAJOR_K16, id_a, (j | k) != 0);
-                umma_commit(qd_empty(st));
-                if (j + 1 == n_tiles) umma_commit(acc_full);
+                for (int k = 0; k < SUBN / 16; ++k)
+                    umma_bf16_ts(tmem_base + COL_DK, col + 32 + k * 16, dqt0 + off + (2 * h + k) * MNMAJOR_K16, id_a, (t | k) != 0);
+                if (h == 1) umma_commit(qd_empty(st));
+                if (t + 1 == n_sub) umma_commit(acc_full);
             }
             __syncwarp();
         }
@@ -708,31 +726,29 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const bool key0 = (n0 + kk) == 0;
         const ClampK ck = make_clamp(scale_log2, clamp_log2);
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        for (int j = 0; j < n_tiles; ++j) {
-            const int st = j % STAGES;
+        for (int t = 0; t < 2 * n_tiles; ++t) {
+            const int j = t >> 1, h = t & 1, st = j % STAGES;
             const unsigned char *slot = rowq + st * ROWQ_BYTES;
-            const uint32_t *mrow = reinterpret_cast<const uint32_t *>(slot) + wsel * BN;   // this key's word of every row
-            const float *s_delta = reinterpret_cast<const float *>(slot + BN * 16);
+            const uint32_t *mrow = reinterpret_cast<const uint32_t *>(slot) + wsel * MT;   // this key's word of every row
+            const float *s_delta = reinterpret_cast<const float *>(slot + MT * 16);
             const float *s_ex0 = s_delta + BN;
-            mbar_wait(qd_full(st), (j / STAGES) & 1);   // the producer lanes' row data of this stage
-            mbar_wait(sc_full, j & 1);
+            if (h == 0) mbar_wait(qd_full(st), (j / STAGES) & 1);   // the producer lanes' row data of this stage
+            mbar_wait(sc_full(t & 1), (t >> 1) & 1);
             fence_after_sync();
-#pragma unroll
-            for (int c16 = 0; c16 < 2; ++c16) {
-                const int c0 = half * 32 + c16 * 16;          // first query row (tile column) of this chunk
-                uint32_t r[16], g[16];
-                tmem_ld16_nowait(lane_base + COL_S + c0, r);
-                tmem_ld16_nowait(lane_base + COL_DP + c0, g);
-                tmem_ld_wait();
-                uint32_t pe[8], pd[8];
-                if (key0) bwdkv_chunk16<true>(r, g, mrow, s_delta, s_ex0, c0, bitmask, ck, pe, pd);
-                else bwdkv_chunk16<false>(r, g, mrow, s_delta, s_ex0, c0, bitmask, ck, pe, pd);
-                tmem_st8(lane_base + COL_S + half * 32 + c16 * 8, pe);    // E^T over consumed S^T columns
-                tmem_st8(lane_base + COL_DP + half * 32 + c16 * 8, pd);   // dS^T over consumed dP'^T columns
-            }
+            const uint32_t col = lane_base + COL_SC + (t & 1) * 64 + half * 16;   // this thread's 16 query rows
+            const int c0 = h * SUBN + half * 16;                                   // ... = rows c0 .. c0 + 15 of the tile
+            uint32_t r[16], g[16];
+            tmem_ld16_nowait(col, r);
+            tmem_ld16_nowait(col + 32, g);
+            tmem_ld_wait();
+            uint32_t pe[8], pd[8];
+            if (key0) bwdkv_chunk16<true>(r, g, mrow, s_delta, s_ex0, c0, bitmask, ck, pe, pd);
+            else bwdkv_chunk16<false>(r, g, mrow, s_delta, s_ex0, c0, bitmask, ck, pe, pd);
+            tmem_st8(col, pe);         // E^T over the S^T columns this thread has consumed
+            tmem_st8(col + 32, pd);    // dS^T over its dP'^T columns
             tmem_st_wait();
             fence_before_sync();
-            mbar_arrive(p_full);
+            mbar_arrive(p_full(t & 1));
         }
         mbar_wait(acc_full, 0);
         fence_after_sync();
