@@ -227,7 +227,9 @@ int spt_group_colsum_bf16(const void *x, const int32_t *bucket_ptr, float *out, 
  * mode 0 (M-grouped; fc1, fc2, dH, dX): C[i, 0:N] = epi(A[i, :] . op(B_g)), i over 128-row tiles,
  *   g = tile_group[i / 128] (-1: skip).  B_g is addressed by the per-group coordinate offsets
  *   b_k_off (along K) and b_mn_off (along N), both multiplied by g.  A must be K-major.
- *   epi: + bias[g * bias_stride + n], activation (0 none, 1 relu, 2 silu), * row_scale[i].
+ *   epi: + bias[g * bias_stride + n], activation (0 none, 1 relu, 2 silu), * row_scale[i]; then, if `gate`
+ *   (bf16 [rows of C, N], leading dimension ldg) is given, the result is zeroed wherever gate <= 0 — the
+ *   ReLU backward mask applied to dH in the epilogue of the GEMM that produces it.
  * mode 1 (K-grouped; weight gradients): for every group g, C_g[0:M, 0:N] = A_g . B_g^T reduced over
  *   rows group_ptr[g] .. group_ptr[g+1] (multiples of 64); C_g origin = (g*c_row_off, g*c_col_off).
  * C is fp32 or bf16 with leading dimension ldc. */
@@ -237,7 +239,8 @@ int spt_grouped_gemm_bf16(int mode, const void *A, long long a_rows, long long a
                           const int32_t *group_ptr, int n_groups, int M, int N, int K, int a_k_off,
                           int a_mn_off, int b_k_off, int b_mn_off, long long c_row_off,
                           long long c_col_off, void *C, long long ldc, int c_dtype, const float *bias,
-                          int bias_stride, const float *row_scale, int act, spt_stream_t stream);
+                          int bias_stride, const float *row_scale, int act, const void *gate, long long ldg,
+                          spt_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -53,7 +53,7 @@ def _load() -> ctypes.CDLL:
     }
     ll = c.c_longlong
     sig["spt_grouped_gemm_bf16"] = (i32, [i32, vp, ll, ll, ll, i32, vp, ll, ll, ll, i32, vp, i32, vp, i32, i32, i32, i32,
-                                          i32, i32, i32, i32, ll, ll, vp, ll, i32, vp, i32, vp, i32, vp])
+                                          i32, i32, i32, i32, ll, ll, vp, ll, i32, vp, i32, vp, i32, vp, ll, vp])
     sig["spt_route_bucket_workspace_bytes"] = (sz, [i64, i32])
     sig["spt_route_bucket"] = (i32, [vp] * 8 + [i64, i32, i32, i64, vp])
     sig["spt_gather_rows_bf16"] = (i32, [vp, vp, vp, i64, i32, vp])

@@ -30,11 +30,16 @@
 namespace spt {
 namespace gemm {
 
-constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16, STAGES = 3;
+// 128 x 256 output tiles: per 64-deep k-block a CTA pulls 16 KB of A and 32 KB of B through L2 for 4.2 MFLOP
+// (85 flop/B; 128 x 128 tiles give 64 flop/B and were measured L2-bandwidth bound, profiles/README.md).
+// Two CTAs per SM (2 x 256 TMEM columns, 2 x 96 KB shared memory): one tile's epilogue runs under the
+// other's main loop, and the two 2-stage rings keep 4 k-blocks in flight per SM.
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 2;
 constexpr int THREADS = 192;
-constexpr int TILE_BYTES = BM * BK * 2;                 // 16 KB per operand per stage
-constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 128;
+constexpr int A_TILE_BYTES = BM * BK * 2;               // 16 KB
+constexpr int B_TILE_BYTES = BN * BK * 2;               // 32 KB
+constexpr int SMEM_BYTES = STAGES * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 256;
 
 struct Params {
     int mode;                      // 0 = M-grouped, 1 = K-grouped
@@ -53,6 +58,8 @@ struct Params {
     int bias_stride;
     const float *row_scale;        // optional, one factor per C row (mode 0)
     int act;                       // 0 none, 1 relu, 2 silu
+    const __nv_bfloat16 *gate;     // optional (mode 0): zero C where gate <= 0, gate[row * ldg + col]
+    long long ldg;
 };
 
 using namespace spt::tc;
@@ -79,8 +86,8 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023) & ~1023u;                 // 128B swizzle needs 1024-byte alignment
     unsigned char *smem = smem_raw + (base - raw);
-    const uint32_t s_a = base, s_b = base + STAGES * TILE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * 2 * TILE_BYTES);
+    const uint32_t s_a = base, s_b = base + STAGES * A_TILE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * (A_TILE_BYTES + B_TILE_BYTES));
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + s * 8; };
     auto empty_bar = [&](int s) { return bar0 + (STAGES + s) * 8; };
@@ -147,20 +154,21 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1);
-                mbar_expect_tx(full_bar(s), 2 * TILE_BYTES);
+                mbar_expect_tx(full_bar(s), A_TILE_BYTES + B_TILE_BYTES);
                 const int k0 = k_begin + kb * BK;
-                const uint32_t da = s_a + s * TILE_BYTES, db = s_b + s * TILE_BYTES;
-                if (p.a_mn_major) {   // tensor map dims: (mn contiguous, k rows); two 64-wide halves
-                    tma_load_2d(da, &map_a, full_bar(s), a_mn, a_k + k0);
-                    tma_load_2d(da + TILE_BYTES / 2, &map_a, full_bar(s), a_mn + 64, a_k + k0);
+                const uint32_t da = s_a + s * A_TILE_BYTES, db = s_b + s * B_TILE_BYTES;
+                if (p.a_mn_major) {   // tensor map dims: (mn contiguous, k rows); 64-wide chunks of 8 KB
+#pragma unroll
+                    for (int h = 0; h < BM / 64; ++h) tma_load_2d(da + h * 8192, &map_a, full_bar(s), a_mn + 64 * h, a_k + k0);
                 } else {              // tensor map dims: (k contiguous, mn rows)
                     tma_load_2d(da, &map_a, full_bar(s), a_k + k0, a_mn);
                 }
                 if (p.b_mn_major) {
-                    tma_load_2d(db, &map_b, full_bar(s), b_mn, b_k + k0);
-                    tma_load_2d(db + TILE_BYTES / 2, &map_b, full_bar(s), b_mn + 64, b_k + k0);
-                } else {
+#pragma unroll
+                    for (int h = 0; h < BN / 64; ++h) tma_load_2d(db + h * 8192, &map_b, full_bar(s), b_mn + 64 * h, b_k + k0);
+                } else {              // two boxes of 128 rows
                     tma_load_2d(db, &map_b, full_bar(s), b_k + k0, b_mn);
+                    tma_load_2d(db + B_TILE_BYTES / 2, &map_b, full_bar(s), b_k + k0, b_mn + 128);
                 }
             }
         }
@@ -179,8 +187,8 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
-                    umma_bf16(tmem_base, operand_desc(s_a + s * TILE_BYTES, p.a_mn_major, k),
-                              operand_desc(s_b + s * TILE_BYTES, p.b_mn_major, k), idesc, (kb | k) != 0);
+                    umma_bf16(tmem_base, operand_desc(s_a + s * A_TILE_BYTES, p.a_mn_major, k),
+                              operand_desc(s_b + s * B_TILE_BYTES, p.b_mn_major, k), idesc, (kb | k) != 0);
                 }
                 umma_commit(empty_bar(s));                      // frees the smem stage when the MMAs retire
             }
@@ -212,6 +220,12 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 float x = __uint_as_float(r[i]);
                 if (p.bias) x += (c0 + i < n_valid) ? p.bias[(long long)g * p.bias_stride + n0 + c0 + i] : 0.0f;
                 v[i] = apply_act(x, p.act) * rs;
+            }
+            if (p.gate) {   // ReLU backward mask of the tensor this GEMM differentiates through
+                const __nv_bfloat16 *gp = p.gate + c_row * p.ldg + c_col0 + c0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c0 + i < n_valid && !(__bfloat162float(gp[i]) > 0.0f)) v[i] = 0.0f;
             }
             const bool full = c0 + 32 <= n_valid;
             if (p.c_dtype == SPT_BF16) {
@@ -274,7 +288,8 @@ extern "C" int spt_grouped_gemm_bf16(int mode, const void *A, long long a_rows, 
                                      const int32_t *group_ptr, int n_groups, int M, int N, int K, int a_k_off,
                                      int a_mn_off, int b_k_off, int b_mn_off, long long c_row_off, long long c_col_off,
                                      void *C, long long ldc, int c_dtype, const float *bias, int bias_stride,
-                                     const float *row_scale, int act, spt_stream_t stream) {
+                                     const float *row_scale, int act, const void *gate, long long ldg,
+                                     spt_stream_t stream) {
     SPT_REQUIRE(A && B && C, "grouped_gemm: null pointer");
     SPT_REQUIRE(mode == 0 || mode == 1, "grouped_gemm: bad mode %d", mode);
     SPT_REQUIRE(mode == 1 || (tile_group && n_m_tiles >= 1 && K >= 1 && !a_mn_major),
@@ -295,6 +310,8 @@ extern "C" int spt_grouped_gemm_bf16(int mode, const void *A, long long a_rows, 
     p.a_k_off = a_k_off; p.a_mn_off = a_mn_off; p.b_k_off = b_k_off; p.b_mn_off = b_mn_off;
     p.c_row_off = c_row_off; p.c_col_off = c_col_off; p.C = C; p.ldc = ldc; p.c_dtype = c_dtype;
     p.bias = bias; p.bias_stride = bias_stride; p.row_scale = row_scale; p.act = act;
+    p.gate = (const __nv_bfloat16 *)gate; p.ldg = ldg;
+    SPT_REQUIRE(!gate || mode == 0, "grouped_gemm: gate is a mode-0 epilogue");
     dim3 grid;
     if (mode == 0) grid = dim3(n_m_tiles, (N + gemm::BN - 1) / gemm::BN, 1);
     else grid = dim3((M + gemm::BM - 1) / gemm::BM, (N + gemm::BN - 1) / gemm::BN, n_groups);

@@ -430,7 +430,7 @@ def grouped_gemm(mode: int, A: torch.Tensor, a_mn_major: bool, B: torch.Tensor, 
                  tile_group=None, group_ptr=None, M: int = 0, N: int, K: int = 0,
                  a_k_off: int = 0, a_mn_off: int = 0, b_k_off: int = 0, b_mn_off: int = 0,
                  c_row_off: int = 0, c_col_off: int = 0, out: torch.Tensor, bias=None, bias_stride: int = 0,
-                 row_scale=None, act: int = 0) -> torch.Tensor:
+                 row_scale=None, act: int = 0, gate=None) -> torch.Tensor:
     """Thin binding of spt_grouped_gemm_bf16 (see include/spt_b200.h).  A, B: 2-D bf16 tensors as
     stored (row-major, possibly with a row stride); `out`: 2-D fp32/bf16 tensor written in place."""
     for name, t in (("A", A), ("B", B)):
@@ -445,7 +445,7 @@ def grouped_gemm(mode: int, A: torch.Tensor, a_mn_major: bool, B: torch.Tensor, 
             mode, _p(A), A.size(0), A.size(1), A.stride(0), int(a_mn_major), _p(B), B.size(0), B.size(1), B.stride(0),
             int(b_mn_major), _p(tile_group), n_m_tiles, _p(group_ptr), n_groups, M, N, K, a_k_off, a_mn_off, b_k_off,
             b_mn_off, c_row_off, c_col_off, _p(out), out.stride(0), _DTYPES[out.dtype], _p(bias), bias_stride,
-            _p(row_scale), act, _stream(A)))
+            _p(row_scale), act, _p(gate), 0 if gate is None else gate.stride(0), _stream(A)))
     return out
 
 

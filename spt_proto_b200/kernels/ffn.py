@@ -48,7 +48,7 @@ class BlockedLinearRows(autograd.Function):
     W [F, K] (fc1 / gate / side layout).  act in {none, relu}; other activations are applied by the caller."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, bucket, bs, act, out_dtype):
+    def forward(ctx, x, weight, bias, bucket, bs, act, out_dtype, grad_premasked=False):
         w16 = weight if weight.dtype == torch.bfloat16 else weight.to(torch.bfloat16)
         y = torch.empty(x.size(0), bs, dtype=out_dtype, device=x.device)
         b32 = None if bias is None else bias.float().contiguous()
@@ -56,6 +56,7 @@ class BlockedLinearRows(autograd.Function):
                          out=y, bias=b32, bias_stride=bs, act=act)
         ctx.save_for_backward(x, w16, y if act == ACT_RELU else None)
         ctx.bucket, ctx.bs, ctx.act = bucket, bs, act
+        ctx.grad_premasked = grad_premasked   # the consumer's backward already applied the ReLU mask (fused epilogue)
         ctx.w_dtype, ctx.w_shape = weight.dtype, weight.shape
         ctx.b_dtype = None if bias is None else bias.dtype
         return y
@@ -65,7 +66,7 @@ class BlockedLinearRows(autograd.Function):
         x, w16, y = ctx.saved_tensors
         b, bs = ctx.bucket, ctx.bs
         grad = grad.contiguous()
-        if ctx.act == ACT_RELU:
+        if ctx.act == ACT_RELU and not ctx.grad_premasked:
             grad = grad * (y > 0)
         if grad.dtype != torch.bfloat16:
             grad = grad.to(torch.bfloat16)
@@ -79,14 +80,15 @@ class BlockedLinearRows(autograd.Function):
             dw = dw32.to(ctx.w_dtype)
         if ctx.b_dtype is not None and ctx.needs_input_grad[2]:
             db = ext.group_colsum(grad, b.bucket_ptr).reshape(-1).to(ctx.b_dtype)
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 class BlockedLinearCols(autograd.Function):
     """y[i, :] = (x[i, :] @ W[:, g*bs:(g+1)*bs].T) * row_scale[i],  W [d, F] (fc2 / down layout)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bucket, bs):
+    def forward(ctx, x, weight, bucket, bs, relu_input=False):
+        ctx.relu_input = relu_input   # x is a ReLU output used only here: mask dx by (x > 0) in the GEMM epilogue
         w16 = weight if weight.dtype == torch.bfloat16 else weight.to(torch.bfloat16)
         d = weight.size(0)
         y = torch.empty(x.size(0), d, dtype=torch.bfloat16, device=x.device)
@@ -104,13 +106,13 @@ class BlockedLinearCols(autograd.Function):
         if ctx.needs_input_grad[0]:   # dx[i, f] = sum_n grad[i, n] W[n, g*bs + f] : W MN-major, N offset g*bs
             dx = torch.empty_like(x)
             ext.grouped_gemm(0, grad, False, w16, True, tile_group=b.tile_group, N=bs, K=grad.size(1), b_mn_off=bs,
-                             out=dx)
+                             out=dx, gate=x if ctx.relu_input else None)
         if ctx.needs_input_grad[1]:   # dW[:, g*bs:(g+1)*bs] = grad_g^T x_g
             dw32 = torch.empty(ctx.w_shape, dtype=torch.float32, device=x.device)
             ext.grouped_gemm(1, grad, True, x, True, group_ptr=b.bucket_ptr, M=grad.size(1), N=bs, c_col_off=bs,
                              out=dw32)
             dw = dw32.to(ctx.w_dtype)
-        return dx, dw, None, None
+        return dx, dw, None, None, None
 
 
 def gather(x, bucket):
@@ -121,14 +123,16 @@ def combine(partial, bucket, bias, out_dtype):
     return CombineRows.apply(partial, bucket, bias, out_dtype)
 
 
-def blocked_linear_rows(x, weight, bias, bucket, bs, act=ACT_NONE, out_dtype=torch.bfloat16):
+def blocked_linear_rows(x, weight, bias, bucket, bs, act=ACT_NONE, out_dtype=torch.bfloat16, grad_premasked=False):
     """out_dtype=torch.float32 keeps the fp32 accumulator (used where the result feeds an activation gate
-    after further additions, so that gates are decided in fp32 like in the reference)."""
-    return BlockedLinearRows.apply(x, weight, bias, bucket, bs, act, out_dtype)
+    after further additions, so that gates are decided in fp32 like in the reference).
+    grad_premasked: with act=relu, the incoming gradient already carries the (y > 0) mask — set together
+    with blocked_linear_cols(relu_input=True) when y feeds that product and nothing else."""
+    return BlockedLinearRows.apply(x, weight, bias, bucket, bs, act, out_dtype, grad_premasked)
 
 
-def blocked_linear_cols(x, weight, bucket, bs):
-    return BlockedLinearCols.apply(x, weight, bucket, bs)
+def blocked_linear_cols(x, weight, bucket, bs, relu_input=False):
+    return BlockedLinearCols.apply(x, weight, bucket, bs, relu_input)
 
 
 class BlockedLinearColsT(autograd.Function):

@@ -57,11 +57,12 @@ class RoutedFFN(Feedforward):
         _, bucket = _route(self.router, x2, self.k_active)
         xp = F.gather(x2.to(torch.bfloat16).contiguous(), bucket)
         relu = isinstance(self.activation, nn.ReLU)
+        # ReLU: applied in the fc1 epilogue, its backward mask in the epilogue of the GEMM that produces dH
         h = F.blocked_linear_rows(xp, self.fc1.weight, self.fc1.bias, bucket, self.block_size,
-                                  act=F.ACT_RELU if relu else F.ACT_NONE)
+                                  act=F.ACT_RELU if relu else F.ACT_NONE, grad_premasked=relu)
         if not relu:
             h = self.activation(h)
-        yp = F.blocked_linear_cols(h, self.fc2.weight, bucket, self.block_size)
+        yp = F.blocked_linear_cols(h, self.fc2.weight, bucket, self.block_size, relu_input=relu)
         y = F.combine(yp, bucket, self.fc2.bias, x.dtype)
         return y.view(x_size)
 
