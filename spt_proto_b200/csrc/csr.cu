@@ -248,12 +248,12 @@ softmax_bwd_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
 // ---- CSR -> CSC ----------------------------------------------------------------------------------
 // Deterministic, stable counting sort by column, tiled over rows:
 //   K1  per (tile of TR rows, batch): shared-memory histogram of the tile's columns -> tile_cnt[b][tile][c]
-//   K2  per batch: exclusive scan over tiles for every column, then exclusive scan over columns ->
-//       col_ptr[b][c]; tile_cnt becomes the start offset of (tile, column)
-//   K3  one warp per (tile, batch): walks the tile's rows in order, 32 entries at a time; equal
-//       columns inside a chunk are ranked by lane with __match_any_sync, so the result does not
-//       depend on scheduling.
-constexpr int C2C_TR = 32;
+//   K2  exclusive scan over tiles for every (batch, column) in parallel (tile_cnt becomes the start offset
+//       of (tile, column)), then a per-batch exclusive scan over the column totals -> col_ptr[b][c]
+//   K3  placement: staged through shared memory (csr2csc_place_staged_kernel below) when it fits, else
+//       one warp per (tile, batch) walking the tile's rows in order, 32 entries at a time, equal columns
+//       ranked by lane with __match_any_sync.  Either way the result does not depend on scheduling.
+constexpr int C2C_TR = 64;
 
 __global__ void __launch_bounds__(256)
 csr2csc_count_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
@@ -272,58 +272,6 @@ csr2csc_count_kernel(const int32_t *__restrict__ indptr, const int32_t *__restri
     __syncthreads();
     int32_t *out = tile_cnt + ((size_t)b * n_tiles + tile) * S;
     for (int c = threadIdx.x; c < S; c += blockDim.x) out[c] = s_cnt[c];
-}
-
-__global__ void __launch_bounds__(1024)
-csr2csc_scan_kernel(int32_t *__restrict__ tile_cnt, int32_t *__restrict__ col_ptr, int S, int n_tiles) {
-    extern __shared__ int32_t s_tot[];  // [S] column totals, then their exclusive scan
-    __shared__ int32_t s_warp[32];
-    __shared__ int32_t s_carry;
-    const int b = blockIdx.x;
-    int32_t *tc = tile_cnt + (size_t)b * n_tiles * S;
-    for (int c = threadIdx.x; c < S; c += blockDim.x) {
-        int32_t run = 0;
-        for (int t = 0; t < n_tiles; ++t) {
-            const int32_t v = tc[(size_t)t * S + c];
-            tc[(size_t)t * S + c] = run;
-            run += v;
-        }
-        s_tot[c] = run;
-    }
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    // block-wide exclusive scan of s_tot in slabs of blockDim.x
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int base = 0; base < S; base += blockDim.x) {
-        const int c = base + threadIdx.x;
-        const int32_t v = c < S ? s_tot[c] : 0;
-        int32_t inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int32_t n = __shfl_up_sync(FULL, inc, o);
-            if (lane >= o) inc += n;
-        }
-        if (lane == 31) s_warp[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            int32_t w = lane < nw ? s_warp[lane] : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int32_t n = __shfl_up_sync(FULL, w, o);
-                if (lane >= o) w += n;
-            }
-            s_warp[lane] = w;  // inclusive
-        }
-        __syncthreads();
-        const int32_t carry = s_carry;
-        const int32_t warp_off = wid > 0 ? s_warp[wid - 1] : 0;
-        if (c < S) s_tot[c] = carry + warp_off + inc - v;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = carry + s_warp[nw - 1];
-        __syncthreads();
-    }
-    for (int c = threadIdx.x; c < S; c += blockDim.x) col_ptr[(size_t)b * (S + 1) + c] = s_tot[c];
-    if (threadIdx.x == 0) col_ptr[(size_t)b * (S + 1) + S] = s_carry;
 }
 
 __global__ void csr2csc_place_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
@@ -364,6 +312,267 @@ __global__ void csr2csc_place_kernel(const int32_t *__restrict__ indptr, const i
             }
             __syncwarp();
         }
+    }
+}
+
+// Parallel first half of the scan: one thread per (batch, column) turns the tile counts into exclusive
+// tile offsets and leaves the column total in col_tot[b][c] (grid (ceil(S/256), B)); the per-batch
+// exclusive scan over columns (csr2csc_colscan_kernel) then gives col_ptr.
+__global__ void __launch_bounds__(256)
+csr2csc_tilescan_kernel(int32_t *__restrict__ tile_cnt, int32_t *__restrict__ col_tot, int S, int n_tiles) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (c >= S) return;
+    int32_t *tc = tile_cnt + (size_t)b * n_tiles * S + c;
+    int32_t run = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+        const int32_t v = tc[(size_t)t * S];
+        tc[(size_t)t * S] = run;
+        run += v;
+    }
+    col_tot[(size_t)b * (S + 1) + c] = run;
+}
+
+// block-wide exclusive scan of n int32 values in shared memory (in place); returns the total
+__device__ __forceinline__ int32_t block_exclusive_scan(int32_t *vals, int n, int32_t *s_warp, int32_t *s_carry) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) *s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int c = base + threadIdx.x;
+        const int32_t v = c < n ? vals[c] : 0;
+        int32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int32_t w = lane < nw ? s_warp[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t t = __shfl_up_sync(FULL, w, o);
+                if (lane >= o) w += t;
+            }
+            s_warp[lane] = w;  // inclusive
+        }
+        __syncthreads();
+        const int32_t carry = *s_carry;
+        const int32_t warp_off = wid > 0 ? s_warp[wid - 1] : 0;
+        if (c < n) vals[c] = carry + warp_off + inc - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) *s_carry = carry + s_warp[nw - 1];
+        __syncthreads();
+    }
+    return *s_carry;
+}
+
+__global__ void __launch_bounds__(1024)
+csr2csc_colscan_kernel(int32_t *__restrict__ col_ptr, int S) {
+    extern __shared__ int32_t s_tot[];
+    __shared__ int32_t s_warp[32];
+    __shared__ int32_t s_carry;
+    int32_t *cp = col_ptr + (size_t)blockIdx.x * (S + 1);
+    for (int c = threadIdx.x; c < S; c += blockDim.x) s_tot[c] = cp[c];
+    __syncthreads();
+    const int32_t total = block_exclusive_scan(s_tot, S, s_warp, &s_carry);
+    for (int c = threadIdx.x; c < S; c += blockDim.x) cp[c] = s_tot[c];
+    if (threadIdx.x == 0) cp[S] = total;
+}
+
+// Staged placement.  A block owns one tile of C2C_TR rows; the tile's entries are consumed in chunks of
+// CAP entries.  Inside a chunk the 8 warps own 8 consecutive entry ranges (so (warp, position) order =
+// entry order = row-major order: the sort is stable) and place (row, entry, column) into shared-memory
+// arrays sorted by column; the block then writes the sorted chunk out, consecutive threads to consecutive
+// addresses of a column's run — instead of the two scattered 4-byte stores per entry of a direct
+// placement.  Counting uses shared-memory atomics (order-free).  Placement takes its slot from an atomic
+// cursor when the 32 columns of a warp instruction are all different (checked through a tag array: the
+// common case, every key of a row is distinct), and ranks equal columns by lane with __match_any_sync
+// otherwise (zero padding runs) — so the result never depends on scheduling.  Deterministic.
+constexpr int C2C_WARPS = 8;
+
+__global__ void __launch_bounds__(C2C_WARPS * 32)
+csr2csc_place_staged_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                            const int32_t *__restrict__ tile_cnt, const int32_t *__restrict__ col_ptr,
+                            int32_t *__restrict__ row_idx, int32_t *__restrict__ perm, int S, int64_t nnz,
+                            int n_tiles, int CAP) {
+    extern __shared__ __align__(16) unsigned char c2c_smem[];
+    __shared__ int32_t s_warp[32];
+    __shared__ int32_t s_carry;
+    __shared__ int32_t s_indptr[C2C_TR + 1];
+    int32_t *s_goff = reinterpret_cast<int32_t *>(c2c_smem);                 // [S] next global slot of column c
+    int32_t *s_lstart = s_goff + S;                                          // [S] chunk-local start of column c
+    int32_t *s_perm = s_lstart + S;                                          // [CAP]
+    int32_t *s_cur = s_perm + CAP;                                           // [8][S] per-warp counts -> cursors
+    uint16_t *s_col = reinterpret_cast<uint16_t *>(s_cur + (size_t)C2C_WARPS * S);   // [CAP]
+    uint8_t *s_row = reinterpret_cast<uint8_t *>(s_col + CAP);               // [CAP]
+    uint8_t *s_tag = s_row + CAP;                                            // [8][S] last lane that touched column c
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tile = blockIdx.x, b = blockIdx.y;
+    const int r0 = tile * C2C_TR, r1 = min(S, r0 + C2C_TR);
+    const int32_t *tc = tile_cnt + ((size_t)b * n_tiles + tile) * S;
+    const int32_t *cp = col_ptr + (size_t)b * (S + 1);
+    const int32_t *ip = indices + (size_t)b * nnz;
+    int32_t *ro = row_idx + (size_t)b * nnz, *po = perm + (size_t)b * nnz;
+    for (int c = threadIdx.x; c < S; c += blockDim.x) s_goff[c] = cp[c] + tc[c];
+    for (int i = threadIdx.x; i <= r1 - r0; i += blockDim.x) s_indptr[i] = indptr[r0 + i];
+    __syncthreads();
+    const int e_begin = s_indptr[0], e_end = s_indptr[r1 - r0];
+    int32_t *cur = s_cur + (size_t)wid * S;
+    uint8_t *tag = s_tag + (size_t)wid * S;
+    for (int cb = e_begin; cb < e_end; cb += CAP) {
+        const int ce = min(e_end, cb + CAP);
+        const int per_warp = ((ce - cb + C2C_WARPS * 32 - 1) / (C2C_WARPS * 32)) * 32;   // multiple of 32
+        const int w0 = cb + wid * per_warp, w1 = min(ce, w0 + per_warp);
+        for (int i = threadIdx.x; i < C2C_WARPS * S; i += blockDim.x) s_cur[i] = 0;
+        __syncthreads();
+        // pass 1: per-warp column counts of its entry range
+        for (int e = w0 + lane; e < w1; e += 32) {
+            const int c = ip[e];
+            if ((unsigned)c < (unsigned)S) atomicAdd(&cur[c], 1);
+        }
+        __syncthreads();
+        // exclusive prefix over the warps for every column, column totals -> local starts
+        for (int c = threadIdx.x; c < S; c += blockDim.x) {
+            int run = 0;
+#pragma unroll
+            for (int w = 0; w < C2C_WARPS; ++w) {
+                const int v = s_cur[(size_t)w * S + c];
+                s_cur[(size_t)w * S + c] = run;
+                run += v;
+            }
+            s_lstart[c] = run;
+        }
+        __syncthreads();
+        const int placed = block_exclusive_scan(s_lstart, S, s_warp, &s_carry);
+        // pass 2: placement into the sorted shared-memory chunk
+        for (int base = w0; base < w1; base += 32) {
+            const int e = base + lane;
+            const int c = e < w1 ? ip[e] : -1;
+            const bool ok = (unsigned)c < (unsigned)S;
+            if (ok) tag[c] = (uint8_t)lane;
+            __syncwarp();
+            const bool dup = ok && tag[c] != (uint8_t)lane;        // another lane of this instruction has my column
+            int slot = 0;
+            if (__any_sync(FULL, dup)) {
+                const unsigned active = __ballot_sync(FULL, ok);
+                if (ok) {
+                    const unsigned same = __match_any_sync(active, c);
+                    const int leader = __ffs(same) - 1;
+                    int start = 0;
+                    if (lane == leader) {
+                        start = cur[c];
+                        cur[c] = start + __popc(same);
+                    }
+                    slot = __shfl_sync(same, start, leader) + __popc(same & ((1u << lane) - 1u));
+                }
+            } else if (ok) {
+                slot = atomicAdd(&cur[c], 1);
+            }
+            if (ok) {
+                const int pos = s_lstart[c] + slot;
+                int lo = 0, hi = r1 - r0;                  // row of entry e: last i with s_indptr[i] <= e
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_indptr[mid] <= e) lo = mid; else hi = mid;
+                }
+                s_perm[pos] = e;
+                s_col[pos] = (uint16_t)c;
+                s_row[pos] = (uint8_t)lo;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // write-out: entry i of the sorted chunk goes to its column's run in the global CSC
+        for (int i = threadIdx.x; i < placed; i += blockDim.x) {
+            const int c = s_col[i];
+            const int g = s_goff[c] + (i - s_lstart[c]);
+            ro[g] = r0 + s_row[i];
+            po[g] = s_perm[i];
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < S; c += blockDim.x) {
+            const int next = c + 1 < S ? s_lstart[c + 1] : placed;
+            s_goff[c] += next - s_lstart[c];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- transposed spmm through the CSC, one BLOCK per output column -----------------------------------
+// Column lengths are very uneven (column 0 collects every row's zero padding: tens of thousands of entries
+// against ~S/8 for a typical column), so a warp per column leaves the whole launch waiting for a few
+// warps.  Here the 8 warps of a block split the column's entries into contiguous ranges, and their
+// partial sums are added in warp order through shared memory: balanced and deterministic.
+template <typename T, typename TO, int L>
+__global__ void __launch_bounds__(CSR_WARPS * 32)
+spmm_t_block_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ row_idx,
+                    const int32_t *__restrict__ perm, const float *__restrict__ values, const T *__restrict__ x,
+                    TO *__restrict__ y, int B, int S, int d, int64_t nnz) {
+    constexpr int VEC = Vec16<T>::N;
+    constexpr int G = 32 / L;
+    __shared__ float s_part[CSR_WARPS][L * VEC];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.x / S, c = blockIdx.x % S;
+    const int sub = lane % L, grp = lane / L;
+    const bool has = sub * VEC < d;
+    const int32_t *pp = col_ptr + (size_t)b * (S + 1);
+    const int c0 = pp[c], c1 = pp[c + 1];
+    const int per_warp = ((c1 - c0 + CSR_WARPS * 32 - 1) / (CSR_WARPS * 32)) * 32;
+    const int e0 = c0 + wid * per_warp, e1 = min(c1, e0 + per_warp);
+    const int32_t *ip = row_idx + (size_t)b * nnz;
+    const int32_t *pm = perm + (size_t)b * nnz;
+    const float *vp = values + (size_t)b * nnz;
+    const T *xb = x + (size_t)b * S * d;
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.0f;
+    for (int base = e0; base < e1; base += 32) {
+        const int e = base + lane;
+        int my_idx = 0;
+        float my_val = 0.0f;
+        if (e < e1) {
+            my_idx = ip[e];
+            my_val = vp[pm[e]];
+        }
+        const int cnt = min(32, e1 - base);
+#pragma unroll
+        for (int st = 0; st < L; ++st) {
+            if (st * G >= cnt) break;  // warp-uniform
+            const int src = st * G + grp;
+            const int row = __shfl_sync(FULL, my_idx, src);
+            const float w = __shfl_sync(FULL, my_val, src);  // 0 for padding lanes
+            if (has) {
+                float xv[VEC];
+                Vec16<T>::load(xb + (size_t)row * d + sub * VEC, xv);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w, xv[i], acc[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+#pragma unroll
+        for (int o = L; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
+    }
+    if (grp == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) s_part[wid][sub * VEC + i] = acc[i];
+    }
+    __syncthreads();
+    if (wid == 0 && grp == 0 && has) {
+        float out[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < CSR_WARPS; ++w) t += s_part[w][sub * VEC + i];
+            out[i] = t;
+        }
+        TO *yp = y + ((size_t)b * S + c) * d + sub * VEC;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) yp[i] = from_f32<TO>(out[i]);
     }
 }
 
@@ -414,7 +623,11 @@ static int launch_spmm(const int32_t *ptr, const int32_t *src_idx, const int32_t
     }
 #define SPT_SPMM_CASE(LL)                                                                                        \
     case LL:                                                                                                     \
-        spmm_kernel<T, TO, LL, TRANS><<<grid, CSR_WARPS * 32, 0, st>>>(ptr, src_idx, perm, values, x, y, B, S, d, nnz); \
+        if (TRANS && rows < ((int64_t)1 << 31))                                                                  \
+            spmm_t_block_kernel<T, TO, LL><<<(unsigned)rows, CSR_WARPS * 32, 0, st>>>(ptr, src_idx, perm, values, x, y, \
+                                                                                      B, S, d, nnz);            \
+        else                                                                                                     \
+            spmm_kernel<T, TO, LL, TRANS><<<grid, CSR_WARPS * 32, 0, st>>>(ptr, src_idx, perm, values, x, y, B, S, d, nnz); \
         break;
     switch (lanes_for(d, VEC)) {
         SPT_SPMM_CASE(1)
@@ -528,12 +741,25 @@ extern "C" int spt_csr2csc(const int32_t *indptr, const int32_t *indices, int32_
     const size_t smem_s = (size_t)S * 4;
     if (smem_s > 48 * 1024) {
         cudaFuncSetAttribute(csr2csc_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
-        cudaFuncSetAttribute(csr2csc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+        cudaFuncSetAttribute(csr2csc_colscan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
     }
     csr2csc_count_kernel<<<dim3(n_tiles, B), 256, smem_s, st>>>(indptr, indices, tile_cnt, S, nnz, n_tiles);
     SPT_LAUNCH_CHECK("csr2csc_count_kernel");
-    csr2csc_scan_kernel<<<B, 1024, smem_s, st>>>(tile_cnt, col_ptr, S, n_tiles);
-    SPT_LAUNCH_CHECK("csr2csc_scan_kernel");
+    csr2csc_tilescan_kernel<<<dim3((S + 255) / 256, B), 256, 0, st>>>(tile_cnt, col_ptr, S, n_tiles);
+    SPT_LAUNCH_CHECK("csr2csc_tilescan_kernel");
+    csr2csc_colscan_kernel<<<B, 1024, smem_s, st>>>(col_ptr, S);
+    SPT_LAUNCH_CHECK("csr2csc_colscan_kernel");
+    // staged placement when its shared-memory arrays fit (S <= 2048 with 16384-entry chunks, S <= 4096 with 4096)
+    const int cap = S <= 2048 ? 16384 : 4096;
+    const size_t smem_st = (size_t)S * 8 + (size_t)cap * 4 + (size_t)C2C_WARPS * S * 4 + (size_t)cap * 2 + (size_t)cap +
+                           (size_t)C2C_WARPS * S;
+    if (smem_st <= 220 * 1024) {
+        cudaFuncSetAttribute(csr2csc_place_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st);
+        csr2csc_place_staged_kernel<<<dim3(n_tiles, B), C2C_WARPS * 32, smem_st, st>>>(indptr, indices, tile_cnt, col_ptr,
+                                                                                      row_idx, perm, S, nnz, n_tiles, cap);
+        SPT_LAUNCH_CHECK("csr2csc_place_staged_kernel");
+        return SPT_OK;
+    }
     const int nw = c2c_warps_per_block(S);
     const size_t smem_p = smem_s * nw;
     if (smem_p > 48 * 1024)
