@@ -53,6 +53,16 @@ def _peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def _traffic():
+    """DRAM bytes per launch of the top kernels at the bench shape, read from a committed `ncu --set full`
+    capture (profiles/r1_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum)."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
 # ---------------------------------------------------------------------------------------------------
 # clocks sampling (B200_PROFILING.md: sample nvidia-smi DURING the timed region)
 # ---------------------------------------------------------------------------------------------------
@@ -292,12 +302,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+    # clocks are sampled (nvidia-smi, 100 ms period) from the warm-up to the end of the e2e loop: the timed
+    # region itself lasts only K x ~1 ms, less than one sampling period for small K
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
     launches0 = ext.launch_count()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -307,7 +319,6 @@ def run_ours(args):
     barrier()
     elapsed = a.elapsed_time(b) * 1e-3
     launches = ext.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host (pinned) buffers in, host buffers out, through the public layer API ---------------
     hq, hk, hv, hdy = (t.detach().cpu().pin_memory() for t in (q, k, v, dy))
@@ -330,6 +341,7 @@ def run_ours(args):
     b2.record()
     barrier()
     elapsed_e2e = a2.elapsed_time(b2) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
         t = torch.tensor([elapsed, elapsed_e2e], device=dev, dtype=torch.float64)
@@ -349,8 +361,13 @@ def run_ours(args):
             roof = {"bound": "tensor", "kernel": dom, "achieved": stages[dom]["achieved_TFLOPs"],
                     "peak": tensor_tflops, "unit": "TFLOP/s", "frac": stages[dom]["frac_tensor"], "traffic": None,
                     "peak_source": peak_kind,
-                    "note": "executed dense-causal-tile MMA flops (the kernel computes masked dense tiles); "
-                            "the selected-pair (algorithmic sparse) flops are 1/4 of these"}
+                    "note": "executed dense-causal-tile MMA flops (the kernels compute masked dense tiles; the selected-"
+                            "pair flops are 1/4 of these).  The kernels are bound by the exp/mask math of the score "
+                            "tile (XU + FMA pipes), not by the tensor pipe: see DESIGN.md section 4"}
+            traffic = _traffic().get(dom)
+            if traffic is not None:
+                roof["traffic"] = traffic["dram_bytes_per_launch"]
+                roof["traffic_source"] = traffic["source"]
         else:
             roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_GBps"], "peak": hbm_gbs,
                     "unit": "GB/s", "frac": stages[dom]["frac_hbm"], "traffic": None, "peak_source": peak_kind}
@@ -368,8 +385,8 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "seqs_per_gpu": n_seq, "global_tokens_per_step": tokens_per_step,
                        "l2": "inputs+intermediates per step exceed L2 (>1 GB vs 126 MB); no explicit flush",
-                       "path": ("fused: pq_encode x2 -> lookup(bitmask) -> masked-dense-tile attention fwd/bwd "
-                                "(mma.sync bf16)" if attn.use_fused else
+                       "path": ("fused: pq_encode(q,k) -> lookup(bitmask) -> masked-dense-tile attention fwd/bwd "
+                                "(tcgen05 + TMEM + TMA, bf16)" if attn.use_fused else
                                 "stage kernels (pq_encode, lookup, sddmm, softmax, spmm, csr2csc, spmm_t)"),
                        "parallelism": f"dp{world} (batch x head sharded, no collective)"},
             "clocks": clocks,
