@@ -4,9 +4,10 @@
     python scripts/finetune_step.py --steps 5 --warmup 2 --seq 2048
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P scripts/finetune_step.py ...
 
-Each rank owns `--batch` sequences (weak scaling).  A step = forward + backward through 4 pre-norm blocks
-(d_model 4096, 32 heads x d_head 128, d_ff 11008) built the way the reference builds and upgrades them
-(script/0-profile.py:87-143,182-189 + utils/adapter.py:94-97,155-184): frozen base weights, rank-16 LoRA
+Each rank owns `--batch` sequences (weak scaling).  A step = forward + backward through 4 pre-norm
+`TransformerBlock`s (d_model 4096, 32 heads x d_head 128, d_ff 11008) built dense and then upgraded by
+`ModuleUpgrader` + `SparseLoRAHandler` exactly as the reference does (script/0-profile.py:87-143,182-189 +
+utils/adapter.py:94-97,155-184): frozen base weights, rank-16 LoRA
 on q/k/v/o and gate/side/down, SparseRotaryAttentionV2 (PQ 16 subspaces x 16 codewords, top-k S/8,
 PQ training loss armed every step like script/4-sparse-tuning-0.py:71-91), LoRARoutedLLaMaFFN
 (block = d_ff/4, half the blocks active); then ONE bucketed NCCL all-reduce of the trainable gradients
@@ -29,40 +30,6 @@ import torch  # noqa: E402
 from torch import nn  # noqa: E402
 
 
-class RMSNorm(nn.Module):
-    def __init__(self, d: int, eps: float = 1e-6):
-        super().__init__()
-        self.weight = nn.Parameter(torch.ones(d))
-        self.eps = eps
-
-    def forward(self, x):
-        v = x.float()
-        return (v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + self.eps)).to(x.dtype) * self.weight
-
-
-class Block(nn.Module):
-    """Pre-norm block: x + o(attn(q(h), k(h), v(h))), x + ffn(h)  (reference basic/transformer.py:78-97)."""
-
-    def __init__(self, layers, d_model, n_heads, d_ff, d_lora):
-        super().__init__()
-        self.n_heads = n_heads
-        mk = lambda: layers.LoRALinear(d_lora=d_lora, in_features=d_model, out_features=d_model, bias=False)
-        self.linear_q, self.linear_k, self.linear_v, self.linear_o = mk(), mk(), mk(), mk()
-        self.attn_fn = layers.SparseRotaryAttentionV2(d_head=d_model // n_heads, p_dropout=0.0, d_codeword=8, n_codewords=16)
-        self.ffd = layers.LoRARoutedLLaMaFFN(d_lora=d_lora, block_size=d_ff // 4, d_model=d_model, d_feedforward=d_ff,
-                                             activation=nn.SiLU())
-        self.norm1, self.norm2 = RMSNorm(d_model), RMSNorm(d_model)
-        for n in (self.norm1, self.norm2):
-            n.weight.requires_grad = False
-
-    def forward(self, x):
-        h = self.norm1(x)
-        shape = (x.size(0), x.size(1), self.n_heads, -1)
-        y = self.attn_fn(self.linear_q(h).view(shape), self.linear_k(h).view(shape), self.linear_v(h).view(shape))
-        x = x + self.linear_o(y.reshape(x.size(0), x.size(1), -1))
-        return x + self.ffd(self.norm2(x))
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
@@ -75,7 +42,7 @@ def main():
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
 
-    from spt_proto_b200 import ext, layers
+    from spt_proto_b200 import ext, layers, utils
     from spt_proto_b200.distributed import allreduce_grads
 
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
@@ -86,10 +53,20 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     d_model, n_heads, d_ff = 4096, 32, 11008
     torch.manual_seed(1234)                       # same weights on every rank (DDP starts from a broadcast)
-    model = nn.Sequential(*[Block(layers, d_model, n_heads, d_ff, args.d_lora) for _ in range(args.layers)])
+    # dense blocks first, then the reference's four-pass upgrade (script/0-profile.py:87-143,182-189)
+    torch.set_default_device(dev)
+    d_head = d_model // n_heads
+    model = nn.Sequential(*[layers.TransformerBlock(
+        d_model=d_model, n_heads=n_heads, layernorm_fn=layers.LlamaRMSNorm(d_model),
+        attention_fn=layers.RotaryAttention(d_head=d_head, p_dropout=0.0),
+        feedforward_fn=layers.LLaMaFeedforward(d_model=d_model, d_feedforward=d_ff, activation=nn.SiLU()),
+        attention_bias=False, pre_norm=True) for _ in range(args.layers)])
+    for stage in ("lora", "ffn", "mha_v1", "mha_v2"):
+        model = utils.ModuleUpgrader(utils.SparseLoRAHandler(d_lora=args.d_lora, stage=stage, verbose=False)).visit(model)
+    torch.set_default_device("cpu")
     model = model.to(dev).bfloat16()
     for blk in model:
-        nn.init.normal_(blk.linear_q.lora.right.weight, std=0.02)   # non-zero LoRA so that every gradient is exercised
+        nn.init.normal_(blk.mha.linear_q.lora.right.weight, std=0.02)   # non-zero LoRA so that every gradient is exercised
         nn.init.normal_(blk.ffd.down.lora.right.weight, std=0.02)
     trainable = [p for p in model.parameters() if p.requires_grad]
     n_train = sum(p.numel() for p in trainable)
@@ -100,10 +77,10 @@ def main():
 
     def step():
         for blk in model:
-            blk.attn_fn.host_trigger = True           # arm the PQ loss (no device->host sync)
+            blk.mha.attn_fn.host_trigger = True           # arm the PQ loss (no device->host sync)
         y = model(x)
         loss = nn.functional.mse_loss(y.float(), target.float())
-        loss = loss + 1e-2 * sum(blk.attn_fn.loss for blk in model)
+        loss = loss + 1e-2 * sum(blk.mha.attn_fn.loss for blk in model)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         n_coll = allreduce_grads(trainable)

@@ -7,11 +7,12 @@ library exists):
     ext      the 7 reference extension entry points (+ new ones) over the C ABI of include/spt_b200.h
     kernels  torch.autograd Functions: cdist, lookup, sddmm, softmax, spmm (naive_gpt/kernels/*.py)
     layers   PQV2, Sparse{Vanilla,Rotary}AttentionV2, RoutedFFN, ... (naive_gpt/layers/*)
+    utils    LoRAHandler / SparseLoRAHandler / ModuleUpgrader (naive_gpt/utils/adapter.py)
     dropin   install() registers this package as `naive_gpt` in sys.modules
 """
 import importlib
 
-__all__ = ["ext", "kernels", "layers", "dropin", "build"]
+__all__ = ["ext", "kernels", "layers", "utils", "dropin", "build"]
 
 
 def __getattr__(name):

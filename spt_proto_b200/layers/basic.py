@@ -107,6 +107,63 @@ class LLaMaFeedforward(nn.Module):
         return self.down(self.activation(self.gate(x)) * self.side(x))
 
 
+class LlamaRMSNorm(nn.Module):
+    """x / rms(x) * weight with the statistics in fp32 (reference basic/utils.py:22-38)."""
+
+    def __init__(self, hidden_size: int, eps: float = 1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.variance_epsilon = eps
+
+    def forward(self, x):
+        inv_rms = torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + self.variance_epsilon)
+        y = x * inv_rms
+        if self.weight.dtype in (torch.float16, torch.bfloat16):
+            y = y.to(self.weight.dtype)
+        return self.weight * y
+
+
+class MultiheadAttention(nn.Module):
+    """q/k/v/o projections around an attention function on [N, S, H, E] (reference basic/transformer.py:6-50).
+    Attribute names (`linear_q` ... `linear_o`, `attn_fn`) are the reference's: they are checkpoint keys and the
+    paths the module upgrader rewrites."""
+
+    def __init__(self, d_model: int, n_heads: int, attention_fn: nn.Module, bias: bool):
+        super().__init__()
+        self.d_model, self.n_heads = d_model, n_heads
+        self.attn_fn = attention_fn
+        self.linear_q, self.linear_k, self.linear_v, self.linear_o = (
+            nn.Linear(d_model, d_model, bias=bias) for _ in range(4))
+
+    def forward(self, q, k, v, attn_mask=None):
+        assert q.size(0) == k.size(0) == v.size(0)
+        split = lambda t: t.view(t.size(0), t.size(1), self.n_heads, -1)
+        y = self.attn_fn(split(self.linear_q(q)), split(self.linear_k(k)), split(self.linear_v(v)), attn_mask=attn_mask)
+        return self.linear_o(y.reshape(y.size(0), y.size(1), -1))
+
+
+class TransformerBlock(nn.Module):
+    """Pre- or post-norm block: attention + feed-forward with residuals (reference basic/transformer.py:53-97)."""
+
+    def __init__(self, d_model: int, n_heads: int, layernorm_fn: nn.Module, attention_fn: nn.Module,
+                 feedforward_fn: nn.Module, attention_bias: bool, pre_norm: bool):
+        super().__init__()
+        import copy
+        self.pre_norm = pre_norm
+        self.mha = MultiheadAttention(d_model=d_model, n_heads=n_heads, attention_fn=attention_fn, bias=attention_bias)
+        self.ffd = copy.deepcopy(feedforward_fn)
+        self.norm1, self.norm2 = copy.deepcopy(layernorm_fn), copy.deepcopy(layernorm_fn)
+
+    def forward(self, x, attn_mask=None):
+        assert x.dim() == 3
+        if self.pre_norm:
+            h = self.norm1(x)
+            x = x + self.mha(h, h, h, attn_mask=attn_mask)
+            return x + self.ffd(self.norm2(x))
+        x = self.norm1(x + self.mha(x, x, x, attn_mask=attn_mask))
+        return self.norm2(x + self.ffd(x))
+
+
 class _PQTrainFused(torch.autograd.Function):
     """PQ 'train' mode as one forward and one backward kernel (csrc/cdist.cu, pq_train_*)."""
 

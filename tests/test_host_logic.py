@@ -106,3 +106,49 @@ def test_shard_range_partitions_exactly():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _small_block(kind):
+    from torch import nn
+    from spt_proto_b200 import layers
+    torch.manual_seed(7)
+    if kind == "llama":
+        return layers.TransformerBlock(
+            d_model=128, n_heads=2, layernorm_fn=layers.LlamaRMSNorm(128),
+            attention_fn=layers.RotaryAttention(d_head=64, p_dropout=0.0),
+            feedforward_fn=layers.LLaMaFeedforward(d_model=128, d_feedforward=512, activation=nn.SiLU()),
+            attention_bias=False, pre_norm=True)
+    return layers.TransformerBlock(
+        d_model=128, n_heads=2, layernorm_fn=nn.LayerNorm(128),
+        attention_fn=layers.VanillaAttention(d_head=64, p_dropout=0.0),
+        feedforward_fn=layers.Feedforward(d_model=128, d_feedforward=512, p_dropout=0.0, activation=nn.ReLU()),
+        attention_bias=True, pre_norm=True)
+
+
+@pytest.mark.parametrize("kind", ["llama", "opt"])
+def test_module_upgrader_matches_reference_upgrade(kind):
+    """The four-pass sparse upgrade (reference utils/adapter.py) yields the same module classes, the same
+    trainable set and the state_dict layout (keys, shapes, dtypes) of the reference's upgraded model
+    (tests/golden/upgrader_state.pt is produced by the unmodified reference, make_upgrader_golden.py)."""
+    import os
+    from spt_proto_b200 import utils
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "upgrader_state.pt"))[kind]
+    model = _small_block(kind)
+    for stage in ("lora", "ffn", "mha_v1", "mha_v2"):
+        model = utils.ModuleUpgrader(utils.SparseLoRAHandler(d_lora=4, stage=stage, verbose=False)).visit(model)
+    assert {n: type(m).__name__ for n, m in model.named_modules()} == gold["classes"]
+    assert sorted(n for n, p in model.named_parameters() if p.requires_grad) == gold["trainable"]
+    ours = model.state_dict()
+    assert set(ours) == set(gold["state_dict"])
+    assert all(tuple(ours[k].shape) == shape and str(ours[k].dtype) == dtype for k, (shape, dtype) in gold["state_dict"].items())
+    ckpt = {k: torch.zeros(shape, dtype=getattr(torch, dtype.split(".")[1])) for k, (shape, dtype) in gold["state_dict"].items()}
+    model.load_state_dict(ckpt, strict=True)      # a checkpoint with the reference's layout loads strictly
+
+
+def test_module_upgrader_requires_default_and_skips_unknown():
+    from spt_proto_b200 import utils
+    with pytest.raises(RuntimeError):
+        utils.ModuleUpgrader(object())
+    lin = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.ReLU())
+    out = utils.ModuleUpgrader(utils.LoRAHandler(d_lora=2, verbose=False)).visit(lin)
+    assert type(out[0]).__name__ == "LoRALinear" and type(out[1]).__name__ == "ReLU"
