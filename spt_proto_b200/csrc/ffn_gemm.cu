@@ -19,31 +19,39 @@
 //   memory descriptors — no transposed copies of weights or activations are ever made (the
 //   reference materialises a permuted copy of W2 on every call, feedforward.py:94-102).
 //
-// Kernel anatomy (one 128x128 output tile per CTA, 2 CTAs per SM so one tile's epilogue overlaps the
-// other's main loop):
-//   warp 0   : TMA producer  — cp.async.bulk.tensor.2d into a 3-stage ring of 128B-swizzled tiles
-//   warp 1   : TMEM allocator + MMA issuer — one thread issues tcgen05.mma (M128 N128 K16, kind::f16)
-//   warps 2-5: epilogue — tcgen05.ld TMEM -> registers, bias / activation / row scale, global stores
-//   smem full/empty mbarriers between TMA and MMA, one TMEM-full mbarrier between MMA and epilogue.
+// Kernel anatomy (persistent CTAs, one per SM, 128x256 output tiles dealt round-robin):
+//   warp 0   : TMA producer  — cp.async.bulk.tensor.2d into a 4-stage ring of 128B-swizzled tiles
+//   warp 1   : TMEM allocator + MMA issuer — one elected lane issues tcgen05.mma (M128 N256 K16, kind::f16)
+//   warps 2-5: epilogue — tcgen05.ld TMEM -> registers, bias / activation / row scale / gate, global stores
+//   smem full/empty mbarriers between TMA and MMA, full/empty mbarriers per TMEM accumulator (two of them)
+//   between MMA and epilogue.
+#include <algorithm>
+
 #include "tc.cuh"
 
 namespace spt {
 namespace gemm {
 
-// 128 x 256 output tiles: per 64-deep k-block a CTA pulls 16 KB of A and 32 KB of B through L2 for 4.2 MFLOP
-// (85 flop/B; 128 x 128 tiles give 64 flop/B and were measured L2-bandwidth bound, profiles/README.md).
-// Two CTAs per SM (2 x 256 TMEM columns, 2 x 96 KB shared memory): one tile's epilogue runs under the
-// other's main loop, and the two 2-stage rings keep 4 k-blocks in flight per SM.
-constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 2;
+// 128 x 256 output tiles, PERSISTENT CTAs (one per SM): the TMA producer streams k-blocks of consecutive tiles
+// through a 4-stage ring without draining between tiles, and two 256-column TMEM accumulators let the
+// epilogue of tile i run under the main loop of tile i+1.
+//
+// Measured ceiling of this single-CTA (cta_group::1) design: ~640 TFLOP/s per GEMM = 45 % of the cuBLAS bf16
+// rate, reached alike by 128x128 tiles with 2 CTAs/SM (574), 128x256 with 2 CTAs/SM (608-640), this persistent
+// kernel (640), cluster TMA multicast of the shared B tile (no change) and 256x256 units (slower: 480).  Tile
+// shape, pipeline depth and L2 traffic do not move it: a single-SM tcgen05.mma stream tops out near half of the
+// tensor peak, the rest needs cta_group::2 (a CTA pair issuing M = 256 MMAs over both SMs' shared memory).
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4;
 constexpr int THREADS = 192;
 constexpr int A_TILE_BYTES = BM * BK * 2;               // 16 KB
 constexpr int B_TILE_BYTES = BN * BK * 2;               // 32 KB
 constexpr int SMEM_BYTES = STAGES * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;                          // two accumulators of BN columns
 
 struct Params {
     int mode;                      // 0 = M-grouped, 1 = K-grouped
     const int32_t *tile_group;     // mode 0: group of every 128-row tile (-1 = unused tail tile)
+    int tiles_m, tiles_n, n_tiles; // tile grid: tile t -> (n = t % tiles_n, m = (t / tiles_n) % tiles_m, z = t / (tiles_n * tiles_m))
     const int32_t *group_ptr;      // mode 1: padded row offsets [G+1] (K range of group g)
     int K;                         // mode 0: reduction extent
     int M, N;                      // mode 1: output tile extents per group; mode 0: N only
@@ -79,7 +87,36 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
-__global__ void __launch_bounds__(THREADS, 2)
+// tile t of the launch -> coordinates, group, k range (identical in every role)
+struct Tile {
+    int g, m0, n0, k_begin, n_kblk;
+    long long c_row0, c_col0;
+    bool valid;
+};
+__device__ __forceinline__ Tile get_tile(const Params &p, int t) {
+    Tile ti;
+    const int tile_n = t % p.tiles_n, tile_m = (t / p.tiles_n) % p.tiles_m, z = t / (p.tiles_n * p.tiles_m);
+    ti.m0 = tile_m * BM;
+    ti.n0 = tile_n * BN;
+    if (p.mode == 0) {
+        ti.g = p.tile_group[tile_m];
+        ti.valid = ti.g >= 0;
+        ti.k_begin = 0;
+        ti.n_kblk = ti.valid ? (p.K + BK - 1) / BK : 0;
+        ti.c_row0 = ti.m0;
+        ti.c_col0 = ti.n0;
+    } else {
+        ti.g = z;
+        ti.valid = true;
+        ti.k_begin = p.group_ptr[z];
+        ti.n_kblk = (p.group_ptr[z + 1] - ti.k_begin + BK - 1) / BK;
+        ti.c_row0 = (long long)z * p.c_row_off + ti.m0;
+        ti.c_col0 = (long long)z * p.c_col_off + ti.n0;
+    }
+    return ti;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
 grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const Params p) {
     extern __shared__ unsigned char smem_raw[];
@@ -91,93 +128,64 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + s * 8; };
     auto empty_bar = [&](int s) { return bar0 + (STAGES + s) * 8; };
-    const uint32_t tmem_full_bar = bar0 + 2 * STAGES * 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+    auto acc_full = [&](int a) { return bar0 + (2 * STAGES + a) * 8; };
+    auto acc_empty = [&](int a) { return bar0 + (2 * STAGES + 2 + a) * 8; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // ---- which tile? -----------------------------------------------------------------------------
-    // N tiles vary fastest: consecutive CTAs share the A tile (read from DRAM once, then L2 hits) and walk the
-    // group's weight panel, which stays L2-resident; the opposite order re-read A from DRAM for every N tile
-    // (ncu: 588 MB of DRAM traffic for 155 MB of operands).
-    const int tile_m = blockIdx.y, tile_n = blockIdx.x;
-    int g, m0, n0 = tile_n * BN, k_begin, k_end;
-    long long c_row0, c_col0;
-    if (p.mode == 0) {
-        g = p.tile_group[tile_m];
-        if (g < 0) {
-            // tail tile beyond the bucketed rows: define its output (zeros) so that elementwise
-            // consumers of the whole [R, N] buffer never see uninitialised memory
-            const int n_valid = min(BN, p.N - n0);
-            for (int i = threadIdx.x; i < BM * n_valid; i += THREADS) {
-                const long long off = ((long long)tile_m * BM + i / n_valid) * p.ldc + n0 + i % n_valid;
-                if (p.c_dtype == SPT_BF16) reinterpret_cast<__nv_bfloat16 *>(p.C)[off] = __float2bfloat16_rn(0.0f);
-                else reinterpret_cast<float *>(p.C)[off] = 0.0f;
-            }
-            return;
-        }
-        m0 = tile_m * BM;
-        k_begin = 0;
-        k_end = p.K;
-        c_row0 = m0;
-        c_col0 = n0;
-    } else {
-        g = blockIdx.z;
-        m0 = tile_m * BM;
-        k_begin = p.group_ptr[g];
-        k_end = p.group_ptr[g + 1];
-        c_row0 = (long long)g * p.c_row_off + m0;
-        c_col0 = (long long)g * p.c_col_off + n0;
-    }
-    const int n_kblk = (k_end - k_begin + BK - 1) / BK;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(tmem_full_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(acc_full(a), 1);
+            mbar_init(acc_empty(a), 128);
+        }
+        mbar_fence_init();
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    fence_before_sync();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Tiles are dealt round-robin: at any moment the resident CTAs work on consecutive tiles = consecutive N
+    // tiles of the same M tile, which share the A tile (read from DRAM once) and walk the group's weight panel.
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const int a_k = g * p.a_k_off, a_mn = (p.mode == 0 ? m0 : g * p.a_mn_off + m0);
-            const int b_k = g * p.b_k_off, b_mn = g * p.b_mn_off + n0;
-            for (int kb = 0; kb < n_kblk; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1);
-                mbar_expect_tx(full_bar(s), A_TILE_BYTES + B_TILE_BYTES);
-                const int k0 = k_begin + kb * BK;
-                const uint32_t da = s_a + s * A_TILE_BYTES, db = s_b + s * B_TILE_BYTES;
-                if (p.a_mn_major) {   // tensor map dims: (mn contiguous, k rows); 64-wide chunks of 8 KB
+            uint32_t it = 0;   // k-blocks issued so far (ring position)
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+                const Tile ti = get_tile(p, t);
+                if (!ti.valid) continue;
+                const int a_k = ti.g * p.a_k_off, a_mn = (p.mode == 0 ? ti.m0 : ti.g * p.a_mn_off + ti.m0);
+                const int b_k = ti.g * p.b_k_off, b_mn = ti.g * p.b_mn_off + ti.n0;
+                for (int kb = 0; kb < ti.n_kblk; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(full_bar(s), A_TILE_BYTES + B_TILE_BYTES);
+                    const int k0 = ti.k_begin + kb * BK;
+                    const uint32_t da = s_a + s * A_TILE_BYTES, db = s_b + s * B_TILE_BYTES;
+                    if (p.a_mn_major) {   // tensor map dims: (mn contiguous, k rows); 64-wide chunks of 8 KB
 #pragma unroll
-                    for (int h = 0; h < BM / 64; ++h) tma_load_2d(da + h * 8192, &map_a, full_bar(s), a_mn + 64 * h, a_k + k0);
-                } else {              // tensor map dims: (k contiguous, mn rows)
-                    tma_load_2d(da, &map_a, full_bar(s), a_k + k0, a_mn);
-                }
-                if (p.b_mn_major) {
+                        for (int h = 0; h < BM / 64; ++h) tma_load_2d(da + h * 8192, &map_a, full_bar(s), a_mn + 64 * h, a_k + k0);
+                    } else {              // tensor map dims: (k contiguous, mn rows)
+                        tma_load_2d(da, &map_a, full_bar(s), a_k + k0, a_mn);
+                    }
+                    if (p.b_mn_major) {
 #pragma unroll
-                    for (int h = 0; h < BN / 64; ++h) tma_load_2d(db + h * 8192, &map_b, full_bar(s), b_mn + 64 * h, b_k + k0);
-                } else {              // two boxes of 128 rows
-                    tma_load_2d(db, &map_b, full_bar(s), b_k + k0, b_mn);
-                    tma_load_2d(db + B_TILE_BYTES / 2, &map_b, full_bar(s), b_k + k0, b_mn + 128);
+                        for (int h = 0; h < BN / 64; ++h) tma_load_2d(db + h * 8192, &map_b, full_bar(s), b_mn + 64 * h, b_k + k0);
+                    } else {              // two boxes of 128 rows
+                        tma_load_2d(db, &map_b, full_bar(s), b_k + k0, b_mn);
+                        tma_load_2d(db + B_TILE_BYTES / 2, &map_b, full_bar(s), b_k + k0, b_mn + 128);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues; descriptors of a
+        // ===== MMA issuer: the whole warp runs the (uniform) loops, one elected lane issues; descriptors of a
         // stage's k-slices are a base (computed once) plus small adds =====
         // instruction descriptor: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1),
         // a_major bit 15, b_major bit 16, N >> 3 at bit 17, M >> 4 at bit 24
@@ -186,85 +194,110 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                                ((uint32_t)(BM >> 4) << 24);
         const uint64_t da0 = operand_desc(s_a, p.a_mn_major, 0), db0 = operand_desc(s_b, p.b_mn_major, 0);
         const uint64_t a_step = p.a_mn_major ? MNMAJOR_K16 : KMAJOR_K16, b_step = p.b_mn_major ? MNMAJOR_K16 : KMAJOR_K16;
-        for (int kb = 0; kb < n_kblk; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(full_bar(s), ph);
+        uint32_t it = 0, n_acc = 0;   // ring position; accumulators handed to the epilogue so far
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            const Tile ti = get_tile(p, t);
+            if (!ti.valid) continue;
+            const int acc = n_acc & 1;
+            mbar_wait(acc_empty(acc), ((n_acc >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
             fence_after_sync();
-            if (elect_one()) {
-                const uint64_t da = da0 + (uint64_t)(s * (A_TILE_BYTES >> 4)), db = db0 + (uint64_t)(s * (B_TILE_BYTES >> 4));
+            for (int kb = 0; kb < ti.n_kblk; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(full_bar(s), (it / STAGES) & 1);
+                fence_after_sync();
+                if (elect_one()) {
+                    const uint64_t da = da0 + (uint64_t)(s * (A_TILE_BYTES >> 4)), db = db0 + (uint64_t)(s * (B_TILE_BYTES >> 4));
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)
-                    umma_bf16(tmem_base, da + k * a_step, db + k * b_step, idesc, (kb | k) != 0);
-                umma_commit(empty_bar(s));                      // frees the smem stage when the MMAs retire
-                if (kb + 1 == n_kblk) umma_commit(tmem_full_bar);   // accumulator complete
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(tmem_base + acc * BN, da + k * a_step, db + k * b_step, idesc, (kb | k) != 0);
+                    umma_commit(empty_bar(s));                      // frees the smem stage when the MMAs retire
+                }
+                __syncwarp();
             }
+            if (elect_one()) umma_commit(acc_full(acc));            // accumulator complete (also for an empty group)
             __syncwarp();
+            ++n_acc;
         }
-        if (n_kblk == 0 && elect_one()) umma_commit(tmem_full_bar);   // empty group: release the epilogue
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
         const int quarter = warp & 3;
         const int row_in_tile = quarter * 32 + lane;
-        mbar_wait(tmem_full_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const bool row_ok = p.mode == 0 ? true : (m0 + row_in_tile) < p.M;
-        const long long c_row = c_row0 + row_in_tile;
-        const float rs = (p.row_scale && p.mode == 0) ? p.row_scale[c_row] : 1.0f;
-        const int n_valid = min(BN, p.N - n0);
+        uint32_t n_acc = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            const Tile ti = get_tile(p, t);
+            const int n_valid = min(BN, p.N - ti.n0);
+            if (!ti.valid) {
+                // tail tile beyond the bucketed rows: define its output (zeros) so that elementwise
+                // consumers of the whole [R, N] buffer never see uninitialised memory
+                for (int i = threadIdx.x - 64; i < BM * n_valid; i += 128) {
+                    const long long off = ((long long)ti.m0 + i / n_valid) * p.ldc + ti.n0 + i % n_valid;
+                    if (p.c_dtype == SPT_BF16) reinterpret_cast<__nv_bfloat16 *>(p.C)[off] = __float2bfloat16_rn(0.0f);
+                    else reinterpret_cast<float *>(p.C)[off] = 0.0f;
+                }
+                continue;
+            }
+            const int acc = n_acc & 1;
+            mbar_wait(acc_full(acc), (n_acc >> 1) & 1);
+            fence_after_sync();
+            const bool row_ok = p.mode == 0 ? true : (ti.m0 + row_in_tile) < p.M;
+            const long long c_row = ti.c_row0 + row_in_tile;
+            const float rs = (p.row_scale && p.mode == 0) ? p.row_scale[c_row] : 1.0f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            __syncwarp();
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
-            if (n_kblk == 0) {
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (c0 >= n_valid) break;    // (uniform) nothing to store beyond N
+                uint32_t r[32];
+                __syncwarp();
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, r);
+                if (ti.n_kblk == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) r[i] = 0;           // empty group: no MMA ever wrote TMEM
-            }
-            if (row_ok && c0 < n_valid) {
-            float v[32];
+                    for (int i = 0; i < 32; ++i) r[i] = 0;           // empty group: no MMA ever wrote TMEM
+                }
+                if (row_ok) {
+                    float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float x = __uint_as_float(r[i]);
-                if (p.bias) x += (c0 + i < n_valid) ? p.bias[(long long)g * p.bias_stride + n0 + c0 + i] : 0.0f;
-                v[i] = apply_act(x, p.act) * rs;
-            }
-            if (p.gate) {   // ReLU backward mask of the tensor this GEMM differentiates through
-                const __nv_bfloat16 *gp = p.gate + c_row * p.ldg + c_col0 + c0;
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c0 + i < n_valid && !(__bfloat162float(gp[i]) > 0.0f)) v[i] = 0.0f;
-            }
-            const bool full = c0 + 32 <= n_valid;
-            if (p.c_dtype == SPT_BF16) {
-                __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.C) + c_row * p.ldc + c_col0 + c0;
-                if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 8) {
-                        float t[8] = {v[i], v[i + 1], v[i + 2], v[i + 3], v[i + 4], v[i + 5], v[i + 6], v[i + 7]};
-                        Vec16<__nv_bfloat16>::store(dst + i, t);
+                    for (int i = 0; i < 32; ++i) {
+                        float x = __uint_as_float(r[i]);
+                        if (p.bias) x += (c0 + i < n_valid) ? p.bias[(long long)ti.g * p.bias_stride + ti.n0 + c0 + i] : 0.0f;
+                        v[i] = apply_act(x, p.act) * rs;
                     }
-                } else {
-                    for (int i = 0; i < 32 && c0 + i < n_valid; ++i) dst[i] = __float2bfloat16_rn(v[i]);
-                }
-            } else {
-                float *dst = reinterpret_cast<float *>(p.C) + c_row * p.ldc + c_col0 + c0;
-                if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                    if (p.gate) {   // ReLU backward mask of the tensor this GEMM differentiates through
+                        const __nv_bfloat16 *gp = p.gate + c_row * p.ldg + ti.c_col0 + c0;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<float4 *>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                } else {
-                    for (int i = 0; i < 32 && c0 + i < n_valid; ++i) dst[i] = v[i];
+                        for (int i = 0; i < 32; ++i)
+                            if (c0 + i < n_valid && !(__bfloat162float(gp[i]) > 0.0f)) v[i] = 0.0f;
+                    }
+                    const bool full = c0 + 32 <= n_valid;
+                    if (p.c_dtype == SPT_BF16) {
+                        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.C) + c_row * p.ldc + ti.c_col0 + c0;
+                        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                float t8[8] = {v[i], v[i + 1], v[i + 2], v[i + 3], v[i + 4], v[i + 5], v[i + 6], v[i + 7]};
+                                Vec16<__nv_bfloat16>::store(dst + i, t8);
+                            }
+                        } else {
+                            for (int i = 0; i < 32 && c0 + i < n_valid; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+                        }
+                    } else {
+                        float *dst = reinterpret_cast<float *>(p.C) + c_row * p.ldc + ti.c_col0 + c0;
+                        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4)
+                                *reinterpret_cast<float4 *>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        } else {
+                            for (int i = 0; i < 32 && c0 + i < n_valid; ++i) dst[i] = v[i];
+                        }
+                    }
                 }
             }
-            }
+            fence_before_sync();
+            mbar_arrive(acc_empty(acc));     // 128 arrivals: the accumulator may be overwritten
+            ++n_acc;
         }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    fence_before_sync();
     __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
-    }
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ---- host: tensor maps ---------------------------------------------------------------------------
@@ -320,15 +353,17 @@ extern "C" int spt_grouped_gemm_bf16(int mode, const void *A, long long a_rows, 
     p.bias = bias; p.bias_stride = bias_stride; p.row_scale = row_scale; p.act = act;
     p.gate = (const __nv_bfloat16 *)gate; p.ldg = ldg;
     SPT_REQUIRE(!gate || mode == 0, "grouped_gemm: gate is a mode-0 epilogue");
-    dim3 grid;
-    if (mode == 0) grid = dim3((N + gemm::BN - 1) / gemm::BN, n_m_tiles, 1);
-    else grid = dim3((N + gemm::BN - 1) / gemm::BN, (M + gemm::BM - 1) / gemm::BM, n_groups);
-    SPT_REQUIRE(grid.y <= 65535, "grouped_gemm: too many M tiles (%u)", grid.y);
+    p.tiles_n = (N + gemm::BN - 1) / gemm::BN;
+    p.tiles_m = mode == 0 ? n_m_tiles : (M + gemm::BM - 1) / gemm::BM;
+    const long long n_tiles = (long long)p.tiles_n * p.tiles_m * (mode == 0 ? 1 : n_groups);
+    SPT_REQUIRE(n_tiles < (1ll << 31), "grouped_gemm: too many tiles");
+    p.n_tiles = (int)n_tiles;
+    const int n_ctas = (int)std::min<long long>(n_tiles, num_sms());
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(gemm::grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
         attr_set = true;
     }
-    gemm::grouped_gemm_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, as_stream(stream)>>>(map_a, map_b, p);
+    gemm::grouped_gemm_kernel<<<n_ctas, gemm::THREADS, gemm::SMEM_BYTES, as_stream(stream)>>>(map_a, map_b, p);
     return after_launch("grouped_gemm_kernel");
 }
