@@ -20,9 +20,10 @@
 //   reference materialises a permuted copy of W2 on every call, feedforward.py:94-102).
 //
 // Kernel anatomy (persistent CTAs, one per SM, 128x256 output tiles dealt round-robin):
-//   warp 0   : TMA producer  — cp.async.bulk.tensor.2d into a 4-stage ring of 128B-swizzled tiles
+//   warp 0   : TMA producer  — cp.async.bulk.tensor.2d into a 3-stage ring of 128B-swizzled tiles
 //   warp 1   : TMEM allocator + MMA issuer — one elected lane issues tcgen05.mma (M128 N256 K16, kind::f16)
-//   warps 2-5: epilogue — tcgen05.ld TMEM -> registers, bias / activation / row scale / gate, global stores
+//   warps 2-9: epilogue — tcgen05.ld TMEM -> registers, bias / activation / row scale / gate, staged through
+//              shared memory into coalesced global stores
 //   smem full/empty mbarriers between TMA and MMA, full/empty mbarriers per TMEM accumulator (two of them)
 //   between MMA and epilogue.
 #include <algorithm>
@@ -33,7 +34,7 @@ namespace spt {
 namespace gemm {
 
 // 128 x 256 output tiles, PERSISTENT CTAs (one per SM): the TMA producer streams k-blocks of consecutive tiles
-// through a 4-stage ring without draining between tiles, and two 256-column TMEM accumulators let the
+// through a 3-stage ring without draining between tiles, and two 256-column TMEM accumulators let the
 // epilogue of tile i run under the main loop of tile i+1.
 //
 // Measured ceiling of this single-CTA (cta_group::1) design: ~640 TFLOP/s per GEMM = 45 % of the cuBLAS bf16
@@ -41,11 +42,13 @@ namespace gemm {
 // kernel (640), cluster TMA multicast of the shared B tile (no change) and 256x256 units (slower: 480).  Tile
 // shape, pipeline depth and L2 traffic do not move it: a single-SM tcgen05.mma stream tops out near half of the
 // tensor peak, the rest needs cta_group::2 (a CTA pair issuing M = 256 MMAs over both SMs' shared memory).
-constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4;
-constexpr int THREADS = 192;
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 3;
+constexpr int EPI_WARPS = 8;                            // two per TMEM lane quarter, each owning 128 of the 256 columns
+constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr int STG_PITCH = 144;                          // staging row pitch in bytes (32 fp32 + pad; 16-byte aligned, conflict-free)
 constexpr int A_TILE_BYTES = BM * BK * 2;               // 16 KB
 constexpr int B_TILE_BYTES = BN * BK * 2;               // 32 KB
-constexpr int SMEM_BYTES = STAGES * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * (A_TILE_BYTES + B_TILE_BYTES) + EPI_WARPS * 32 * STG_PITCH + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int TMEM_COLS = 512;                          // two accumulators of BN columns
 
 struct Params {
@@ -124,7 +127,8 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t base = (raw + 1023) & ~1023u;                 // 128B swizzle needs 1024-byte alignment
     unsigned char *smem = smem_raw + (base - raw);
     const uint32_t s_a = base, s_b = base + STAGES * A_TILE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * (A_TILE_BYTES + B_TILE_BYTES));
+    unsigned char *s_stage = smem + STAGES * (A_TILE_BYTES + B_TILE_BYTES);                  // epilogue staging, per warp
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_stage + EPI_WARPS * 32 * STG_PITCH);
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + s * 8; };
     auto empty_bar = [&](int s) { return bar0 + (STAGES + s) * 8; };
@@ -141,7 +145,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(acc_full(a), 1);
-            mbar_init(acc_empty(a), 128);
+            mbar_init(acc_empty(a), EPI_WARPS * 32);
         }
         mbar_fence_init();
     }
@@ -190,7 +194,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // instruction descriptor: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1),
         // a_major bit 15, b_major bit 16, N >> 3 at bit 17, M >> 4 at bit 24
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn_major << 15) |
-                               ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)p.b_mn_major << 16) | ((uint32_t)((BN / 2) >> 3) << 17) |
                                ((uint32_t)(BM >> 4) << 24);
         const uint64_t da0 = operand_desc(s_a, p.a_mn_major, 0), db0 = operand_desc(s_b, p.b_mn_major, 0);
         const uint64_t a_step = p.a_mn_major ? MNMAJOR_K16 : KMAJOR_K16, b_step = p.b_mn_major ? MNMAJOR_K16 : KMAJOR_K16;
@@ -207,9 +211,15 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 fence_after_sync();
                 if (elect_one()) {
                     const uint64_t da = da0 + (uint64_t)(s * (A_TILE_BYTES >> 4)), db = db0 + (uint64_t)(s * (B_TILE_BYTES >> 4));
+                    // Back-to-back MMAs into the SAME accumulator are serialised by the accumulate dependency (~93 clk
+                    // each in a micro-benchmark, whatever N); the tile is therefore issued as two N = 128 halves whose
+                    // k-steps alternate: consecutive instructions are independent and run at the MMA floor.
+                    const uint64_t db_hi = db + (uint64_t)((B_TILE_BYTES / 2) >> 4);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
                         umma_bf16(tmem_base + acc * BN, da + k * a_step, db + k * b_step, idesc, (kb | k) != 0);
+                        umma_bf16(tmem_base + acc * BN + BN / 2, da + k * a_step, db_hi + k * b_step, idesc, (kb | k) != 0);
+                    }
                     umma_commit(empty_bar(s));                      // frees the smem stage when the MMAs retire
                 }
                 __syncwarp();
@@ -219,9 +229,16 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             ++n_acc;
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        const int quarter = warp & 3;
+        // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4; the two warps of a quarter split the 256 columns.
+        // A 32-row x 32-column chunk goes TMEM -> registers (thread = row) -> bias / activation / scale / gate ->
+        // a per-warp shared-memory tile -> global memory with consecutive lanes on consecutive 16-byte segments
+        // of a row (full sectors).  The first version stored 16 bytes per lane to 32 different rows and did
+        // everything per element with run-time branches: it took 185 us per GEMM against 108 us of main loop.
+        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
         const int row_in_tile = quarter * 32 + lane;
+        unsigned char *stage = s_stage + (warp - 2) * 32 * STG_PITCH;
+        const bool out_bf16 = p.c_dtype == SPT_BF16;
+        const int esz = out_bf16 ? 2 : 4;
         uint32_t n_acc = 0;
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
             const Tile ti = get_tile(p, t);
@@ -229,9 +246,9 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (!ti.valid) {
                 // tail tile beyond the bucketed rows: define its output (zeros) so that elementwise
                 // consumers of the whole [R, N] buffer never see uninitialised memory
-                for (int i = threadIdx.x - 64; i < BM * n_valid; i += 128) {
+                for (int i = threadIdx.x - 64; i < BM * n_valid; i += EPI_WARPS * 32) {
                     const long long off = ((long long)ti.m0 + i / n_valid) * p.ldc + ti.n0 + i % n_valid;
-                    if (p.c_dtype == SPT_BF16) reinterpret_cast<__nv_bfloat16 *>(p.C)[off] = __float2bfloat16_rn(0.0f);
+                    if (out_bf16) reinterpret_cast<__nv_bfloat16 *>(p.C)[off] = __float2bfloat16_rn(0.0f);
                     else reinterpret_cast<float *>(p.C)[off] = 0.0f;
                 }
                 continue;
@@ -239,59 +256,95 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int acc = n_acc & 1;
             mbar_wait(acc_full(acc), (n_acc >> 1) & 1);
             fence_after_sync();
-            const bool row_ok = p.mode == 0 ? true : (ti.m0 + row_in_tile) < p.M;
+            const int rows_ok = p.mode == 0 ? BM : min(BM, p.M - ti.m0);      // valid rows of the tile
             const long long c_row = ti.c_row0 + row_in_tile;
             const float rs = (p.row_scale && p.mode == 0) ? p.row_scale[c_row] : 1.0f;
+            unsigned char *c_base = reinterpret_cast<unsigned char *>(p.C);
+            const bool aligned = ((reinterpret_cast<uintptr_t>(p.C) + (size_t)ti.c_col0 * esz) % 16 == 0) && ((p.ldc * esz) % 16 == 0);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
                 if (c0 >= n_valid) break;    // (uniform) nothing to store beyond N
                 uint32_t r[32];
                 __syncwarp();
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, r);
+                float v[32];
+                const bool full = c0 + 32 <= n_valid;
                 if (ti.n_kblk == 0) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) r[i] = 0;           // empty group: no MMA ever wrote TMEM
                 }
-                if (row_ok) {
-                    float v[32];
+                if (p.bias) {
+                    const float *bp = p.bias + (long long)ti.g * p.bias_stride + ti.n0 + c0;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = __uint_as_float(r[i]);
-                        if (p.bias) x += (c0 + i < n_valid) ? p.bias[(long long)ti.g * p.bias_stride + ti.n0 + c0 + i] : 0.0f;
-                        v[i] = apply_act(x, p.act) * rs;
-                    }
-                    if (p.gate) {   // ReLU backward mask of the tensor this GEMM differentiates through
-                        const __nv_bfloat16 *gp = p.gate + c_row * p.ldg + ti.c_col0 + c0;
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + ((full || c0 + i < n_valid) ? __ldg(bp + i) : 0.0f);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                }
+                if (p.act == 1) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+                } else if (p.act == 2) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = v[i] / (1.0f + __expf(-v[i]));
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= rs;
+                if (p.gate && row_in_tile < rows_ok) {   // ReLU backward mask of the tensor this GEMM differentiates through
+                    const __nv_bfloat16 *gp = p.gate + c_row * p.ldg + ti.c_col0 + c0;
+                    if (full && (reinterpret_cast<uintptr_t>(gp) % 16 == 0)) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            float gv[8];
+                            Vec16<__nv_bfloat16>::load(gp + i, gv);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (!(gv[u] > 0.0f)) v[i + u] = 0.0f;
+                        }
+                    } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             if (c0 + i < n_valid && !(__bfloat162float(gp[i]) > 0.0f)) v[i] = 0.0f;
                     }
-                    const bool full = c0 + 32 <= n_valid;
-                    if (p.c_dtype == SPT_BF16) {
-                        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.C) + c_row * p.ldc + ti.c_col0 + c0;
-                        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                }
+                if (full && aligned) {
+                    // registers -> staging tile (thread = row) -> coalesced global stores (lane = 16-byte segment)
+                    unsigned char *srow = stage + lane * STG_PITCH;
+                    if (out_bf16) {
 #pragma unroll
-                            for (int i = 0; i < 32; i += 8) {
-                                float t8[8] = {v[i], v[i + 1], v[i + 2], v[i + 3], v[i + 4], v[i + 5], v[i + 6], v[i + 7]};
-                                Vec16<__nv_bfloat16>::store(dst + i, t8);
-                            }
-                        } else {
-                            for (int i = 0; i < 32 && c0 + i < n_valid; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+                        for (int i = 0; i < 32; i += 8) {
+                            float t8[8] = {v[i], v[i + 1], v[i + 2], v[i + 3], v[i + 4], v[i + 5], v[i + 6], v[i + 7]};
+                            Vec16<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16 *>(srow) + i, t8);
                         }
                     } else {
-                        float *dst = reinterpret_cast<float *>(p.C) + c_row * p.ldc + ti.c_col0 + c0;
-                        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4)
-                                *reinterpret_cast<float4 *>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        } else {
-                            for (int i = 0; i < 32 && c0 + i < n_valid; ++i) dst[i] = v[i];
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4 *>(srow + i * 4) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    }
+                    __syncwarp();
+                    const int segs = out_bf16 ? 4 : 8;                 // 16-byte segments per row of the chunk
+                    const int rows_per = 32 / segs;
+                    const int seg = lane % segs, rsub = lane / segs;
+                    for (int r0 = 0; r0 < 32; r0 += rows_per) {
+                        const int rr = r0 + rsub;
+                        if (quarter * 32 + rr < rows_ok) {
+                            const uint4 val = *reinterpret_cast<const uint4 *>(stage + rr * STG_PITCH + seg * 16);
+                            unsigned char *dst = c_base + ((ti.c_row0 + quarter * 32 + rr) * p.ldc + ti.c_col0 + c0) * esz + seg * 16;
+                            *reinterpret_cast<uint4 *>(dst) = val;
                         }
+                    }
+                } else if (row_in_tile < rows_ok) {
+                    if (out_bf16) {
+                        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.C) + c_row * p.ldc + ti.c_col0 + c0;
+                        for (int i = 0; i < 32 && c0 + i < n_valid; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+                    } else {
+                        float *dst = reinterpret_cast<float *>(p.C) + c_row * p.ldc + ti.c_col0 + c0;
+                        for (int i = 0; i < 32 && c0 + i < n_valid; ++i) dst[i] = v[i];
                     }
                 }
             }
             fence_before_sync();
-            mbar_arrive(acc_empty(acc));     // 128 arrivals: the accumulator may be overwritten
+            mbar_arrive(acc_empty(acc));     // 256 arrivals: the accumulator may be overwritten
             ++n_acc;
         }
     }
