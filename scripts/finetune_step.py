@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="sequences per GPU per step")
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--d-lora", type=int, default=16)
+    ap.add_argument("--graph", action="store_true",
+                    help="capture forward + backward + all-reduce + optimizer of one step in a CUDA graph and replay it")
     args = ap.parse_args()
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
@@ -70,7 +72,7 @@ def main():
         nn.init.normal_(blk.ffd.down.lora.right.weight, std=0.02)
     trainable = [p for p in model.parameters() if p.requires_grad]
     n_train = sum(p.numel() for p in trainable)
-    opt = torch.optim.AdamW(trainable, lr=1e-4, weight_decay=1e-2)
+    opt = torch.optim.AdamW(trainable, lr=1e-4, weight_decay=1e-2, capturable=args.graph)
     torch.manual_seed(1234 + rank)
     x = torch.randn(args.batch, args.seq, d_model, device=dev).bfloat16()
     target = torch.randn(args.batch, args.seq, d_model, device=dev).bfloat16()
@@ -93,9 +95,34 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        loss, n_coll = step()
+    if args.graph:
+        # whole-network capture recipe: warm up on a side stream so that no autograd node (AccumulateGrad of the
+        # parameters in particular) stays tied to the legacy default stream, which cannot be joined during capture
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(args.warmup, 3)):
+                loss, n_coll = step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+    else:
+        for _ in range(args.warmup):
+            loss, n_coll = step()
     barrier()
+    if args.graph:
+        # ~1300 small launches per step: replaying one captured graph removes the launch gaps.  Nothing on the path
+        # synchronises with the host (host_trigger, device-side bucketing), so the whole step is capturable.
+        eager_step = step
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss, n_coll = eager_step()
+
+        def step():
+            graph.replay()
+            return loss, n_coll
+
+        for _ in range(2):
+            step()
+        barrier()
     launches0 = ext.launch_count()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -117,7 +144,7 @@ def main():
                                        f"+ LoRA routed FFN), seq {args.seq}, {args.batch} seq/GPU",
                            "d_model": d_model, "n_heads": n_heads, "d_ff": d_ff, "d_lora": args.d_lora,
                            "trainable_params": n_train, "allreduce_calls_per_step": n_coll,
-                           "parallelism": f"dp{world} + NCCL all-reduce of trainable grads"},
+                           "parallelism": f"dp{world} + NCCL all-reduce of trainable grads", "cuda_graph": bool(args.graph)},
                 "loss": float(loss.detach()), "gpu_launches": ext.launch_count() - launches0}
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:

@@ -197,10 +197,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 inline EncodeTiledFn encode_fn() {
     // cuTensorMapEncodeTiled is a driver-API call: it needs the device's primary context bound to the
     // calling thread.  A thread whose first CUDA action is this call (an autograd worker entering a
-    // backward pass) has none yet (CUDA_ERROR_INVALID_CONTEXT); any runtime-API call binds it.
+    // backward pass) has none yet (CUDA_ERROR_INVALID_CONTEXT).
     static thread_local bool bound = false;
-    if (!bound) {
-        cudaFree(nullptr);
+    if (!bound) {   // cudaSetDevice binds the primary context and is not a stream operation (safe under graph capture)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaSetDevice(dev);
         bound = true;
     }
     static EncodeTiledFn fn = nullptr;
