@@ -511,12 +511,13 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             fence_after_sync();
             if (elect_one()) {
                 const uint64_t off = (uint64_t)(st * (T_BYTES >> 4));
+                // S and dP' are independent accumulators: alternating their k-steps keeps consecutive MMAs independent
+                // (back-to-back MMAs into one accumulator are serialised by the accumulate dependency, ~93 clk each)
 #pragma unroll
-                for (int k = 0; k < D / 16; ++k)
+                for (int k = 0; k < D / 16; ++k) {
                     umma_bf16(tmem_base + COL_S, dq0 + kslice<OWN_SUB>(k), dk0 + off + kslice<T_SUB>(k), id_s, k != 0);
-#pragma unroll
-                for (int k = 0; k < D / 16; ++k)
                     umma_bf16(tmem_base + COL_DP, ddy0 + kslice<OWN_SUB>(k), dv0 + off + kslice<T_SUB>(k), id_s, k != 0);
+                }
                 umma_commit(sc_full);
             }
             __syncwarp();
@@ -685,12 +686,12 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 // rows 32 h .. 32 h + 31 of the stage's 64-row tiles: + 32 rows * 128 B inside every 64-wide sub-tile
                 const uint64_t off = (uint64_t)((st * T_BYTES + h * SUBN * 128) >> 4);
                 const uint32_t col = tmem_base + COL_SC + (t & 1) * 64;
+                // S^T and dP'^T are independent accumulators: alternate their k-steps (see the dQ kernel)
 #pragma unroll
-                for (int k = 0; k < D / 16; ++k)
+                for (int k = 0; k < D / 16; ++k) {
                     umma_bf16(col, dk0 + kslice<OWN_SUB>(k), dq0 + off + kslice<T_SUB>(k), id_s, k != 0);
-#pragma unroll
-                for (int k = 0; k < D / 16; ++k)
                     umma_bf16(col + 32, dv0 + kslice<OWN_SUB>(k), ddy0 + off + kslice<T_SUB>(k), id_s, k != 0);
+                }
                 umma_commit(sc_full(t & 1));
             }
             __syncwarp();
@@ -707,11 +708,10 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 const uint32_t col = tmem_base + COL_SC + (t & 1) * 64;
                 // query rows 16 k .. 16 k + 15 of the sub-tile sit in columns 16 k .. 16 k + 7 (the writer's own half)
 #pragma unroll
-                for (int k = 0; k < SUBN / 16; ++k)
+                for (int k = 0; k < SUBN / 16; ++k) {   // dV and dK alternate as well
                     umma_bf16_ts(tmem_base + COL_DV, col + k * 16, ddyt0 + off + (2 * h + k) * MNMAJOR_K16, id_a, (t | k) != 0);
-#pragma unroll
-                for (int k = 0; k < SUBN / 16; ++k)
                     umma_bf16_ts(tmem_base + COL_DK, col + 32 + k * 16, dqt0 + off + (2 * h + k) * MNMAJOR_K16, id_a, (t | k) != 0);
+                }
                 if (h == 1) umma_commit(qd_empty(st));
                 if (t + 1 == n_sub) umma_commit(acc_full);
             }

@@ -7,13 +7,19 @@ and its torch-autograd backward), on the tcgen05 grouped GEMM:
     Yp       = blocked_linear_cols(H, W2)               [R, d]    block g uses W2[:, g*bs:(g+1)*bs]
     y        = combine(Yp, bucket, b2)                  [T, d]    backward: gather
 
-All GEMM operands are bf16 (fp32 accumulation); weight gradients come out in fp32."""
+All GEMM operands are bf16 (fp32 accumulation); weight gradients come out in the parameter's dtype (bf16) or fp32."""
 import torch
 from torch import autograd
 
 from .. import ext
 
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
+
+
+def _grad_buffer(shape, dtype, device):
+    """Weight-gradient output of the K-grouped GEMM: bf16 parameters get their gradient written in bf16 by the
+    GEMM epilogue (fp32 accumulation in TMEM), everything else an fp32 buffer (converted by the caller)."""
+    return torch.empty(shape, dtype=torch.bfloat16 if dtype == torch.bfloat16 else torch.float32, device=device)
 
 
 class GatherRows(autograd.Function):
@@ -75,9 +81,9 @@ class BlockedLinearRows(autograd.Function):
             dx = torch.empty_like(x)
             ext.grouped_gemm(0, grad, False, w16, True, tile_group=b.tile_group, N=x.size(1), K=bs, b_k_off=bs, out=dx)
         if ctx.needs_input_grad[1]:   # dW_g = grad_g^T x_g over the bucket's rows
-            dw32 = torch.empty(ctx.w_shape, dtype=torch.float32, device=x.device)
-            ext.grouped_gemm(1, grad, True, x, True, group_ptr=b.bucket_ptr, M=bs, N=x.size(1), c_row_off=bs, out=dw32)
-            dw = dw32.to(ctx.w_dtype)
+            dw = _grad_buffer(ctx.w_shape, ctx.w_dtype, x.device)   # written in the parameter's dtype by the epilogue
+            ext.grouped_gemm(1, grad, True, x, True, group_ptr=b.bucket_ptr, M=bs, N=x.size(1), c_row_off=bs, out=dw)
+            dw = dw.to(ctx.w_dtype)
         if ctx.b_dtype is not None and ctx.needs_input_grad[2]:
             db = ext.group_colsum(grad, b.bucket_ptr).reshape(-1).to(ctx.b_dtype)
         return dx, dw, db, None, None, None, None, None
@@ -108,10 +114,10 @@ class BlockedLinearCols(autograd.Function):
             ext.grouped_gemm(0, grad, False, w16, True, tile_group=b.tile_group, N=bs, K=grad.size(1), b_mn_off=bs,
                              out=dx, gate=x if ctx.relu_input else None)
         if ctx.needs_input_grad[1]:   # dW[:, g*bs:(g+1)*bs] = grad_g^T x_g
-            dw32 = torch.empty(ctx.w_shape, dtype=torch.float32, device=x.device)
+            dw = _grad_buffer(ctx.w_shape, ctx.w_dtype, x.device)
             ext.grouped_gemm(1, grad, True, x, True, group_ptr=b.bucket_ptr, M=grad.size(1), N=bs, c_col_off=bs,
-                             out=dw32)
-            dw = dw32.to(ctx.w_dtype)
+                             out=dw)
+            dw = dw.to(ctx.w_dtype)
         return dx, dw, None, None, None
 
 
@@ -160,10 +166,10 @@ class BlockedLinearColsT(autograd.Function):
             ext.grouped_gemm(0, grad, False, w16, False, tile_group=b.tile_group, N=bs, K=grad.size(1), b_mn_off=bs,
                              out=dx)
         if ctx.needs_input_grad[1]:   # dW[g*bs:(g+1)*bs, :] = x_g^T grad_g
-            dw32 = torch.empty(ctx.w_shape, dtype=torch.float32, device=x.device)
+            dw = _grad_buffer(ctx.w_shape, ctx.w_dtype, x.device)
             ext.grouped_gemm(1, x, True, grad, True, group_ptr=b.bucket_ptr, M=bs, N=grad.size(1), c_row_off=bs,
-                             out=dw32)
-            dw = dw32.to(ctx.w_dtype)
+                             out=dw)
+            dw = dw.to(ctx.w_dtype)
         return dx, dw, None, None
 
 
