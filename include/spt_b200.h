@@ -242,6 +242,21 @@ int spt_grouped_gemm_bf16(int mode, const void *A, long long a_rows, long long a
                           int bias_stride, const float *row_scale, int act, const void *gate, long long ldg,
                           spt_stream_t stream);
 
+/* Fused elementwise stages of the LoRA-routed FFN (naive_gpt/layers/tuning/lora_ffn.py:87-115,201-222).
+ * coeff [R] fp32 = 2 * router probability of the bucket row.  dtypes: SPT_F32 / SPT_BF16.  C % 4 == 0.
+ *   scale_add: out = coeff[r] * a + b;   bwd: da = coeff[r] * dout (a's dtype), dcoeff[r] = sum_c dout * a.
+ *   lora_glu : h (bf16) = silu(coeff*bg + lg) * (coeff*bs + ls), all inputs fp32 [R, C];
+ *              bwd: gradients of the four inputs (fp32) and dcoeff[r]. */
+int spt_scale_add_fwd(const float *coeff, const void *a, int a_dtype, const void *b, int b_dtype, void *out,
+                      int o_dtype, int64_t R, int C, spt_stream_t stream);
+int spt_scale_add_bwd(const float *coeff, const void *a, int a_dtype, const void *dout, int g_dtype, void *da,
+                      float *dcoeff, int64_t R, int C, spt_stream_t stream);
+int spt_lora_glu_fwd(const float *coeff, const float *bg, const float *lg, const float *bs, const float *ls,
+                     void *h, int64_t R, int C, spt_stream_t stream);
+int spt_lora_glu_bwd(const float *coeff, const float *bg, const float *lg, const float *bs, const float *ls,
+                     const void *dh, float *d_bg, float *d_lg, float *d_bs, float *d_ls, float *dcoeff,
+                     int64_t R, int C, spt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,10 @@ def _load() -> ctypes.CDLL:
     ll = c.c_longlong
     sig["spt_grouped_gemm_bf16"] = (i32, [i32, vp, ll, ll, ll, i32, vp, ll, ll, ll, i32, vp, i32, vp, i32, i32, i32, i32,
                                           i32, i32, i32, i32, ll, ll, vp, ll, i32, vp, i32, vp, i32, vp, ll, vp])
+    sig["spt_scale_add_fwd"] = (i32, [vp, vp, i32, vp, i32, vp, i32, i64, i32, vp])
+    sig["spt_scale_add_bwd"] = (i32, [vp, vp, i32, vp, i32, vp, vp, i64, i32, vp])
+    sig["spt_lora_glu_fwd"] = (i32, [vp] * 6 + [i64, i32, vp])
+    sig["spt_lora_glu_bwd"] = (i32, [vp] * 11 + [i64, i32, vp])
     sig["spt_route_bucket_workspace_bytes"] = (sz, [i64, i32])
     sig["spt_route_bucket"] = (i32, [vp] * 8 + [i64, i32, i32, i64, vp])
     sig["spt_gather_rows_bf16"] = (i32, [vp, vp, vp, i64, i32, vp])

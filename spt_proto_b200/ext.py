@@ -512,3 +512,64 @@ def group_colsum(x: torch.Tensor, bucket_ptr: torch.Tensor) -> torch.Tensor:
     with _on_device(x):
         check(lib.spt_group_colsum_bf16(_p(x), _p(bucket_ptr), _p(out), _p(ws), G, C, _stream(x)))
     return out
+
+
+# ---- fused elementwise stages of the LoRA-routed FFN (csrc/lora_fuse.cu) ---------------------------------------------
+def _rows_cols(a: torch.Tensor, name: str):
+    _check_dim(a, 2, name)
+    if not a.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    return a.size(0), a.size(1)
+
+
+def scale_add_fwd(coeff: torch.Tensor, a: torch.Tensor, b: torch.Tensor, out_dtype) -> torch.Tensor:
+    """out[r, :] = coeff[r] * a[r, :] + b[r, :];  coeff [R] fp32, a / b / out fp32 or bf16."""
+    R, C = _rows_cols(a, "a")
+    _check_type(coeff, torch.float32, "coeff")
+    if b.shape != a.shape or coeff.numel() != R or not b.is_contiguous() or not coeff.is_contiguous():
+        raise RuntimeError("scale_add: shape mismatch")
+    out = torch.empty(R, C, dtype=out_dtype, device=a.device)
+    with _on_device(a):
+        check(lib.spt_scale_add_fwd(_p(coeff), _p(a), _float_code(a, "a"), _p(b), _float_code(b, "b"), _p(out),
+                                    _float_code(out, "out"), R, C, _stream(a)))
+    return out
+
+
+def scale_add_bwd(coeff: torch.Tensor, a: torch.Tensor, grad: torch.Tensor):
+    """-> (da = coeff * grad in a's dtype, dcoeff [R] fp32 = rowsum(grad * a))."""
+    R, C = _rows_cols(a, "a")
+    if grad.shape != a.shape or not grad.is_contiguous():
+        raise RuntimeError("scale_add_bwd: shape mismatch")
+    da = torch.empty_like(a)
+    dcoeff = torch.empty(R, dtype=torch.float32, device=a.device)
+    with _on_device(a):
+        check(lib.spt_scale_add_bwd(_p(coeff), _p(a), _float_code(a, "a"), _p(grad), _float_code(grad, "grad"), _p(da),
+                                    _p(dcoeff), R, C, _stream(a)))
+    return da, dcoeff
+
+
+def lora_glu_fwd(coeff, bg, lg, bs, ls) -> torch.Tensor:
+    """h (bf16) = silu(coeff * bg + lg) * (coeff * bs + ls); all inputs fp32 [R, C], coeff [R]."""
+    R, C = _rows_cols(bg, "bg")
+    for t, n in ((bg, "bg"), (lg, "lg"), (bs, "bs"), (ls, "ls"), (coeff, "coeff")):
+        _check_type(t, torch.float32, n)
+        if n != "coeff" and (t.shape != bg.shape or not t.is_contiguous()):
+            raise RuntimeError("lora_glu: shape mismatch")
+    h = torch.empty(R, C, dtype=torch.bfloat16, device=bg.device)
+    with _on_device(bg):
+        check(lib.spt_lora_glu_fwd(_p(coeff), _p(bg), _p(lg), _p(bs), _p(ls), _p(h), R, C, _stream(bg)))
+    return h
+
+
+def lora_glu_bwd(coeff, bg, lg, bs, ls, grad_h):
+    """-> (d_bg, d_lg, d_bs, d_ls fp32 [R, C], dcoeff [R] fp32); grad_h bf16."""
+    R, C = _rows_cols(bg, "bg")
+    _check_type(grad_h, torch.bfloat16, "grad_h")
+    if grad_h.shape != bg.shape or not grad_h.is_contiguous():
+        raise RuntimeError("lora_glu_bwd: shape mismatch")
+    outs = [torch.empty_like(bg) for _ in range(4)]
+    dcoeff = torch.empty(R, dtype=torch.float32, device=bg.device)
+    with _on_device(bg):
+        check(lib.spt_lora_glu_bwd(_p(coeff), _p(bg), _p(lg), _p(bs), _p(ls), _p(grad_h), *[_p(o) for o in outs],
+                                   _p(dcoeff), R, C, _stream(bg)))
+    return (*outs, dcoeff)

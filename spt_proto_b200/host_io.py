@@ -18,7 +18,7 @@ class HostPipeline:
     ([N, S, H, E] each) in pinned host memory.  `chunk` sequences per pipeline stage, `depth` device
     staging slots."""
 
-    def __init__(self, layer: Callable, device: torch.device, chunk: int = 1, depth: int = 3):
+    def __init__(self, layer: Callable, device: torch.device, chunk: int = 1, depth: int = 4):
         self.layer, self.device, self.chunk, self.depth = layer, device, chunk, depth
         self.s_in = torch.cuda.Stream(device)
         self.s_out = torch.cuda.Stream(device)

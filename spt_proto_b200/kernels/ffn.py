@@ -175,3 +175,46 @@ class BlockedLinearColsT(autograd.Function):
 
 def blocked_linear_cols_t(x, weight, bucket, bs):
     return BlockedLinearColsT.apply(x, weight, bucket, bs)
+
+
+class ScaleAdd(autograd.Function):
+    """out = coeff[:, None] * a + b in one pass (coeff [R] fp32 carries the router gradient of the LoRA FFN)."""
+
+    @staticmethod
+    def forward(ctx, coeff, a, b, out_dtype):
+        coeff = coeff.contiguous()
+        ctx.save_for_backward(coeff, a)
+        ctx.b_dtype = b.dtype
+        return ext.scale_add_fwd(coeff, a, b, out_dtype)
+
+    @staticmethod
+    def backward(ctx, grad):
+        coeff, a = ctx.saved_tensors
+        grad = grad.contiguous()
+        da, dcoeff = ext.scale_add_bwd(coeff, a, grad)
+        db = grad if grad.dtype == ctx.b_dtype else grad.to(ctx.b_dtype)
+        return dcoeff, da, db, None
+
+
+class LoraGLU(autograd.Function):
+    """h = silu(coeff * bg + lg) * (coeff * bs + ls) -> bf16 in one pass; backward in one pass as well."""
+
+    @staticmethod
+    def forward(ctx, coeff, bg, lg, bs, ls):
+        coeff = coeff.contiguous()
+        ctx.save_for_backward(coeff, bg, lg, bs, ls)
+        return ext.lora_glu_fwd(coeff, bg, lg, bs, ls)
+
+    @staticmethod
+    def backward(ctx, grad):
+        coeff, bg, lg, bs, ls = ctx.saved_tensors
+        d_bg, d_lg, d_bs, d_ls, dcoeff = ext.lora_glu_bwd(coeff, bg, lg, bs, ls, grad.contiguous())
+        return dcoeff, d_bg, d_lg, d_bs, d_ls
+
+
+def scale_add(coeff, a, b, out_dtype):
+    return ScaleAdd.apply(coeff, a, b, out_dtype)
+
+
+def lora_glu(coeff, bg, lg, bs, ls):
+    return LoraGLU.apply(coeff, bg, lg, bs, ls)

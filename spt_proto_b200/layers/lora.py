@@ -10,9 +10,10 @@ coeff = 2 * prob that carries the router's gradient, and the LoRA paths:
     y += coeff * (h W2_i) + (h L2_i) R2^T                   y += b2
 
 Here every product with a base weight block or a blocked LoRA factor is a grouped GEMM on the tcgen05
-tensor cores over the bucketed tokens; the rank-r dense factors (x L1, . R2^T) and the elementwise
-glue are torch ops, so autograd yields exactly the reference's gradients (router via coeff, LoRA
-factors; no gradient for the frozen base)."""
+tensor cores over the bucketed tokens; the rank-r dense factors (x L1, . R2^T) are torch GEMMs and the
+elementwise glue (coeff * base + lora, the SiLU gate) runs in the fused kernels of csrc/lora_fuse.cu
+(autograd Functions in kernels/ffn.py), so autograd yields exactly the reference's gradients (router
+via coeff, LoRA factors; no gradient for the frozen base)."""
 from __future__ import annotations
 
 import torch
@@ -79,7 +80,7 @@ def _row_coeff(prob: torch.Tensor, bucket) -> torch.Tensor:
     group = bucket.tile_group.clamp(min=0).long().repeat_interleave(128)
     valid = bucket.row_token >= 0
     flat = bucket.row_token.clamp(min=0).long() * nb + group
-    return (2.0 * prob.reshape(-1)[flat] * valid).unsqueeze(-1)
+    return 2.0 * prob.reshape(-1)[flat] * valid
 
 
 def _bf16(t: torch.Tensor) -> torch.Tensor:
@@ -151,18 +152,18 @@ class LoRARoutedFFN(RoutedFFN):
         x_size, bs = x.size(), self.block_size
         x2 = x.reshape(-1, self.d_model)
         prob, bucket = _route(self.router, x2, self.k_active)
-        coeff = _row_coeff(prob.float(), bucket)                               # [R, 1] fp32
+        coeff = _row_coeff(prob.float(), bucket)                               # [R] fp32
         xp = F.gather(_bf16(x2).contiguous(), bucket)                           # [R, d]
         f32 = torch.float32   # pre-activations stay fp32 so that activation gates are decided as in the reference
         base = F.blocked_linear_rows(xp, self.fc1.weight, self.fc1.bias, bucket, bs, out_dtype=f32)   # x W1_i^T + b1_i
         t1 = _down_proj_split(xp, _pad8(self.fc1.lora.left.weight))             # [R, 2r] = [hi | lo]
         lora = F.blocked_linear_rows(t1, _twice(_pad8(self.fc1.lora.right.weight)), None, bucket, bs,
                                      out_dtype=f32)                             # (x L1) R1_i^T
-        h = self.activation(coeff * base + lora).to(torch.bfloat16)
+        h = self.activation(F.scale_add(coeff, base, lora, f32)).to(torch.bfloat16)
         y_base = F.blocked_linear_cols(h, self.fc2.weight, bucket, bs)          # h W2_i
         t2 = F.blocked_linear_cols_t(h, _pad8(self.fc2.lora.left.weight), bucket, bs)   # h L2_i   [R, r]
         y_lora = t2 @ _bf16(_pad8(self.fc2.lora.right.weight)).t()              # (h L2_i) R2^T
-        yp = (coeff * y_base.float() + y_lora.float()).to(torch.bfloat16)
+        yp = F.scale_add(coeff, y_base, y_lora, torch.bfloat16)
         y = F.combine(yp, bucket, self.fc2.bias, x.dtype)
         return y.view(x_size)
 
@@ -188,12 +189,13 @@ class LoRARoutedLLaMaFFN(RoutedLLaMaFFN):
     def k_active(self) -> int:
         return self.n_blocks // 2            # the LoRA variant activates half (lora_ffn.py:172)
 
-    def _proj(self, lin: LoRALinear, xp, coeff, bucket):
+    def _proj(self, lin: LoRALinear, xp, bucket):
+        """-> (x W_i^T, (x L) R_i^T), both fp32 [R, bs]; the caller forms coeff * base + lora."""
         base = F.blocked_linear_rows(xp, lin.weight, None, bucket, self.block_size, out_dtype=torch.float32)
         lora = F.blocked_linear_rows(_down_proj_split(xp, _pad8(lin.lora.left.weight)),
                                      _twice(_pad8(lin.lora.right.weight)), None, bucket, self.block_size,
                                      out_dtype=torch.float32)
-        return coeff * base + lora
+        return base, lora
 
     def forward(self, x: torch.Tensor):
         if not x.is_cuda:
@@ -203,10 +205,15 @@ class LoRARoutedLLaMaFFN(RoutedLLaMaFFN):
         prob, bucket = _route(self.router, x2, self.k_active)
         coeff = _row_coeff(prob.float(), bucket)
         xp = F.gather(_bf16(x2).contiguous(), bucket)
-        h = (self.activation(self._proj(self.gate, xp, coeff, bucket)) * self._proj(self.side, xp, coeff, bucket))
-        h = h.to(torch.bfloat16)
+        bg, lg = self._proj(self.gate, xp, bucket)
+        bsd, lsd = self._proj(self.side, xp, bucket)
+        if isinstance(self.activation, nn.SiLU):       # the LLaMA case: one fused kernel per direction
+            h = F.lora_glu(coeff, bg, lg, bsd, lsd)
+        else:
+            h = (self.activation(F.scale_add(coeff, bg, lg, torch.float32))
+                 * F.scale_add(coeff, bsd, lsd, torch.float32)).to(torch.bfloat16)
         y_base = F.blocked_linear_cols(h, self.down.weight, bucket, bs)
         t2 = F.blocked_linear_cols_t(h, _pad8(self.down.lora.left.weight), bucket, bs)
-        yp = (coeff * y_base.float() + (t2 @ _bf16(_pad8(self.down.lora.right.weight)).t()).float()).to(torch.bfloat16)
+        yp = F.scale_add(coeff, y_base, t2 @ _bf16(_pad8(self.down.lora.right.weight)).t(), torch.bfloat16)
         y = F.combine(yp, bucket, None, x.dtype)
         return y.view(x_size)

@@ -308,3 +308,50 @@ def test_lora_routed_ffn_matches_reference_golden():
         for n, p in ffn.named_parameters():
             if p.requires_grad:
                 assert rel(p.grad, case["grads"][n]) < 8e-2, (key, n, rel(p.grad, case["grads"][n]))
+
+
+# ---------------------------------------------------------------------------- fused elementwise glue (lora_fuse.cu)
+@pytest.mark.parametrize("a_dt,b_dt,o_dt", [(torch.float32, torch.float32, torch.float32),
+                                            (torch.bfloat16, torch.bfloat16, torch.bfloat16),
+                                            (torch.float32, torch.bfloat16, torch.bfloat16)])
+def test_scale_add_matches_torch(a_dt, b_dt, o_dt):
+    from spt_proto_b200.kernels import ffn as F
+    g = torch.Generator(device="cpu").manual_seed(5)
+    R, C = 384, 1032
+    coeff = torch.rand(R, generator=g).to(DEV).requires_grad_()
+    a = torch.randn(R, C, generator=g).to(DEV).to(a_dt).requires_grad_()
+    b = torch.randn(R, C, generator=g).to(DEV).to(b_dt).requires_grad_()
+    out = F.scale_add(coeff, a, b, o_dt)
+    ref = (coeff.detach()[:, None] * a.detach().float() + b.detach().float())
+    assert out.dtype == o_dt
+    tol = 1e-6 if o_dt == torch.float32 else 1.6e-2
+    torch.testing.assert_close(out.float(), ref, atol=tol, rtol=tol)
+    go = torch.randn(R, C, generator=g).to(DEV).to(o_dt)
+    out.backward(go)
+    gf = go.float()
+    torch.testing.assert_close(a.grad.float(), coeff.detach()[:, None] * gf, atol=tol, rtol=tol)
+    torch.testing.assert_close(b.grad.float(), gf, atol=0, rtol=0)
+    torch.testing.assert_close(coeff.grad, (gf * a.detach().float()).sum(1), atol=1e-3, rtol=1e-4)
+
+
+def test_lora_glu_matches_torch_autograd():
+    from spt_proto_b200.kernels import ffn as F
+    g = torch.Generator(device="cpu").manual_seed(6)
+    R, C = 256, 520
+    mk = lambda: torch.randn(R, C, generator=g).to(DEV)
+    coeff = torch.rand(R, generator=g).to(DEV)
+    ts = [mk() for _ in range(4)]
+    leaf = [t.clone().requires_grad_() for t in ts]
+    cf = coeff.clone().requires_grad_()
+    h = F.lora_glu(cf, *leaf)
+    ref_in = [t.clone().double().requires_grad_() for t in ts]
+    cr = coeff.clone().double().requires_grad_()
+    href = torch.nn.functional.silu(cr[:, None] * ref_in[0] + ref_in[1]) * (cr[:, None] * ref_in[2] + ref_in[3])
+    assert h.dtype == torch.bfloat16
+    torch.testing.assert_close(h.float(), href.float(), atol=1e-2, rtol=1e-2)
+    go = torch.randn(R, C, generator=g).to(DEV).to(torch.bfloat16)
+    h.backward(go)
+    href.backward(go.double())
+    for t, r in zip(leaf, ref_in):
+        torch.testing.assert_close(t.grad, r.grad.float(), atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(cf.grad, cr.grad.float(), atol=1e-3, rtol=1e-4)
