@@ -81,6 +81,34 @@ __device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
     asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t pk_f32x2(float lo, float hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ float lo_f32x2(uint64_t v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo;
+}
+__device__ __forceinline__ float hi_f32x2(uint64_t v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return hi;
+}
+__device__ __forceinline__ uint64_t shfl_xor_f32x2(uint64_t v, int o) {
+    return pk_f32x2(__shfl_xor_sync(0xffffffffu, lo_f32x2(v), o), __shfl_xor_sync(0xffffffffu, hi_f32x2(v), o));
+}
 __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
     uint64_t d;
     asm("add.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -399,78 +427,321 @@ namespace spt {
 
 constexpr int PQT_THREADS = 256;
 
-template <typename T, int DC>
-__device__ __forceinline__ void load_row(const T *zp, float (&zv)[DC]) {
-    if constexpr (DC % Vec16<T>::N == 0) {
+// g_loss = dLoss * 2 / (rows * m * dc).  grad_zq (optional, fp32 [rows, m*dc]) is the gradient that reached the
+// hard-centroid output.  grad_z in z's dtype; grad_table partials [gridDim.x][m][C][DC] fp32.
+//
+// Four threads share one (row, subspace) item, each owning C/4 codewords: its slice of the codebook (32 floats) and
+// of the codebook-gradient accumulator (32 floats) live in registers for the whole kernel, so the inner loops
+// touch no memory at all; the few per-item scalars and the 8-vectors zw / grad_z are combined with quad shuffles.
+// (First version: one thread per item with a 128-register accumulator — 255 registers, spills, one block per SM:
+// 285 us per 1 M items.)
+constexpr int PQB_SPLIT = 4;
+
+template <typename T>
+struct RawRow;   // one 8-element row held as raw 16-byte words (prefetched one iteration ahead)
+template <>
+struct RawRow<__nv_bfloat16> {
+    uint4 v;
+    __device__ __forceinline__ void load(const __nv_bfloat16 *p) { v = *reinterpret_cast<const uint4 *>(p); }
+    __device__ __forceinline__ void unpack(float (&f)[8]) const {
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int i = 0; i < DC; i += Vec16<T>::N) {
-            float tmp[Vec16<T>::N];
-            Vec16<T>::load(zp + i, tmp);
-#pragma unroll
-            for (int j = 0; j < Vec16<T>::N; ++j) zv[i + j] = tmp[j];
+        for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __uint_as_float(u[i] << 16);
+            f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
         }
-    } else {
-#pragma unroll
-        for (int i = 0; i < DC; ++i) zv[i] = to_f32(zp[i]);
     }
+};
+template <>
+struct RawRow<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float *p) {
+        a = *reinterpret_cast<const float4 *>(p);
+        b = *reinterpret_cast<const float4 *>(p + 4);
+    }
+    __device__ __forceinline__ void unpack(float (&f)[8]) const {
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+};
+template <typename T, int DC, int C>
+__global__ void __launch_bounds__(PQT_THREADS, 2)
+pq_train_bwd_kernel(const T *__restrict__ z, const float *__restrict__ table, const float *__restrict__ grad_zq,
+                    const float *__restrict__ grad_loss, float loss_scale, T *__restrict__ grad_z,
+                    float *__restrict__ grad_table_partial, int64_t total, int m) {
+    static_assert(DC == 8 && C % PQB_SPLIT == 0, "quad layout assumes 8-wide codewords");
+    constexpr int KC = C / PQB_SPLIT;
+    extern __shared__ __align__(16) float s_mem[];   // [m][PAD] codebook, then [m][C*DC] block gradient
+    constexpr int PAD = C * DC + 4;
+    float *s_w = s_mem, *s_g = s_mem + (size_t)m * PAD;
+    for (int i = threadIdx.x; i < m * C * DC; i += blockDim.x) {
+        s_w[(i / (C * DC)) * PAD + i % (C * DC)] = table[i];
+        s_g[i] = 0.0f;
+    }
+    __syncthreads();
+    const float gl = grad_loss[0] * loss_scale;
+    const int j = threadIdx.x & (PQB_SPLIT - 1);     // which quarter of the codewords
+    const int64_t item0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / PQB_SPLIT;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x / PQB_SPLIT;   // a multiple of m: s is fixed per thread
+    const int s = (int)(item0 % m);
+    const float *wt = s_w + (size_t)s * PAD;
+    // element pairs (2p, 2p+1) are kept packed: the multiply-add parts run as FFMA2 / FADD2 (add.f32x2, fma.rn.f32x2)
+    constexpr int NP = DC / 2;
+    uint64_t w2[KC][NP], acc2[KC][NP];
+#pragma unroll
+    for (int k = 0; k < KC; ++k)
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            w2[k][p] = pk_f32x2(wt[(j * KC + k) * DC + 2 * p], wt[(j * KC + k) * DC + 2 * p + 1]);
+            acc2[k][p] = 0ull;
+        }
+    // the shuffles need converged warps: the trip count is block-uniform and the tail is predicated.
+    // The row of the NEXT iteration is fetched before this one's math (the loads were the largest stall).
+    const uint64_t gl2 = pk_f32x2(gl, gl);
+    RawRow<T> nxt;
+    nxt.load(z + (size_t)(item0 < total ? item0 : total - 1) * DC);
+    const int64_t block_item0 = (int64_t)blockIdx.x * (PQT_THREADS / PQB_SPLIT);
+    const int n_iter = block_item0 < total ? (int)((total - block_item0 + stride - 1) / stride) : 0;   // block-uniform
+    for (int it = 0; it < n_iter; ++it) {
+        const int64_t g = item0 + (int64_t)it * stride;
+        const bool on = g < total;
+        float zv[DC];
+        nxt.unpack(zv);
+        {
+            const int64_t gn = g + stride;
+            nxt.load(z + (size_t)(gn < total ? gn : total - 1) * DC);
+        }
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;          // gradient that reached the hard centroid
+        if (grad_zq != nullptr && on) {
+            q0 = *reinterpret_cast<const float4 *>(grad_zq + (size_t)g * DC);
+            q1 = *reinterpret_cast<const float4 *>(grad_zq + (size_t)g * DC + 4);
+        }
+        uint64_t zv2[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) zv2[p] = pk_f32x2(zv[2 * p], zv[2 * p + 1]);
+        // distances / soft weights of my codewords; quad-wide argmin (lowest index on ties) and weight sum
+        float wgt[KC], a_sum = 0.0f, best = 1e13f;
+        int idx = 0;
+        uint32_t live = 0;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            float d = 0.0f;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                d += fabsf(zv[2 * p] - lo_f32x2(w2[k][p]));
+                d += fabsf(zv[2 * p + 1] - hi_f32x2(w2[k][p]));
+            }
+            if (d < best) {
+                best = d;
+                idx = j * KC + k;
+            }
+            live |= (d > 1e-5f ? 1u : 0u) << k;
+            wgt[k] = 1.0f / fmaxf(d, 1e-5f);
+            a_sum += wgt[k];
+        }
+#pragma unroll
+        for (int o = 1; o < PQB_SPLIT; o <<= 1) {
+            a_sum += __shfl_xor_sync(0xffffffffu, a_sum, o);
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ob < best || (ob == best && oi < idx)) {
+                best = ob;
+                idx = oi;
+            }
+        }
+        const float inv_a = 1.0f / a_sum;
+        uint64_t zw2[NP], wk2[KC];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) zw2[p] = 0ull;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            wgt[k] *= inv_a;
+            wk2[k] = pk_f32x2(wgt[k], wgt[k]);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) zw2[p] = fma_f32x2(wk2[k], w2[k][p], zw2[p]);
+        }
+#pragma unroll
+        for (int o = 1; o < PQB_SPLIT; o <<= 1)
+#pragma unroll
+            for (int p = 0; p < NP; ++p) zw2[p] = add_f32x2(zw2[p], shfl_xor_f32x2(zw2[p], o));
+        // e1 = g (zw - zq) (soft-assignment error), e2 = g (z - zq);  grad_z starts from e2 (a quarter per lane:
+        // the quad sum below restores it exactly), the hard centroid W_idx receives gzq - e1 - e2 on its owner lane
+        uint64_t e12[NP], gz2[NP];
+        {
+            const float4 c0 = *reinterpret_cast<const float4 *>(wt + idx * DC);
+            const float4 c1 = *reinterpret_cast<const float4 *>(wt + idx * DC + 4);
+            const uint64_t zq2[NP] = {pk_f32x2(c0.x, c0.y), pk_f32x2(c0.z, c0.w), pk_f32x2(c1.x, c1.y), pk_f32x2(c1.z, c1.w)};
+            const uint64_t gin2[NP] = {pk_f32x2(q0.x, q0.y), pk_f32x2(q0.z, q0.w), pk_f32x2(q1.x, q1.y), pk_f32x2(q1.z, q1.w)};
+            const uint64_t quarter2 = pk_f32x2(0.25f, 0.25f);
+            static_assert(PQB_SPLIT == 4 && NP == 4, "the 0.25 above is 1 / PQB_SPLIT");
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                e12[p] = mul_f32x2(gl2, sub_f32x2(zw2[p], zq2[p]));
+                const uint64_t e22 = mul_f32x2(gl2, sub_f32x2(zv2[p], zq2[p]));
+                gz2[p] = mul_f32x2(quarter2, e22);
+                const uint64_t gq2 = sub_f32x2(sub_f32x2(gin2[p], e12[p]), e22);
+#pragma unroll
+                for (int k = 0; k < KC; ++k)
+                    if (on && idx == j * KC + k) acc2[k][p] = add_f32x2(acc2[k][p], gq2);
+            }
+        }
+        // gw_c = e1 . W_c ;  t = sum_c gw_c w_c ;  dd_c = -(a_c)^2 (gw_c - t) / A  with a_c = w_c A
+        float gw[KC], t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            uint64_t v2 = 0ull;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) v2 = fma_f32x2(e12[p], w2[k][p], v2);
+            gw[k] = lo_f32x2(v2) + hi_f32x2(v2);
+            t = fmaf(gw[k], wgt[k], t);
+        }
+#pragma unroll
+        for (int o = 1; o < PQB_SPLIT; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (on) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                // -sg = -dd * sign(z - w): the sign bit of the difference flips -dd (a zero difference counts as positive)
+                const uint32_t ndd = __float_as_uint(((live >> k) & 1u) ? (wgt[k] * wgt[k]) * a_sum * (gw[k] - t) : 0.0f);
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const uint64_t diff2 = sub_f32x2(zv2[p], w2[k][p]);
+                    const uint32_t n_lo = ndd ^ (__float_as_uint(lo_f32x2(diff2)) & 0x80000000u);
+                    const uint32_t n_hi = ndd ^ (__float_as_uint(hi_f32x2(diff2)) & 0x80000000u);
+                    const uint64_t nsg2 = pk_f32x2(__uint_as_float(n_lo), __uint_as_float(n_hi));
+                    gz2[p] = sub_f32x2(gz2[p], nsg2);
+                    acc2[k][p] = add_f32x2(fma_f32x2(wk2[k], e12[p], acc2[k][p]), nsg2);
+                }
+            }
+        }
+        // reduce-scatter of grad_z over the quad: lane j ends with the pair (2j, 2j+1)
+        uint64_t h[2], out2;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const uint64_t keep = (j & 2) ? gz2[2 + p] : gz2[p], send = (j & 2) ? gz2[p] : gz2[2 + p];
+            h[p] = add_f32x2(keep, shfl_xor_f32x2(send, 2));
+        }
+        {
+            const uint64_t keep = (j & 1) ? h[1] : h[0], send = (j & 1) ? h[0] : h[1];
+            out2 = add_f32x2(keep, shfl_xor_f32x2(send, 1));
+        }
+        if (on) {
+            T *op = grad_z + (size_t)g * DC + 2 * j;
+            if constexpr (sizeof(T) == 2) {
+                *reinterpret_cast<__nv_bfloat162 *>(op) = __floats2bfloat162_rn(lo_f32x2(out2), hi_f32x2(out2));
+            } else {
+                *reinterpret_cast<float2 *>(op) = make_float2(lo_f32x2(out2), hi_f32x2(out2));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KC; ++k)
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            atomicAdd(&s_g[(s * C + j * KC + k) * DC + 2 * p], lo_f32x2(acc2[k][p]));
+            atomicAdd(&s_g[(s * C + j * KC + k) * DC + 2 * p + 1], hi_f32x2(acc2[k][p]));
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m * C * DC; i += blockDim.x)
+        grad_table_partial[(size_t)blockIdx.x * m * C * DC + i] = s_g[i];
 }
 
-// distances, argmin, soft weights of one (row, subspace) item; wt = this subspace's [C][DC] codebook in smem
-template <int DC, int C>
-__device__ __forceinline__ void pq_soft(const float (&zv)[DC], const float *wt, float (&dist)[C], float (&wgt)[C],
-                                        int &idx, float &inv_a) {
-    float best = 1e13f;
-    idx = 0;
-    float a_sum = 0.0f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        float d = 0.0f;
-#pragma unroll
-        for (int i = 0; i < DC; ++i) d += fabsf(zv[i] - wt[c * DC + i]);
-        dist[c] = d;
-        if (d < best) {
-            best = d;
-            idx = c;
-        }
-        wgt[c] = 1.0f / fmaxf(d, 1e-5f);
-        a_sum += wgt[c];
-    }
-    inv_a = 1.0f / a_sum;
-#pragma unroll
-    for (int c = 0; c < C; ++c) wgt[c] *= inv_a;
-}
-
+// Forward of the 'train' mode: hard centroids (zq_out, optional) and the per-block partial sums of
+// |zw - zq|^2 + |z - zq|^2.  Same quad layout as the backward: four lanes per (row, subspace) item, each with
+// C/4 codewords in registers (one thread per item reading the codebook from shared memory took 2x longer).
 template <typename T, int DC, int C>
 __global__ void __launch_bounds__(PQT_THREADS)
 pq_train_fwd_kernel(const T *__restrict__ z, const float *__restrict__ table, float *__restrict__ zq_out,
                     float *__restrict__ partial, int64_t total, int m) {
+    static_assert(DC == 8 && C % PQB_SPLIT == 0, "quad layout assumes 8-wide codewords");
+    constexpr int KC = C / PQB_SPLIT, NP = DC / 2;
     extern __shared__ __align__(16) float s_w[];   // [m][C*DC + 4] (padded: lanes differ in subspace)
     __shared__ float s_red[PQT_THREADS / 32];
     constexpr int PAD = C * DC + 4;
     for (int i = threadIdx.x; i < m * C * DC; i += blockDim.x) s_w[(i / (C * DC)) * PAD + i % (C * DC)] = table[i];
     __syncthreads();
-    float local = 0.0f;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        const float *wt = s_w + (size_t)(g % m) * PAD;
-        float zv[DC], dist[C], wgt[C], inv_a;
-        int idx;
-        load_row<T, DC>(z + (size_t)g * DC, zv);
-        pq_soft<DC, C>(zv, wt, dist, wgt, idx, inv_a);
-        float zw[DC];
+    const int j = threadIdx.x & (PQB_SPLIT - 1);
+    const int64_t item0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / PQB_SPLIT;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x / PQB_SPLIT;   // a multiple of m
+    const float *wt = s_w + (size_t)(item0 % m) * PAD;
+    uint64_t w2[KC][NP];
 #pragma unroll
-        for (int i = 0; i < DC; ++i) zw[i] = 0.0f;
+    for (int k = 0; k < KC; ++k)
 #pragma unroll
-        for (int c = 0; c < C; ++c)
+        for (int p = 0; p < NP; ++p)
+            w2[k][p] = pk_f32x2(wt[(j * KC + k) * DC + 2 * p], wt[(j * KC + k) * DC + 2 * p + 1]);
+    RawRow<T> nxt;
+    nxt.load(z + (size_t)(item0 < total ? item0 : total - 1) * DC);
+    const int64_t block_item0 = (int64_t)blockIdx.x * (PQT_THREADS / PQB_SPLIT);
+    const int n_iter = block_item0 < total ? (int)((total - block_item0 + stride - 1) / stride) : 0;   // block-uniform
+    uint64_t local2 = 0ull;
+    for (int it = 0; it < n_iter; ++it) {
+        const int64_t g = item0 + (int64_t)it * stride;
+        const bool on = g < total;
+        float zv[DC];
+        nxt.unpack(zv);
+        {
+            const int64_t gn = g + stride;
+            nxt.load(z + (size_t)(gn < total ? gn : total - 1) * DC);
+        }
+        float wgt[KC], a_sum = 0.0f, best = 1e13f;
+        int idx = 0;
 #pragma unroll
-            for (int i = 0; i < DC; ++i) zw[i] = fmaf(wgt[c], wt[c * DC + i], zw[i]);
+        for (int k = 0; k < KC; ++k) {
+            float d = 0.0f;
 #pragma unroll
-        for (int i = 0; i < DC; ++i) {
-            const float zq = wt[idx * DC + i];
-            const float e1 = zw[i] - zq, e2 = zv[i] - zq;
-            local = fmaf(e1, e1, fmaf(e2, e2, local));
-            if (zq_out) zq_out[(size_t)g * DC + i] = zq;
+            for (int p = 0; p < NP; ++p) {
+                d += fabsf(zv[2 * p] - lo_f32x2(w2[k][p]));
+                d += fabsf(zv[2 * p + 1] - hi_f32x2(w2[k][p]));
+            }
+            if (d < best) {
+                best = d;
+                idx = j * KC + k;
+            }
+            wgt[k] = 1.0f / fmaxf(d, 1e-5f);
+            a_sum += wgt[k];
+        }
+#pragma unroll
+        for (int o = 1; o < PQB_SPLIT; o <<= 1) {
+            a_sum += __shfl_xor_sync(0xffffffffu, a_sum, o);
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ob < best || (ob == best && oi < idx)) {
+                best = ob;
+                idx = oi;
+            }
+        }
+        const float inv_a = 1.0f / a_sum;
+        uint64_t zw2[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) zw2[p] = 0ull;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const float wk = wgt[k] * inv_a;
+            const uint64_t wk2 = pk_f32x2(wk, wk);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) zw2[p] = fma_f32x2(wk2, w2[k][p], zw2[p]);
+        }
+        // reduce-scatter over the quad: lane j ends with the pair (2j, 2j+1) of zw, and handles that pair of the loss
+        uint64_t h[2], zwj;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const uint64_t keep = (j & 2) ? zw2[2 + p] : zw2[p], send = (j & 2) ? zw2[p] : zw2[2 + p];
+            h[p] = add_f32x2(keep, shfl_xor_f32x2(send, 2));
+        }
+        {
+            const uint64_t keep = (j & 1) ? h[1] : h[0], send = (j & 1) ? h[0] : h[1];
+            zwj = add_f32x2(keep, shfl_xor_f32x2(send, 1));
+        }
+        if (on) {
+            const float2 zq = *reinterpret_cast<const float2 *>(wt + idx * DC + 2 * j);
+            const uint64_t zq2 = pk_f32x2(zq.x, zq.y);
+            const float za = (j & 2) ? ((j & 1) ? zv[6] : zv[4]) : ((j & 1) ? zv[2] : zv[0]);
+            const float zb = (j & 2) ? ((j & 1) ? zv[7] : zv[5]) : ((j & 1) ? zv[3] : zv[1]);
+            const uint64_t e1 = sub_f32x2(zwj, zq2), e2 = sub_f32x2(pk_f32x2(za, zb), zq2);
+            local2 = fma_f32x2(e1, e1, fma_f32x2(e2, e2, local2));
+            if (zq_out) *reinterpret_cast<float2 *>(zq_out + (size_t)g * DC + 2 * j) = zq;
         }
     }
+    float local = lo_f32x2(local2) + hi_f32x2(local2);
     local = warp_sum(local);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
     __syncthreads();
@@ -481,109 +752,14 @@ pq_train_fwd_kernel(const T *__restrict__ z, const float *__restrict__ table, fl
     }
 }
 
-// g_loss = dLoss * 2 / (rows * m * dc).  grad_zq (optional, fp32 [rows, m*dc]) is the gradient that reached the
-// hard-centroid output.  grad_z in z's dtype; grad_table partials [gridDim.x][m][C][DC] fp32.
-template <typename T, int DC, int C>
-__global__ void __launch_bounds__(PQT_THREADS)
-pq_train_bwd_kernel(const T *__restrict__ z, const float *__restrict__ table, const float *__restrict__ grad_zq,
-                    const float *__restrict__ grad_loss, float loss_scale, T *__restrict__ grad_z,
-                    float *__restrict__ grad_table_partial, int64_t total, int m) {
-    extern __shared__ __align__(16) float s_mem[];   // [m][PAD] codebook, then [m][C*DC] block gradient
-    constexpr int PAD = C * DC + 4;
-    float *s_w = s_mem, *s_g = s_mem + (size_t)m * PAD;
-    for (int i = threadIdx.x; i < m * C * DC; i += blockDim.x) {
-        s_w[(i / (C * DC)) * PAD + i % (C * DC)] = table[i];
-        s_g[i] = 0.0f;
-    }
-    __syncthreads();
-    const float gl = grad_loss[0] * loss_scale;
-    const int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = (int)(g0 % m);                    // the grid stride is a multiple of m: s is fixed per thread
-    const float *wt = s_w + (size_t)s * PAD;
-    float acc[C][DC];
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-#pragma unroll
-        for (int i = 0; i < DC; ++i) acc[c][i] = 0.0f;
-    for (int64_t g = g0; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        float zv[DC], dist[C], wgt[C], inv_a;
-        int idx;
-        load_row<T, DC>(z + (size_t)g * DC, zv);
-        pq_soft<DC, C>(zv, wt, dist, wgt, idx, inv_a);
-        float zw[DC];
-#pragma unroll
-        for (int i = 0; i < DC; ++i) zw[i] = 0.0f;
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int i = 0; i < DC; ++i) zw[i] = fmaf(wgt[c], wt[c * DC + i], zw[i]);
-        float e1[DC], gz[DC], gq[DC];    // gq: gradient into the hard centroid W_idx
-#pragma unroll
-        for (int i = 0; i < DC; ++i) {
-            const float zq = wt[idx * DC + i];
-            e1[i] = gl * (zw[i] - zq);
-            const float e2 = gl * (zv[i] - zq);
-            gz[i] = e2;
-            gq[i] = -e1[i] - e2 + (grad_zq ? grad_zq[(size_t)g * DC + i] : 0.0f);
-        }
-        // gw_c = e1 . W_c ;  t = sum_c gw_c w_c ;  dd_c = -(a_c)^2 (gw_c - t) / A  with a_c = w_c A
-        // (gw_c is recomputed in the second pass instead of being kept: registers are the scarce resource)
-        float t = 0.0f;
-        uint32_t live = 0;   // bit c: d_c > 1e-5 (the clamp passes gradient)
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            float v = 0.0f;
-#pragma unroll
-            for (int i = 0; i < DC; ++i) v = fmaf(e1[i], wt[c * DC + i], v);
-            t = fmaf(v, wgt[c], t);
-            live |= (dist[c] > 1e-5f ? 1u : 0u) << c;
-        }
-        const float a_sum = 1.0f / inv_a;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            float v = 0.0f;
-#pragma unroll
-            for (int i = 0; i < DC; ++i) v = fmaf(e1[i], wt[c * DC + i], v);
-            const float dd = ((live >> c) & 1u) ? -(wgt[c] * wgt[c]) * a_sum * (v - t) : 0.0f;
-#pragma unroll
-            for (int i = 0; i < DC; ++i) {
-                const float sg = (zv[i] - wt[c * DC + i]) > 0.0f ? dd : -dd;
-                gz[i] += sg;
-                acc[c][i] += fmaf(wgt[c], e1[i], -sg);
-            }
-        }
-        // the hard centroid's gradient goes straight to the block accumulator (8 shared-memory adds per item)
-#pragma unroll
-        for (int i = 0; i < DC; ++i) atomicAdd(&s_g[(s * C + idx) * DC + i], gq[i]);
-        T *op = grad_z + (size_t)g * DC;
-        if constexpr (DC % Vec16<T>::N == 0) {
-#pragma unroll
-            for (int i = 0; i < DC; i += Vec16<T>::N) {
-                float tmp[Vec16<T>::N];
-#pragma unroll
-                for (int j = 0; j < Vec16<T>::N; ++j) tmp[j] = gz[i + j];
-                Vec16<T>::store(op + i, tmp);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < DC; ++i) op[i] = from_f32<T>(gz[i]);
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-#pragma unroll
-        for (int i = 0; i < DC; ++i) atomicAdd(&s_g[(s * C + c) * DC + i], acc[c][i]);
-    __syncthreads();
-    for (int i = threadIdx.x; i < m * C * DC; i += blockDim.x)
-        grad_table_partial[(size_t)blockIdx.x * m * C * DC + i] = s_g[i];
-}
-
 static int pq_train_grid(int64_t total, int m) {
-    int64_t want = (total + PQT_THREADS - 1) / PQT_THREADS;
+    // one grid for both directions (the backward runs PQB_SPLIT threads per item, the forward one)
+    constexpr int per_block = PQT_THREADS / PQB_SPLIT;
+    int64_t want = (total + per_block - 1) / per_block;
     int64_t cap = (int64_t)num_sms() * 2;
     int64_t g = want < cap ? want : cap;
-    // the grid stride (g * PQT_THREADS) must be a multiple of m so that a thread keeps its subspace
-    while ((g * PQT_THREADS) % m != 0) ++g;
+    // the grid stride in items (g * per_block, g * PQT_THREADS) must be a multiple of m: a thread keeps its subspace
+    while ((g * per_block) % m != 0) ++g;
     return (int)g;
 }
 
