@@ -19,29 +19,35 @@
 //   memory descriptors — no transposed copies of weights or activations are ever made (the
 //   reference materialises a permuted copy of W2 on every call, feedforward.py:94-102).
 //
-// Kernel anatomy (persistent CTAs, one per SM, 128x256 output tiles dealt round-robin):
-//   warp 0   : TMA producer  — cp.async.bulk.tensor.2d into a 3-stage ring of 128B-swizzled tiles
-//   warp 1   : TMEM allocator + MMA issuer — one elected lane issues tcgen05.mma (M128 N256 K16, kind::f16)
+// Two kernels share the operand layout and the epilogue:
+//   grouped_gemm_pair_kernel (default): CTA pairs (tcgen05 cta_group::2), 256x256 units, see its header below
+//   grouped_gemm_kernel      (SPT_GEMM_CTA_PAIR=0, or more than 1024 m-tiles): one CTA per SM, 128x256 tiles
+// Anatomy of both (persistent CTAs, tiles dealt round-robin):
+//   warp 0   : TMA producer  — cp.async.bulk.tensor.2d into a ring of 128B-swizzled tiles
+//   warp 1   : TMEM allocator + MMA issuer — one elected lane issues tcgen05.mma (kind::f16)
 //   warps 2-9: epilogue — tcgen05.ld TMEM -> registers, bias / activation / row scale / gate, staged through
 //              shared memory into coalesced global stores
 //   smem full/empty mbarriers between TMA and MMA, full/empty mbarriers per TMEM accumulator (two of them)
 //   between MMA and epilogue.
 #include <algorithm>
+#include <cstdlib>
 
 #include "tc.cuh"
 
 namespace spt {
 namespace gemm {
 
-// 128 x 256 output tiles, PERSISTENT CTAs (one per SM): the TMA producer streams k-blocks of consecutive tiles
-// through a 3-stage ring without draining between tiles, and two 256-column TMEM accumulators let the
-// epilogue of tile i run under the main loop of tile i+1.
+// Single-CTA kernel: 128 x 256 output tiles, PERSISTENT CTAs (one per SM): the TMA producer streams k-blocks of
+// consecutive tiles through a 3-stage ring without draining between tiles, and two 256-column TMEM accumulators
+// let the epilogue of tile i run under the main loop of tile i+1.  An N = 256 MMA of one CTA reads 12 KB of shared
+// memory per k-step while TMA writes the next stage: the stream runs at ~2/3 of the MMA floor (171 clk measured
+// against 128), which is what the CTA-pair kernel below removes.
 //
-// Measured ceiling of this single-CTA (cta_group::1) design: ~640 TFLOP/s per GEMM = 45 % of the cuBLAS bf16
-// rate, reached alike by 128x128 tiles with 2 CTAs/SM (574), 128x256 with 2 CTAs/SM (608-640), this persistent
-// kernel (640), cluster TMA multicast of the shared B tile (no change) and 256x256 units (slower: 480).  Tile
-// shape, pipeline depth and L2 traffic do not move it: a single-SM tcgen05.mma stream tops out near half of the
-// tensor peak, the rest needs cta_group::2 (a CTA pair issuing M = 256 MMAs over both SMs' shared memory).
+// Round-1 measurements on the FFN step of bench.py (6 GEMMs, 0.825 TFLOP): first version 1.70 ms; epilogue through
+// shared memory + N-fastest tile order 0.91 ms; CTA pairs 0.78 ms; epilogue values kept in registers (a run-time
+// loop bound in the ragged-edge path had put the 32-value row buffer in local memory in EVERY path) 0.63 ms
+// = 1.30 PFLOP/s.  With the epilogue switched off the pair kernel needs 0.565 ms, the MMA stream alone 0.50 ms
+// (1.65 PFLOP/s, the cuBLAS burst figure of MEASURED_PEAKS.json), TMA alone 0.48 ms (12.9 TB/s out of L2).
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 3;
 constexpr int EPI_WARPS = 8;                            // two per TMEM lane quarter, each owning 128 of the 256 columns
 constexpr int THREADS = 64 + EPI_WARPS * 32;
@@ -336,10 +342,14 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 } else if (row_in_tile < rows_ok) {
                     if (out_bf16) {
                         __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.C) + c_row * p.ldc + ti.c_col0 + c0;
-                        for (int i = 0; i < 32 && c0 + i < n_valid; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)      // static indices: a run-time bound would put v[] in local memory
+                            if (c0 + i < n_valid) dst[i] = __float2bfloat16_rn(v[i]);
                     } else {
                         float *dst = reinterpret_cast<float *>(p.C) + c_row * p.ldc + ti.c_col0 + c0;
-                        for (int i = 0; i < 32 && c0 + i < n_valid; ++i) dst[i] = v[i];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c0 + i < n_valid) dst[i] = v[i];
                     }
                 }
             }
@@ -351,6 +361,344 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// =====================================================================================================
+// CTA-pair version (tcgen05 cta_group::2): the two CTAs of a cluster sit on the two SMs of a TPC and run ONE
+// M = 256, N = 256 MMA stream.  Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256
+// columns), so a k-step costs every SM 8 KB of shared-memory reads instead of 12 KB: the single-CTA kernel
+// above is bound by exactly that (N = 256 MMAs took 171 clk against a floor of 128).  Stages shrink to 32 KB,
+// the ring grows to 5.
+//
+//   unit          : 256 rows x 256 columns = m-tiles (2i, 2i+1) x one n-tile.  In mode 0 a pair that straddles two
+//                   groups is run twice, once per group, with the other CTA's half computed on the wrong weights
+//                   and thrown away (at most one such pair per group boundary).
+//   leader (rank 0): expects the bytes of both CTAs on its full barrier, issues the MMAs, multicasts the
+//                   commits (stage free / accumulator full) to both CTAs
+//   both CTAs     : TMA producer warp (loads complete on the leader's barrier), 8 epilogue warps over their own
+//                   128 TMEM lanes; one arrive per epilogue warp on the leader's accumulator-empty barrier
+constexpr int STAGES2 = 5;
+constexpr int HALF_BYTES = 128 * BK * 2;                // 16 KB: A rows of this CTA, or its half of B
+constexpr int MAX_LIST = 1024;                          // mode 0: (pair, sub) entries -> up to 1024 m-tiles
+constexpr int SMEM2_BYTES = STAGES2 * 2 * HALF_BYTES + EPI_WARPS * 32 * STG_PITCH + MAX_LIST * 2 + 1024 + 256;
+
+struct Unit {
+    int g, n0, k_begin, n_kblk;
+    int a_mn, b_mn;          // this CTA's TMA coordinates along M / N
+    long long c_row0, c_col0;  // this CTA's output origin
+    bool mma;                // the unit runs MMAs (false: tail pair without rows -> zero fill only)
+    int role;                // this CTA: 0 = idle (its half is discarded), 1 = active, 2 = zero-fill its rows
+    int rows_ok;             // valid rows of this CTA's half
+};
+
+__device__ __forceinline__ Unit get_unit(const Params &p, int u, const uint16_t *list, int rank) {
+    Unit un;
+    const int tile_n = u % p.tiles_n;
+    un.n0 = tile_n * BN;
+    un.b_mn = un.n0 + rank * (BN / 2);
+    un.c_col0 = un.n0;
+    if (p.mode == 0) {
+        const int e = list[u / p.tiles_n], pair = e >> 1, sub = e & 1;
+        const int t0 = 2 * pair, t1 = 2 * pair + 1;
+        const int g0 = p.tile_group[t0], g1 = t1 < p.tiles_m ? p.tile_group[t1] : -2;   // -2: no such tile
+        un.g = sub ? g1 : g0;
+        un.mma = un.g >= 0;
+        const int mine = rank ? g1 : g0;
+        un.role = (un.mma && mine == un.g) ? 1 : ((mine == -1 && sub == 0) ? 2 : 0);
+        un.k_begin = 0;
+        un.n_kblk = un.mma ? (p.K + BK - 1) / BK : 0;
+        un.a_mn = (t0 + rank) * BM;
+        un.c_row0 = (long long)(t0 + rank) * BM;
+        un.rows_ok = BM;
+        un.b_mn += un.g * p.b_mn_off;
+    } else {
+        const int pairs_m = (p.tiles_m + 1) / 2;
+        const int pm = (u / p.tiles_n) % pairs_m, z = u / (p.tiles_n * pairs_m);
+        const int m0 = (2 * pm + rank) * BM;
+        un.g = z;
+        un.mma = true;
+        un.role = 1;
+        un.k_begin = p.group_ptr[z];
+        un.n_kblk = (p.group_ptr[z + 1] - un.k_begin + BK - 1) / BK;
+        un.a_mn = z * p.a_mn_off + m0;
+        un.c_row0 = (long long)z * p.c_row_off + m0;
+        un.c_col0 += (long long)z * p.c_col_off;
+        un.rows_ok = min(BM, p.M - m0);     // <= 0 for the phantom half of an odd tile count
+        un.b_mn += z * p.b_mn_off;
+    }
+    return un;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const Params p, const int n_units_mode1) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023) & ~1023u;
+    unsigned char *smem = smem_raw + (base - raw);
+    const uint32_t s_a = base, s_b = base + STAGES2 * HALF_BYTES;
+    unsigned char *s_stage = smem + STAGES2 * 2 * HALF_BYTES;
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_stage + EPI_WARPS * 32 * STG_PITCH);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(s_list) + MAX_LIST * 2);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + s * 8; };
+    auto empty_bar = [&](int s) { return bar0 + (STAGES2 + s) * 8; };
+    auto acc_full = [&](int a) { return bar0 + (2 * STAGES2 + a) * 8; };
+    auto acc_empty = [&](int a) { return bar0 + (2 * STAGES2 + 2 + a) * 8; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES2 + 4);
+    int *s_scan = reinterpret_cast<int *>(tmem_slot + 2);       // [THREADS / 32 + 1] warp totals of the list scan
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES2; ++s) {
+            mbar_init(full_bar(s), 1);       // leader's: its producer's arrive.expect_tx (bytes of both CTAs)
+            mbar_init(empty_bar(s), 1);      // one multicast commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(acc_full(a), 1);
+            mbar_init(acc_empty(a), 2 * EPI_WARPS);   // leader's: one arrive per epilogue warp of both CTAs
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc_pair<TMEM_COLS>(smem_u32(tmem_slot));
+
+    // mode 0: the list of (pair, sub) entries that exist.  sub 0 always; sub 1 only where the pair's second tile
+    // belongs to another group.  Both CTAs build the same list.
+    int n_units = n_units_mode1;
+    if (p.mode == 0) {
+        const int n_cand = 2 * ((p.tiles_m + 1) / 2);
+        int base_cnt = 0;
+        for (int c0 = 0; c0 < n_cand; c0 += THREADS) {
+            const int c = c0 + threadIdx.x;
+            bool real = false;
+            if (c < n_cand) {
+                const int t0 = c & ~1, t1 = t0 + 1;
+                if ((c & 1) == 0) real = true;
+                else if (t1 < p.tiles_m) {
+                    const int g1 = p.tile_group[t1];
+                    real = g1 >= 0 && g1 != p.tile_group[t0];
+                }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, real);
+            if (lane == 0) s_scan[warp] = __popc(bal);
+            __syncthreads();
+            int before = base_cnt, total = base_cnt;
+            for (int w = 0; w < THREADS / 32; ++w) {
+                const int cnt = s_scan[w];
+                if (w < warp) before += cnt;
+                total += cnt;
+            }
+            if (real) s_list[before + __popc(bal & ((1u << lane) - 1))] = (uint16_t)c;
+            base_cnt = total;
+            __syncthreads();
+        }
+        n_units = base_cnt * p.tiles_n;
+    }
+    fence_before_sync();
+    cluster_sync_all();          // barriers of both CTAs initialised, TMEM allocated, list visible
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own A rows + own half of B; bytes are counted on the leader's barrier =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int u = cluster_id; u < n_units; u += n_clusters) {
+                const Unit un = get_unit(p, u, s_list, rank);
+                if (!un.mma) continue;
+                const int a_k = un.g * p.a_k_off, b_k = un.g * p.b_k_off;
+                for (int kb = 0; kb < un.n_kblk; ++kb, ++it) {
+                    const int s = it % STAGES2;
+                    mbar_wait(empty_bar(s), ((it / STAGES2) & 1) ^ 1);
+                    if (rank == 0) mbar_expect_tx(full_bar(s), 4 * HALF_BYTES);
+                    const int k0 = un.k_begin + kb * BK;
+                    const uint32_t da = s_a + s * HALF_BYTES, db = s_b + s * HALF_BYTES;
+                    if (p.a_mn_major) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) tma_load_2d_pair(da + h * 8192, &map_a, full_bar(s), un.a_mn + 64 * h, a_k + k0);
+                    } else {
+                        tma_load_2d_pair(da, &map_a, full_bar(s), a_k + k0, un.a_mn);
+                    }
+                    if (p.b_mn_major) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) tma_load_2d_pair(db + h * 8192, &map_b, full_bar(s), un.b_mn + 64 * h, b_k + k0);
+                    } else {
+                        tma_load_2d_pair(db, &map_b, full_bar(s), b_k + k0, un.b_mn);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ===== MMA issuer (leader only): M = 256 over both CTAs, N = 256, K = 16 per instruction =====
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn_major << 15) |
+                                   ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)((2 * BM) >> 4) << 24);
+            const uint64_t da0 = operand_desc(s_a, p.a_mn_major, 0), db0 = operand_desc(s_b, p.b_mn_major, 0);
+            const uint64_t a_step = p.a_mn_major ? MNMAJOR_K16 : KMAJOR_K16, b_step = p.b_mn_major ? MNMAJOR_K16 : KMAJOR_K16;
+            uint32_t it = 0, n_acc = 0;
+            for (int u = cluster_id; u < n_units; u += n_clusters) {
+                const Unit un = get_unit(p, u, s_list, rank);
+                if (!un.mma) continue;
+                const int acc = n_acc & 1;
+                mbar_wait(acc_empty(acc), ((n_acc >> 1) & 1) ^ 1);   // both CTAs have drained this accumulator
+                fence_after_sync();
+                for (int kb = 0; kb < un.n_kblk; ++kb, ++it) {
+                    const int s = it % STAGES2;
+                    mbar_wait(full_bar(s), (it / STAGES2) & 1);
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint64_t da = da0 + (uint64_t)(s * (HALF_BYTES >> 4)), db = db0 + (uint64_t)(s * (HALF_BYTES >> 4));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16_pair(tmem_base + acc * BN, da + k * a_step, db + k * b_step, idesc, (kb | k) != 0);
+                        umma_commit_pair(empty_bar(s), 0b11);         // frees the stage in both CTAs
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) umma_commit_pair(acc_full(acc), 0b11);
+                __syncwarp();
+                ++n_acc;
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): as in the single-CTA kernel, over this CTA's 128 rows of the unit =====
+        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
+        const int row_in_tile = quarter * 32 + lane;
+        unsigned char *stage = s_stage + (warp - 2) * 32 * STG_PITCH;
+        const bool out_bf16 = p.c_dtype == SPT_BF16;
+        const int esz = out_bf16 ? 2 : 4;
+        uint32_t n_acc = 0;
+        for (int u = cluster_id; u < n_units; u += n_clusters) {
+            const Unit un = get_unit(p, u, s_list, rank);
+            const int n_valid = min(BN, p.N - un.n0);
+            if (un.role == 2) {
+                // tail tile beyond the bucketed rows: define its output (zeros)
+                for (int i = threadIdx.x - 64; i < BM * n_valid; i += EPI_WARPS * 32) {
+                    const long long off = (un.c_row0 + i / n_valid) * p.ldc + un.c_col0 + i % n_valid;
+                    if (out_bf16) reinterpret_cast<__nv_bfloat16 *>(p.C)[off] = __float2bfloat16_rn(0.0f);
+                    else reinterpret_cast<float *>(p.C)[off] = 0.0f;
+                }
+            }
+            if (!un.mma) continue;
+            const int acc = n_acc & 1;
+            mbar_wait(acc_full(acc), (n_acc >> 1) & 1);
+            fence_after_sync();
+            if (un.role == 1 && un.rows_ok > 0) {
+                const int rows_ok = un.rows_ok;
+                const long long c_row = un.c_row0 + row_in_tile;
+                const float rs = (p.row_scale && p.mode == 0) ? p.row_scale[c_row] : 1.0f;
+                unsigned char *c_base = reinterpret_cast<unsigned char *>(p.C);
+                const bool aligned = ((reinterpret_cast<uintptr_t>(p.C) + (size_t)un.c_col0 * esz) % 16 == 0) && ((p.ldc * esz) % 16 == 0);
+#pragma unroll 1
+                for (int c64 = chalf * (BN / 2); c64 < (chalf + 1) * (BN / 2); c64 += 64) {
+                    if (c64 >= n_valid) break;
+                    // one 64-column tcgen05.ld per step, processed as two 32-column halves through the staging tile
+                    uint32_t r64[64];
+                    __syncwarp();
+                    tmem_ld64_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c64, r64);
+                    tmem_ld_wait();
+#pragma unroll
+                  for (int hh = 0; hh < 2; ++hh) {
+                    const int c0 = c64 + 32 * hh;
+                    if (c0 >= n_valid) break;
+                    uint32_t r[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = r64[32 * hh + i];
+                    __syncwarp();          // the staging tile is reused: everyone has read the previous half
+                    float v[32];
+                    const bool full = c0 + 32 <= n_valid;
+                    if (un.n_kblk == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = 0;
+                    }
+                    if (p.bias) {
+                        const float *bp = p.bias + (long long)un.g * p.bias_stride + un.n0 + c0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + ((full || c0 + i < n_valid) ? __ldg(bp + i) : 0.0f);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    }
+                    if (p.act == 1) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+                    } else if (p.act == 2) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = v[i] / (1.0f + __expf(-v[i]));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] *= rs;
+                    if (p.gate && row_in_tile < rows_ok) {
+                        const __nv_bfloat16 *gp = p.gate + c_row * p.ldg + un.c_col0 + c0;
+                        if (full && (reinterpret_cast<uintptr_t>(gp) % 16 == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                float gv[8];
+                                Vec16<__nv_bfloat16>::load(gp + i, gv);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    if (!(gv[q] > 0.0f)) v[i + q] = 0.0f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (c0 + i < n_valid && !(__bfloat162float(gp[i]) > 0.0f)) v[i] = 0.0f;
+                        }
+                    }
+                    if (full && aligned) {
+                        unsigned char *srow = stage + lane * STG_PITCH;
+                        if (out_bf16) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                float t8[8] = {v[i], v[i + 1], v[i + 2], v[i + 3], v[i + 4], v[i + 5], v[i + 6], v[i + 7]};
+                                Vec16<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16 *>(srow) + i, t8);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4)
+                                *reinterpret_cast<float4 *>(srow + i * 4) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        }
+                        __syncwarp();
+                        const int segs = out_bf16 ? 4 : 8;
+                        const int rows_per = 32 / segs;
+                        const int seg = lane % segs, rsub = lane / segs;
+                        for (int r0 = 0; r0 < 32; r0 += rows_per) {
+                            const int rr = r0 + rsub;
+                            if (quarter * 32 + rr < rows_ok) {
+                                const uint4 val = *reinterpret_cast<const uint4 *>(stage + rr * STG_PITCH + seg * 16);
+                                unsigned char *dst = c_base + ((un.c_row0 + quarter * 32 + rr) * p.ldc + un.c_col0 + c0) * esz + seg * 16;
+                                *reinterpret_cast<uint4 *>(dst) = val;
+                            }
+                        }
+                    } else if (row_in_tile < rows_ok) {
+                        if (out_bf16) {
+                            __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.C) + c_row * p.ldc + un.c_col0 + c0;
+    #pragma unroll
+                        for (int i = 0; i < 32; ++i)      // static indices: a run-time bound would put v[] in local memory
+                            if (c0 + i < n_valid) dst[i] = __float2bfloat16_rn(v[i]);
+                        } else {
+                            float *dst = reinterpret_cast<float *>(p.C) + c_row * p.ldc + un.c_col0 + c0;
+    #pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c0 + i < n_valid) dst[i] = v[i];
+                        }
+                    }
+                  }
+                }
+            }
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty(acc), 0);   // 16 arrivals on the leader: accumulator may be overwritten
+            ++n_acc;
+        }
+    }
+    fence_before_sync();
+    cluster_sync_all();          // nobody leaves (or frees TMEM) while the partner may still signal or be read
+    if (warp == 1) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
 }
 
 // ---- host: tensor maps ---------------------------------------------------------------------------
@@ -411,6 +759,24 @@ extern "C" int spt_grouped_gemm_bf16(int mode, const void *A, long long a_rows, 
     const long long n_tiles = (long long)p.tiles_n * p.tiles_m * (mode == 0 ? 1 : n_groups);
     SPT_REQUIRE(n_tiles < (1ll << 31), "grouped_gemm: too many tiles");
     p.n_tiles = (int)n_tiles;
+    static const bool use_pair = [] {
+        const char *e = getenv("SPT_GEMM_CTA_PAIR");       // "0": keep the single-CTA kernel (A/B measurements)
+        return !(e && e[0] == '0');
+    }();
+    if (use_pair && (mode == 1 || p.tiles_m <= gemm::MAX_LIST)) {
+        const int pairs_m = (p.tiles_m + 1) / 2;
+        const long long units_cap = (long long)p.tiles_n * (mode == 0 ? 2ll * pairs_m : (long long)pairs_m * n_groups);
+        SPT_REQUIRE(units_cap < (1ll << 31), "grouped_gemm: too many tiles");
+        const int n_units1 = mode == 1 ? (int)units_cap : 0;    // mode 0 counts its units on the device
+        const int n_clusters = (int)std::min<long long>(mode == 1 ? units_cap : (long long)p.tiles_n * pairs_m, num_sms() / 2);
+        static bool attr2_set = false;
+        if (!attr2_set) {
+            cudaFuncSetAttribute(gemm::grouped_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM2_BYTES);
+            attr2_set = true;
+        }
+        gemm::grouped_gemm_pair_kernel<<<2 * n_clusters, gemm::THREADS, gemm::SMEM2_BYTES, as_stream(stream)>>>(map_a, map_b, p, n_units1);
+        return after_launch("grouped_gemm_pair_kernel");
+    }
     const int n_ctas = (int)std::min<long long>(n_tiles, num_sms());
     static bool attr_set = false;
     if (!attr_set) {
