@@ -115,22 +115,34 @@ place_kernel(const float *__restrict__ prob, const unsigned long long *__restric
     }
 }
 
-// dst[r, :] = src[row_token[r], :] (zeros for padding rows); 16-byte chunks, C % 8 == 0 (bf16)
+// dst[r, :] = src[row_token[r], :] (zeros for padding rows); 16-byte chunks, C % 8 == 0 (bf16).
+// One warp per (row, 2 KB span): every lane moves four 16-byte chunks, all four loads in flight before the stores.
+constexpr int GR_UNROLL = 4;
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const __nv_bfloat16 *__restrict__ src, const int32_t *__restrict__ row_token,
-                   __nv_bfloat16 *__restrict__ dst, long long R, int C) {
+                   __nv_bfloat16 *__restrict__ dst, long long R, int C, int spans) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= R * spans) return;
+    const long long r = w / spans;
+    const int c0 = (int)(w % spans) * (GR_UNROLL * 32) + lane;   // first chunk of this lane
     const int chunks = C / 8;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= R * chunks) return;
-    const long long r = idx / chunks;
-    const int c = (int)(idx % chunks);
     const int t = row_token[r];
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (t >= 0) v = *reinterpret_cast<const uint4 *>(src + (long long)t * C + c * 8);
-    *reinterpret_cast<uint4 *>(dst + r * C + c * 8) = v;
+    const uint4 *sp = reinterpret_cast<const uint4 *>(src + (long long)(t < 0 ? 0 : t) * C);
+    uint4 *dp = reinterpret_cast<uint4 *>(dst + r * C);
+    uint4 v[GR_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GR_UNROLL; ++u) {
+        v[u] = make_uint4(0, 0, 0, 0);
+        if (t >= 0 && c0 + 32 * u < chunks) v[u] = sp[c0 + 32 * u];
+    }
+#pragma unroll
+    for (int u = 0; u < GR_UNROLL; ++u)
+        if (c0 + 32 * u < chunks) dp[c0 + 32 * u] = v[u];
 }
 
-// y[t, :] = bias + sum_j part[token_rows[t, j], :]  (j ascending = block order), fp32 accumulation
+// y[t, :] = bias + sum_j part[token_rows[t, j], :]  (j ascending = block order), fp32 accumulation.
+// The k rows are fetched four at a time (independent loads), then added in ascending j.
 template <typename TP, typename TY>
 __global__ void __launch_bounds__(256)
 combine_kernel(const TP *__restrict__ part, const int32_t *__restrict__ token_rows, const float *__restrict__ bias,
@@ -144,15 +156,27 @@ combine_kernel(const TP *__restrict__ part, const int32_t *__restrict__ token_ro
     float acc[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[i] = bias ? bias[c + i] : 0.0f;
-    for (int j = 0; j < k; ++j) {
-        const int row = token_rows[t * k + j];
-        float v[V];
-        Vec16<TP>::load(part + (long long)row * C + c, v);
+    for (int j0 = 0; j0 < k; j0 += 4) {
+        int row[4];
+        float v[4][V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] += v[i];
+        for (int u = 0; u < 4; ++u) row[u] = j0 + u < k ? token_rows[t * k + j0 + u] : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (row[u] >= 0) Vec16<TP>::load(part + (long long)row[u] * C + c, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (row[u] >= 0) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) acc[i] += v[u][i];
+            }
     }
+    if constexpr (sizeof(TY) == 2 && V == 8) {
+        Vec16<TY>::store(y + t * C + c, acc);
+    } else {
 #pragma unroll
-    for (int i = 0; i < V; ++i) y[t * C + c + i] = from_f32<TY>(acc[i]);
+        for (int i = 0; i < V; ++i) y[t * C + c + i] = from_f32<TY>(acc[i]);
+    }
 }
 
 // out[g, c] = sum over rows bucket_ptr[g] .. bucket_ptr[g+1] of x[row, c]; two deterministic stages
@@ -234,9 +258,11 @@ extern "C" int spt_gather_rows_bf16(const void *src, const int32_t *row_token, v
                                     spt_stream_t stream) {
     SPT_REQUIRE(src && row_token && dst, "gather_rows: null pointer");
     SPT_REQUIRE(R >= 1 && C >= 8 && C % 8 == 0, "gather_rows: C must be a positive multiple of 8 (got %d)", C);
-    const long long n = (long long)R * (C / 8);
+    const int spans = (C / 8 + route::GR_UNROLL * 32 - 1) / (route::GR_UNROLL * 32);
+    const long long n = (long long)R * spans * 32;     // one warp per (row, span)
+    SPT_REQUIRE((n + 255) / 256 < (1ll << 31), "gather_rows: too many rows");
     route::gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
-        (const __nv_bfloat16 *)src, row_token, (__nv_bfloat16 *)dst, R, C);
+        (const __nv_bfloat16 *)src, row_token, (__nv_bfloat16 *)dst, R, C, spans);
     return after_launch("gather_rows_kernel");
 }
 

@@ -22,6 +22,18 @@ def _grad_buffer(shape, dtype, device):
     return torch.empty(shape, dtype=torch.bfloat16 if dtype == torch.bfloat16 else torch.float32, device=device)
 
 
+_WHOLE_PTR = {}
+
+
+def _whole_ptr(rows: int, device) -> torch.Tensor:
+    """[0, rows] int32 on `device`: the one-group row pointer that turns group_colsum into a plain column sum."""
+    key = (rows, str(device))
+    t = _WHOLE_PTR.get(key)
+    if t is None:
+        t = _WHOLE_PTR[key] = torch.tensor([0, rows], dtype=torch.int32, device=device)
+    return t
+
+
 class GatherRows(autograd.Function):
     @staticmethod
     def forward(ctx, x, bucket):
@@ -45,7 +57,9 @@ class CombineRows(autograd.Function):
     def backward(ctx, grad):
         g16 = grad.contiguous().to(torch.bfloat16)
         d_partial = ext.gather_rows(g16, ctx.bucket.row_token).to(ctx.p_dtype)
-        d_bias = grad.float().sum(0).to(ctx.bias_dtype) if ctx.has_bias else None
+        d_bias = None
+        if ctx.has_bias:   # column sum of the bf16 gradient in fp32, one pass (was .float().sum(0): 65 us at T 8192)
+            d_bias = ext.group_colsum(g16, _whole_ptr(g16.size(0), g16.device)).reshape(-1).to(ctx.bias_dtype)
         return d_partial, None, d_bias, None
 
 
