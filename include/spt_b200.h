@@ -242,6 +242,12 @@ int spt_grouped_gemm_bf16(int mode, const void *A, long long a_rows, long long a
                           int bias_stride, const float *row_scale, int act, const void *gate, long long ldg,
                           spt_stream_t stream);
 
+/* Host-side replay of the CTA-pair grouped GEMM's mode-0 schedule (no GPU needed; used by the CPU tests).
+ * tile_group is a HOST array [n_m_tiles] (n_m_tiles <= 1024).  One record of 6 ints per (unit, CTA rank):
+ *   unit, rank, group, m_tile, n_tile, role | mma << 4     (role: 0 idle, 1 active, 2 zero-fill).
+ * Returns the number of records (at most `cap` are written), or a negative spt_status. */
+int spt_grouped_gemm_plan(const int32_t *tile_group, int n_m_tiles, int tiles_n, int32_t *out, int cap);
+
 /* Fused elementwise stages of the LoRA-routed FFN (naive_gpt/layers/tuning/lora_ffn.py:87-115,201-222).
  * coeff [R] fp32 = 2 * router probability of the bucket row.  dtypes: SPT_F32 / SPT_BF16.  C % 4 == 0.
  *   scale_add: out = coeff[r] * a + b;   bwd: da = coeff[r] * dout (a's dtype), dcoeff[r] = sum_c dout * a.

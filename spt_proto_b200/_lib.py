@@ -54,6 +54,7 @@ def _load() -> ctypes.CDLL:
     ll = c.c_longlong
     sig["spt_grouped_gemm_bf16"] = (i32, [i32, vp, ll, ll, ll, i32, vp, ll, ll, ll, i32, vp, i32, vp, i32, i32, i32, i32,
                                           i32, i32, i32, i32, ll, ll, vp, ll, i32, vp, i32, vp, i32, vp, ll, vp])
+    sig["spt_grouped_gemm_plan"] = (i32, [vp, i32, i32, vp, i32])
     sig["spt_scale_add_fwd"] = (i32, [vp, vp, i32, vp, i32, vp, i32, i64, i32, vp])
     sig["spt_scale_add_bwd"] = (i32, [vp, vp, i32, vp, i32, vp, vp, i64, i32, vp])
     sig["spt_lora_glu_fwd"] = (i32, [vp] * 6 + [i64, i32, vp])

@@ -97,13 +97,13 @@ __device__ __forceinline__ uint64_t pk_f32x2(float lo, float hi) {
     return d;
 }
 __device__ __forceinline__ float lo_f32x2(uint64_t v) {
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    float lo;
+    asm("{\n\t.reg .b32 t;\n\tmov.b64 {%0, t}, %1;\n\t}" : "=f"(lo) : "l"(v));
     return lo;
 }
 __device__ __forceinline__ float hi_f32x2(uint64_t v) {
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    float hi;
+    asm("{\n\t.reg .b32 t;\n\tmov.b64 {t, %0}, %1;\n\t}" : "=f"(hi) : "l"(v));
     return hi;
 }
 __device__ __forceinline__ uint64_t shfl_xor_f32x2(uint64_t v, int o) {

@@ -391,7 +391,17 @@ struct Unit {
     int rows_ok;             // valid rows of this CTA's half
 };
 
-__device__ __forceinline__ Unit get_unit(const Params &p, int u, const uint16_t *list, int rank) {
+// mode 0 candidates c = 2 * pair + sub: sub 0 always exists; sub 1 only where the pair's second m-tile belongs to
+// another (valid) group.  Shared by the kernel and the host-side plan (spt_grouped_gemm_plan, used by the CPU tests).
+__host__ __device__ inline bool unit_exists(const int32_t *tile_group, int tiles_m, int c) {
+    if ((c & 1) == 0) return true;
+    const int t0 = c & ~1, t1 = t0 + 1;
+    if (t1 >= tiles_m) return false;
+    const int g1 = tile_group[t1];
+    return g1 >= 0 && g1 != tile_group[t0];
+}
+
+__host__ __device__ inline Unit get_unit(const Params &p, int u, const uint16_t *list, int rank) {
     Unit un;
     const int tile_n = u % p.tiles_n;
     un.n0 = tile_n * BN;
@@ -423,7 +433,7 @@ __device__ __forceinline__ Unit get_unit(const Params &p, int u, const uint16_t 
         un.a_mn = z * p.a_mn_off + m0;
         un.c_row0 = (long long)z * p.c_row_off + m0;
         un.c_col0 += (long long)z * p.c_col_off;
-        un.rows_ok = min(BM, p.M - m0);     // <= 0 for the phantom half of an odd tile count
+        un.rows_ok = p.M - m0 < BM ? p.M - m0 : BM;     // <= 0 for the phantom half of an odd tile count
         un.b_mn += z * p.b_mn_off;
     }
     return un;
@@ -473,15 +483,7 @@ grouped_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         int base_cnt = 0;
         for (int c0 = 0; c0 < n_cand; c0 += THREADS) {
             const int c = c0 + threadIdx.x;
-            bool real = false;
-            if (c < n_cand) {
-                const int t0 = c & ~1, t1 = t0 + 1;
-                if ((c & 1) == 0) real = true;
-                else if (t1 < p.tiles_m) {
-                    const int g1 = p.tile_group[t1];
-                    real = g1 >= 0 && g1 != p.tile_group[t0];
-                }
-            }
+            const bool real = c < n_cand && unit_exists(p.tile_group, p.tiles_m, c);
             const uint32_t bal = __ballot_sync(0xffffffffu, real);
             if (lane == 0) s_scan[warp] = __popc(bal);
             __syncthreads();
@@ -785,4 +787,32 @@ extern "C" int spt_grouped_gemm_bf16(int mode, const void *A, long long a_rows, 
     }
     gemm::grouped_gemm_kernel<<<n_ctas, gemm::THREADS, gemm::SMEM_BYTES, as_stream(stream)>>>(map_a, map_b, p);
     return after_launch("grouped_gemm_kernel");
+}
+
+// Host-side replay of the CTA-pair kernel's mode-0 schedule (same unit_exists / get_unit code as the device), for
+// tests without a GPU.  tile_group is a HOST array.  Writes one record of 6 ints per (unit, CTA rank):
+//   unit, rank, group, m_tile, n_tile, role | mma << 4      (role: 0 idle, 1 active, 2 zero-fill)
+// and returns the number of records (nothing is written beyond `cap` records), or a negative spt_status.
+extern "C" int spt_grouped_gemm_plan(const int32_t *tile_group, int n_m_tiles, int tiles_n, int32_t *out, int cap) {
+    if (!tile_group || n_m_tiles < 1 || n_m_tiles > gemm::MAX_LIST || tiles_n < 1 || (!out && cap > 0)) {
+        fail(SPT_ERR_INVALID_ARGUMENT, "grouped_gemm_plan: bad arguments");
+        return -SPT_ERR_INVALID_ARGUMENT;
+    }
+    gemm::Params p{};
+    p.mode = 0; p.tile_group = tile_group; p.tiles_m = n_m_tiles; p.tiles_n = tiles_n; p.K = gemm::BK;
+    uint16_t list[gemm::MAX_LIST];
+    int n_list = 0;
+    const int n_cand = 2 * ((n_m_tiles + 1) / 2);
+    for (int c = 0; c < n_cand; ++c)
+        if (gemm::unit_exists(tile_group, n_m_tiles, c)) list[n_list++] = (uint16_t)c;
+    int n = 0;
+    for (int u = 0; u < n_list * tiles_n; ++u)
+        for (int rank = 0; rank < 2; ++rank, ++n) {
+            if (n >= cap) continue;
+            const gemm::Unit un = gemm::get_unit(p, u, list, rank);
+            int32_t *r = out + 6 * (size_t)n;
+            r[0] = u; r[1] = rank; r[2] = un.g; r[3] = (int)(un.c_row0 / gemm::BM); r[4] = un.n0 / gemm::BN;
+            r[5] = un.role | ((int)un.mma << 4);
+        }
+    return n;
 }

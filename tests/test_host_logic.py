@@ -152,3 +152,69 @@ def test_module_upgrader_requires_default_and_skips_unknown():
     lin = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.ReLU())
     out = utils.ModuleUpgrader(utils.LoRAHandler(d_lora=2, verbose=False)).visit(lin)
     assert type(out[0]).__name__ == "LoRALinear" and type(out[1]).__name__ == "ReLU"
+
+
+# ------------------------------------------------------------------ grouped GEMM on CTA pairs: the unit schedule
+def _pair_plan(tile_group, tiles_n):
+    """Replay of the device schedule through the C ABI (host code shared with the kernel: ffn_gemm.cu get_unit)."""
+    import ctypes
+
+    import numpy as np
+    from spt_proto_b200._lib import lib
+    tg = np.asarray(tile_group, dtype=np.int32)
+    n = lib.spt_grouped_gemm_plan(tg.ctypes.data_as(ctypes.c_void_p), len(tg), tiles_n, None, 0)
+    assert n >= 0
+    out = np.zeros((n, 6), dtype=np.int32)
+    assert lib.spt_grouped_gemm_plan(tg.ctypes.data_as(ctypes.c_void_p), len(tg), tiles_n,
+                                     out.ctypes.data_as(ctypes.c_void_p), n) == n
+    return out
+
+
+@pytest.mark.parametrize("sizes,tails,tiles_n", [
+    ([1], 0, 1), ([2], 0, 3), ([3, 0, 1, 5], 2, 2), ([1, 1, 1, 1, 1], 1, 1), ([2, 2, 3], 0, 4), ([0, 0, 4], 3, 1),
+    ([5, 1, 0, 0, 7, 2], 4, 2), ([16, 15, 17], 0, 8)])
+def test_pair_gemm_schedule_covers_every_tile_once(sizes, tails, tiles_n):
+    """Every (m-tile, n-tile) of a group is computed by exactly one active CTA on its own group's weights, every
+    tail tile is zero-filled exactly once, and a pair that straddles two groups costs one extra unit."""
+    tile_group = [g for g, n in enumerate(sizes) for _ in range(n)] + [-1] * tails
+    if not tile_group:
+        pytest.skip("no tiles")
+    plan = _pair_plan(tile_group, tiles_n)
+    tiles_m = len(tile_group)
+    active, zero = {}, {}
+    units = {}
+    for unit, rank, g, mt, nt, flags in plan.tolist():
+        role, mma = flags & 15, flags >> 4
+        units.setdefault(unit, []).append((rank, g, mt, nt, role, mma))
+        assert mt // 2 == units[unit][0][2] // 2 and nt == units[unit][0][3]      # the two CTAs of a unit: one m-pair, one n-tile
+        if role == 1:
+            assert mma == 1 and 0 <= mt < tiles_m and tile_group[mt] == g >= 0      # computed on its own group's weights
+            active[(mt, nt)] = active.get((mt, nt), 0) + 1
+        elif role == 2:
+            assert 0 <= mt < tiles_m and tile_group[mt] == -1
+            zero[(mt, nt)] = zero.get((mt, nt), 0) + 1
+    for u, recs in units.items():
+        assert sorted(r[0] for r in recs) == [0, 1]
+        assert recs[0][5] == recs[1][5] and recs[0][1] == recs[1][1]               # both CTAs agree on mma and group
+    for mt, g in enumerate(tile_group):
+        for nt in range(tiles_n):
+            if g >= 0:
+                assert active.get((mt, nt)) == 1 and (mt, nt) not in zero
+            else:
+                assert zero.get((mt, nt)) == 1 and (mt, nt) not in active
+    assert sum(active.values()) == sum(1 for g in tile_group if g >= 0) * tiles_n
+    # cost: one unit per pair, plus one where a pair's two tiles belong to different (valid) groups
+    straddle = sum(1 for t in range(0, tiles_m - 1, 2) if tile_group[t + 1] >= 0 and tile_group[t + 1] != tile_group[t])
+    assert len(units) == ((tiles_m + 1) // 2 + straddle) * tiles_n
+
+
+def test_pair_gemm_plan_rejects_bad_arguments():
+    import ctypes
+
+    import numpy as np
+    from spt_proto_b200._lib import lib
+    tg = np.zeros(4, dtype=np.int32)
+    assert lib.spt_grouped_gemm_plan(None, 4, 1, None, 0) < 0
+    assert lib.spt_grouped_gemm_plan(tg.ctypes.data_as(ctypes.c_void_p), 0, 1, None, 0) < 0
+    assert lib.spt_grouped_gemm_plan(tg.ctypes.data_as(ctypes.c_void_p), 4, 0, None, 0) < 0
+    assert lib.spt_grouped_gemm_plan(tg.ctypes.data_as(ctypes.c_void_p), 2000, 1, None, 0) < 0
