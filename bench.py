@@ -176,6 +176,21 @@ def _time_cuda(fn, iters=5, warm=2):
 
 
 FUSED_PATH = ["pq_encode", "lookup_mask", "attn_fwd", "attn_bwd"]
+# what bounds each kernel according to its ncu capture (profiles/README.md): the HBM fraction
+# reported beside it is NOT the target for the issue-bound ones
+STAGE_BOUND = {
+    "attn_fwd": "exp/mask math of the score tile (XU + FMA issue); tensor pipe ~29 % active",
+    "attn_bwd": "small-MMA cadence of the tensor pipe (~50 clk per tcgen05.mma) + element-math issue",
+    "pq_encode": "fp32-add issue (L1 distances, packed FADD2); DRAM = algorithmic bytes",
+    "lookup_mask": "integer issue (bit-sliced adder tree + selection)",
+    "lookup": "integer issue + index write",
+    "sddmm": "instruction issue per gathered pair (not L2)",
+    "spmm": "instruction issue per gathered pair (not L2)",
+    "spmm_t": "instruction issue per gathered pair (not L2)",
+    "softmax_fwd": "hbm",
+    "softmax_bwd": "hbm",
+    "csr2csc": "shared-memory atomics / occupancy of the staged placement",
+}
 STAGE_PATH = ["pq_encode", "lookup", "sddmm", "softmax_fwd", "spmm", "softmax_bwd", "csr2csc", "spmm_t"]
 
 
@@ -226,12 +241,12 @@ def stage_roofline(n_seq: int, dev, hbm_gbs: float, tensor_tflops: float):
         n_sparse = 2 if name == "attn_fwd" else 6
         out[name] = {"ms": t * 1e3, "executed_dense_GFLOP": n_gemm * tile_flops * B / 1e9, "achieved_TFLOPs": tf,
                      "frac_tensor": tf / tensor_tflops,
-                     "algorithmic_sparse_TFLOPs": n_sparse * sparse_flops * B / t / 1e12}
+                     "algorithmic_sparse_TFLOPs": n_sparse * sparse_flops * B / t / 1e12, "bound": STAGE_BOUND[name]}
     for name, (fn, bytes_per_head) in stages.items():
         t = _time_cuda(fn)
         gbs = bytes_per_head * B / t / 1e9
         out[name] = {"ms": t * 1e3, "algorithmic_GB": bytes_per_head * B / 1e9, "achieved_GBps": gbs,
-                     "frac_hbm": gbs / hbm_gbs}
+                     "frac_hbm": gbs / hbm_gbs, "bound": STAGE_BOUND.get(name, "hbm")}
     return out
 
 
@@ -381,7 +396,8 @@ def run_ours(args):
                     "peak_source": peak_kind,
                     "note": "executed dense-causal-tile MMA flops (the kernels compute masked dense tiles; the selected-"
                             "pair flops are 1/4 of these).  The kernels are bound by the exp/mask math of the score "
-                            "tile (XU + FMA pipes), not by the tensor pipe: see DESIGN.md section 4"}
+                            "tile (XU + FMA issue) and by the per-instruction cadence of small tcgen05.mma (~50 clk "
+                            "each whatever N), not by tensor-pipe flops: see DESIGN.md section 4.1"}
             traffic = _traffic().get(dom)
             if traffic is not None:
                 roof["traffic"] = traffic["dram_bytes_per_launch"]

@@ -113,8 +113,10 @@ def main():
         # synchronises with the host (host_trigger, device-side bucketing), so the whole step is capturable.
         eager_step = step
         graph = torch.cuda.CUDAGraph()
+        captured0 = ext.launch_count()
         with torch.cuda.graph(graph):
             loss, n_coll = eager_step()
+        captured = ext.launch_count() - captured0     # launches of libspt_b200 kernels recorded in the graph
 
         def step():
             graph.replay()
@@ -123,6 +125,8 @@ def main():
         for _ in range(2):
             step()
         barrier()
+    if not args.graph:
+        captured = 0
     launches0 = ext.launch_count()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -145,7 +149,9 @@ def main():
                            "d_model": d_model, "n_heads": n_heads, "d_ff": d_ff, "d_lora": args.d_lora,
                            "trainable_params": n_train, "allreduce_calls_per_step": n_coll,
                            "parallelism": f"dp{world} + NCCL all-reduce of trainable grads", "cuda_graph": bool(args.graph)},
-                "loss": float(loss.detach()), "gpu_launches": ext.launch_count() - launches0}
+                "loss": float(loss.detach()),
+                # a replayed graph launches its captured kernels without passing through the library's counter
+                "gpu_launches": (captured * args.steps) if args.graph else ext.launch_count() - launches0}
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
