@@ -242,6 +242,20 @@ int spt_grouped_gemm_bf16(int mode, const void *A, long long a_rows, long long a
                           int bias_stride, const float *row_scale, int act, const void *gate, long long ldg,
                           spt_stream_t stream);
 
+/* LlamaRMSNorm (naive_gpt/layers/basic/utils.py:22-38) and RotaryEmbedding (basic/position.py:5-48) of the block
+ * around the SPT operators, one kernel per direction, bf16 with the torch expression's intermediate roundings.
+ *   rmsnorm: x, out [R, C] bf16, w [C] bf16, inv_rms [R] fp32 (saved for backward); C % 8 == 0, C <= 8192.
+ *            backward writes dx [R, C] bf16 and dw_partial [spt_rmsnorm_bwd_blocks(R), C] fp32 (sum over dim 0 = dw).
+ *   rope   : x, out [N, S, H, E] bf16 (rows = N*S*H), cos / sin [S, E] bf16 gathered by position; E % 16 == 0;
+ *            transpose != 0 applies the transposed rotation (the backward). */
+int spt_rmsnorm_bwd_blocks(int64_t R);
+int spt_rmsnorm_fwd_bf16(const void *x, const void *w, void *out, float *inv_rms, int64_t R, int C, float eps,
+                         spt_stream_t stream);
+int spt_rmsnorm_bwd_bf16(const void *g, const void *x, const void *w, const float *inv_rms, void *dx,
+                         float *dw_partial, int64_t R, int C, spt_stream_t stream);
+int spt_rope_bf16(const void *x, const void *cos, const void *sin, void *out, int64_t rows, int S, int H, int E,
+                  int transpose, spt_stream_t stream);
+
 /* Host-side replay of the CTA-pair grouped GEMM's mode-0 schedule (no GPU needed; used by the CPU tests).
  * tile_group is a HOST array [n_m_tiles] (n_m_tiles <= 1024).  One record of 6 ints per (unit, CTA rank):
  *   unit, rank, group, m_tile, n_tile, role | mma << 4     (role: 0 idle, 1 active, 2 zero-fill).

@@ -54,6 +54,10 @@ def _load() -> ctypes.CDLL:
     ll = c.c_longlong
     sig["spt_grouped_gemm_bf16"] = (i32, [i32, vp, ll, ll, ll, i32, vp, ll, ll, ll, i32, vp, i32, vp, i32, i32, i32, i32,
                                           i32, i32, i32, i32, ll, ll, vp, ll, i32, vp, i32, vp, i32, vp, ll, vp])
+    sig["spt_rmsnorm_bwd_blocks"] = (i32, [i64])
+    sig["spt_rmsnorm_fwd_bf16"] = (i32, [vp, vp, vp, vp, i64, i32, f32, vp])
+    sig["spt_rmsnorm_bwd_bf16"] = (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp])
+    sig["spt_rope_bf16"] = (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp])
     sig["spt_grouped_gemm_plan"] = (i32, [vp, i32, i32, vp, i32])
     sig["spt_scale_add_fwd"] = (i32, [vp, vp, i32, vp, i32, vp, i32, i64, i32, vp])
     sig["spt_scale_add_bwd"] = (i32, [vp, vp, i32, vp, i32, vp, vp, i64, i32, vp])

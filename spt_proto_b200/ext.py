@@ -573,3 +573,48 @@ def lora_glu_bwd(coeff, bg, lg, bs, ls, grad_h):
         check(lib.spt_lora_glu_bwd(_p(coeff), _p(bg), _p(lg), _p(bs), _p(ls), _p(grad_h), *[_p(o) for o in outs],
                                    _p(dcoeff), R, C, _stream(bg)))
     return (*outs, dcoeff)
+
+
+# ---- RMSNorm / RoPE of the block around the SPT operators (csrc/norm_rope.cu) ------------------------------------
+def rmsnorm_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    C = x.size(-1)
+    return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.is_cuda
+            and C % 8 == 0 and 8 <= C <= 8192 and x.numel() > 0)
+
+
+def rmsnorm_fwd(x: torch.Tensor, weight: torch.Tensor, eps: float):
+    """-> (out like x, inv_rms [rows] fp32); x [..., C] bf16 contiguous, weight [C] bf16."""
+    C = x.size(-1)
+    rows = x.numel() // C
+    out = torch.empty_like(x)
+    inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+    with _on_device(x):
+        check(lib.spt_rmsnorm_fwd_bf16(_p(x), _p(weight), _p(out), _p(inv), rows, C, float(eps), _stream(x)))
+    return out, inv
+
+
+def rmsnorm_bwd(grad: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, inv: torch.Tensor):
+    """-> (dx like x, dw [C] fp32)."""
+    C = x.size(-1)
+    rows = x.numel() // C
+    dx = torch.empty_like(x)
+    partial = torch.empty(lib.spt_rmsnorm_bwd_blocks(rows), C, dtype=torch.float32, device=x.device)
+    with _on_device(x):
+        check(lib.spt_rmsnorm_bwd_bf16(_p(grad), _p(x), _p(weight), _p(inv), _p(dx), _p(partial), rows, C, _stream(x)))
+    return dx, partial.sum(0)
+
+
+def rope_supported(x: torch.Tensor, cos: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dim() == 4 and x.dtype == torch.bfloat16 and cos.dtype == torch.bfloat16
+            and x.size(-1) % 16 == 0 and x.numel() > 0)
+
+
+def rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+    """x [N, S, H, E] bf16 contiguous; cos / sin [S, E] bf16 contiguous (gathered by position)."""
+    N, S, H, E = x.shape
+    if cos.shape != (S, E) or sin.shape != (S, E):
+        raise RuntimeError("rope: cos / sin must be [S, E]")
+    out = torch.empty_like(x)
+    with _on_device(x):
+        check(lib.spt_rope_bf16(_p(x), _p(cos), _p(sin), _p(out), N * S * H, S, H, E, int(transpose), _stream(x)))
+    return out

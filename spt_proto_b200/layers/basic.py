@@ -8,6 +8,7 @@ import torch
 from torch import nn
 
 from .. import ext, kernels
+from ..kernels import norm_rope
 
 
 class RotaryEmbedding(nn.Module):
@@ -27,10 +28,15 @@ class RotaryEmbedding(nn.Module):
         lo, hi = x.chunk(2, dim=-1)
         return torch.cat((-hi, lo), dim=-1)
 
+    fused = True    # one CUDA kernel per direction for bf16 inputs on the GPU (same roundings as the expression below)
+
     def forward(self, x: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
         assert x.dim() == 4 and ids.dim() == 1
-        cos = self.cos_cached[ids].view(1, -1, 1, x.size(-1))
-        sin = self.sin_cached[ids].view(1, -1, 1, x.size(-1))
+        cos, sin = self.cos_cached[ids], self.sin_cached[ids]
+        if self.fused and ids.numel() == x.size(1) and ext.rope_supported(x, cos):
+            return norm_rope.rope(x, cos.contiguous(), sin.contiguous())
+        cos = cos.view(1, -1, 1, x.size(-1))
+        sin = sin.view(1, -1, 1, x.size(-1))
         return x * cos + self.rotate_half(x) * sin
 
 
@@ -115,7 +121,11 @@ class LlamaRMSNorm(nn.Module):
         self.weight = nn.Parameter(torch.ones(hidden_size))
         self.variance_epsilon = eps
 
+    fused = True    # one CUDA kernel per direction for bf16 input and weight on the GPU
+
     def forward(self, x):
+        if self.fused and ext.rmsnorm_supported(x, self.weight):
+            return norm_rope.rmsnorm(x, self.weight, self.variance_epsilon)
         inv_rms = torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + self.variance_epsilon)
         y = x * inv_rms
         if self.weight.dtype in (torch.float16, torch.bfloat16):

@@ -394,3 +394,49 @@ def test_pq_train_fused_matches_torch_formulation(dtype, shape, m):
     zd2 = z.to(DEV).requires_grad_()
     zq2, loss2 = mod("train", z=zd2)
     assert abs(loss2.item() - loss.item()) < 1e-4 * max(1.0, abs(loss.item()))
+
+
+# ------------------------------------------------------------------------------ fused RMSNorm / RoPE (norm_rope.cu)
+@pytest.mark.parametrize("shape", [(2, 70, 4096), (3, 5, 64), (1, 9, 8192), (300, 2048)])
+def test_rmsnorm_fused_matches_torch_expression(shape):
+    from spt_proto_b200 import layers
+    g = torch.Generator(device="cpu").manual_seed(sum(shape))
+    C = shape[-1]
+    norm = layers.LlamaRMSNorm(C).to(DEV).bfloat16()
+    with torch.no_grad():
+        norm.weight.copy_((torch.rand(C, generator=g) + 0.5).to(DEV))
+    x = (torch.randn(*shape, generator=g) * 1.7).to(DEV).bfloat16()
+    go = torch.randn(*shape, generator=g).to(DEV).bfloat16()
+    res = {}
+    for fused in (True, False):
+        norm.fused = fused
+        norm.weight.grad = None
+        xi = x.clone().requires_grad_()
+        y = norm(xi)
+        y.backward(go)
+        res[fused] = (y.detach().float(), xi.grad.float(), norm.weight.grad.float())
+    assert res[True][0].dtype == res[False][0].dtype
+    torch.testing.assert_close(res[True][0], res[False][0], atol=2e-2, rtol=1.6e-2)      # one bf16 ulp: the fp32 sums differ in order
+    torch.testing.assert_close(res[True][1], res[False][1], atol=3e-2, rtol=3e-2)
+    rows = x.numel() // C
+    torch.testing.assert_close(res[True][2], res[False][2], atol=0.05 * rows ** 0.5, rtol=3e-2)
+
+
+@pytest.mark.parametrize("shape", [(2, 33, 4, 128), (1, 16, 3, 64), (3, 128, 2, 32)])
+def test_rope_fused_matches_torch_expression(shape):
+    from spt_proto_b200 import layers
+    g = torch.Generator(device="cpu").manual_seed(sum(shape))
+    N, S, H, E = shape
+    emb = layers.RotaryEmbedding(256, E).to(DEV).bfloat16()
+    ids = torch.arange(S, device=DEV)
+    x = torch.randn(*shape, generator=g).to(DEV).bfloat16()
+    go = torch.randn(*shape, generator=g).to(DEV).bfloat16()
+    res = {}
+    for fused in (True, False):
+        emb.fused = fused
+        xi = x.clone().requires_grad_()
+        y = emb(xi, ids)
+        y.backward(go)
+        res[fused] = (y.detach(), xi.grad)
+    assert torch.equal(res[True][0], res[False][0])          # same roundings as the torch expression: bit-exact
+    assert torch.equal(res[True][1], res[False][1])
