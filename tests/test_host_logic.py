@@ -208,6 +208,26 @@ def test_pair_gemm_schedule_covers_every_tile_once(sizes, tails, tiles_n):
     assert len(units) == ((tiles_m + 1) // 2 + straddle) * tiles_n
 
 
+@pytest.mark.parametrize("tile_group", [[-1, 0, 0, 1], [0, -1, 1, 1, -1, 2], [-1], [-1, -1, 3], [2, 2, -1, -1, 0]])
+def test_pair_gemm_schedule_with_unused_tiles_anywhere(tile_group):
+    """The ABI allows -1 (unused) for any 128-row tile, not only in the tail: valid neighbours are still computed once."""
+    tiles_n = 2
+    plan = _pair_plan(tile_group, tiles_n)
+    active, zero = {}, {}
+    for unit, rank, g, mt, nt, flags in plan.tolist():
+        role = flags & 15
+        if role == 1:
+            assert tile_group[mt] == g >= 0
+            active[(mt, nt)] = active.get((mt, nt), 0) + 1
+        elif role == 2:
+            assert tile_group[mt] == -1
+            zero[(mt, nt)] = zero.get((mt, nt), 0) + 1
+    for mt, g in enumerate(tile_group):
+        for nt in range(tiles_n):
+            assert (active if g >= 0 else zero).get((mt, nt)) == 1
+            assert (mt, nt) not in (zero if g >= 0 else active)
+
+
 def test_pair_gemm_plan_rejects_bad_arguments():
     import ctypes
 
