@@ -2,7 +2,6 @@
 Equivalent to  spmm(softmax(clamp_(scale * sddmm(q, k), -10, 10)), v)  on the lookup's pattern
 (reference layers/sparse/attention.py:122-141 + the three backward passes), computed as masked dense
 tiles on the tensor cores from the lookup's bitmask output."""
-import torch
 from torch import autograd
 
 from .. import ext

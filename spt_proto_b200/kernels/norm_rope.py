@@ -1,7 +1,6 @@
 """Autograd wrappers of the fused RMSNorm / RoPE kernels (csrc/norm_rope.cu): the two elementwise layers of a
 LLaMA-style block around the SPT operators (reference naive_gpt/layers/basic/utils.py:22-38, position.py:5-48),
 one kernel per direction instead of a chain of torch elementwise ops."""
-import torch
 from torch import autograd
 
 from .. import ext

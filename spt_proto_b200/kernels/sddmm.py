@@ -2,7 +2,6 @@
 forward : values = sample(Q K^T) on the CSR pattern
 backward: dQ = spmm(dvalues, K);  dK = spmm^T(dvalues, Q) through the cached CSC (deterministic;
           the reference forks a side stream around cuSPARSE's transposed SpMM instead)."""
-import torch
 from torch import autograd
 
 from .. import ext

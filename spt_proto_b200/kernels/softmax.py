@@ -1,5 +1,4 @@
 """CSR softmax autograd Function (reference naive_gpt/kernels/softmax.py:6-38)."""
-import torch
 from torch import autograd
 
 from .. import ext

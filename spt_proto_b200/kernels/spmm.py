@@ -1,7 +1,6 @@
 """spmm autograd Function (reference naive_gpt/kernels/spmm.py:6-58).
 forward : y = A x
 backward: dA = sddmm(dy, x) on the pattern;  dx = A^T dy through the cached CSC."""
-import torch
 from torch import autograd
 
 from .. import ext
