@@ -25,6 +25,8 @@ class HostPipeline:
         self._slots: List[List[torch.Tensor]] = []
         self._slot_free: List[torch.cuda.Event] = []
         self._key = None
+        self._pending = None          # results of the previous run(): referenced until their D2H copies are done
+        self._pending_ev = None
 
     def _ensure_slots(self, like: torch.Tensor) -> None:
         key = (tuple(like.shape[1:]), like.dtype)
@@ -80,5 +82,18 @@ class HostPipeline:
                 self.s_out.wait_event(done)
                 for dst, src in zip(host_out, results):
                     dst[lo:hi].copy_(src, non_blocking=True)
+        # Do not stall the compute stream on this step's D2H copies (the next run() may start its kernels while the
+        # last results are still on their way to the host): keep the result tensors referenced and order the compute
+        # stream only after the copies of the PREVIOUS run, which are long finished by now.  finish() closes a sequence.
+        ev = torch.cuda.Event()
+        ev.record(self.s_out)
+        if self._pending_ev is not None:
+            main.wait_event(self._pending_ev)
+        self._pending, self._pending_ev = keep, ev
+
+    def finish(self) -> None:
+        """Order the current stream after every outstanding device-to-host copy (call before reading the host
+        buffers or before recording the end of a timed region) and drop the references to the last results."""
+        main = torch.cuda.current_stream(self.device)
         main.wait_stream(self.s_out)
-        del keep
+        self._pending, self._pending_ev = None, None

@@ -174,3 +174,11 @@ def test_host_pipeline_equals_direct_call():
             torch.cuda.synchronize()
             for a, b in zip(host_out, want):
                 assert torch.equal(a, b)
+        # back-to-back runs into the same host buffers, closed by finish(): the stream is then ordered after every copy
+        host_out = [torch.zeros(N, S, H, E, dtype=torch.bfloat16).pin_memory() for _ in range(4)]
+        for _ in range(3):
+            pipe.run(host_in, host_out)
+        pipe.finish()
+        torch.cuda.current_stream().synchronize()
+        for a, b in zip(host_out, want):
+            assert torch.equal(a, b)
