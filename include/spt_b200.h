@@ -146,13 +146,18 @@ int spt_csr2csc(const int32_t *indptr, const int32_t *indices, int32_t *col_ptr,
  * Row softmax over the stored entries with the causal predicate (indices[e] <= row) as a 0/1
  * factor, no max subtraction, denominator clamped to >= 1e-9 (softmax.cu:16-46).
  * Backward is the TRUE gradient y * (dy - sum(y*dy)) — the reference kernel's clamp of the sum to
- * >= 1e-9 (softmax.cu:69) is a bug and is not reproduced.
+ * >= 1e-9 (softmax.cu:69) is a bug and is not reproduced by default.
+ * spt_softmax_bwd_ex(reference_clamp = 1) reproduces the shipped kernel for A/B training-parity
+ * runs (Python: ext.REFERENCE_SOFTMAX_CLAMP / env SPT_REFERENCE_SOFTMAX_CLAMP=1).
  * ------------------------------------------------------------------------------------------ */
 int spt_softmax_fwd(const int32_t *indptr, const int32_t *indices, const float *values, float *output,
                     int B, int S, int64_t nnz, spt_stream_t stream);
 int spt_softmax_bwd(const int32_t *indptr, const int32_t *indices, const float *output,
                     const float *grad_output, float *grad_values, int B, int S, int64_t nnz,
                     spt_stream_t stream);
+int spt_softmax_bwd_ex(const int32_t *indptr, const int32_t *indices, const float *output,
+                       const float *grad_output, float *grad_values, int B, int S, int64_t nnz,
+                       int reference_clamp, spt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused sparse attention (fast path of SparseVanillaAttentionV2 / SparseRotaryAttentionV2,

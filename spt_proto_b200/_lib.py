@@ -46,6 +46,7 @@ def _load() -> ctypes.CDLL:
         "spt_csr2csc": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp]),
         "spt_softmax_fwd": (i32, [vp, vp, vp, vp, i32, i32, i64, vp]),
         "spt_softmax_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i64, vp]),
+        "spt_softmax_bwd_ex": (i32, [vp, vp, vp, vp, vp, i32, i32, i64, i32, vp]),
         "spt_lookup_mask_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "spt_sparse_attn_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, i32, vp]),
         "spt_sparse_attn_bwd_workspace_bytes": (sz, [i32, i32]),

@@ -45,14 +45,15 @@ inline int after_launch(const char *what) {
 
 inline cudaStream_t as_stream(spt_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-inline int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
+inline int num_sms() {   // of the CURRENT device (one process may drive several): cached per device index
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cache[dev] = n;   // benign race: every writer stores the same value
     return n;
 }
 

@@ -215,7 +215,7 @@ softmax_fwd_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
 __global__ void __launch_bounds__(CSR_WARPS * 32)
 softmax_bwd_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                    const float *__restrict__ output, const float *__restrict__ grad_output,
-                   float *__restrict__ grad_values, int B, int S, int64_t nnz) {
+                   float *__restrict__ grad_values, int B, int S, int64_t nnz, int reference_clamp) {
     const int lane = threadIdx.x & 31;
     const int64_t row_id = (int64_t)blockIdx.x * CSR_WARPS + (threadIdx.x >> 5);
     if (row_id >= (int64_t)B * S) return;
@@ -236,6 +236,7 @@ softmax_bwd_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
         sum = fmaf(yv, gv, sum);
     }
     sum = warp_sum(sum);
+    if (reference_clamp) sum = fmaxf(1e-9f, sum);   // opt-in: the shipped kernel's clamp (softmax.cu:69), for A/B parity runs
     it = 0;
     for (int e = e0 + lane; e < e1; e += 32, ++it) {
         float yv, gv;
@@ -710,16 +711,22 @@ extern "C" int spt_softmax_fwd(const int32_t *indptr, const int32_t *indices, co
     return after_launch("softmax_fwd_kernel");
 }
 
-extern "C" int spt_softmax_bwd(const int32_t *indptr, const int32_t *indices, const float *output,
-                               const float *grad_output, float *grad_values, int B, int S, int64_t nnz,
-                               spt_stream_t stream) {
+extern "C" int spt_softmax_bwd_ex(const int32_t *indptr, const int32_t *indices, const float *output,
+                                  const float *grad_output, float *grad_values, int B, int S, int64_t nnz,
+                                  int reference_clamp, spt_stream_t stream) {
     SPT_REQUIRE(indptr && indices && output && grad_output && grad_values, "softmax_bwd: null pointer");
     SPT_CHECK_CSR("softmax_bwd");
     if (nnz == 0) return SPT_OK;
     const int64_t rows = (int64_t)B * S;
     softmax_bwd_kernel<<<(unsigned)((rows + CSR_WARPS - 1) / CSR_WARPS), CSR_WARPS * 32, 0, as_stream(stream)>>>(
-        indptr, indices, output, grad_output, grad_values, B, S, nnz);
+        indptr, indices, output, grad_output, grad_values, B, S, nnz, reference_clamp);
     return after_launch("softmax_bwd_kernel");
+}
+
+extern "C" int spt_softmax_bwd(const int32_t *indptr, const int32_t *indices, const float *output,
+                               const float *grad_output, float *grad_values, int B, int S, int64_t nnz,
+                               spt_stream_t stream) {
+    return spt_softmax_bwd_ex(indptr, indices, output, grad_output, grad_values, B, S, nnz, 0, stream);
 }
 
 extern "C" size_t spt_csr2csc_workspace_bytes(int B, int S, int64_t nnz) {

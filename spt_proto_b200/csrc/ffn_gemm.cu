@@ -771,20 +771,14 @@ extern "C" int spt_grouped_gemm_bf16(int mode, const void *A, long long a_rows, 
         SPT_REQUIRE(units_cap < (1ll << 31), "grouped_gemm: too many tiles");
         const int n_units1 = mode == 1 ? (int)units_cap : 0;    // mode 0 counts its units on the device
         const int n_clusters = (int)std::min<long long>(mode == 1 ? units_cap : (long long)p.tiles_n * pairs_m, num_sms() / 2);
-        static bool attr2_set = false;
-        if (!attr2_set) {
-            cudaFuncSetAttribute(gemm::grouped_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM2_BYTES);
-            attr2_set = true;
-        }
+        // the attribute is per DEVICE and ext._on_device lets one process drive several GPUs: set it on every call
+        // (cheap, and what attn_tc.cu / lookup.cu do) instead of caching a process-wide flag
+        cudaFuncSetAttribute(gemm::grouped_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM2_BYTES);
         gemm::grouped_gemm_pair_kernel<<<2 * n_clusters, gemm::THREADS, gemm::SMEM2_BYTES, as_stream(stream)>>>(map_a, map_b, p, n_units1);
         return after_launch("grouped_gemm_pair_kernel");
     }
     const int n_ctas = (int)std::min<long long>(n_tiles, num_sms());
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gemm::grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
-        attr_set = true;
-    }
+    cudaFuncSetAttribute(gemm::grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
     gemm::grouped_gemm_kernel<<<n_ctas, gemm::THREADS, gemm::SMEM_BYTES, as_stream(stream)>>>(map_a, map_b, p);
     return after_launch("grouped_gemm_kernel");
 }

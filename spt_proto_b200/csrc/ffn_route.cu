@@ -22,16 +22,24 @@ namespace route {
 
 constexpr int CHUNK = 256;  // tokens per CTA
 
+// Total order on router probabilities, as torch.topk has it: NaN is the greatest value, then +inf ... -inf
+// (-0 == +0).  Every comparison with NaN being false would give a NaN entry rank 0 WITHOUT ever outranking
+// another entry, so a row with NaNs could mark more than k blocks active (and an all-NaN row all of them).
+__device__ __forceinline__ uint32_t order_key(float p) {
+    if (p != p) return 0xFFFFFFFFu;
+    const uint32_t u = __float_as_uint(p + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 // active-block mask of one token: block i is active iff fewer than k blocks beat it
-// (p_j > p_i, or p_j == p_i with j < i).
+// (key_j > key_i, or key_j == key_i with j < i) — exactly k blocks for any input, NaN / inf included.
 __device__ __forceinline__ unsigned long long topk_mask(const float *p, int nb, int k) {
     unsigned long long m = 0;
     for (int i = 0; i < nb; ++i) {
-        const float pi = p[i];
+        const uint32_t ki = order_key(p[i]);
         int rank = 0;
         for (int j = 0; j < nb; ++j) {
-            const float pj = p[j];
-            rank += (pj > pi) || (pj == pi && j < i);
+            const uint32_t kj = order_key(p[j]);
+            rank += (kj > ki) || (kj == ki && j < i);
         }
         if (rank < k) m |= 1ull << i;
     }
@@ -105,7 +113,7 @@ place_kernel(const float *__restrict__ prob, const unsigned long long *__restric
         int off = 0;
         for (int w = 0; w < warp; ++w) off += s_warp[w];
         __syncthreads();
-        if (on) {
+        if (on && slot < k) {   // slot < k always holds (topk_mask marks exactly k blocks); kept as a guard
             const int row = bucket_ptr[g] + chunk_base[(long long)blockIdx.x * nb + g] + off + __popc(bal & ((1u << lane) - 1u));
             row_token[row] = (int32_t)t;
             row_prob[row] = prob[t * nb + g];

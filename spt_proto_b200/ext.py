@@ -23,6 +23,15 @@ from ._lib import SPT_BF16, SPT_F32, check, lib
 
 _DTYPES = {torch.float32: SPT_F32, torch.bfloat16: SPT_BF16}
 
+# softmax_backward_cuda computes the TRUE softmax gradient.  The shipped reference kernel clamps the row
+# dot product sum(y * dy) to >= 1e-9 (extension/softmax.cu:69), which is wrong whenever that sum is
+# negative.  Set this flag (or SPT_REFERENCE_SOFTMAX_CLAMP=1 in the environment) to reproduce the shipped
+# kernel bit for bit in training-parity A/B runs; it applies to the stage kernel (the fused attention
+# path always uses the true gradient: route through the stage path with use_fused=False for such runs).
+import os as _os
+
+REFERENCE_SOFTMAX_CLAMP = _os.environ.get("SPT_REFERENCE_SOFTMAX_CLAMP", "0") not in ("", "0")
+
 
 # ---- validation helpers (mirror CHECK_DIM / CHECK_TYPE, extension/common.h:13-21) -----------------
 def _check_dim(x: torch.Tensor, d: int, name: str) -> None:
@@ -331,7 +340,8 @@ def softmax_forward_cuda(indptr, indices, values) -> torch.Tensor:
 
 
 def softmax_backward_cuda(indptr, indices, output, grad_output) -> torch.Tensor:
-    """True softmax gradient on the kept entries (extension/softmax.cu:116-148 without its clamp bug)."""
+    """True softmax gradient on the kept entries (extension/softmax.cu:116-148 without its clamp bug;
+    REFERENCE_SOFTMAX_CLAMP = True reproduces the shipped kernel, clamp included)."""
     _check_dim(output, 2, "output")
     _check_dim(grad_output, 2, "grad_output")
     _check_csr(indptr, indices, indptr.size(-1) - 1)
@@ -343,8 +353,8 @@ def softmax_backward_cuda(indptr, indices, output, grad_output) -> torch.Tensor:
     S = indptr.size(-1) - 1
     grad_values = torch.empty_like(output)
     with _on_device(output):
-        check(lib.spt_softmax_bwd(_p(indptr), _p(indices), _p(output), _p(grad_output), _p(grad_values), B, S, nnz,
-                                  _stream(output)))
+        check(lib.spt_softmax_bwd_ex(_p(indptr), _p(indices), _p(output), _p(grad_output), _p(grad_values), B, S, nnz,
+                                     int(REFERENCE_SOFTMAX_CLAMP), _stream(output)))
     return grad_values
 
 

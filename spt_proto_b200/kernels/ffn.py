@@ -58,7 +58,8 @@ class CombineRows(autograd.Function):
         g16 = grad.contiguous().to(torch.bfloat16)
         d_partial = ext.gather_rows(g16, ctx.bucket.row_token).to(ctx.p_dtype)
         d_bias = None
-        if ctx.has_bias:   # column sum of the bf16 gradient in fp32, one pass (was .float().sum(0): 65 us at T 8192)
+        # column sum of the bf16 gradient in fp32, one pass; skipped when the bias is frozen (LoRARoutedFFN's fc2.bias)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
             d_bias = ext.group_colsum(g16, _whole_ptr(g16.size(0), g16.device)).reshape(-1).to(ctx.bias_dtype)
         return d_partial, None, d_bias, None
 

@@ -56,9 +56,11 @@ class _SparseV2Mixin:
     # The shipped reference un-transposes the 3-D result with `y.transpose(1, 2).contiguous()
     # .view(v_size)` (attention.py:139-142), which swaps S and E instead of S and H: its output is
     # a re-interpretation of [N*H, E, S] memory as [N, S, H, E] (invisible to its all-ones layer
-    # test).  False (default) returns the intended layout — identical to the reference's dense
-    # VanillaAttention on the same pattern; True reproduces the shipped layer bit for bit.
-    reference_output_layout: bool = False
+    # test).  True (default) reproduces the shipped layer bit for bit — checkpoints fine-tuned with
+    # the reference learned `linear_o` / LoRA against that layout, so the drop-in must return it;
+    # False is the opt-in corrected layout (identical to the reference's dense VanillaAttention on
+    # the same pattern).  Also a constructor keyword.  INTEGRATION.md, "Output layout".
+    reference_output_layout: bool = True
     # bf16, d_head 64 or 128, S % 128 == 0 on CUDA: run lookup -> bitmask -> fused masked-dense attention on
     # the tensor cores instead of the stage chain (same result up to bf16 rounding).
     use_fused: bool = True
@@ -152,9 +154,11 @@ class _SparseV2Mixin:
 
 
 class SparseVanillaAttentionV2(_SparseV2Mixin, VanillaAttention):
-    def __init__(self, d_head: int, d_codeword: int, n_codewords: int, p_dropout: float):
+    def __init__(self, d_head: int, d_codeword: int, n_codewords: int, p_dropout: float,
+                 reference_output_layout: bool = True):
         VanillaAttention.__init__(self, d_head=d_head, p_dropout=p_dropout)
         self._init_v2(d_head, d_codeword, n_codewords)
+        self.reference_output_layout = reference_output_layout
 
     @staticmethod
     def from_pretrained(source: SparseVanillaAttentionV1):
@@ -170,9 +174,11 @@ class SparseVanillaAttentionV2(_SparseV2Mixin, VanillaAttention):
 
 
 class SparseRotaryAttentionV2(_SparseV2Mixin, RotaryAttention):
-    def __init__(self, d_head: int, p_dropout: float, d_codeword: int, n_codewords: int):
+    def __init__(self, d_head: int, p_dropout: float, d_codeword: int, n_codewords: int,
+                 reference_output_layout: bool = True):
         RotaryAttention.__init__(self, d_head=d_head, p_dropout=p_dropout)
         self._init_v2(d_head, d_codeword, n_codewords)
+        self.reference_output_layout = reference_output_layout
 
     @staticmethod
     def from_pretrained(source: SparseRotaryAttentionV1):

@@ -355,3 +355,137 @@ def test_lora_glu_matches_torch_autograd():
     for t, r in zip(leaf, ref_in):
         torch.testing.assert_close(t.grad, r.grad.float(), atol=1e-5, rtol=1e-4)
     torch.testing.assert_close(cf.grad, cr.grad.float(), atol=1e-3, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------- headline shapes (BENCH / configs[3])
+def _exact_router(ffn, gain=4.0):
+    """Router whose logits are single products (weight row i = gain * e_i): CPU and GPU then compute
+    bit-identical logits whatever their summation order, so the top-k selection cannot flip on a near-tie
+    between the two sides — the parity check below compares GEMM arithmetic, not a routing coin toss."""
+    with torch.no_grad():
+        w = ffn.router[0].weight
+        w.zero_()
+        for i in range(w.size(0)):
+            w[i, i] = gain
+        ffn.router[0].bias.zero_()
+
+
+@pytest.mark.parametrize("bs", [1024, 2048])
+def test_routed_ffn_bench_shape_matches_oracle(bs):
+    """The shape bench.py times (d 2048, F 8192, block 1024 | 2048), reduced only in T (2048 tokens): K = 2048
+    accumulation, 256x256 pair units.  Reference contract: test/layer/test_sparse_ffn.py:41-113."""
+    from oracle import spt_oracle as O
+    from spt_proto_b200 import layers
+    torch.manual_seed(bs)
+    d, Fdim, T = 2048, 8192, 2048
+    ffn = layers.RoutedFFN(d_model=d, d_feedforward=Fdim, block_size=bs, activation=torch.nn.ReLU()).to(DEV)
+    _exact_router(ffn)
+    with torch.no_grad():
+        for p in ffn.parameters():
+            p.copy_(_bf(p))
+    x = _bf(torch.randn(4, T // 4, d)).to(DEV).requires_grad_()
+    y = ffn(x)
+    dy = _bf(torch.randn_like(y))
+    y.backward(dy)
+    sd = {k: v.detach().cpu() for k, v in ffn.state_dict().items()}
+    xc = x.detach().cpu().requires_grad_()
+    ps = {n: sd[n].clone().requires_grad_() for n in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")}
+    y_ref = O.routed_ffn(xc, sd["router.0.weight"], sd["router.0.bias"], ps["fc1.weight"], ps["fc1.bias"],
+                         ps["fc2.weight"], ps["fc2.bias"], bs, (Fdim // bs) // 2)
+    y_ref.backward(dy.cpu())
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    assert rel(y, y_ref.detach()) < 1e-2
+    assert rel(x.grad, xc.grad) < 1e-2
+    got = dict(ffn.named_parameters())
+    for n, p in ps.items():
+        assert rel(got[n].grad, p.grad) < 1e-2, (n, rel(got[n].grad, p.grad))
+
+
+def test_routed_llama_ffn_llama7b_shape_matches_oracle():
+    """LLaMA-7B shape (d 4096, F 11008, block 2752 = 21.5 x 128: ragged N / K tiles of the pair kernel), plain form
+    (n_blocks // 4 = 1 active block, feedforward.py:156)."""
+    from oracle import spt_oracle as O
+    from spt_proto_b200 import layers
+    torch.manual_seed(7)
+    d, Fdim, bs, T = 4096, 11008, 2752, 1024
+    ffn = layers.RoutedLLaMaFFN(d_model=d, d_feedforward=Fdim, block_size=bs, activation=torch.nn.SiLU()).to(DEV)
+    _exact_router(ffn)
+    with torch.no_grad():
+        for p in ffn.parameters():
+            p.copy_(_bf(p))
+    x = _bf(torch.randn(T, d)).to(DEV).requires_grad_()
+    y = ffn(x)
+    dy = _bf(torch.randn_like(y))
+    y.backward(dy)
+    sd = {k: v.detach().cpu() for k, v in ffn.state_dict().items()}
+    xc = x.detach().cpu().requires_grad_()
+    ps = {n: sd[n].clone().requires_grad_() for n in ("gate.weight", "side.weight", "down.weight")}
+    y_ref = O.routed_llama_ffn(xc, sd["router.0.weight"], sd["router.0.bias"], ps["gate.weight"], ps["side.weight"],
+                               ps["down.weight"], bs, (Fdim // bs) // 4)
+    y_ref.backward(dy.cpu())
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    assert rel(y, y_ref.detach()) < 1.5e-2
+    assert rel(x.grad, xc.grad) < 1.5e-2
+    got = dict(ffn.named_parameters())
+    for n, p in ps.items():
+        assert rel(got[n].grad, p.grad) < 1.5e-2, (n, rel(got[n].grad, p.grad))
+
+
+def test_lora_routed_llama_ffn_llama7b_shape_matches_oracle():
+    """configs[3]'s FFN: LoRARoutedLLaMaFFN at d 4096, F 11008, block 2752, rank 16, half the blocks active
+    (tuning/lora_ffn.py:164-225); router, LoRA factors and x gradients vs the oracle."""
+    from oracle import spt_oracle as O
+    from spt_proto_b200 import layers
+    d, Fdim, bs, r, T = 4096, 11008, 2752, 16, 1024
+    ffn, x = _lora_setup(layers.LoRARoutedLLaMaFFN, torch.nn.SiLU(), d, Fdim, bs, r, T, 13)
+    _exact_router(ffn, gain=1.0)
+    y = ffn(x)
+    dy = _bf(torch.randn_like(y))
+    y.backward(dy)
+    sd = {k: v.detach().cpu() for k, v in ffn.state_dict().items()}
+    names = [n for n, p in ffn.named_parameters() if p.requires_grad]
+    p = {n: sd[n].clone().requires_grad_() for n in names}
+    xc = x.detach().cpu().requires_grad_()
+    y_ref = O.lora_routed_llama_ffn(
+        xc, p["router.0.weight"], p["router.0.bias"], sd["gate.weight"], sd["side.weight"], sd["down.weight"],
+        p["gate.lora.left.weight"], p["gate.lora.right.weight"], p["side.lora.left.weight"],
+        p["side.lora.right.weight"], p["down.lora.left.weight"], p["down.lora.right.weight"], bs, (Fdim // bs) // 2)
+    y_ref.backward(dy.cpu())
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    assert rel(y, y_ref.detach()) < 1.5e-2
+    assert rel(x.grad, xc.grad) < 2e-2
+    got = dict(ffn.named_parameters())
+    for n in names:
+        assert rel(got[n].grad, p[n].grad) < 3e-2, (n, rel(got[n].grad, p[n].grad))
+
+
+def test_route_bucket_nan_and_inf_rows():
+    """torch.topk treats NaN as the greatest value and always returns exactly k indices; the bucketing must mark
+    exactly k blocks for ANY row (a diverged bf16 step produces NaN / inf probabilities) — never more, which
+    would write past token_rows / the static row capacity."""
+    from spt_proto_b200 import ext
+    T, nb, k = 300, 8, 4
+    g = torch.Generator().manual_seed(1)
+    prob = torch.sigmoid(torch.randn(T, nb, generator=g))
+    prob[3] = float("nan")
+    prob[5, 2] = float("nan")
+    prob[7, :] = float("inf")
+    prob[9, 1] = float("inf"); prob[9, 6] = float("nan"); prob[9, 0] = float("-inf")
+    prob[T - 1] = float("nan")                                  # the last token: an overrun would leave the buffers
+    b = ext.route_bucket(prob.to(DEV), k)
+    torch.cuda.synchronize()
+    rows = b.bucket_rows.cpu()
+    assert int(rows.sum()) == T * k
+    want = torch.topk(prob, k, dim=-1).indices
+    ptr, row_token = b.bucket_ptr.cpu(), b.row_token.cpu()
+    member = torch.zeros(T, nb, dtype=torch.bool)
+    for gi in range(nb):
+        toks = row_token[ptr[gi]: ptr[gi] + rows[gi]].long()
+        assert (toks >= 0).all()
+        member[toks, gi] = True
+    assert (member.sum(1) == k).all()
+    for t in (5, 9):                                            # unambiguous rows: same SET as torch.topk
+        assert set(torch.nonzero(member[t]).flatten().tolist()) == set(want[t].tolist())
+    assert member[3, :k].all() and member[7, :k].all() and member[T - 1, :k].all()   # all-equal rows: lowest indices
+    tr = b.token_rows.cpu()
+    assert ((tr >= 0) & (tr < b.R)).all()
