@@ -70,6 +70,7 @@ class _SparseV2Mixin:
     # 71-78).  Setting host_trigger to a bool makes the decision on the host, with no synchronisation:
     # True = compute the PQ loss on the next forward (then resets to False), False = skip it.
     host_trigger = None
+    last_path = None      # "fused" | "stage": which implementation the last forward() used (diagnostics / benches)
 
     def _init_v2(self, d_head, d_codeword, n_codewords):
         self.quantizer = PQV2(d_codeword=d_codeword, n_codewords=n_codewords, n_subspaces=d_head // d_codeword)
@@ -169,7 +170,9 @@ class SparseVanillaAttentionV2(_SparseV2Mixin, VanillaAttention):
 
     def forward(self, q, k, v, attn_mask=None):
         if self._fused_ok(q):
+            self.last_path = "fused"
             return self._fused_forward(q, k, v)
+        self.last_path = "stage"
         return VanillaAttention.forward(self, q, k, v, attn_mask)
 
 
@@ -189,5 +192,7 @@ class SparseRotaryAttentionV2(_SparseV2Mixin, RotaryAttention):
 
     def forward(self, q, k, v, attn_mask=None):
         if self._fused_ok(q):
+            self.last_path = "fused"
             return self._fused_forward(self._rotate(q), self._rotate(k), v)
+        self.last_path = "stage"
         return VanillaAttention.forward(self, q, k, v, attn_mask)

@@ -39,7 +39,34 @@ def _worker(rank, world, port, ret):
     dist.all_gather(gathered, local[0])
     want = sum(gathered) / world
     ok_grad = torch.allclose(model[1].weight.grad, want) and model[0].weight.grad is None
-    ret[rank] = (ok_shard, ok_grad, n_calls)
+
+    # (3) GradReducer: flat persistent buffer, bucketed, launched from backward hooks; two steps (the second checks
+    # that zero_grad() re-arms the hooks and that the views survive), mixed dtypes, one parameter without a gradient
+    from spt_proto_b200.distributed import GradReducer
+    torch.manual_seed(1)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 16), torch.nn.Linear(16, 4))
+    extra = torch.nn.Parameter(torch.ones(16, dtype=torch.float64))   # a second dtype group
+    for p in net[0].parameters():
+        p.requires_grad = False
+    unused = torch.nn.Parameter(torch.ones(3))                  # never reached by backward: reduced by finish()
+    trainable = [p for p in net.parameters() if p.requires_grad] + [extra, unused]
+    reducer = GradReducer(trainable, n_buckets=3)
+    ok_reducer = reducer.n_buckets >= 2
+    for step in range(2):
+        xs = torch.full((2, 8), float(rank + 1 + step))
+        reducer.zero_grad()
+        h = net[1](net[0](xs)) * extra.float()
+        (net[2](h.float()).sum() * (rank + 1)).backward()
+        local = {id(p): p.grad.clone() for p in trainable}
+        n_coll = reducer.finish()
+        ok_reducer &= n_coll == reducer.n_buckets
+        for p in trainable:
+            parts = [torch.zeros_like(local[id(p)]) for _ in range(world)]
+            dist.all_gather(parts, local[id(p)])
+            ok_reducer &= torch.allclose(p.grad, sum(parts) / world)
+            ok_reducer &= any(p.grad.data_ptr() >= f.data_ptr() and
+                              p.grad.data_ptr() < f.data_ptr() + f.numel() * f.element_size() for f in reducer.flats)
+    ret[rank] = (ok_shard, ok_grad, n_calls, bool(ok_reducer))
     dist.destroy_process_group()
 
 
@@ -51,5 +78,5 @@ def test_two_rank_sharding_and_grad_allreduce():
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert len(ret) == world
     for rank in range(world):
-        ok_shard, ok_grad, n_calls = ret[rank]
-        assert ok_shard and ok_grad and n_calls >= 1
+        ok_shard, ok_grad, n_calls, ok_reducer = ret[rank]
+        assert ok_shard and ok_grad and n_calls >= 1 and ok_reducer
