@@ -179,18 +179,34 @@ int spt_softmax_bwd_ex(const int32_t *indptr, const int32_t *indices, const floa
  * [N, S, H, m]; q/k/v/y and their gradients [N, S, H, d]) — the kernels stride over it directly, so
  * the reference's transpose(1,2).contiguous() copies (attention.py:92-95,138-142) disappear.
  * mask / extra0 / zsum are always head-major [B, S, ...].
+ * _ex variants take `flags`: SPT_ATTN_Y_TRANSPOSED = y (forward output, and y / grad_y of the
+ * backward) live in the SHIPPED reference layer's output layout — _apply_attn un-transposes the
+ * [N*H, S, E] result with transpose(1, 2).contiguous().view(v_size) (attention.py:139-142), i.e.
+ * y^T [B, d, S] memory re-interpreted as [N, S, H, E].  The kernels write / read that memory
+ * directly (forward epilogue, backward row prologue): the drop-in default costs no extra pass.
  * ------------------------------------------------------------------------------------------ */
+#define SPT_ATTN_Y_TRANSPOSED 1
 int spt_lookup_mask_fwd(const int32_t *query_codes, const int32_t *key_codes, int32_t *output,
                         uint32_t *mask, int32_t *extra0, void *workspace, int B, int S, int m, int nnz,
                         int H, spt_stream_t stream);
 int spt_sparse_attn_fwd(const void *q, const void *k, const void *v, const uint32_t *mask,
                         const int32_t *extra0, void *y, float *zsum, int B, int S, int d, int H,
                         float scale, float clamp, int dtype, spt_stream_t stream);
+int spt_sparse_attn_fwd_ex(const void *q, const void *k, const void *v, const uint32_t *mask,
+                           const int32_t *extra0, void *y, float *zsum, int B, int S, int d, int H,
+                           float scale, float clamp, int dtype, int flags, spt_stream_t stream);
 size_t spt_sparse_attn_bwd_workspace_bytes(int B, int S);
 int spt_sparse_attn_bwd(const void *q, const void *k, const void *v, const void *y, const void *grad_y,
                         const uint32_t *mask, const int32_t *extra0, const float *zsum, void *grad_q,
                         void *grad_k, void *grad_v, void *workspace, int B, int S, int d, int H,
                         float scale, float clamp, int dtype, spt_stream_t stream);
+/* diagnostics: in-kernel phase timers of the attention kernels, 3 kernels x 16 slots of summed clock64() deltas
+ * (zeros and return value 0 unless the library was built with -DSPT_ATTN_PROF); reset != 0 clears them */
+int spt_debug_attn_prof(unsigned long long *out48, int reset);
+int spt_sparse_attn_bwd_ex(const void *q, const void *k, const void *v, const void *y, const void *grad_y,
+                           const uint32_t *mask, const int32_t *extra0, const float *zsum, void *grad_q,
+                           void *grad_k, void *grad_v, void *workspace, int B, int S, int d, int H,
+                           float scale, float clamp, int dtype, int flags, spt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (6) routed FFN — the grouped GEMM the reference only sketches (legacy/routed.cpp:10-68,

@@ -44,4 +44,4 @@ template <int N> void run(int a_tmem, int n_acc) {
     double clk = (double)h[0] / (iters * 4);
     printf("N=%3d acc=%d A=%s: %.1f clk per MMA (M128 K16) -> %.0f flop/clk/SM  err=%s\n", N, n_acc, a_tmem ? "tmem" : "smem", clk, 2.0 * 128 * N * 16 / clk, cudaGetErrorString(cudaGetLastError()));
 }
-int main() { for (int na : {1, 2, 4}) { run<64>(0, na); run<128>(0, na < 3 ? na : 3); } run<256>(0, 1); run<64>(1, 1); run<64>(1, 2); run<64>(1, 4); run<128>(1, 2); run<256>(1, 1); return 0; }
+int main() { for (int na : {1, 2, 4, 8}) { run<32>(0, na); run<64>(0, na); run<128>(0, na < 3 ? na : 3); } run<256>(0, 1); run<32>(1, 1); run<32>(1, 2); run<32>(1, 4); run<64>(1, 1); run<64>(1, 2); run<64>(1, 4); run<128>(1, 2); run<256>(1, 1); return 0; }

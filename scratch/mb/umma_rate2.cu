@@ -41,4 +41,4 @@ template <int N, int TS> void run(int ctas) {
     long long h[296]; cudaMemcpy(h, d, ctas * 8, cudaMemcpyDeviceToHost);
     printf("N=%3d %s, %3d CTAs: %.1f clk per MMA per CTA  err=%s\n", N, TS ? "A tmem" : "A smem", ctas, (double)h[0] / (iters * 4), cudaGetErrorString(cudaGetLastError()));
 }
-int main() { run<64, 0>(148); run<64, 0>(296); run<64, 1>(148); run<64, 1>(296); run<128, 0>(148); run<128, 0>(296); return 0; }
+int main() { run<32, 0>(148); run<32, 0>(296); run<32, 1>(296); run<64, 0>(148); run<64, 0>(296); run<64, 1>(148); run<64, 1>(296); run<128, 0>(148); run<128, 0>(296); return 0; }

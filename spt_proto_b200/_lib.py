@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libspt_b200.so")
 SPT_OK = 0
 SPT_F32 = 0
 SPT_BF16 = 1
+SPT_ATTN_Y_TRANSPOSED = 1
 
 
 class SptLibraryMissing(ImportError):
@@ -49,7 +50,10 @@ def _load() -> ctypes.CDLL:
         "spt_softmax_bwd_ex": (i32, [vp, vp, vp, vp, vp, i32, i32, i64, i32, vp]),
         "spt_lookup_mask_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "spt_sparse_attn_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, i32, vp]),
+        "spt_sparse_attn_fwd_ex": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, i32, i32, vp]),
+        "spt_sparse_attn_bwd_ex": (i32, [vp] * 12 + [i32, i32, i32, i32, f32, f32, i32, i32, vp]),
         "spt_sparse_attn_bwd_workspace_bytes": (sz, [i32, i32]),
+        "spt_debug_attn_prof": (i32, [vp, i32]),
         "spt_sparse_attn_bwd": (i32, [vp] * 12 + [i32, i32, i32, i32, f32, f32, i32, vp]),
     }
     ll = c.c_longlong

@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if (not force and os.path.exists(obj)
                 and os.path.getmtime(obj) >= max(os.path.getmtime(src), dep_t)):
             continue
-        jobs.append([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj])
+        jobs.append([nvcc, *NVCC_FLAGS, *os.environ.get("SPT_NVCC_EXTRA", "").split(), "-c", src, "-o", obj])
     if jobs:
         with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as pool:
             for cmd, res in zip(jobs, pool.map(

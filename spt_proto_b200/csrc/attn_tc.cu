@@ -34,6 +34,9 @@
 // other CTA's MMAs and barrier round trips are in flight.  Score tiles of the next iteration are
 // issued while the current one is still in the math phase (double-buffered S in the forward; in the
 // dQ kernel the score columns are released as soon as they are in registers).
+#include <cstdlib>
+#include <cstring>
+
 #include "tc.cuh"
 
 namespace spt {
@@ -88,121 +91,262 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&h);
 }
-// The element math is written for pipe balance: per element the XU pipe (ex2) is the floor, so
-// everything else is pushed onto the FMA pipe and kept off the half-rate ALU pipe.
-//   clamp:  u = sat(s * a + 0.5) with a = scale / (2 clamp)  (FFMA.SAT), arg = u * 2L - L  (FFMA)
-//           replaces FMUL + 2 FMNMX (ALU);  |scale s| <= clamp  <=>  the unsaturated value equals u
-//   mask :  bit test straight into a predicate (one LOP3), then a predicated multiply by zero (FMA
-//           pipe) instead of shift + and + int->float + FSEL
-__device__ __forceinline__ float fma_sat(float a, float b, float c) {
-    float d;
-    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+// ---- element math --------------------------------------------------------------------------------
+// Per score element the three kernels need  e = w * exp(clamp(scale s, -10, 10))  (and, in the backward,
+// ds = e (dp - delta') [|scale s| <= 10]).  The first version spent ~11-15 instructions per element on it and was
+// issue-bound; this one spends ~5-7:
+//   * fp32 pairs are processed with the packed sm_100 instructions (mul.f32x2 / add.f32x2 / fma.rn.f32x2 = FMUL2 /
+//     FADD2 / FFMA2: two elements per issue slot), on the register pairs tcgen05.ld delivers;
+//   * the clamp is resolved per warp and 32-column chunk: one FMNMX3 per two elements tracks max |s|; only when some
+//     lane of the warp holds a score beyond the clamp (a vote) does the chunk take the exact path with min/max and the
+//     zero-gradient indicator.  Otherwise clamp(x) = x and the indicator is 1 — bit-identical results either way;
+//   * the selection mask is applied to the PACKED bf16 pair with one LOP3: the mask bits of four columns are moved to
+//     the sign bits of the four bytes of a register (one shift per four elements), and PRMT's sign-replicate mode
+//     expands two of them into a 0xFFFF / 0x0000 pair mask (one PRMT per two elements);
+//   * a fraction of the exp2 (the XU pipe, 16 / clk / SM, is the floor once the rest is this cheap) is evaluated on the
+//     FMA pipe: Cody-Waite range reduction + a cubic (max relative error 7.5e-5, bf16 keeps 3.9e-3).
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
     return d;
 }
-__device__ __forceinline__ float sat01(float v) {
-    float d;
-    asm("add.sat.f32 %0, %1, 0f00000000;" : "=f"(d) : "f"(v));
+__device__ __forceinline__ void up2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-__device__ __forceinline__ float keep_if_bit(float e, uint32_t w, uint32_t bitmask) {   // e if w & bitmask, else 0
-    asm("{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b32 t;\n\t"
-        "and.b32 t, %1, %2;\n\t"
-        "setp.eq.u32 p, t, 0;\n\t"
-        "@p mul.f32 %0, %0, 0f00000000;\n\t"
-        "}" : "+f"(e) : "r"(w), "r"(bitmask));
-    return e;
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
 }
-__device__ __forceinline__ float zero_if_ne(float g, float u, float v) {   // g if u == v, else 0
-    asm("{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.neu.f32 p, %1, %2;\n\t"
-        "@p mul.f32 %0, %0, 0f00000000;\n\t"
-        "}" : "+f"(g) : "f"(u), "f"(v));
-    return g;
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ float max3abs(float a, float b, float c) {   // max(a, |b|, |c|): one FMNMX3
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(fabsf(b)), "f"(fabsf(c)));
+    return d;
 }
 
-
-struct ClampK {     // constants of the FMA-pipe clamp: u = sat(s * a + 0.5), arg = u * two_l + neg_l
-    float a, two_l, neg_l;
+struct MathK {      // arg = s * c (log2 units);  |scale s| <= clamp  <=>  |s| <= thr  <=>  |arg| <= L
+    float c, thr, L;
 };
-__device__ __forceinline__ ClampK make_clamp(float scale_log2, float clamp_log2) {
-    return {scale_log2 / (2.0f * clamp_log2), 2.0f * clamp_log2, -clamp_log2};
+__device__ __forceinline__ MathK make_math(float scale_log2, float clamp_log2) {
+    return {scale_log2, clamp_log2 / scale_log2, clamp_log2};
+}
+// does any lane of the warp hold a raw score beyond the clamp among its N values?  (warp-uniform result)
+template <int N>
+__device__ __forceinline__ bool warp_needs_clamp(const uint32_t (&r)[N], float thr) {
+    float mx = 0.0f;
+#pragma unroll
+    for (int i = 0; i < N; i += 2) mx = max3abs(mx, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+    return __any_sync(0xffffffffu, mx > thr);
+}
+// exp2 of a pair.  POLY: on the FMA pipe.  r = a + 1.5 * 2^23 holds round(a) in its low mantissa bits; f = a - round(a)
+// in [-0.5, 0.5]; 2^f by a cubic; 2^round(a) by adding round(a) << 23 to the exponent field.
+template <bool POLY>
+__device__ __forceinline__ void ex2_pair(uint64_t a, float &e0, float &e1) {
+    if constexpr (!POLY) {
+        float a0, a1;
+        up2(a, a0, a1);
+        e0 = ex2(a0);
+        e1 = ex2(a1);
+    } else {
+        const uint64_t magic = pk2(12582912.0f, 12582912.0f), nmagic = pk2(-12582912.0f, -12582912.0f);
+        const uint64_t r = add2(a, magic);
+        const uint64_t f = fma2(add2(r, nmagic), pk2(-1.0f, -1.0f), a);
+        uint64_t p = fma2(pk2(0.0551716685295105f, 0.0551716685295105f), f, pk2(0.2426111251115799f, 0.2426111251115799f));
+        p = fma2(p, f, pk2(0.6932609677314758f, 0.6932609677314758f));
+        p = fma2(p, f, pk2(0.9999280571937561f, 0.9999280571937561f));
+        float r0, r1, p0, p1;
+        up2(r, r0, r1);
+        up2(p, p0, p1);
+        e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+        e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+    }
+}
+// which pairs of a chunk go to the FMA pipe: pair index p (0 .. N/2-1); POLY_MOD = 0: none, else every POLY_MOD-th
+#ifndef SPT_ATTN_POLY_MOD
+#define SPT_ATTN_POLY_MOD 0
+#endif
+__device__ __forceinline__ constexpr bool poly_pair(int p) { return SPT_ATTN_POLY_MOD > 0 && (p % SPT_ATTN_POLY_MOD) == SPT_ATTN_POLY_MOD - 1; }
+
+// e of one pair of raw scores: exp2(clamp(s c)); CLAMP: exact path, also returns the per-element gradient indicators
+template <bool CLAMP, bool POLY>
+__device__ __forceinline__ void exp_pair(float s0, float s1, const MathK mk, float &e0, float &e1, bool &in0, bool &in1) {
+    uint64_t a = mul2(pk2(s0, s1), pk2(mk.c, mk.c));
+    if constexpr (CLAMP) {
+        float a0, a1;
+        up2(a, a0, a1);
+        in0 = fabsf(s0) <= mk.thr;
+        in1 = fabsf(s1) <= mk.thr;
+        a = pk2(fminf(fmaxf(a0, -mk.L), mk.L), fminf(fmaxf(a1, -mk.L), mk.L));
+    }
+    ex2_pair<POLY>(a, e0, e1);
 }
 
-// Forward: 32 score columns of one row -> 16 packed bf16 pairs of e = w * exp(clamp(scale s)), row sum.
-// w[t] = lane-major mask word t shifted so that column i tests bit i >> 2.  FIRST: column 0 is key 0.
-template <bool FIRST>
-__device__ __forceinline__ void fwd_chunk32(const uint32_t (&r)[32], const uint32_t (&w)[4], const ClampK ck, float ex0,
-                                            float &sum, uint32_t (&pk)[16]) {
+// The 32 score columns [32 half, 32 half + 32) of key tile j of one query row: gathers, from the row's four lane-major
+// mask words of key group j >> 1, the byte (index 2 (j & 1) + half) that covers them.  Result X: byte t bit n <=> column
+// 4 n + t of the chunk.
+__device__ __forceinline__ uint32_t chunk_mask_bytes(const uint4 mw, int byte_idx) {
+    const uint32_t sel = (uint32_t)(((4 + byte_idx) << 4) | byte_idx);
+    return prmt(prmt(mw.x, mw.y, sel), prmt(mw.z, mw.w, sel), 0x5410u);
+}
+// pair masks of columns (4 n, 4 n + 1) and (4 n + 2, 4 n + 3) of a chunk
+__device__ __forceinline__ void pair_masks(uint32_t X, int n, uint32_t &m01, uint32_t &m23) {
+    const uint32_t Y = X << (7 - n);
+    m01 = prmt(Y, 0u, 0x9988u);
+    m23 = prmt(Y, 0u, 0xBBAAu);
+}
+__device__ __forceinline__ uint64_t unpack_bf16x2(uint32_t p) { return pk2(__uint_as_float(p << 16), __uint_as_float(p & 0xffff0000u)); }
+
+// Forward: 32 score columns of one row -> 16 masked packed bf16 pairs of e = w * exp(clamp(scale s)); the row sum
+// accumulates the bf16-rounded values (exactly the weights the P V product uses).  FIRST: column 0 is key 0, which also
+// carries the row's zero-padding multiplicity ex0 (mult0 = bit + ex0 when > 0).
+template <bool FIRST, bool CLAMP>
+__device__ __forceinline__ void fwd_chunk32(const uint32_t (&r)[32], uint32_t X, const MathK mk, float ex0, uint64_t &sum2,
+                                            uint32_t (&pk)[16]) {
+    float mult0 = 1.0f;
+    if (FIRST) {
+        mult0 = (float)(X & 1u) + ex0;
+        if (mult0 > 0.0f) X |= 1u;
+        else mult0 = 1.0f;
+    }
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-        float e0 = ex2(fmaf(fma_sat(__uint_as_float(r[i]), ck.a, 0.5f), ck.two_l, ck.neg_l));
-        float e1 = ex2(fmaf(fma_sat(__uint_as_float(r[i + 1]), ck.a, 0.5f), ck.two_l, ck.neg_l));
-        if (FIRST && i == 0) e0 *= (float)(w[0] & 1u) + ex0;     // key 0 carries the zero-padding multiplicity
-        else e0 = keep_if_bit(e0, w[i & 3], 1u << (i >> 2));
-        e1 = keep_if_bit(e1, w[(i + 1) & 3], 1u << (i >> 2));
-        sum += e0 + e1;
-        pk[i >> 1] = pack_bf16(e0, e1);
+    for (int n = 0; n < 8; ++n) {
+        uint32_t m01, m23;
+        pair_masks(X, n, m01, m23);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = 4 * n + 2 * h;
+            float e0, e1;
+            bool in0, in1;
+            if (poly_pair(i >> 1)) exp_pair<CLAMP, true>(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), mk, e0, e1, in0, in1);
+            else exp_pair<CLAMP, false>(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), mk, e0, e1, in0, in1);
+            if (FIRST && i == 0) e0 *= mult0;
+            const uint32_t p = pack_bf16(e0, e1) & (h ? m23 : m01);
+            sum2 = add2(sum2, unpack_bf16x2(p));
+            pk[i >> 1] = p;
+        }
     }
 }
 
-// Backward element: s = q.k, dp = dO'.v, masked weight applied by the caller through `e`.
-//   e_raw = exp(clamp(scale s));   ds = e * (dp - delta') * [|scale s| <= clamp]
-__device__ __forceinline__ float bwd_exp(float s_raw, const ClampK ck, float &u, float &v) {
-    v = fmaf(s_raw, ck.a, 0.5f);
-    u = sat01(v);
-    return ex2(fmaf(u, ck.two_l, ck.neg_l));
-}
-__device__ __forceinline__ float bwd_ds(float e, float dp, float delta, float u, float v) {
-    return zero_if_ne(e * (dp - delta), u, v);
-}
-
-// dQ kernel: 32 columns (keys) of one query row.  w[t] as in fwd_chunk32.
-template <bool FIRST>
-__device__ __forceinline__ void bwdq_chunk32(const uint32_t (&r)[32], const uint32_t (&g)[32], const uint32_t (&w)[4],
-                                             const ClampK ck, float delta, float ex0, uint32_t (&pk)[16]) {
+// dQ kernel: 32 columns (keys) of one query row -> 16 masked packed pairs of ds = e (dp - delta') [unclamped].
+template <bool FIRST, bool CLAMP>
+__device__ __forceinline__ void bwdq_chunk32(const uint32_t (&r)[32], const uint32_t (&g)[32], uint32_t X, const MathK mk,
+                                             float delta, float ex0, uint32_t (&pk)[16]) {
+    float mult0 = 1.0f;
+    if (FIRST) {
+        mult0 = (float)(X & 1u) + ex0;
+        if (mult0 > 0.0f) X |= 1u;
+        else mult0 = 1.0f;
+    }
+    const uint64_t nd2 = pk2(-delta, -delta);
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-        float u0, v0, u1, v1;
-        float e0 = bwd_exp(__uint_as_float(r[i]), ck, u0, v0);
-        float e1 = bwd_exp(__uint_as_float(r[i + 1]), ck, u1, v1);
-        if (FIRST && i == 0) e0 *= (float)(w[0] & 1u) + ex0;
-        else e0 = keep_if_bit(e0, w[i & 3], 1u << (i >> 2));
-        e1 = keep_if_bit(e1, w[(i + 1) & 3], 1u << (i >> 2));
-        pk[i >> 1] = pack_bf16(bwd_ds(e0, __uint_as_float(g[i]), delta, u0, v0),
-                               bwd_ds(e1, __uint_as_float(g[i + 1]), delta, u1, v1));
+    for (int n = 0; n < 8; ++n) {
+        uint32_t m01, m23;
+        pair_masks(X, n, m01, m23);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = 4 * n + 2 * h;
+            float e0, e1;
+            bool in0 = true, in1 = true;
+            if (poly_pair(i >> 1)) exp_pair<CLAMP, true>(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), mk, e0, e1, in0, in1);
+            else exp_pair<CLAMP, false>(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), mk, e0, e1, in0, in1);
+            if (FIRST && i == 0) e0 *= mult0;
+            float d0, d1;
+            up2(mul2(pk2(e0, e1), add2(pk2(__uint_as_float(g[i]), __uint_as_float(g[i + 1])), nd2)), d0, d1);
+            if (CLAMP) {
+                d0 = in0 ? d0 : 0.0f;
+                d1 = in1 ? d1 : 0.0f;
+            }
+            pk[i >> 1] = pack_bf16(d0, d1) & (h ? m23 : m01);
+        }
     }
 }
 
-// dK/dV kernel: 16 columns (query rows c0 .. c0+15) of one key.  mrow = this key's lane-major word of every
-// row, [64] in shared memory; bitmask selects the key's bit.  KEY0: this thread is key 0 (adds extra0[row]).
-template <bool KEY0>
-__device__ __forceinline__ void bwdkv_chunk16(const uint32_t (&r)[16], const uint32_t (&g)[16], const uint32_t *mrow,
-                                              const float *s_delta, const float *s_ex0, int c0, uint32_t bitmask,
-                                              const ClampK ck, uint32_t (&pe)[8], uint32_t (&pd)[8]) {
+// dK/dV kernel: 16 columns (query rows c0 .. c0+15) of one key.  mrow = this key's lane-major word of every row of the
+// stage ([64] in shared memory), shl moves the key's bit to bit 31; s_ndelta = -delta' of the rows.
+// KEY0: this thread is key 0 (adds the rows' zero-padding multiplicity s_ex0).
+// r / g hold NR values of which [OFF, OFF + 16) are processed; c0 = tile row of r[OFF].
+template <bool KEY0, bool CLAMP, int OFF = 0, int NR = 16>
+__device__ __forceinline__ void bwdkv_chunk16(const uint32_t (&rr)[NR], const uint32_t (&gg)[NR], const uint32_t *mrow,
+                                              const float *s_ndelta, const float *s_ex0, int c0, int shl, const MathK mk,
+                                              uint32_t (&pe)[8], uint32_t (&pd)[8]) {
+    uint32_t r[16], g[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        r[i] = rr[OFF + i];
+        g[i] = gg[OFF + i];
+    }
 #pragma unroll
     for (int q4 = 0; q4 < 16; q4 += 4) {
         const uint4 mw = *reinterpret_cast<const uint4 *>(mrow + c0 + q4);
-        const float4 dl = *reinterpret_cast<const float4 *>(s_delta + c0 + q4);
-        const uint32_t mwv[4] = {mw.x, mw.y, mw.z, mw.w};
-        const float dlv[4] = {dl.x, dl.y, dl.z, dl.w};
-        float e[4], d[4];
+        const float4 nd = *reinterpret_cast<const float4 *>(s_ndelta + c0 + q4);
+        const uint32_t mwv[4] = {mw.x << shl, mw.y << shl, mw.z << shl, mw.w << shl};
+        const float ndv[4] = {nd.x, nd.y, nd.z, nd.w};
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            float u, v;
-            e[t] = bwd_exp(__uint_as_float(r[q4 + t]), ck, u, v);
-            if (KEY0) e[t] *= (float)((mwv[t] & bitmask) != 0u) + s_ex0[c0 + q4 + t];
-            else e[t] = keep_if_bit(e[t], mwv[t], bitmask);
-            d[t] = bwd_ds(e[t], __uint_as_float(g[q4 + t]), dlv[t], u, v);
+        for (int h = 0; h < 2; ++h) {
+            const int i = q4 + 2 * h;
+            float e0, e1;
+            bool in0 = true, in1 = true;
+            if (poly_pair(i >> 1)) exp_pair<CLAMP, true>(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), mk, e0, e1, in0, in1);
+            else exp_pair<CLAMP, false>(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), mk, e0, e1, in0, in1);
+            uint32_t ma = mwv[2 * h], mb = mwv[2 * h + 1];
+            if (KEY0) {     // key 0: weight = bit + zero-padding multiplicity of the row
+                const float w0 = (float)(ma >> 31) + s_ex0[c0 + i], w1 = (float)(mb >> 31) + s_ex0[c0 + i + 1];
+                e0 *= w0;
+                e1 *= w1;
+                ma = w0 > 0.0f ? 0x80000000u : 0u;
+                mb = w1 > 0.0f ? 0x80000000u : 0u;
+            }
+            const uint32_t m = prmt(ma, mb, 0xFFBBu);      // sign of ma -> low half, sign of mb -> high half
+            float d0, d1;
+            up2(mul2(pk2(e0, e1), add2(pk2(__uint_as_float(g[i]), __uint_as_float(g[i + 1])), pk2(ndv[2 * h], ndv[2 * h + 1]))),
+                d0, d1);
+            if (CLAMP) {
+                d0 = in0 ? d0 : 0.0f;
+                d1 = in1 ? d1 : 0.0f;
+            }
+            pe[i >> 1] = pack_bf16(e0, e1) & m;
+            pd[i >> 1] = pack_bf16(d0, d1) & m;
         }
-        pe[(q4 >> 1)] = pack_bf16(e[0], e[1]);
-        pe[(q4 >> 1) + 1] = pack_bf16(e[2], e[3]);
-        pd[(q4 >> 1)] = pack_bf16(d[0], d[1]);
-        pd[(q4 >> 1) + 1] = pack_bf16(d[2], d[3]);
     }
 }
+
+// ---- optional in-kernel phase timers (build with -DSPT_ATTN_PROF; read with spt_debug_attn_prof) ----------------------
+// One math thread (warp 0, lane 0) and the MMA-issuer lane of every CTA accumulate clock64() deltas per phase and add them
+// to g_prof[kernel][slot] at exit.  Slots 0-7: math thread (0 wait scores, 1 tcgen05.ld, 2 element math, 3 tcgen05.st +
+// arrive, 4 iterations, 5 whole loop); 8-15: issuer (8 wait operands, 9 wait math, 10 issue, 11 whole loop, 12 iterations).
+#ifdef SPT_ATTN_PROF
+__device__ unsigned long long g_prof[3][16];
+struct Prof {
+    long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long last;
+    __device__ __forceinline__ void start() { last = clock64(); }
+    __device__ __forceinline__ void lap(int slot) {
+        const long long now = clock64();
+        t[slot] += now - last;
+        last = now;
+    }
+    __device__ __forceinline__ void flush(int kernel, int base, bool on) {
+        if (on)
+            for (int i = 0; i < 8; ++i) atomicAdd(&g_prof[kernel][base + i], (unsigned long long)t[i]);
+    }
+};
+#define PROF(x) x
+#else
+#define PROF(x)
+#endif
 
 struct Smem {
     uint32_t base;            // 1024-aligned shared address
@@ -235,9 +379,10 @@ __global__ void __launch_bounds__(THREADS, Dim<D>::CTAS)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, const uint32_t *__restrict__ mask,
                    const int32_t *__restrict__ extra0, __nv_bfloat16 *__restrict__ y, float *__restrict__ zsum, int S,
-                   int H, float scale_log2, float clamp_log2) {
+                   int H, float scale_log2, float clamp_log2, int y_transposed) {
     constexpr int OWN_BYTES = Dim<D>::OWN_BYTES, T_BYTES = Dim<D>::T_BYTES, OWN_SUB = Dim<D>::OWN_SUB, T_SUB = Dim<D>::T_SUB,
                   TMEM_COLS = Dim<D>::TMEM_COLS;
+    constexpr int NBUF = 3;                            // score buffers
     extern __shared__ unsigned char smem_raw[];
     const Smem sm = align_smem(smem_raw);
     const uint32_t s_q = sm.base, s_k = s_q + OWN_BYTES, s_v = s_k + STAGES * T_BYTES;
@@ -249,10 +394,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     auto k_empty = [&](int s) { return bar0 + 16 + (STAGES + s) * 8; };
     auto v_full = [&](int s) { return bar0 + 16 + (2 * STAGES + s) * 8; };
     auto v_empty = [&](int s) { return bar0 + 16 + (3 * STAGES + s) * 8; };
-    auto s_full = [&](int b) { return bar0 + 16 + (4 * STAGES + b) * 8; };
-    auto p_full = [&](int b) { return bar0 + 16 + (4 * STAGES + 2 + b) * 8; };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 + 4 * STAGES + 4);
+    auto s_full = [&](int b) { return bar0 + 16 + (4 * STAGES + b) * 8; };          // b = 0 .. NBUF-1
+    auto p_full = [&](int b) { return bar0 + 16 + (4 * STAGES + NBUF + b) * 8; };   // b = warpgroup 0, 1
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 + 4 * STAGES + NBUF + 2);
 
+    PROF(const long long t_entry = clock64(); unsigned long long ns0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = gridDim.x - 1 - blockIdx.x;      // heaviest (last) query tiles first
     const int b = blockIdx.y;
@@ -269,10 +415,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             mbar_init(v_full(s), 1);
             mbar_init(v_empty(s), 1);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(s_full(i), 1);
-            mbar_init(p_full(i), N_MATH);
-        }
+        for (int i = 0; i < NBUF; ++i) mbar_init(s_full(i), 1);
+        for (int i = 0; i < 2; ++i) mbar_init(p_full(i), N_MATH / 2);          // one arrival per thread of a warpgroup
         mbar_fence_init();
     }
     if (warp == 9) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
@@ -280,7 +424,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;
+    // TMEM columns: score buffers S[b] at 64 b (fp32 128 x 64); P (bf16 pairs, 32 columns) is written IN PLACE over the
+    // first half of its own score buffer; O at 192.  Three buffers for two warpgroups: the scores of a group's next tile
+    // are computed while it is still in the element math of its current one.
+    constexpr uint32_t COL_S = 0, COL_O = NBUF * BN;
 
     if (warp == 8) {
         // ===== TMA producer =====
@@ -303,6 +450,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         constexpr uint32_t id_s = idesc_bf16(BM, BN, 0, 0);   // S = Q K^T   (both K-major)
         constexpr uint32_t id_o = idesc_bf16(BM, D, 0, 1);    // O += P V    (A from TMEM, V MN-major)
         const uint64_t dq0 = desc_kmajor(s_q, 0), dk0 = desc_kmajor(s_k, 0), dv0 = desc_mnmajor(s_v, 0, T_SUB);
+        // S = Q K^T runs two tiles ahead of O += P V, into the third (free) buffer, so the k-steps of S(j + 2) and of
+        // PV(j) touch different TMEM columns and are interleaved: two accumulator chains in flight (consecutive MMAs into
+        // one accumulator are serialised, ~93 clk each).
+        // (Running three ahead — S(j + 3) into tile j's own buffer right behind PV(j) — was built and produced NaNs under
+        // load even with a full drain between the two, for a reason not understood; not used.)
         auto issue_s = [&](int j) {
             const int st = j % STAGES;
             mbar_wait(k_full(st), (j / STAGES) & 1);
@@ -311,31 +463,47 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 const uint64_t dk = dk0 + (uint64_t)(st * (T_BYTES >> 4));
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k)
-                    umma_bf16(tmem_base + COL_S + (j & 1) * BN, dq0 + kslice<OWN_SUB>(k), dk + kslice<T_SUB>(k), id_s, k != 0);
-                umma_commit(s_full(j & 1));
+                    umma_bf16(tmem_base + COL_S + (j % NBUF) * BN, dq0 + kslice<OWN_SUB>(k), dk + kslice<T_SUB>(k), id_s, k != 0);
+                umma_commit(s_full(j % NBUF));
                 umma_commit(k_empty(st));
             }
             __syncwarp();
         };
         mbar_wait(q_full, 0);
         issue_s(0);
+        if (n_tiles > 1) issue_s(1);
+        PROF(Prof pf; pf.start(); const long long t0 = pf.last;)
         for (int j = 0; j < n_tiles; ++j) {
-            if (j + 1 < n_tiles) issue_s(j + 1);   // S buffer (j+1)&1 was released by p_full of tile j-1
-            mbar_wait(p_full(j & 1), (j >> 1) & 1);
+            mbar_wait(p_full(j & 1), (j >> 1) & 1);      // warpgroup j & 1 has written P_j
+            PROF(pf.lap(1);)
             const int st = j % STAGES;
             mbar_wait(v_full(st), (j / STAGES) & 1);
+            const bool has_next = j + 2 < n_tiles;
+            const int stn = (j + 2) % STAGES;
+            if (has_next) mbar_wait(k_full(stn), ((j + 2) / STAGES) & 1);
+            PROF(pf.lap(0);)
             fence_after_sync();
             if (elect_one()) {
                 const uint64_t dv = dv0 + (uint64_t)(st * (T_BYTES >> 4));
+                const uint64_t dk = dk0 + (uint64_t)(stn * (T_BYTES >> 4));
+                const uint32_t s_next = tmem_base + COL_S + ((j + 2) % NBUF) * BN, p_cur = tmem_base + COL_S + (j % NBUF) * BN;
+                constexpr int KS = D / 16, KP = BN / 16;
 #pragma unroll
-                for (int k = 0; k < BN / 16; ++k)
-                    umma_bf16_ts(tmem_base + COL_O, tmem_base + COL_P + (j & 1) * 32 + k * 8, dv + k * MNMAJOR_K16, id_o,
-                                 (j | k) != 0);
+                for (int k = 0; k < (KS > KP ? KS : KP); ++k) {
+                    if (k < KS && has_next) umma_bf16(s_next, dq0 + kslice<OWN_SUB>(k), dk + kslice<T_SUB>(k), id_s, k != 0);
+                    if (k < KP) umma_bf16_ts(tmem_base + COL_O, p_cur + k * 8, dv + k * MNMAJOR_K16, id_o, (j | k) != 0);
+                }
+                if (has_next) {
+                    umma_commit(s_full((j + 2) % NBUF));
+                    umma_commit(k_empty(stn));
+                }
                 umma_commit(v_empty(st));
                 if (j + 1 == n_tiles) umma_commit(o_full);
             }
             __syncwarp();
+            PROF(pf.lap(2);)
         }
+        PROF(pf.t[3] = clock64() - t0; pf.t[4] = n_tiles; pf.flush(0, 8, lane == 0);)
     } else {
         // ===== softmax warps: thread = (query row = TMEM lane, column half) =====
         const int quarter = warp & 3, half = warp >> 2;
@@ -345,27 +513,53 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const uint4 *mrow = reinterpret_cast<const uint4 *>(mask + grow * (S / 32));
         const float ex0 = (float)extra0[grow];
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        float sum = 0.0f;
-        const ClampK ck = make_clamp(scale_log2, clamp_log2);
-        uint4 mw = __ldg(mrow), mw_next = mw;
-        for (int j = 0; j < n_tiles; ++j) {
-            const int bsel = j & 1;
-            if (bsel == 0 && j + 2 < n_tiles) mw_next = __ldg(mrow + (j >> 1) + 1);
-            mbar_wait(s_full(bsel), (j >> 1) & 1);
+        // Ping-pong: warpgroup `half` (warps 4 half .. 4 half + 3, one per scheduler) owns the key tiles j = half (mod 2) and
+        // score buffer `half`; a thread processes ALL 64 columns of its row as two 32-column chunks.  The two groups of a
+        // CTA (and the two CTAs of the SM) are then in different phases by construction: while one group is in its
+        // element math the other waits for / loads its scores, instead of all eight warps contending for the same
+        // issue slots and then idling together (measured: 1640 clk per tile and CTA of which 380 waiting, with every
+        // warp of the CTA on every tile).
+        uint64_t sum2 = pk2(0.0f, 0.0f);
+        const MathK mk = make_math(scale_log2, clamp_log2);
+        uint4 mw = __ldg(mrow);
+        PROF(Prof pf; pf.start(); const long long t0 = pf.last; pf.t[6] = t0 - t_entry;)
+        for (int j = half, it = 0; j < n_tiles; j += 2, ++it) {
+            // tile j = keys 64 j .. 64 j + 63 = bits 16 half .. 16 half + 15 of the lane-major words of key group it = j >> 1
+            const uint4 mw_next = (j + 2 < n_tiles) ? __ldg(mrow + it + 1) : mw;
+            const uint32_t buf = lane_base + COL_S + (uint32_t)(j % NBUF) * BN;
+            mbar_wait(s_full(j % NBUF), (j / NBUF) & 1);
+            PROF(pf.lap(0);)
             fence_after_sync();
-            uint32_t r[32];
-            tmem_ld32(lane_base + COL_S + bsel * BN + half * 32, r);
-            // tile column c = 32 half + i is key 64 j + c of group j >> 1: word c & 3, bit 16 (j & 1) + (c >> 2)
-            const int b0 = 16 * bsel + 8 * half;
-            const uint32_t w[4] = {mw.x >> b0, mw.y >> b0, mw.z >> b0, mw.w >> b0};
-            uint32_t pk[16];
-            if (j == 0 && half == 0) fwd_chunk32<true>(r, w, ck, ex0, sum, pk);
-            else fwd_chunk32<false>(r, w, ck, ex0, sum, pk);
-            tmem_st16(lane_base + COL_P + bsel * 32 + half * 16, pk);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+                tmem_ld32(buf + c * 32, r);
+                PROF(pf.lap(1);)
+                const uint32_t X = chunk_mask_bytes(mw, 2 * half + c);
+                uint32_t pk[16];
+                const bool first = (j == 0 && c == 0);
+                if (!warp_needs_clamp(r, mk.thr)) {
+                    if (first) fwd_chunk32<true, false>(r, X, mk, ex0, sum2, pk);
+                    else fwd_chunk32<false, false>(r, X, mk, ex0, sum2, pk);
+                } else {
+                    if (first) fwd_chunk32<true, true>(r, X, mk, ex0, sum2, pk);
+                    else fwd_chunk32<false, true>(r, X, mk, ex0, sum2, pk);
+                }
+                PROF(pf.lap(2);)
+                tmem_st16(buf + c * 16, pk);             // in place: these columns were consumed by this thread's chunk 0
+            }
             tmem_st_wait();
             fence_before_sync();
-            mbar_arrive(p_full(bsel));
-            if (bsel == 1) mw = mw_next;
+            mbar_arrive(p_full(half));
+            PROF(pf.lap(3);)
+            mw = mw_next;
+        }
+        PROF(pf.t[5] = clock64() - t0; pf.t[4] = n_tiles / 2; const long long t_loop_end = clock64();)
+        float sum;
+        {
+            float lo, hi;
+            up2(sum2, lo, hi);
+            sum = lo + hi;
         }
         s_part[half * BM + rt] = sum;
         math_warps_sync();
@@ -374,17 +568,38 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const float inv = 1.0f / sum;
         mbar_wait(o_full, 0);
         fence_after_sync();
-        __nv_bfloat16 *dst = y + (((size_t)hn * S + row) * H + hh) * D + half * (D / 2);
+        if (!y_transposed) {
+            __nv_bfloat16 *dst = y + (((size_t)hn * S + row) * H + hh) * D + half * (D / 2);
 #pragma unroll
-        for (int c = 0; c < D / 64; ++c) {
-            uint32_t r[32];
-            tmem_ld32(lane_base + COL_O + half * (D / 2) + c * 32, r);
-            store_row32(dst + c * 32, r, inv);
+            for (int c = 0; c < D / 64; ++c) {
+                uint32_t r[32];
+                tmem_ld32(lane_base + COL_O + half * (D / 2) + c * 32, r);
+                store_row32(dst + c * 32, r, inv);
+            }
+        } else {
+            // the shipped reference layer's output layout (attention.py:139-142): y^T [B, D, S] memory; a warp's 32
+            // consecutive rows of one feature are 64 contiguous bytes
+            __nv_bfloat16 *dst = y + ((size_t)b * D + half * (D / 2)) * S + row;
+#pragma unroll
+            for (int c = 0; c < D / 64; ++c) {
+                uint32_t r[32];
+                tmem_ld32(lane_base + COL_O + half * (D / 2) + c * 32, r);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dst[(size_t)(c * 32 + i) * S] = __float2bfloat16(__uint_as_float(r[i]) * inv);
+            }
         }
+        PROF(pf.t[7] = clock64() - t_loop_end; pf.flush(0, 0, threadIdx.x == 0);)
     }
     fence_before_sync();
     __syncthreads();
     if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem_base);
+    PROF(if (threadIdx.x == 0) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        atomicAdd(&g_prof[0][15], (unsigned long long)(clock64() - t_entry));
+        atomicAdd(&g_prof[0][14], 1ull);
+        atomicAdd(&g_prof[0][13], ns1 - ns0);
+    })
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -416,6 +631,48 @@ attn_bwd_prep_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *
     if (sub == 0) delta[row] = acc * inv;
 }
 
+// The same for dO and y in the reference layer's output layout (y^T, dO^T: [B, D, S] memory): a block transposes a
+// [D] x [64 rows] tile of each through shared memory; dO' is written in the standard [N, S, H, D] layout the TMA maps read.
+template <int D>
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_t_kernel(const __nv_bfloat16 *__restrict__ dyt, const __nv_bfloat16 *__restrict__ yt,
+                       const float *__restrict__ zsum, float *__restrict__ delta, __nv_bfloat16 *__restrict__ dys, int S,
+                       int H) {
+    constexpr int TR = 64, LD = TR + 8;
+    __shared__ __align__(16) __nv_bfloat16 s_dy[D][LD];
+    __shared__ __align__(16) __nv_bfloat16 s_y[D][LD];
+    const int b = blockIdx.y, r0 = blockIdx.x * TR;
+    const size_t base = (size_t)b * D * S + r0;
+    for (int id = threadIdx.x; id < D * (TR / 8); id += 256) {
+        const int e = id / (TR / 8), c = (id % (TR / 8)) * 8;
+        *reinterpret_cast<uint4 *>(&s_dy[e][c]) = *reinterpret_cast<const uint4 *>(dyt + base + (size_t)e * S + c);
+        *reinterpret_cast<uint4 *>(&s_y[e][c]) = *reinterpret_cast<const uint4 *>(yt + base + (size_t)e * S + c);
+    }
+    __syncthreads();
+    const int r = threadIdx.x >> 2, qd = threadIdx.x & 3;
+    constexpr int EPT = D / 4;                       // features per thread
+    float a[EPT];
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+        a[i] = __bfloat162float(s_dy[qd * EPT + i][r]);
+        acc = fmaf(a[i], __bfloat162float(s_y[qd * EPT + i][r]), acc);
+    }
+    acc = group_sum<4>(acc);
+    const size_t grow = (size_t)b * S + r0 + r;
+    const float inv = 1.0f / zsum[grow];
+    const int hn = b / H, hh = b % H;
+    __nv_bfloat16 *dst = dys + (((size_t)hn * S + r0 + r) * H + hh) * D + qd * EPT;
+#pragma unroll
+    for (int i = 0; i < EPT; i += 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = a[i + u] * inv;
+        Vec16<__nv_bfloat16>::store(dst + i, t);
+    }
+    if (qd == 0) delta[grow] = acc * inv;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Backward, dQ: owner = 128 query rows (Q, dO'), loop over 64-key tiles (K_j, V_j).
 // TMEM columns: S 0, dP' 64 (128x64 fp32 each), dS[2] 128/160 (bf16 pairs), dQ 192.
@@ -437,11 +694,14 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t s_q = sm.base, s_dy = s_q + OWN_BYTES, s_k = s_dy + OWN_BYTES, s_v = s_k + STAGES * T_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm.ptr + 2 * OWN_BYTES + 2 * STAGES * T_BYTES);
     const uint32_t bar0 = smem_u32(bars);
-    const uint32_t own_full = bar0, acc_full = bar0 + 8, sc_full = bar0 + 16, s_read = bar0 + 24;
+    const uint32_t own_full = bar0, acc_full = bar0 + 8, s_read = bar0 + 24;
+    // one "scores ready" barrier per warpgroup (tile parity): the two groups may be a phase apart, and a parity wait
+    // cannot tell "phase j+1 complete" from "phase j-1 complete"
+    auto sc_full = [&](int i) { return i == 0 ? bar0 + 16 : bar0 + 48 + 2 * STAGES * 8; };
     auto p_full = [&](int i) { return bar0 + 32 + i * 8; };
     auto kv_full = [&](int s) { return bar0 + 48 + s * 8; };
     auto kv_empty = [&](int s) { return bar0 + 48 + (STAGES + s) * 8; };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6 + 2 * STAGES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7 + 2 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = gridDim.x - 1 - blockIdx.x;
@@ -453,10 +713,11 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     if (threadIdx.x == 0) {
         mbar_init(own_full, 1);
         mbar_init(acc_full, 1);
-        mbar_init(sc_full, 1);
-        mbar_init(s_read, N_MATH);
-        mbar_init(p_full(0), N_MATH);
-        mbar_init(p_full(1), N_MATH);
+        mbar_init(sc_full(0), 1);
+        mbar_init(sc_full(1), 1);
+        mbar_init(s_read, N_MATH / 2);                // one warpgroup per tile
+        mbar_init(p_full(0), N_MATH / 2);
+        mbar_init(p_full(1), N_MATH / 2);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(kv_full(s), 1);
             mbar_init(kv_empty(s), 1);
@@ -488,6 +749,10 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         constexpr uint32_t id_a = idesc_bf16(BM, D, 0, 1);    // dQ += dS K   (A from TMEM, K MN-major)
         const uint64_t dq0 = desc_kmajor(s_q, 0), ddy0 = desc_kmajor(s_dy, 0), dk0 = desc_kmajor(s_k, 0),
                        dv0 = desc_kmajor(s_v, 0), dkt0 = desc_mnmajor(s_k, 0, T_SUB);
+        // The score MMAs of tile j are issued as soon as tile j-1's scores are in the math warps' registers (s_read): they are
+        // on the critical path (the math warps wait for them), the accumulating MMAs dQ += dS_{j-1} K_{j-1} are not and
+        // follow once dS_{j-1} is written.  (Interleaving the three chains in one group was measured slower: 2125 vs 1940
+        // clk per tile — it delays the scores behind p_full.)
         auto issue_acc = [&](int j, bool last) {                  // dQ += dS_j K_j
             const int st = j % STAGES;
             mbar_wait(p_full(j & 1), (j >> 1) & 1);
@@ -504,10 +769,13 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             __syncwarp();
         };
         mbar_wait(own_full, 0);
+        PROF(Prof pf; pf.start(); const long long t0 = pf.last;)
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j % STAGES;
             mbar_wait(kv_full(st), (j / STAGES) & 1);
+            PROF(pf.lap(0);)
             if (j > 0) mbar_wait(s_read, (j - 1) & 1);        // tile j-1's scores are in registers
+            PROF(pf.lap(1);)
             fence_after_sync();
             if (elect_one()) {
                 const uint64_t off = (uint64_t)(st * (T_BYTES >> 4));
@@ -518,12 +786,15 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     umma_bf16(tmem_base + COL_S, dq0 + kslice<OWN_SUB>(k), dk0 + off + kslice<T_SUB>(k), id_s, k != 0);
                     umma_bf16(tmem_base + COL_DP, ddy0 + kslice<OWN_SUB>(k), dv0 + off + kslice<T_SUB>(k), id_s, k != 0);
                 }
-                umma_commit(sc_full);
+                umma_commit(sc_full(j & 1));
             }
             __syncwarp();
+            PROF(pf.lap(2);)
             if (j > 0) issue_acc(j - 1, false);
+            PROF(pf.lap(5);)
         }
         issue_acc(n_tiles - 1, true);
+        PROF(pf.t[3] = clock64() - t0; pf.t[4] = n_tiles; pf.flush(1, 8, lane == 0);)
     } else {
         const int quarter = warp & 3, half = warp >> 2;
         const int row = m0 + quarter * 32 + lane;
@@ -532,30 +803,48 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const float ex0 = (float)extra0[grow];
         const float dl = delta[grow];
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const ClampK ck = make_clamp(scale_log2, clamp_log2);
-        uint4 mw = __ldg(mrow), mw_next = mw;
-        for (int j = 0; j < n_tiles; ++j) {
-            const int bsel = j & 1;
-            if (bsel == 0 && j + 2 < n_tiles) mw_next = __ldg(mrow + (j >> 1) + 1);
-            mbar_wait(sc_full, j & 1);
+        const MathK mk = make_math(scale_log2, clamp_log2);
+        uint4 mw = __ldg(mrow);
+        PROF(Prof pf; pf.start(); const long long t0 = pf.last;)
+        // Ping-pong (see the forward kernel): warpgroup `half` owns the key tiles j = half (mod 2) and dS buffer `half`; a
+        // thread processes all 64 columns of its row as two 32-column chunks, and releases the (single) score buffer as
+        // soon as the second chunk is in registers.
+        for (int j = half, it = 0; j < n_tiles; j += 2, ++it) {
+            const uint4 mw_next = (j + 2 < n_tiles) ? __ldg(mrow + it + 1) : mw;
+            mbar_wait(sc_full(half), it & 1);
+            PROF(pf.lap(0);)
             fence_after_sync();
-            uint32_t r[32], g[32];
-            tmem_ld32_nowait(lane_base + COL_S + half * 32, r);
-            tmem_ld32_nowait(lane_base + COL_DP + half * 32, g);
-            tmem_ld_wait();
-            fence_before_sync();
-            mbar_arrive(s_read);
-            const int b0 = 16 * bsel + 8 * half;
-            const uint32_t w[4] = {mw.x >> b0, mw.y >> b0, mw.z >> b0, mw.w >> b0};
-            uint32_t pk[16];
-            if (j == 0 && half == 0) bwdq_chunk32<true>(r, g, w, ck, dl, ex0, pk);
-            else bwdq_chunk32<false>(r, g, w, ck, dl, ex0, pk);
-            tmem_st16(lane_base + COL_DS + bsel * 32 + half * 16, pk);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32], g[32];
+                tmem_ld32_nowait(lane_base + COL_S + c * 32, r);
+                tmem_ld32_nowait(lane_base + COL_DP + c * 32, g);
+                tmem_ld_wait();
+                if (c == 1) {
+                    fence_before_sync();
+                    mbar_arrive(s_read);
+                }
+                PROF(pf.lap(1);)
+                const uint32_t X = chunk_mask_bytes(mw, 2 * half + c);
+                uint32_t pk[16];
+                const bool first = (j == 0 && c == 0);
+                if (!warp_needs_clamp(r, mk.thr)) {
+                    if (first) bwdq_chunk32<true, false>(r, g, X, mk, dl, ex0, pk);
+                    else bwdq_chunk32<false, false>(r, g, X, mk, dl, ex0, pk);
+                } else {
+                    if (first) bwdq_chunk32<true, true>(r, g, X, mk, dl, ex0, pk);
+                    else bwdq_chunk32<false, true>(r, g, X, mk, dl, ex0, pk);
+                }
+                PROF(pf.lap(2);)
+                tmem_st16(lane_base + COL_DS + half * 32 + c * 16, pk);
+            }
             tmem_st_wait();
             fence_before_sync();
-            mbar_arrive(p_full(bsel));
-            if (bsel == 1) mw = mw_next;
+            mbar_arrive(p_full(half));
+            PROF(pf.lap(3);)
+            mw = mw_next;
         }
+        PROF(pf.t[5] = clock64() - t0; pf.t[4] = n_tiles / 2; pf.flush(1, 0, threadIdx.x == 0);)
         mbar_wait(acc_full, 0);
         fence_after_sync();
         __nv_bfloat16 *dst = dq + (((size_t)hn * S + row) * H + hh) * D + half * (D / 2);
@@ -621,7 +910,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         mbar_init(acc_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(sc_full(i), 1);
-            mbar_init(p_full(i), N_MATH);
+            mbar_init(p_full(i), N_MATH / 2);          // one warpgroup per score buffer
         }
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(qd_full(s), 1 + 32);             // expect_tx arrive + the 32 producer lanes' row data
@@ -664,7 +953,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 mt[MT + rr] = mw.y;
                 mt[2 * MT + rr] = mw.z;
                 mt[3 * MT + rr] = mw.w;
-                reinterpret_cast<float *>(slot + MT * 16)[rr] = delta[gr];
+                reinterpret_cast<float *>(slot + MT * 16)[rr] = -delta[gr];     // the math adds it: dp - delta'
                 reinterpret_cast<float *>(slot + MT * 16 + BN * 4)[rr] = (float)extra0[gr];
             }
             mbar_arrive(qd_full(st));
@@ -698,58 +987,81 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         };
         mbar_wait(own_full, 0);
         issue_scores(0);
+        PROF(Prof pf; pf.start(); const long long t0 = pf.last;)
         for (int t = 0; t < n_sub; ++t) {
             if (t + 1 < n_sub) issue_scores(t + 1);   // its buffer was last read by the accumulating MMAs of t - 1 (in order)
+            PROF(pf.lap(0);)
             const int j = t >> 1, h = t & 1, st = j % STAGES;
             mbar_wait(p_full(t & 1), (t >> 1) & 1);
+            PROF(pf.lap(1);)
             fence_after_sync();
             if (elect_one()) {
                 const uint64_t off = (uint64_t)((st * T_BYTES) >> 4);
                 const uint32_t col = tmem_base + COL_SC + (t & 1) * 64;
-                // query rows 16 k .. 16 k + 15 of the sub-tile sit in columns 16 k .. 16 k + 7 (the writer's own half)
+                // query rows 16 k .. 16 k + 15 of the sub-tile sit in columns 8 k .. 8 k + 7 of E^T (over S^T) / dS^T (over dP'^T)
 #pragma unroll
                 for (int k = 0; k < SUBN / 16; ++k) {   // dV and dK alternate as well
-                    umma_bf16_ts(tmem_base + COL_DV, col + k * 16, ddyt0 + off + (2 * h + k) * MNMAJOR_K16, id_a, (t | k) != 0);
-                    umma_bf16_ts(tmem_base + COL_DK, col + 32 + k * 16, dqt0 + off + (2 * h + k) * MNMAJOR_K16, id_a, (t | k) != 0);
+                    umma_bf16_ts(tmem_base + COL_DV, col + k * 8, ddyt0 + off + (2 * h + k) * MNMAJOR_K16, id_a, (t | k) != 0);
+                    umma_bf16_ts(tmem_base + COL_DK, col + 32 + k * 8, dqt0 + off + (2 * h + k) * MNMAJOR_K16, id_a, (t | k) != 0);
                 }
                 if (h == 1) umma_commit(qd_empty(st));
                 if (t + 1 == n_sub) umma_commit(acc_full);
             }
             __syncwarp();
+            PROF(pf.lap(2);)
         }
+        PROF(pf.t[3] = clock64() - t0; pf.t[4] = n_sub; pf.flush(2, 8, lane == 0);)
     } else {
         // thread = (key n0 + kk = TMEM lane kk, column half): lane-major word kk & 3 of the row's group kt, bit kk >> 2
         const int quarter = warp & 3, half = warp >> 2;
         const int kk = quarter * 32 + lane;
         const int wsel = kk & 3;
-        const uint32_t bitmask = 1u << (kk >> 2);
+        const int shl = 31 - (kk >> 2);                 // moves this key's bit of a lane-major word to the sign bit
         const bool key0 = (n0 + kk) == 0;
-        const ClampK ck = make_clamp(scale_log2, clamp_log2);
+        const MathK mk = make_math(scale_log2, clamp_log2);
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        for (int t = 0; t < 2 * n_tiles; ++t) {
-            const int j = t >> 1, h = t & 1, st = j % STAGES;
+        PROF(Prof pf; pf.start(); const long long t0 = pf.last;)
+        // Ping-pong: warpgroup `half` owns the sub-tiles t = 2 j + half (rows 32 half .. 32 half + 31 of every 64-row tile)
+        // and score buffer `half`; a thread processes all 32 query rows of its key's sub-tile (see the forward kernel).
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j % STAGES, h = half;
             const unsigned char *slot = rowq + st * ROWQ_BYTES;
             const uint32_t *mrow = reinterpret_cast<const uint32_t *>(slot) + wsel * MT;   // this key's word of every row
-            const float *s_delta = reinterpret_cast<const float *>(slot + MT * 16);
-            const float *s_ex0 = s_delta + BN;
-            if (h == 0) mbar_wait(qd_full(st), (j / STAGES) & 1);   // the producer lanes' row data of this stage
-            mbar_wait(sc_full(t & 1), (t >> 1) & 1);
+            const float *s_ndelta = reinterpret_cast<const float *>(slot + MT * 16);
+            const float *s_ex0 = s_ndelta + BN;
+            mbar_wait(qd_full(st), (j / STAGES) & 1);   // the producer lanes' row data of this stage
+            mbar_wait(sc_full(h), j & 1);
+            PROF(pf.lap(0);)
             fence_after_sync();
-            const uint32_t col = lane_base + COL_SC + (t & 1) * 64 + half * 16;   // this thread's 16 query rows
-            const int c0 = h * SUBN + half * 16;                                   // ... = rows c0 .. c0 + 15 of the tile
-            uint32_t r[16], g[16];
-            tmem_ld16_nowait(col, r);
-            tmem_ld16_nowait(col + 32, g);
+            const uint32_t col = lane_base + COL_SC + h * 64;       // S^T at col, dP'^T at col + 32
+            const int c0 = h * SUBN;                                 // rows c0 .. c0 + 31 of the tile
+            uint32_t r[32], g[32];
+            tmem_ld32_nowait(col, r);
+            tmem_ld32_nowait(col + 32, g);
             tmem_ld_wait();
+            PROF(pf.lap(1);)
+            const bool clamp = warp_needs_clamp(r, mk.thr);
             uint32_t pe[8], pd[8];
-            if (key0) bwdkv_chunk16<true>(r, g, mrow, s_delta, s_ex0, c0, bitmask, ck, pe, pd);
-            else bwdkv_chunk16<false>(r, g, mrow, s_delta, s_ex0, c0, bitmask, ck, pe, pd);
-            tmem_st8(col, pe);         // E^T over the S^T columns this thread has consumed
-            tmem_st8(col + 32, pd);    // dS^T over its dP'^T columns
+#define SPT_KV_HALF(OFF)                                                                                                   \
+            if (key0) {                                                                                                    \
+                if (clamp) bwdkv_chunk16<true, true, OFF, 32>(r, g, mrow, s_ndelta, s_ex0, c0 + OFF, shl, mk, pe, pd);     \
+                else bwdkv_chunk16<true, false, OFF, 32>(r, g, mrow, s_ndelta, s_ex0, c0 + OFF, shl, mk, pe, pd);          \
+            } else {                                                                                                       \
+                if (clamp) bwdkv_chunk16<false, true, OFF, 32>(r, g, mrow, s_ndelta, s_ex0, c0 + OFF, shl, mk, pe, pd);    \
+                else bwdkv_chunk16<false, false, OFF, 32>(r, g, mrow, s_ndelta, s_ex0, c0 + OFF, shl, mk, pe, pd);         \
+            }                                                                                                              \
+            tmem_st8(col + (OFF) / 2, pe);      /* E^T over the S^T columns this thread has consumed */                    \
+            tmem_st8(col + 32 + (OFF) / 2, pd); /* dS^T over its dP'^T columns */
+            SPT_KV_HALF(0)
+            SPT_KV_HALF(16)
+#undef SPT_KV_HALF
+            PROF(pf.lap(2);)
             tmem_st_wait();
             fence_before_sync();
-            mbar_arrive(p_full(t & 1));
+            mbar_arrive(p_full(h));
+            PROF(pf.lap(3);)
         }
+        PROF(pf.t[5] = clock64() - t0; pf.t[4] = n_tiles; pf.flush(2, 0, threadIdx.x == 0);)
         mbar_wait(acc_full, 0);
         fence_after_sync();
         const size_t off = (((size_t)hn * S + n0 + kk) * H + hh) * D + half * (D / 2);
@@ -786,16 +1098,21 @@ static int make_map(CUtensorMap *map, const void *base, int N, int S, int H, int
 template <int D>
 static int launch_fwd(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const uint32_t *mask,
                       const int32_t *extra0, __nv_bfloat16 *y, float *zsum, int B, int S, int H, float scale, float clamp,
-                      cudaStream_t st) {
-    cudaFuncSetAttribute(attn_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dim<D>::FWD_SMEM);
-    attn_fwd_tc_kernel<D><<<dim3(S / BM, B), THREADS, Dim<D>::FWD_SMEM, st>>>(mq, mk, mv, mask, extra0, y, zsum, S, H,
-                                                                              scale * LOG2E, clamp * LOG2E);
+                      int y_transposed, cudaStream_t st) {
+    static const int extra_smem = [] { const char *e = getenv("SPT_ATTN_EXTRA_SMEM"); return e ? atoi(e) : 0; }();   // diagnostics: forces 1 CTA / SM
+    cudaFuncSetAttribute(attn_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dim<D>::FWD_SMEM + extra_smem);
+    attn_fwd_tc_kernel<D><<<dim3(S / BM, B), THREADS, Dim<D>::FWD_SMEM + extra_smem, st>>>(mq, mk, mv, mask, extra0, y, zsum, S, H,
+                                                                              scale * LOG2E, clamp * LOG2E, y_transposed);
     return after_launch("attn_fwd_tc_kernel");
 }
 
 template <int D>
 static int launch_prep(const __nv_bfloat16 *y, const __nv_bfloat16 *grad_y, const float *zsum, float *delta,
-                       __nv_bfloat16 *dys, int B, int S, int H, cudaStream_t st) {
+                       __nv_bfloat16 *dys, int B, int S, int H, int y_transposed, cudaStream_t st) {
+    if (y_transposed) {
+        attn_bwd_prep_t_kernel<D><<<dim3(S / 64, B), 256, 0, st>>>(grad_y, y, zsum, delta, dys, S, H);
+        return after_launch("attn_bwd_prep_t_kernel");
+    }
     const int64_t rows = (int64_t)B * S;
     constexpr int RPB = 256 / (D / 8);
     attn_bwd_prep_kernel<D><<<(unsigned)((rows + RPB - 1) / RPB), 256, 0, st>>>(grad_y, y, zsum, delta, dys, rows, S, H);
@@ -835,7 +1152,14 @@ static int check_attn_args(const char *what, int B, int S, int d, int H, int dty
 extern "C" int spt_sparse_attn_fwd(const void *q, const void *k, const void *v, const uint32_t *mask,
                                    const int32_t *extra0, void *y, float *zsum, int B, int S, int d, int H,
                                    float scale, float clamp, int dtype, spt_stream_t stream) {
+    return spt_sparse_attn_fwd_ex(q, k, v, mask, extra0, y, zsum, B, S, d, H, scale, clamp, dtype, 0, stream);
+}
+
+extern "C" int spt_sparse_attn_fwd_ex(const void *q, const void *k, const void *v, const uint32_t *mask,
+                                      const int32_t *extra0, void *y, float *zsum, int B, int S, int d, int H,
+                                      float scale, float clamp, int dtype, int flags, spt_stream_t stream) {
     SPT_REQUIRE(q && k && v && mask && extra0 && y && zsum, "sparse_attn_fwd: null pointer");
+    const int yt = (flags & SPT_ATTN_Y_TRANSPOSED) ? 1 : 0;
     int rc = check_attn_args("sparse_attn_fwd", B, S, d, H, dtype);
     if (rc != SPT_OK) return rc;
     SPT_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)y) % 16 == 0, "sparse_attn_fwd: operands must be 16-byte aligned");
@@ -844,8 +1168,25 @@ extern "C" int spt_sparse_attn_fwd(const void *q, const void *k, const void *v, 
     if ((rc = attn_tc::make_map(&mq, q, B / H, S, H, d)) != SPT_OK) return rc;
     if ((rc = attn_tc::make_map(&mk, k, B / H, S, H, d)) != SPT_OK) return rc;
     if ((rc = attn_tc::make_map(&mv, v, B / H, S, H, d)) != SPT_OK) return rc;
-    if (d == 64) return attn_tc::launch_fwd<64>(mq, mk, mv, mask, extra0, (bf *)y, zsum, B, S, H, scale, clamp, as_stream(stream));
-    return attn_tc::launch_fwd<128>(mq, mk, mv, mask, extra0, (bf *)y, zsum, B, S, H, scale, clamp, as_stream(stream));
+    if (d == 64) return attn_tc::launch_fwd<64>(mq, mk, mv, mask, extra0, (bf *)y, zsum, B, S, H, scale, clamp, yt, as_stream(stream));
+    return attn_tc::launch_fwd<128>(mq, mk, mv, mask, extra0, (bf *)y, zsum, B, S, H, scale, clamp, yt, as_stream(stream));
+}
+
+// diagnostics: phase timers of the attention kernels (all zeros unless built with -DSPT_ATTN_PROF); reset != 0 clears them
+extern "C" int spt_debug_attn_prof(unsigned long long *out48, int reset) {
+#ifdef SPT_ATTN_PROF
+    if (out48 && cudaMemcpyFromSymbol(out48, attn_tc::g_prof, sizeof(unsigned long long) * 48) != cudaSuccess)
+        return fail(SPT_ERR_CUDA, "debug_attn_prof: copy failed");
+    if (reset) {
+        static unsigned long long zeros[48] = {0};
+        if (cudaMemcpyToSymbol(attn_tc::g_prof, zeros, sizeof(zeros)) != cudaSuccess) return fail(SPT_ERR_CUDA, "debug_attn_prof: reset failed");
+    }
+    return 1;
+#else
+    (void)reset;
+    if (out48) memset(out48, 0, sizeof(unsigned long long) * 48);
+    return 0;
+#endif
 }
 
 // workspace: delta' [B, S] fp32, then dO' (bf16, same shape as grad_y; sized for the largest head dim)
@@ -857,6 +1198,15 @@ extern "C" int spt_sparse_attn_bwd(const void *q, const void *k, const void *v, 
                                    const uint32_t *mask, const int32_t *extra0, const float *zsum, void *grad_q,
                                    void *grad_k, void *grad_v, void *workspace, int B, int S, int d, int H,
                                    float scale, float clamp, int dtype, spt_stream_t stream) {
+    return spt_sparse_attn_bwd_ex(q, k, v, y, grad_y, mask, extra0, zsum, grad_q, grad_k, grad_v, workspace, B, S, d, H,
+                                  scale, clamp, dtype, 0, stream);
+}
+
+extern "C" int spt_sparse_attn_bwd_ex(const void *q, const void *k, const void *v, const void *y, const void *grad_y,
+                                      const uint32_t *mask, const int32_t *extra0, const float *zsum, void *grad_q,
+                                      void *grad_k, void *grad_v, void *workspace, int B, int S, int d, int H,
+                                      float scale, float clamp, int dtype, int flags, spt_stream_t stream) {
+    const int yt = (flags & SPT_ATTN_Y_TRANSPOSED) ? 1 : 0;
     SPT_REQUIRE(q && k && v && y && grad_y && mask && extra0 && zsum && grad_q && grad_k && grad_v && workspace,
                 "sparse_attn_bwd: null pointer");
     int rc = check_attn_args("sparse_attn_bwd", B, S, d, H, dtype);
@@ -868,8 +1218,8 @@ extern "C" int spt_sparse_attn_bwd(const void *q, const void *k, const void *v, 
     bf *dys = (bf *)((char *)workspace + (size_t)B * S * sizeof(float));
     // the row kernel goes first: besides producing dO' and delta' it is a runtime-API launch, which binds the
     // device's primary context to this (autograd worker) thread before the driver-API tensor-map encoder runs
-    rc = d == 64 ? attn_tc::launch_prep<64>((const bf *)y, (const bf *)grad_y, zsum, delta, dys, B, S, H, as_stream(stream))
-                 : attn_tc::launch_prep<128>((const bf *)y, (const bf *)grad_y, zsum, delta, dys, B, S, H, as_stream(stream));
+    rc = d == 64 ? attn_tc::launch_prep<64>((const bf *)y, (const bf *)grad_y, zsum, delta, dys, B, S, H, yt, as_stream(stream))
+                 : attn_tc::launch_prep<128>((const bf *)y, (const bf *)grad_y, zsum, delta, dys, B, S, H, yt, as_stream(stream));
     if (rc != SPT_OK) return rc;
     CUtensorMap mq, mk, mv, md;
     if ((rc = attn_tc::make_map(&mq, q, B / H, S, H, d)) != SPT_OK) return rc;

@@ -19,7 +19,7 @@ from typing import List, Tuple
 
 import torch
 
-from ._lib import SPT_BF16, SPT_F32, check, lib
+from ._lib import SPT_ATTN_Y_TRANSPOSED, SPT_BF16, SPT_F32, check, lib
 
 _DTYPES = {torch.float32: SPT_F32, torch.bfloat16: SPT_BF16}
 
@@ -409,29 +409,33 @@ def _check_attn(q, k, v):
     return B, S, q.size(-1), H
 
 
-def sparse_attn_fwd(q, k, v, mask, extra0, scale: float, clamp: float = 10.0):
+def sparse_attn_fwd(q, k, v, mask, extra0, scale: float, clamp: float = 10.0, reference_layout: bool = False):
     """q, k, v: [B,S,d] head-major or [N,S,H,d] (native layer layout, no transposes) bf16
-    -> (y, same layout as q; zsum [B,S] fp32).  See include/spt_b200.h."""
+    -> (y, same shape as q; zsum [B,S] fp32).  reference_layout: y's MEMORY is the shipped layer's y^T [B, d, S]
+    (attention.py:139-142), returned viewed with q's shape.  See include/spt_b200.h."""
     B, S, d, H = _check_attn(q, k, v)
     y = torch.empty_like(q)
     zsum = torch.empty((B, S), dtype=torch.float32, device=q.device)
     with _on_device(q):
-        check(lib.spt_sparse_attn_fwd(_p(q), _p(k), _p(v), _p(mask), _p(extra0), _p(y), _p(zsum), B, S, d, H,
-                                      float(scale), float(clamp), SPT_BF16, _stream(q)))
+        check(lib.spt_sparse_attn_fwd_ex(_p(q), _p(k), _p(v), _p(mask), _p(extra0), _p(y), _p(zsum), B, S, d, H,
+                                         float(scale), float(clamp), SPT_BF16,
+                                         SPT_ATTN_Y_TRANSPOSED if reference_layout else 0, _stream(q)))
     return y, zsum
 
 
-def sparse_attn_bwd(q, k, v, y, grad_y, mask, extra0, zsum, scale: float, clamp: float = 10.0):
-    """-> (grad_q, grad_k, grad_v) bf16."""
+def sparse_attn_bwd(q, k, v, y, grad_y, mask, extra0, zsum, scale: float, clamp: float = 10.0,
+                    reference_layout: bool = False):
+    """-> (grad_q, grad_k, grad_v) bf16.  reference_layout: y and grad_y are in the layout sparse_attn_fwd(...,
+    reference_layout=True) returned."""
     B, S, d, H = _check_attn(q, k, v)
     _check_dim(grad_y, q.dim(), "grad_y")
     _check_type(grad_y, torch.bfloat16, "grad_y")
     gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
     ws = _workspace(lib.spt_sparse_attn_bwd_workspace_bytes(B, S), q)
     with _on_device(q):
-        check(lib.spt_sparse_attn_bwd(_p(q), _p(k), _p(v), _p(y), _p(grad_y), _p(mask), _p(extra0), _p(zsum),
-                                      _p(gq), _p(gk), _p(gv), _p(ws), B, S, d, H, float(scale), float(clamp), SPT_BF16,
-                                      _stream(q)))
+        check(lib.spt_sparse_attn_bwd_ex(_p(q), _p(k), _p(v), _p(y), _p(grad_y), _p(mask), _p(extra0), _p(zsum),
+                                         _p(gq), _p(gk), _p(gv), _p(ws), B, S, d, H, float(scale), float(clamp), SPT_BF16,
+                                         SPT_ATTN_Y_TRANSPOSED if reference_layout else 0, _stream(q)))
     return gq, gk, gv
 
 

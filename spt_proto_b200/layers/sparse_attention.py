@@ -124,10 +124,10 @@ class _SparseV2Mixin:
         self._maybe_train_loss(q, k)           # PQ loss is a mean over rows: layout-invariant
         q_c, k_c = ext.pq_encode_pair(q, k, self.quantizer.weight)   # quantizer('encode') of both: [N, S, H, m]
         mask, extra0, _ = ext.lookup_mask(q_c, k_c, self.sparse_coeff)
-        y = kernels.sparse_attention(q, k, v, mask, extra0, self.scaling)      # [N, S, H, E]
-        if self.reference_output_layout:   # the shipped layer's re-interpretation of [N*H, E, S] memory
-            return y.permute(0, 2, 3, 1).contiguous().view(v.size())
-        return y
+        # [N, S, H, E]; with reference_output_layout the kernel writes the shipped layer's re-interpretation of
+        # [N*H, E, S] memory itself (forward epilogue / backward row prologue): no permute pass either way
+        return kernels.sparse_attention(q, k, v, mask, extra0, self.scaling,
+                                        reference_layout=self.reference_output_layout)
 
     def _sparse_get_attn(self, q, k):
         assert q.size() == k.size()

@@ -70,10 +70,11 @@ def test_fused_attention_matches_oracle(B, S, scale_mul, d):
     tol = dict(atol=2e-2, rtol=2e-2)
     assert torch.allclose(y.float().cpu(), y_ref.detach(), **tol)
     # gradients grow with the head dim (|dk| up to 15 at d = 128 vs 7 at d = 64): bf16-output atol follows
-    g_atol = 4e-2 if d == 64 else 8e-2
-    assert torch.allclose(vd.grad.float().cpu(), vf.grad, atol=g_atol, rtol=3e-2)
-    assert torch.allclose(qd.grad.float().cpu(), qf.grad, atol=g_atol, rtol=3e-2)
-    assert torch.allclose(kd.grad.float().cpu(), kf.grad, atol=g_atol, rtol=3e-2)
+    # and with the magnitude of the gradient itself (row 0 of dk collects every query's zero-padding mass: |dk| up
+    # to 8 at S 2048): atol = 1.5 % of the largest entry, at least the d-dependent floor
+    for got, want in ((vd.grad, vf.grad), (qd.grad, qf.grad), (kd.grad, kf.grad)):
+        g_atol = max(4e-2 if d == 64 else 8e-2, 1.5e-2 * want.abs().max().item())
+        assert torch.allclose(got.float().cpu(), want, atol=g_atol, rtol=3e-2)
     # tighter, scale-free check: relative Frobenius error
     for got, want in ((y, y_ref.detach()), (qd.grad, qf.grad), (kd.grad, kf.grad), (vd.grad, vf.grad)):
         err = (got.float().cpu() - want).norm() / want.norm()
