@@ -46,6 +46,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// 1-D bulk copy global -> shared (bytes and both addresses multiples of 16); completes on the mbarrier like a tensor load
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // One lane of a converged warp (warp-uniform control flow around it keeps operands in uniform registers).
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
