@@ -31,10 +31,10 @@ torch.cuda.synchronize()
 if lib.spt_debug_attn_prof(buf, 2):
     names = ["fwd128", "bwd_q128", "bwd_kv128"]
     mlab = ["wait_scores", "tmem_ld", "math", "st+arrive", "iters", "epilogue", "total", "-"]
-    ilab = ["scores(wait+issue)", "wait_math", "issue_acc", "total", "iters", "-", "-", "-"]
+    ilab = ["issue_scores", "wait_math", "issue_acc", "total", "iters", "wait_k_full", "wait_s_read", "other"]
     for kidx, name in enumerate(names):
         r = [buf[kidx * 16 + i] for i in range(16)]
         if r[4] == 0: continue
         it_m, it_i = max(r[4], 1), max(r[12], 1)
         print(name, "math thread, clk per tile:", {mlab[i]: round(r[i] / it_m, 1) for i in (0, 1, 2, 3, 5, 6)}, "tiles", r[4])
-        print(name, "issuer, clk per tile:", {ilab[i]: round(r[8 + i] / it_i, 1) for i in (0, 1, 2, 3)}, "tiles", r[12])
+        print(name, "issuer, clk per tile:", {ilab[i]: round(r[8 + i] / it_i, 1) for i in (0, 1, 2, 3, 5, 6, 7)}, "tiles", r[12])

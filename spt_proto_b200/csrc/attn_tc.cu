@@ -764,9 +764,15 @@ static int make_map(CUtensorMap *map, const void *base, int N, int S, int H, int
     return SPT_OK;
 }
 
-// head dim 64 runs on the 128 x 128-tile kernels of attn_tc128.cu unless SPT_ATTN_TILE=64 (A/B switch)
+// head dim 64: the backward runs on the 128 x 128-tile kernels of attn_tc128.cu unless SPT_ATTN_TILE=64 (A/B switch); the
+// forward stays on the 128 x 64 two-CTAs-per-SM kernel, which is as fast (0.145 vs 0.151 ms at the bench shape: it is
+// bound by the exp unit, not by the tensor pipe) unless SPT_ATTN_FWD128=1
 static bool tile128() {
     static const bool on = [] { const char *e = getenv("SPT_ATTN_TILE"); return !(e && atoi(e) == 64); }();
+    return on;
+}
+static bool fwd128() {
+    static const bool on = [] { const char *e = getenv("SPT_ATTN_FWD128"); return e && atoi(e) == 1; }();
     return on;
 }
 
@@ -774,7 +780,7 @@ template <int D>
 static int launch_fwd(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const uint32_t *mask,
                       const int32_t *extra0, __nv_bfloat16 *y, float *zsum, int B, int S, int H, float scale, float clamp,
                       int y_transposed, cudaStream_t st) {
-    if (D == 64 && tile128()) return attn_tc128::launch_fwd128(mq, mk, mv, mask, extra0, y, zsum, B, S, H, scale, clamp, y_transposed, st);
+    if (D == 64 && fwd128()) return attn_tc128::launch_fwd128(mq, mk, mv, mask, extra0, y, zsum, B, S, H, scale, clamp, y_transposed, st);
     static const int extra_smem = [] { const char *e = getenv("SPT_ATTN_EXTRA_SMEM"); return e ? atoi(e) : 0; }();   // diagnostics: forces 1 CTA / SM
     cudaFuncSetAttribute(attn_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dim<D>::FWD_SMEM + extra_smem);
     attn_fwd_tc_kernel<D><<<dim3(S / BM, B), THREADS, Dim<D>::FWD_SMEM + extra_smem, st>>>(mq, mk, mv, mask, extra0, y, zsum, S, H,
