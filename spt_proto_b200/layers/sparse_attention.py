@@ -193,6 +193,8 @@ class SparseRotaryAttentionV2(_SparseV2Mixin, RotaryAttention):
     def forward(self, q, k, v, attn_mask=None):
         if self._fused_ok(q):
             self.last_path = "fused"
-            return self._fused_forward(self._rotate(q), self._rotate(k), v)
+            # fp32 rotation tables promote a bf16 input to fp32 (as in the reference); the fused kernels take the rotated
+            # operands in the input's own dtype
+            return self._fused_forward(self._rotate(q).to(q.dtype), self._rotate(k).to(k.dtype), v)
         self.last_path = "stage"
         return VanillaAttention.forward(self, q, k, v, attn_mask)

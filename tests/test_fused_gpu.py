@@ -202,3 +202,66 @@ def test_host_pipeline_equals_direct_call():
     for j, b in enumerate(want):
         got = read_operand(s_out, j)
         assert torch.equal(got[:N], b) and torch.equal(got[N:], b[:n_pad - N])
+
+
+def _rope_cpu(x, cos, sin):
+    """The reference's RotaryEmbedding expression (basic/position.py:34-48) in fp32 on the CPU."""
+    lo, hi = x.chunk(2, dim=-1)
+    return x * cos.view(1, -1, 1, x.size(-1)) + torch.cat((-hi, lo), dim=-1) * sin.view(1, -1, 1, x.size(-1))
+
+
+@pytest.mark.parametrize("N,S,H,E", [(1, 256, 2, 128), (2, 512, 3, 64)])
+def test_sparse_rotary_attention_v2_matches_oracle(N, S, H, E):
+    """SparseRotaryAttentionV2.forward (reference layers/sparse/attention.py:195-299): rotate q, k, then the PQ-sparse path;
+    fwd + bwd against the oracle layer applied to the rotated tensors (the gradient flows back through the rotation).
+    E = 128 is the LLaMA-7B head (m = 16 subspaces); both cases take the fused tcgen05 path."""
+    from spt_proto_b200 import layers
+    torch.manual_seed(3)
+    attn = layers.SparseRotaryAttentionV2(d_head=E, p_dropout=0.0, d_codeword=8, n_codewords=16,
+                                          reference_output_layout=False).to(DEV)
+    q, k, v, dy = (torch.randn(N, S, H, E).bfloat16() for _ in range(4))
+    qd, kd, vd = (t.to(DEV).requires_grad_() for t in (q, k, v))
+    y = attn(qd, kd, vd)
+    assert attn.last_path == "fused"
+    y.backward(dy.to(DEV))
+    # oracle: rotation in fp32 on the bf16-rounded rotated operands the kernels see
+    emb = attn.embedding
+    cos, sin = emb.cos_cached[:S].float().cpu(), emb.sin_cached[:S].float().cpu()
+    qf, kf, vf = (t.float().requires_grad_() for t in (q, k, v))
+    qr = _rope_cpu(qf, cos, sin)
+    kr = _rope_cpu(kf, cos, sin)
+    # the layer rounds the rotated tensors to bf16 before the PQ / attention kernels: do the same (straight-through)
+    qr_b = qr + (qr.detach().bfloat16().float() - qr.detach())
+    kr_b = kr + (kr.detach().bfloat16().float() - kr.detach())
+    w = attn.quantizer.weight.detach().float().cpu()
+    y_ref = O.sparse_mha_layer(qr_b, kr_b, vf, w, 8)
+    y_ref.backward(dy.float())
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    assert rel(y.detach(), y_ref.detach()) < 1e-2
+    assert rel(vd.grad, vf.grad) < 1.5e-2
+    assert rel(qd.grad, qf.grad) < 2e-2
+    assert rel(kd.grad, kf.grad) < 2e-2
+
+
+def test_config1_layer_matches_oracle():
+    """BASELINE configs[0] exactly: SparseVanillaAttentionV2, N 1, S 256, H 12, d_head 64, PQ 8 x 16, top-k 32, fwd + bwd
+    (reference test/layer/test_sparse_mha.py:7-43 shape family), both output layouts."""
+    from spt_proto_b200 import layers
+    torch.manual_seed(11)
+    N, S, H, E = 1, 256, 12, 64
+    q, k, v, dy = (torch.randn(N, S, H, E).bfloat16() for _ in range(4))
+    for ref_layout in (False, True):
+        attn = layers.SparseVanillaAttentionV2(d_head=E, d_codeword=8, n_codewords=16, p_dropout=0.0,
+                                               reference_output_layout=ref_layout).to(DEV)
+        qd, kd, vd = (t.to(DEV).requires_grad_() for t in (q, k, v))
+        y = attn(qd, kd, vd)
+        assert attn.last_path == "fused"
+        y.backward(dy.to(DEV))
+        qf, kf, vf = (t.float().requires_grad_() for t in (q, k, v))
+        y_ref = O.sparse_mha_layer(qf, kf, vf, attn.quantizer.weight.detach().float().cpu(), 8,
+                                   reference_output_layout=ref_layout)
+        y_ref.backward(dy.float())
+        rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+        assert rel(y.detach(), y_ref.detach()) < 1e-2
+        for got, want in ((qd.grad, qf.grad), (kd.grad, kf.grad), (vd.grad, vf.grad)):
+            assert rel(got, want) < 2e-2
