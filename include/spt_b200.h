@@ -117,6 +117,12 @@ int spt_sddmm_fwd(const int32_t *indptr, const int32_t *indices, const void *que
                   float *values, int B, int S, int d, int64_t nnz, float scale, float clamp,
                   int dtype, spt_stream_t stream);
 
+/* Backward of the fused scale + clamp of spt_sddmm_fwd (the reference does them as two eager passes whose autograd
+ * backward is a masked multiply, layers/sparse/attention.py:125-127): out = scale * grad where |clamped| < clamp, else 0.
+ * n (multiple of 4) fp32 elements, 16-byte aligned; clamp <= 0 means no clamp. */
+int spt_clamp_scale_bwd(const float *grad, const float *clamped, float *out, int64_t n, float scale, float clamp,
+                        spt_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * (5) spmm — replaces spmm_forward_cuda (extension/spmm.cpp:3-72).
  * trans = 0: y[b, r, :]  = sum_{e in row r} values[b, e] * x[b, indices[b, e], :]

@@ -41,6 +41,7 @@ def _load() -> ctypes.CDLL:
         "spt_lookup_workspace_bytes": (sz, [i32, i32, i32, i32]),
         "spt_lookup_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "spt_sddmm_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i64, f32, f32, i32, vp]),
+        "spt_clamp_scale_bwd": (i32, [vp, vp, vp, i64, f32, f32, vp]),
         "spt_spmm_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, vp]),
         "spt_spmm_t_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, vp]),
         "spt_csr2csc_workspace_bytes": (sz, [i32, i32, i64]),

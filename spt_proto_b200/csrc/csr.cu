@@ -683,6 +683,36 @@ extern "C" int spt_sddmm_fwd(const int32_t *indptr, const int32_t *indices, cons
     return fail(SPT_ERR_INVALID_ARGUMENT, "sddmm_fwd: unknown dtype %d", dtype);
 }
 
+// gradient of  v = clamp(scale * raw, -clamp, clamp)  w.r.t. raw, from the clamped values:  scale * g where |v| < clamp, else 0
+// (torch's clamp backward, attention.py:125-127 via autograd); one streaming pass instead of five elementwise kernels
+__global__ void __launch_bounds__(256)
+clamp_scale_bwd_kernel(const float4 *__restrict__ grad, const float4 *__restrict__ clamped, float4 *__restrict__ out,
+                       int64_t n4, float scale, float clamp) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 g = grad[i], v = clamped[i];
+        float4 o;
+        o.x = (clamp <= 0.0f || fabsf(v.x) < clamp) ? g.x * scale : 0.0f;
+        o.y = (clamp <= 0.0f || fabsf(v.y) < clamp) ? g.y * scale : 0.0f;
+        o.z = (clamp <= 0.0f || fabsf(v.z) < clamp) ? g.z * scale : 0.0f;
+        o.w = (clamp <= 0.0f || fabsf(v.w) < clamp) ? g.w * scale : 0.0f;
+        out[i] = o;
+    }
+}
+
+extern "C" int spt_clamp_scale_bwd(const float *grad, const float *clamped, float *out, int64_t n, float scale, float clamp,
+                                   spt_stream_t stream) {
+    SPT_REQUIRE(grad && clamped && out, "clamp_scale_bwd: null pointer");
+    SPT_REQUIRE(n >= 0 && n % 4 == 0, "clamp_scale_bwd: element count must be a multiple of 4 (got %lld)", (long long)n);
+    SPT_REQUIRE(((uintptr_t)grad | (uintptr_t)clamped | (uintptr_t)out) % 16 == 0, "clamp_scale_bwd: operands must be 16-byte aligned");
+    if (n == 0) return SPT_OK;
+    const int64_t n4 = n / 4;
+    const int64_t want = (n4 + 255) / 256;
+    const int grid = (int)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
+    clamp_scale_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>((const float4 *)grad, (const float4 *)clamped, (float4 *)out, n4,
+                                                              scale, clamp);
+    return after_launch("clamp_scale_bwd_kernel");
+}
+
 extern "C" int spt_spmm_fwd(const int32_t *indptr, const int32_t *indices, const float *values, const void *x, void *y,
                             int B, int S, int d, int64_t nnz, int dtype, int out_dtype, spt_stream_t stream) {
     SPT_REQUIRE(indptr && indices && values && x && y, "spmm_fwd: null pointer");

@@ -253,6 +253,18 @@ def sddmm_scaled(indptr, indices, query, key, scale: float = 1.0, clamp: float =
     return values
 
 
+def clamp_scale_bwd(grad: torch.Tensor, clamped: torch.Tensor, scale: float, clamp: float) -> torch.Tensor:
+    """Gradient of clamp(scale * raw, -clamp, clamp) w.r.t. raw, given the clamped values (one pass)."""
+    _check_type(grad, torch.float32, "grad")
+    _check_type(clamped, torch.float32, "clamped")
+    if grad.shape != clamped.shape or not grad.is_contiguous() or not clamped.is_contiguous():
+        raise RuntimeError("grad and clamped must be contiguous tensors of the same shape")
+    out = torch.empty_like(grad)
+    with _on_device(grad):
+        check(lib.spt_clamp_scale_bwd(_p(grad), _p(clamped), _p(out), grad.numel(), float(scale), float(clamp), _stream(grad)))
+    return out
+
+
 def sddmm_forward_cuda(trans_lhs, trans_rhs, indptr, indices, query, key) -> torch.Tensor:
     """values[b, e] = <query[b, row(e)], key[b, indices[b, e]]> (extension/sddmm.cpp:3-73).  Only the
     (N, T) operand layout the reference ever uses (kernels/sddmm.py:19-22, kernels/spmm.py:37-40)."""

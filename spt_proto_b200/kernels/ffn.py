@@ -8,6 +8,8 @@ and its torch-autograd backward), on the tcgen05 grouped GEMM:
     y        = combine(Yp, bucket, b2)                  [T, d]    backward: gather
 
 All GEMM operands are bf16 (fp32 accumulation); weight gradients come out in the parameter's dtype (bf16) or fp32."""
+import weakref
+
 import torch
 from torch import autograd
 
@@ -20,6 +22,27 @@ def _grad_buffer(shape, dtype, device):
     """Weight-gradient output of the K-grouped GEMM: bf16 parameters get their gradient written in bf16 by the
     GEMM epilogue (fp32 accumulation in TMEM), everything else an fp32 buffer (converted by the caller)."""
     return torch.empty(shape, dtype=torch.bfloat16 if dtype == torch.bfloat16 else torch.float32, device=device)
+
+
+_W16 = weakref.WeakKeyDictionary()   # parameter -> (version, bf16 copy)
+
+
+def _bf16(weight: torch.Tensor) -> torch.Tensor:
+    """bf16 operand of a GEMM weight.  bf16 parameters are used in place; an fp32 parameter (the reference trains in
+    fp32, script/4-sparse-tuning-0.py:184) is converted ONCE per parameter version instead of on every call — the frozen
+    base weights of the LoRA FFN are never converted again, trained ones once per optimizer step."""
+    if weight.dtype == torch.bfloat16:
+        return weight
+    if weight.requires_grad and weight.is_cuda and torch.cuda.is_current_stream_capturing():
+        # a trained fp32 weight inside a captured step: the conversion must be part of the graph (replays do not re-run
+        # Python, so a cached copy would go stale after the captured optimizer update)
+        return weight.detach().to(torch.bfloat16)
+    hit = _W16.get(weight)
+    if hit is not None and hit[0] == weight._version and hit[1].device == weight.device:
+        return hit[1]
+    w16 = weight.detach().to(torch.bfloat16)
+    _W16[weight] = (weight._version, w16)
+    return w16
 
 
 _WHOLE_PTR = {}
@@ -70,7 +93,7 @@ class BlockedLinearRows(autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, bucket, bs, act, out_dtype, grad_premasked=False):
-        w16 = weight if weight.dtype == torch.bfloat16 else weight.to(torch.bfloat16)
+        w16 = _bf16(weight)
         y = torch.empty(x.size(0), bs, dtype=out_dtype, device=x.device)
         b32 = None if bias is None else bias.float().contiguous()
         ext.grouped_gemm(0, x, False, w16, False, tile_group=bucket.tile_group, N=bs, K=x.size(1), b_mn_off=bs,
@@ -110,7 +133,7 @@ class BlockedLinearCols(autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bucket, bs, relu_input=False):
         ctx.relu_input = relu_input   # x is a ReLU output used only here: mask dx by (x > 0) in the GEMM epilogue
-        w16 = weight if weight.dtype == torch.bfloat16 else weight.to(torch.bfloat16)
+        w16 = _bf16(weight)
         d = weight.size(0)
         y = torch.empty(x.size(0), d, dtype=torch.bfloat16, device=x.device)
         ext.grouped_gemm(0, x, False, w16, False, tile_group=bucket.tile_group, N=d, K=bs, b_k_off=bs, out=y)
@@ -162,7 +185,7 @@ class BlockedLinearColsT(autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bucket, bs):
-        w16 = weight if weight.dtype == torch.bfloat16 else weight.to(torch.bfloat16)
+        w16 = _bf16(weight)
         n = weight.size(1)
         y = torch.empty(x.size(0), n, dtype=torch.bfloat16, device=x.device)
         ext.grouped_gemm(0, x, False, w16, True, tile_group=bucket.tile_group, N=n, K=bs, b_k_off=bs, out=y)

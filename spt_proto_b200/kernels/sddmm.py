@@ -28,3 +28,31 @@ class SDDMM(autograd.Function):
 
 def sddmm(indptr, indices, query, key):
     return SDDMM.apply(indptr, indices, query, key)
+
+
+class SDDMMScaled(autograd.Function):
+    """clamp(scale * sddmm(q, k), -clamp, clamp) in one kernel (the reference's eager `clamp_(scaling * values)`,
+    layers/sparse/attention.py:125-127); the backward applies the clamp's zero-gradient mask and the scale in one pass
+    before the two products of SDDMM.backward."""
+
+    @staticmethod
+    def forward(ctx, indptr, indices, query, key, scale, clamp):
+        values = ext.sddmm_scaled(indptr, indices, query, key, scale, clamp)
+        ctx.save_for_backward(indptr, indices, query, key, values)
+        ctx.scale, ctx.clamp = float(scale), float(clamp)
+        return values
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        indptr, indices, query, key, values = ctx.saved_tensors
+        grad_raw = ext.clamp_scale_bwd(grad_output.contiguous(), values, ctx.scale, ctx.clamp)
+        grad_query = grad_key = None
+        if ctx.needs_input_grad[2]:
+            grad_query = ext.spmm_forward_cuda(False, False, indptr, indices, grad_raw, key)
+        if ctx.needs_input_grad[3]:
+            grad_key = ext.spmm_csc(get_csc(indptr, indices), grad_raw, query)
+        return None, None, grad_query, grad_key, None, None
+
+
+def sddmm_scaled(indptr, indices, query, key, scale: float, clamp: float):
+    return SDDMMScaled.apply(indptr, indices, query, key, scale, clamp)

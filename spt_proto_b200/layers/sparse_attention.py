@@ -139,8 +139,8 @@ class _SparseV2Mixin:
         topk = kernels.lookup(q_c, k_c, sparse_coeff=self.sparse_coeff)
         csr_indices = topk.flatten(start_dim=1)
         indptr = self._fixed_indptr(seq_length, seq_length // self.sparse_coeff, q.device)
-        values = kernels.sddmm(indptr, csr_indices, query=q, key=k)
-        values = torch.clamp_(self.scaling * values, min=-10.0, max=10.0)
+        # sddmm + scale + clamp(-10, 10) of attention.py:122-127 in one kernel each way (no eager elementwise passes)
+        values = kernels.sddmm_scaled(indptr, csr_indices, q, k, self.scaling, 10.0)
         values = kernels.softmax(indptr, csr_indices, values=values)
         return indptr, csr_indices, values
 

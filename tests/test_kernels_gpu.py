@@ -440,3 +440,27 @@ def test_rope_fused_matches_torch_expression(shape):
         res[fused] = (y.detach(), xi.grad)
     assert torch.equal(res[True][0], res[False][0])          # same roundings as the torch expression: bit-exact
     assert torch.equal(res[True][1], res[False][1])
+
+
+def test_sddmm_scaled_matches_eager_clamp_chain():
+    """kernels.sddmm_scaled (one kernel each way) == the reference's eager chain clamp_(scaling * sddmm(q, k), -10, 10)
+    (layers/sparse/attention.py:122-127) incl. the clamp's zero gradient; scores scaled so that some are clamped."""
+    from spt_proto_b200 import kernels
+    torch.manual_seed(21)
+    B, S, d, k = 3, 256, 64, 32
+    q = (torch.randn(B, S, d, device=DEV) * 3.0).requires_grad_()
+    kk = (torch.randn(B, S, d, device=DEV) * 3.0).requires_grad_()
+    idx = torch.stack([torch.stack([torch.randperm(S, device=DEV)[:k].sort().values for _ in range(S)]) for _ in range(B)])
+    idx = idx.to(torch.int32).flatten(1).contiguous()
+    indptr = torch.arange(0, k * S + 1, k, dtype=torch.int32, device=DEV)
+    g = torch.randn(B, S * k, device=DEV)
+    scale = d ** -0.5
+    v1 = kernels.sddmm_scaled(indptr, idx, q, kk, scale, 10.0)
+    v1.backward(g)
+    g1 = (q.grad.clone(), kk.grad.clone())
+    q.grad = kk.grad = None
+    v2 = torch.clamp_(scale * kernels.sddmm(indptr, idx, q, kk), min=-10.0, max=10.0)
+    v2.backward(g)
+    assert (v2.detach().abs() >= 10.0).any() and (v2.detach().abs() < 10.0).any()
+    assert torch.allclose(v1, v2, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(g1[0], q.grad, atol=1e-4, rtol=1e-4) and torch.allclose(g1[1], kk.grad, atol=1e-4, rtol=1e-4)
