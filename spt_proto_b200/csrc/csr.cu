@@ -7,6 +7,8 @@
 // order and zero padding).  Memory-bound stages: the index / value streams are read with coalesced
 // 128-byte warp accesses; dense rows of q/k/v/x are gathered with 16-byte lane loads, L lanes per
 // gathered row (L * 16 B >= row bytes) so that each gathered 128-byte line is touched once.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace spt {
@@ -577,6 +579,15 @@ spmm_t_block_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restri
     }
 }
 
+// bf16 tensor-core variants (csr_mma.cu)
+namespace csr_mma {
+bool supported(int d, const void *a, const void *b);
+int launch_sddmm(const int32_t *indptr, const int32_t *indices, const __nv_bfloat16 *q, const __nv_bfloat16 *k, float *values,
+                 int B, int S, int d, int64_t nnz, float scale, float clamp, cudaStream_t st);
+int launch_spmm(bool trans, const int32_t *ptr, const int32_t *src_idx, const int32_t *perm, const float *values,
+                const __nv_bfloat16 *x, void *y, bool y_bf16, int B, int S, int d, int64_t nnz, cudaStream_t st);
+}  // namespace csr_mma
+
 // ---- launch helpers ------------------------------------------------------------------------------
 static inline int lanes_for(int d, int vec) {
     int need = (d + vec - 1) / vec, L = 1;
@@ -589,6 +600,10 @@ static int launch_sddmm(const int32_t *indptr, const int32_t *indices, const T *
                         int S, int d, int64_t nnz, float scale, float clamp, cudaStream_t st) {
     constexpr int VEC = Vec16<T>::N;
     const int64_t rows = (int64_t)B * S;
+    if constexpr (sizeof(T) == 2) {
+        if (csr_mma::supported(d, q, k) && rows < ((int64_t)1 << 31))
+            return csr_mma::launch_sddmm(indptr, indices, q, k, values, B, S, d, nnz, scale, clamp, st);
+    }
     const unsigned grid = (unsigned)((rows + CSR_WARPS - 1) / CSR_WARPS);
     const bool vec_ok = (d % VEC == 0) && (d <= 32 * VEC) && ((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0);
     if (!vec_ok) {
@@ -616,6 +631,13 @@ static int launch_spmm(const int32_t *ptr, const int32_t *src_idx, const int32_t
                        const T *x, TO *y, int B, int S, int d, int64_t nnz, cudaStream_t st) {
     constexpr int VEC = Vec16<T>::N;
     const int64_t rows = (int64_t)B * S;
+    if constexpr (sizeof(T) == 2) {
+        // the tensor-core spmm is correct but measured slower than the SIMT kernels (its B-fragment layout forces
+        // 16-byte loads that coalesce per 32 bytes only: 4 LSU wavefronts per gathered row); opt-in for experiments
+        static const bool on = [] { const char *e = getenv("SPT_CSR_MMA_SPMM"); return e && atoi(e) == 1; }();
+        if (on && csr_mma::supported(d, x, y) && rows < ((int64_t)1 << 31))
+            return csr_mma::launch_spmm(TRANS, ptr, src_idx, perm, values, x, y, sizeof(TO) == 2, B, S, d, nnz, st);
+    }
     const unsigned grid = (unsigned)((rows + CSR_WARPS - 1) / CSR_WARPS);
     const bool vec_ok = (d % VEC == 0) && (d <= 32 * VEC) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
     if (!vec_ok) {
