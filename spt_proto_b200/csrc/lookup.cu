@@ -22,6 +22,8 @@
 //     selection logic; the choice is made on the device through a flag, no host sync.
 //
 // Bound: integer-issue (S^2/2 * m bit-ops per head) and the S*nnz*4-byte index write; see DESIGN.md.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace spt {
@@ -497,6 +499,179 @@ lookup_maskonly_kernel(const int32_t *__restrict__ query_codes, const uint32_t *
     }
 }
 
+// ---- mask-only path, second version ---------------------------------------------------------------
+// Same algorithm and shared-memory layout as lookup_maskonly_kernel, written for instruction count (that kernel spends
+// ~270 warp instructions per (thread, 32-key word); ncu: integer-issue bound):
+//   * both passes handle the only partially valid word (the last one: words below the diagonal word are fully valid
+//     for every row of the group) outside their loops — no per-word validity mask;
+//   * pass 2 takes every completely selected bucket with three LOP3 (a per-thread all-ones / zero flag per bucket
+//     muxed by the two bit-planes) and runs the "lowest q keys" selection only for the bucket that is cut, as a
+//     five-step popcount search instead of a bit-by-bit loop (a second cut bucket — possible when a bucket overflows
+//     its capacity — goes through the same code once more);
+//   * the clobber bookkeeping (which needs the last key of two buckets) only runs in warps that have such a row.
+__device__ __forceinline__ uint32_t lowest_bits(uint32_t m, int q) {        // the q lowest set bits of m, 0 < q < popc(m)
+    uint32_t lowmask = 0;   // bits below the position reached so far
+    int pos = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t probe = ((1u << s) - 1u) << pos;
+        const int c = __popc(m & probe);
+        const bool up = q > c;          // the q-th bit lies above this probe window
+        q -= up ? c : 0;
+        lowmask |= up ? probe : 0u;
+        pos += up ? s : 0;
+    }
+    // now q == 1 and the wanted bit is at `pos` (if set) — take everything below pos plus bit pos
+    return m & (lowmask | (1u << pos));
+}
+
+template <int M, bool TRACK>
+__device__ __forceinline__ void lkm2_select(uint32_t *s_pl, int tw, int tid, uint32_t last_valid, const int (&take)[4],
+                                            const int (&len)[4], int s_need, int track, int t, int &j_old, int &last_j) {
+    // per-bucket flags: F = taken completely, P = cut (0 < take < len)
+    uint32_t F[4];
+    int q[4];
+    bool cut[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        F[s] = (take[s] == len[s] && len[s] > 0) ? 0xffffffffu : 0u;
+        cut[s] = take[s] > 0 && take[s] < len[s];
+        q[s] = take[s];
+    }
+#pragma unroll 1
+    for (int w = 0; w < tw; ++w) {
+        const uint32_t lo = s_pl[(2 * w) * LKM_THREADS + tid], hi = s_pl[(2 * w + 1) * LKM_THREADS + tid];
+        const uint32_t valid = (w == tw - 1) ? last_valid : 0xffffffffu;
+        // completely taken buckets: bucket = 2 hi + lo
+        const uint32_t fa = (lo & F[3]) | (~lo & F[2]), fb = (lo & F[1]) | (~lo & F[0]);
+        uint32_t sel = ((hi & fa) | (~hi & fb)) & valid;
+#pragma unroll
+        for (int s = 3; s >= 0; --s) {
+            if (cut[s] && q[s] > 0) {
+                const uint32_t ms = ((s & 2) ? hi : ~hi) & ((s & 1) ? lo : ~lo) & valid;
+                const int c = __popc(ms);
+                if (c <= q[s]) {
+                    sel |= ms;
+                    q[s] -= c;
+                } else {
+                    sel |= lowest_bits(ms, q[s]);
+                    q[s] = 0;
+                }
+            }
+        }
+        s_pl[(2 * w) * LKM_THREADS + tid] = sel;
+        if (TRACK) {
+            if (s_need >= 0) {
+                const uint32_t ms = ((s_need & 2) ? hi : ~hi) & ((s_need & 1) ? lo : ~lo) & sel;
+                if (ms) j_old = 4 * (32 * w + 31 - __clz(ms)) + t;
+            }
+            if (track >= 0) {
+                const uint32_t mt = ((track & 2) ? hi : ~hi) & ((track & 1) ? lo : ~lo) & valid;
+                if (mt) last_j = 4 * (32 * w + 31 - __clz(mt)) + t;
+            }
+        }
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(LKM_THREADS)
+lookup_maskonly2_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__restrict__ kb,
+                        const int *__restrict__ flag, uint32_t *__restrict__ mask_out,
+                        int32_t *__restrict__ extra0_out, int S, int nnz, int W, int H) {
+    if (*flag) return;  // some key code >= 16: the generic kernel handles this call
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.y;
+    const int tile = gridDim.x - 1 - blockIdx.x;  // heaviest (last) rows first
+    const int tw = tile + 1;                       // 128-key words a row of this group can see
+    uint32_t *s_kb = reinterpret_cast<uint32_t *>(smem_raw);                 // [M][tw][16][4]
+    uint32_t *s_pl = s_kb + (size_t)M * tw * LK_WORD_U32;                    // [2 tw][LKM_THREADS]
+    const int tid = threadIdx.x;
+    const int rl = tid >> 2, t = tid & 3;
+    const int r = tile * LKM_ROWS + rl;            // S % 128 == 0: every row is live
+    const int quarter = nnz / 4;
+    const int nkeys = r >= t ? (r - t) / 4 + 1 : 0;
+    const int lim = min(r + 1, nnz);
+    const int n_t = lim > t ? (lim - t + 3) / 4 : 0;
+    const uint32_t last_valid = valid_mask(tw - 1, nkeys);   // words 0 .. tw - 2 are fully valid for every row of the group
+
+    {
+        const uint32_t *kb_head = kb + (size_t)b * M * W * LK_WORD_U32;
+        const int per_s = tw * LK_WORD_U32 / 4;  // uint4 per subspace
+        for (int i = tid; i < M * per_s; i += LKM_THREADS) {
+            const int s = i / per_s, o = i - s * per_s;
+            reinterpret_cast<uint4 *>(s_kb)[i] = reinterpret_cast<const uint4 *>(kb_head + (size_t)s * W * LK_WORD_U32)[o];
+        }
+    }
+    // this row's bitmap column of every subspace: s_kb[s][w][q_s][t] = s_kb[koff[s] + 64 w]; a query code the bitmaps do
+    // not cover (>= 16) matches no key: handled by clearing the loaded word (warp-uniformly skipped when no lane has one)
+    uint32_t koff[M];
+    uint32_t badq = 0;
+    {
+        const int32_t *qp = query_codes + (((size_t)(b / H) * S + r) * H + (b % H)) * M;
+#pragma unroll
+        for (int s = 0; s < M; ++s) {
+            const unsigned qc = (unsigned)qp[s] & 0xffffu;
+            badq |= (qc >= (unsigned)LK_CV) ? (1u << s) : 0u;
+            koff[s] = (uint32_t)((s * tw * LK_CV + (qc & (LK_CV - 1))) * 4 + t);
+        }
+    }
+    const bool any_bad = __any_sync(FULL, badq != 0);
+    __syncthreads();
+
+    constexpr int DIV = M / 4;
+    int len1 = 0, len2 = 0, len3 = 0;
+    const uint32_t *pw = s_kb;                      // warp-uniform word base
+#pragma unroll 1
+    for (int w = 0; w < tw; ++w, pw += LK_WORD_U32) {
+        uint32_t x[M];
+#pragma unroll
+        for (int s = 0; s < M; ++s) x[s] = pw[koff[s]];
+        if (any_bad) {
+#pragma unroll
+            for (int s = 0; s < M; ++s) x[s] = ((badq >> s) & 1u) ? 0u : x[s];
+        }
+        uint32_t bits[BitCount<M>::NB];
+        BitCount<M>::run(x, bits);
+        const uint32_t g1 = ge_const(bits, DIV), g2 = ge_const(bits, 2 * DIV), g3 = ge_const(bits, 3 * DIV);
+        s_pl[(2 * w) * LKM_THREADS + tid] = g1 ^ g2 ^ g3;   // lo (g3 <= g2 <= g1 as sets)
+        s_pl[(2 * w + 1) * LKM_THREADS + tid] = g2;         // hi
+        const uint32_t valid = (w == tw - 1) ? last_valid : 0xffffffffu;
+        len3 += __popc(g3 & valid);
+        len2 += __popc(g2 & valid);
+        len1 += __popc(g1 & valid);
+    }
+    LaneState st;
+    st.len[3] = len3;
+    st.len[2] = len2 - len3;
+    st.len[1] = len1 - len2;
+    st.len[0] = nkeys - len1;
+    plan_lane(st, t, n_t, quarter);
+
+    int j_old = -1, last_j = -1;
+    if (__any_sync(FULL, st.s_need >= 0 || st.track >= 0))
+        lkm2_select<M, true>(s_pl, tw, tid, last_valid, st.take, st.len, st.s_need, st.track, t, j_old, last_j);
+    else
+        lkm2_select<M, false>(s_pl, tw, tid, last_valid, st.take, st.len, st.s_need, st.track, t, j_old, last_j);
+    // lanes 2/3 report the last key of the tracked bucket; the owner (lane 1/0) swaps its own last taken key
+    // of that bucket for it if a later warp instruction of the reference kernel would have overwritten the slot
+    const int recv = __shfl_xor_sync(FULL, last_j, 3);
+    const int swap_old = (st.s_need >= 0 && recv >= 0 && j_old >= 0 && (recv >> 2) > (j_old >> 2)) ? j_old : -1;
+    const int partner_swapped = __shfl_xor_sync(FULL, swap_old >= 0 ? 1 : 0, 3);
+    if (swap_old >= 0) s_pl[(2 * (swap_old >> 7)) * LKM_THREADS + tid] &= ~(1u << mask_bit(swap_old));
+    if (partner_swapped && last_j >= 0) s_pl[(2 * (last_j >> 7)) * LKM_THREADS + tid] |= 1u << mask_bit(last_j);
+    store_extra0(st, extra0_out, b, r, S, nnz, true, t);
+    __syncthreads();
+
+    // flush: thread -> (row, word w): 16 B = the four lane words; words the group cannot see are zero
+    uint4 *dst = reinterpret_cast<uint4 *>(mask_out + ((size_t)b * S + (size_t)tile * LKM_ROWS) * (S / 32));
+    for (int i = tid; i < LKM_ROWS * W; i += LKM_THREADS) {
+        const int w = i / LKM_ROWS, row = i - w * LKM_ROWS;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (w < tw) v = *reinterpret_cast<const uint4 *>(s_pl + (size_t)(2 * w) * LKM_THREADS + row * 4);
+        dst[(size_t)row * W + w] = v;
+    }
+}
+
 // ---- generic path ----------------------------------------------------------------------------
 // smem: [ out image ][ query codes LK_ROWS * m u16 ]
 __global__ void __launch_bounds__(LK_THREADS)
@@ -620,12 +795,21 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
     const size_t msmem = (per_word + 2 * LKM_THREADS * 4) * (size_t)W;
     if (mask_out && !output && (m == 8 || m == 16) && msmem <= 200 * 1024) {
         const dim3 mgrid(S / LKM_ROWS, B);
-        if (m == 8) {
-            cudaFuncSetAttribute(lookup_maskonly_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
-            lookup_maskonly_kernel<8><<<mgrid, LKM_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H);
+        static const bool v1 = [] { const char *e = getenv("SPT_LOOKUP_MASK_V1"); return e && atoi(e) == 1; }();   // A/B switch
+        if (v1) {
+            if (m == 8) {
+                cudaFuncSetAttribute(lookup_maskonly_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+                lookup_maskonly_kernel<8><<<mgrid, LKM_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H);
+            } else {
+                cudaFuncSetAttribute(lookup_maskonly_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+                lookup_maskonly_kernel<16><<<mgrid, LKM_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H);
+            }
+        } else if (m == 8) {
+            cudaFuncSetAttribute(lookup_maskonly2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+            lookup_maskonly2_kernel<8><<<mgrid, LKM_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H);
         } else {
-            cudaFuncSetAttribute(lookup_maskonly_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
-            lookup_maskonly_kernel<16><<<mgrid, LKM_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H);
+            cudaFuncSetAttribute(lookup_maskonly2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+            lookup_maskonly2_kernel<16><<<mgrid, LKM_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H);
         }
         SPT_LAUNCH_CHECK("lookup_maskonly_kernel");
         lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, mask_out,
