@@ -579,6 +579,128 @@ spmm_t_block_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restri
     }
 }
 
+// ---- transposed spmm, second version: columns grouped by length ------------------------------------------------------
+// spmm_t_block_kernel gives every column a block of 8 warps; for the typical column (a few hundred entries) that is one
+// batch per warp plus a block-wide reduction.  Here a block owns CSR_WARPS consecutive output columns: a column of up to
+// SPMM_T_HEAVY entries is summed by ONE warp; longer ones (column 0 of a lookup pattern collects every row's zero
+// padding, the first ~k columns are selected by almost every row) are split among the block's warps afterwards, whose
+// partial sums are added in warp order.  Same per-entry arithmetic and order inside a warp as above.
+// (Also tried for both products: all row loads of a batch issued before any arithmetic + packed fma.rn.f32x2 — 102
+// registers, 23 % occupancy, 1.4x SLOWER than the simple loop; dropped.)
+template <typename T, int L, bool PERM>
+__device__ __forceinline__ void spmm_accumulate(float (&acc)[Vec16<T>::N], const int32_t *__restrict__ ip,
+                                                const int32_t *__restrict__ pm, const float *__restrict__ vp,
+                                                const T *__restrict__ xb, int e0, int e1, int lane, int d, bool has) {
+    constexpr int VEC = Vec16<T>::N, G = 32 / L;
+    const int sub = lane % L, grp = lane / L;
+    for (int base = e0; base < e1; base += 32) {
+        const int e = base + lane;
+        int my_idx = 0;
+        float my_val = 0.0f;
+        if (e < e1) {
+            my_idx = ip[e];
+            my_val = vp[PERM ? pm[e] : e];
+        }
+        const int cnt = min(32, e1 - base);
+#pragma unroll
+        for (int st = 0; st < L; ++st) {
+            if (st * G >= cnt) break;  // warp-uniform
+            const int src = st * G + grp;
+            const int row = __shfl_sync(FULL, my_idx, src);
+            const float w = __shfl_sync(FULL, my_val, src);  // 0 for padding lanes
+            if (has) {
+                float xv[VEC];
+                Vec16<T>::load(xb + (size_t)row * d + sub * VEC, xv);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w, xv[i], acc[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+#pragma unroll
+        for (int o = L; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
+    }
+}
+
+template <typename T, typename TO>
+__device__ __forceinline__ void spmm_store(TO *yp, const float (&out)[Vec16<T>::N]) {
+    constexpr int VEC = Vec16<T>::N;
+    if constexpr (sizeof(TO) == 4 && VEC == 8) {
+        float lo[4] = {out[0], out[1], out[2], out[3]}, hi[4] = {out[4], out[5], out[6], out[7]};
+        Vec16<float>::store(reinterpret_cast<float *>(yp), lo);
+        Vec16<float>::store(reinterpret_cast<float *>(yp) + 4, hi);
+    } else if constexpr (sizeof(TO) == 4) {
+        Vec16<float>::store(reinterpret_cast<float *>(yp), out);
+    } else if constexpr (VEC == 8) {
+        Vec16<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16 *>(yp), out);
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) yp[i] = from_f32<TO>(out[i]);
+    }
+}
+
+constexpr int SPMM_T_HEAVY = 1024;
+template <typename T, typename TO, int L>
+__global__ void __launch_bounds__(CSR_WARPS * 32)
+spmm2_t_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ row_idx, const int32_t *__restrict__ perm,
+               const float *__restrict__ values, const T *__restrict__ x, TO *__restrict__ y, int S, int d, int64_t nnz) {
+    constexpr int VEC = Vec16<T>::N;
+    __shared__ float s_part[CSR_WARPS][L * VEC];
+    __shared__ int s_len[CSR_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int blocks_per_head = (S + CSR_WARPS - 1) / CSR_WARPS;
+    const int b = blockIdx.x / blocks_per_head, cb = (blockIdx.x % blocks_per_head) * CSR_WARPS;
+    const int sub = lane % L;
+    const bool has = sub * VEC < d;
+    const int32_t *pp = col_ptr + (size_t)b * (S + 1);
+    const int32_t *ip = row_idx + (size_t)b * nnz;
+    const int32_t *pm = perm + (size_t)b * nnz;
+    const float *vp = values + (size_t)b * nnz;
+    const T *xb = x + (size_t)b * S * d;
+    {
+        const int c = cb + wid;
+        const int c0 = c < S ? pp[c] : 0, c1 = c < S ? pp[c + 1] : 0;
+        if (lane == 0) s_len[wid] = c1 - c0;
+        if (c < S && c1 - c0 <= SPMM_T_HEAVY) {
+            float acc[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = 0.0f;
+            spmm_accumulate<T, L, true>(acc, ip, pm, vp, xb, c0, c1, lane, d, has);
+            if (lane < L && has) spmm_store<T, TO>(y + ((size_t)b * S + c) * d + sub * VEC, acc);
+        }
+    }
+    __syncthreads();
+    for (int u = 0; u < CSR_WARPS; ++u) {
+        if (s_len[u] <= SPMM_T_HEAVY) continue;                       // block-uniform
+        const int c = cb + u;
+        const int c0 = pp[c], c1 = pp[c + 1];
+        const int per_warp = ((c1 - c0 + CSR_WARPS * 32 - 1) / (CSR_WARPS * 32)) * 32;
+        const int e0 = c0 + wid * per_warp, e1 = min(c1, e0 + per_warp);
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.0f;
+        spmm_accumulate<T, L, true>(acc, ip, pm, vp, xb, e0, e1, lane, d, has);
+        if (lane < L) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) s_part[wid][sub * VEC + i] = acc[i];
+        }
+        __syncthreads();
+        if (wid == 0 && lane < L && has) {
+            float sum[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                float t = 0.0f;
+#pragma unroll
+                for (int w = 0; w < CSR_WARPS; ++w) t += s_part[w][sub * VEC + i];
+                sum[i] = t;
+            }
+            spmm_store<T, TO>(y + ((size_t)b * S + c) * d + sub * VEC, sum);
+        }
+        __syncthreads();
+    }
+}
+
 // bf16 tensor-core variants (csr_mma.cu)
 namespace csr_mma {
 bool supported(int d, const void *a, const void *b);
@@ -644,9 +766,13 @@ static int launch_spmm(const int32_t *ptr, const int32_t *src_idx, const int32_t
         spmm_scalar_kernel<T, TO, TRANS><<<grid, CSR_WARPS * 32, 0, st>>>(ptr, src_idx, perm, values, x, y, B, S, d, nnz);
         return after_launch("spmm_scalar_kernel");
     }
+    static const bool v1 = [] { const char *e = getenv("SPT_SPMM_V1"); return e && atoi(e) == 1; }();   // A/B switch
 #define SPT_SPMM_CASE(LL)                                                                                        \
     case LL:                                                                                                     \
-        if (TRANS && rows < ((int64_t)1 << 31))                                                                  \
+        if (TRANS && !v1 && rows < ((int64_t)1 << 31))                                                           \
+            spmm2_t_kernel<T, TO, LL><<<(unsigned)(B * ((S + CSR_WARPS - 1) / CSR_WARPS)), CSR_WARPS * 32, 0, st>>>( \
+                ptr, src_idx, perm, values, x, y, S, d, nnz);                                                    \
+        else if (TRANS && rows < ((int64_t)1 << 31))                                                             \
             spmm_t_block_kernel<T, TO, LL><<<(unsigned)rows, CSR_WARPS * 32, 0, st>>>(ptr, src_idx, perm, values, x, y, \
                                                                                       B, S, d, nnz);            \
         else                                                                                                     \
