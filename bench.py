@@ -206,8 +206,8 @@ FUSED_PATH = ["pq_encode", "lookup_mask", "attn_fwd", "attn_bwd"]
 # what bounds each kernel according to its ncu capture (profiles/README.md): the HBM fraction
 # reported beside it is NOT the target for the issue-bound ones
 STAGE_BOUND = {
-    "attn_fwd": "exp/mask math of the score tile (XU + FMA issue); tensor pipe ~29 % active",
-    "attn_bwd": "small-MMA cadence of the tensor pipe (~50 clk per tcgen05.mma) + element-math issue",
+    "attn_fwd": "exp unit (one ex2 per score element: 512 clk per 128x64 tile, loop at 702) + per-CTA prologue / epilogue; tensor pipe 24 % active",
+    "attn_bwd": "element math (XU, ALU and issue all near saturation in the math phase) + MMA<->math-warp handshake latency of the single chain per CTA; tensor pipe 31 % active (128x128 tiles, N=128 score MMAs)",
     "pq_encode": "fp32-add issue (L1 distances, packed FADD2); DRAM = algorithmic bytes",
     "lookup_mask": "integer issue (bit-sliced adder tree + selection)",
     "lookup": "integer issue + index write",
