@@ -24,7 +24,7 @@ template <typename T, int DC>
 __global__ void __launch_bounds__(CDIST_THREADS)
 cdist_fwd_kernel(const T *__restrict__ query, const float *__restrict__ table, float *__restrict__ distance,
                  int32_t *__restrict__ indices, int64_t n, int c, int dc_rt) {
-    extern __shared__ float s_table[];  // [c][dc]
+    extern __shared__ __align__(16) float s_table[];  // [c][dc]
     const int dc = DC > 0 ? DC : dc_rt;
     const int s = blockIdx.y;
     for (int i = threadIdx.x; i < c * dc; i += blockDim.x) s_table[i] = table[(size_t)s * c * dc + i];
@@ -33,7 +33,21 @@ cdist_fwd_kernel(const T *__restrict__ query, const float *__restrict__ table, f
     if (q >= n) return;
     const T *qp = query + ((size_t)s * n + q) * dc;
     float qv[DC > 0 ? DC : 1];
-    if (DC > 0) {
+    if constexpr (DC > 0 && DC % Vec16<T>::N == 0) {
+        // 16-byte loads (a sub-vector is DC * sizeof(T) contiguous bytes; the vector path needs 16-byte alignment)
+        if ((reinterpret_cast<uintptr_t>(query) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < DC; i += Vec16<T>::N) {
+                float tmp[Vec16<T>::N];
+                Vec16<T>::load(qp + i, tmp);
+#pragma unroll
+                for (int j = 0; j < Vec16<T>::N; ++j) qv[i + j] = tmp[j];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < DC; ++i) qv[i] = to_f32(qp[i]);
+        }
+    } else if (DC > 0) {
 #pragma unroll
         for (int i = 0; i < DC; ++i) qv[i] = to_f32(qp[i]);
     }
@@ -42,10 +56,60 @@ cdist_fwd_kernel(const T *__restrict__ query, const float *__restrict__ table, f
     int min_index = 0;
     float min_distance = 1e13f;
     float4 pack;
+    if constexpr (DC > 0 && DC % 4 == 0) {
+        // c == 16 with a distance output (the reference layout's common case): the 16 distances stay in registers and
+        // the warp's 32 x 64-byte block leaves through its shared-memory slice as full 512-byte store instructions
+        // (a thread's own 64 bytes written 16 at a time touch every 32-byte sector twice)
+        if (vec_store && c == 16 && (blockDim.x & 31) == 0 && ((blockIdx.x + 1) * (int64_t)blockDim.x <= n)) {
+            float dist[16];
+#pragma unroll
+            for (int w = 0; w < 16; ++w) {
+                const float *tp = s_table + w * DC;
+                float reduced = 0.0f;
+#pragma unroll
+                for (int i = 0; i < DC; i += 4) {
+                    const float4 t4 = *reinterpret_cast<const float4 *>(tp + i);
+                    reduced += fabsf(qv[i] - t4.x);
+                    reduced += fabsf(qv[i + 1] - t4.y);
+                    reduced += fabsf(qv[i + 2] - t4.z);
+                    reduced += fabsf(qv[i + 3] - t4.w);
+                }
+                dist[w] = reduced;
+                if (reduced < min_distance) {
+                    min_distance = reduced;
+                    min_index = w;
+                }
+            }
+            indices[(size_t)s * n + q] = min_index;
+            // staging area behind the table: [warps][32 rows][16 + 4 pad] floats (row stride 80 B: conflict-free 16-byte accesses)
+            float *stage = s_table + ((c * DC + 3) & ~3) + (threadIdx.x >> 5) * (32 * 20);
+            const int lane = threadIdx.x & 31;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<float4 *>(stage + lane * 20 + 4 * u) = make_float4(dist[4 * u], dist[4 * u + 1], dist[4 * u + 2], dist[4 * u + 3]);
+            __syncwarp();
+            float *wp = distance + ((size_t)s * n + (q - lane)) * 16;          // the warp's 2 KB block
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int id = lane + 32 * u;                                    // 16-byte chunk of the block
+                st_stream(reinterpret_cast<float4 *>(wp) + id, *reinterpret_cast<const float4 *>(stage + (id >> 2) * 20 + 4 * (id & 3)));
+            }
+            return;
+        }
+    }
     for (int w = 0; w < c; ++w) {
         const float *tp = s_table + w * dc;
         float reduced = 0.0f;
-        if (DC > 0) {
+        if constexpr (DC > 0 && DC % 4 == 0) {          // codeword read as 16-byte broadcasts (same summation order)
+#pragma unroll
+            for (int i = 0; i < DC; i += 4) {
+                const float4 t4 = *reinterpret_cast<const float4 *>(tp + i);
+                reduced += fabsf(qv[i] - t4.x);
+                reduced += fabsf(qv[i + 1] - t4.y);
+                reduced += fabsf(qv[i + 2] - t4.z);
+                reduced += fabsf(qv[i + 3] - t4.w);
+            }
+        } else if (DC > 0) {
 #pragma unroll
             for (int i = 0; i < DC; ++i) reduced += fabsf(qv[i] - tp[i]);
         } else {
@@ -273,7 +337,8 @@ template <typename T>
 static int launch_cdist_fwd(const T *query, const float *table, float *distance, int32_t *indices, int m,
                             int64_t n, int c, int dc, cudaStream_t st) {
     dim3 grid((unsigned)((n + CDIST_THREADS - 1) / CDIST_THREADS), m);
-    size_t smem = (size_t)c * dc * sizeof(float);
+    // codebook slice + (c == 16 with distances) the per-warp store staging of cdist_fwd_kernel
+    size_t smem = (((size_t)c * dc + 3) & ~(size_t)3) * sizeof(float) + (size_t)(CDIST_THREADS / 32) * 32 * 20 * sizeof(float);
 #define SPT_CDIST_CASE(D)                                                                               \
     case D:                                                                                             \
         if (smem > 48 * 1024)                                                                           \

@@ -67,6 +67,63 @@ sddmm_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ ind
     }
 }
 
+// fp32 rows with 256-bit lane loads (sm_100 LDG.E.256): 8 floats per lane, so a d = 64 row takes 8 lanes instead of 16 —
+// one shuffle step less in every group sum and half as many steps per batch (the kernel is LSU / shuffle bound)
+template <int L>
+__global__ void __launch_bounds__(CSR_WARPS * 32)
+sddmm_f32w_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ q,
+                  const float *__restrict__ k, float *__restrict__ values, int B, int S, int d, int64_t nnz, float scale,
+                  float clamp) {
+    constexpr int VEC = 8;
+    constexpr int G = 32 / L;
+    const int lane = threadIdx.x & 31;
+    const int64_t row_id = (int64_t)blockIdx.x * CSR_WARPS + (threadIdx.x >> 5);
+    if (row_id >= (int64_t)B * S) return;
+    const int b = (int)(row_id / S), r = (int)(row_id % S);
+    const int sub = lane % L, grp = lane / L;
+    const bool has = sub * VEC < d;
+    auto ld8 = [](const float *p, float (&v)[8]) {
+        uint32_t u[8];
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "l"(p));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(u[i]);
+    };
+    float qv[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) qv[i] = 0.0f;
+    if (has) ld8(q + ((size_t)b * S + r) * d + sub * VEC, qv);
+    const int e0 = indptr[r], e1 = indptr[r + 1];
+    const int32_t *ip = indices + (size_t)b * nnz;
+    float *vp = values + (size_t)b * nnz;
+    const float *kb = k + (size_t)b * S * d;
+    for (int base = e0; base < e1; base += 32) {
+        const int e = base + lane;
+        const int my_idx = e < e1 ? ip[e] : 0;
+        float mine = 0.0f;
+        const int cnt = min(32, e1 - base);
+#pragma unroll
+        for (int st = 0; st < L; ++st) {  // 32 entries = L steps of G entries
+            if (st * G >= cnt) break;     // warp-uniform
+            const int col = __shfl_sync(FULL, my_idx, st * G + grp);
+            float kv[VEC], acc = 0.0f;
+            if (has) {
+                ld8(kb + (size_t)col * d + sub * VEC, kv);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc = fmaf(qv[i], kv[i], acc);
+            }
+            acc = group_sum<L>(acc);
+            const float got = __shfl_sync(FULL, acc, (lane % G) * L);
+            if (lane / G == st) mine = got;
+        }
+        if (e < e1) {
+            float v = mine * scale;
+            if (clamp > 0.0f) v = fminf(fmaxf(v, -clamp), clamp);
+            vp[e] = v;
+        }
+    }
+}
+
 // scalar fallback for head dims that are not a multiple of the 16-byte vector
 template <typename T>
 __global__ void __launch_bounds__(CSR_WARPS * 32)
@@ -727,6 +784,20 @@ static int launch_sddmm(const int32_t *indptr, const int32_t *indices, const T *
             return csr_mma::launch_sddmm(indptr, indices, q, k, values, B, S, d, nnz, scale, clamp, st);
     }
     const unsigned grid = (unsigned)((rows + CSR_WARPS - 1) / CSR_WARPS);
+    if constexpr (sizeof(T) == 4) {
+        static const bool narrow = [] { const char *e = getenv("SPT_SDDMM_F32_NARROW"); return e && atoi(e) == 1; }();   // A/B switch
+        if (!narrow && d % 8 == 0 && d <= 256 && ((uintptr_t)q % 32 == 0) && ((uintptr_t)k % 32 == 0)) {
+            switch (lanes_for(d, 8)) {
+                case 1: sddmm_f32w_kernel<1><<<grid, CSR_WARPS * 32, 0, st>>>(indptr, indices, q, k, values, B, S, d, nnz, scale, clamp); break;
+                case 2: sddmm_f32w_kernel<2><<<grid, CSR_WARPS * 32, 0, st>>>(indptr, indices, q, k, values, B, S, d, nnz, scale, clamp); break;
+                case 4: sddmm_f32w_kernel<4><<<grid, CSR_WARPS * 32, 0, st>>>(indptr, indices, q, k, values, B, S, d, nnz, scale, clamp); break;
+                case 8: sddmm_f32w_kernel<8><<<grid, CSR_WARPS * 32, 0, st>>>(indptr, indices, q, k, values, B, S, d, nnz, scale, clamp); break;
+                case 16: sddmm_f32w_kernel<16><<<grid, CSR_WARPS * 32, 0, st>>>(indptr, indices, q, k, values, B, S, d, nnz, scale, clamp); break;
+                default: sddmm_f32w_kernel<32><<<grid, CSR_WARPS * 32, 0, st>>>(indptr, indices, q, k, values, B, S, d, nnz, scale, clamp); break;
+            }
+            return after_launch("sddmm_f32w_kernel");
+        }
+    }
     const bool vec_ok = (d % VEC == 0) && (d <= 32 * VEC) && ((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0);
     if (!vec_ok) {
         sddmm_scalar_kernel<T><<<grid, CSR_WARPS * 32, 0, st>>>(indptr, indices, q, k, values, B, S, d, nnz, scale, clamp);
