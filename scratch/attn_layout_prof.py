@@ -19,6 +19,9 @@ for name, conv in (("interleaved [N,S,H,E]", lambda t: t), ("head-major [B,S,E]"
     q, k, v, dy = (conv(t) for t in (q4, k4, v4, dy4))
     mask, extra0, _ = ext.lookup_mask(ext.pq_encode(q, w), ext.pq_encode(k, w), 8)
     y, z = ext.sparse_attn_fwd(q, k, v, mask, extra0, E ** -0.5)
+    yr, zr = ext.sparse_attn_fwd(q, k, v, mask, extra0, E ** -0.5, reference_layout=True)
+    print(name, "REFERENCE output layout: fwd ms %.4f" % ev(lambda: ext.sparse_attn_fwd(q, k, v, mask, extra0, E ** -0.5, reference_layout=True)),
+          "bwd ms %.4f" % ev(lambda: ext.sparse_attn_bwd(q, k, v, yr, dy, mask, extra0, zr, E ** -0.5, reference_layout=True)))
     print(name, "fwd ms %.4f" % ev(lambda: ext.sparse_attn_fwd(q, k, v, mask, extra0, E ** -0.5)),
           "bwd ms %.4f" % ev(lambda: ext.sparse_attn_bwd(q, k, v, y, dy, mask, extra0, z, E ** -0.5)),
           "encode ms %.4f" % ev(lambda: ext.pq_encode_pair(q, k, w)),

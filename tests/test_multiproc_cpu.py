@@ -72,10 +72,16 @@ def _worker(rank, world, port, ret):
 
 def test_two_rank_sharding_and_grad_allreduce():
     world = 2
-    port = _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    for attempt in range(3):          # the probed port can be taken between the probe and the rendezvous: retry on a new one
+        ret.clear()
+        try:
+            mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+            break
+        except Exception:
+            if attempt == 2:
+                raise
     assert len(ret) == world
     for rank in range(world):
         ok_shard, ok_grad, n_calls, ok_reducer = ret[rank]
