@@ -69,8 +69,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
     PROF(const long long t_entry = clock64(); unsigned long long ns0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = gridDim.x - 1 - blockIdx.x;      // heaviest (last) query tiles first
-    const int b = blockIdx.y;
+    // grid (heads, query tiles): blockIdx.x (fastest) = head, so the heaviest (last) query tile of EVERY head is scheduled
+    // before any lighter tile — the launch ends on the lightest CTAs
+    const int tile = gridDim.y - 1 - blockIdx.y;
+    const int b = blockIdx.x;
     const int m0 = tile * BM;
     const int n_tiles = (m0 + BM) / BN;                // key tiles 0 .. (causal)
     const int hn = b / H, hh = b % H;
@@ -373,8 +375,8 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7 + 2 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = gridDim.x - 1 - blockIdx.x;
-    const int b = blockIdx.y;
+    const int tile = gridDim.y - 1 - blockIdx.y;      // grid (heads, tiles): every head's heaviest tile first (see the forward)
+    const int b = blockIdx.x;
     const int m0 = tile * BM;
     const int n_tiles = (m0 + BM) / BN;
     const int hn = b / H, hh = b % H;
@@ -565,8 +567,8 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6 + 2 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kt = blockIdx.x;                         // key tile (early key tiles are the heaviest)
-    const int b = blockIdx.y;
+    const int kt = blockIdx.y;                         // key tile (early key tiles are the heaviest); grid (heads, tiles):
+    const int b = blockIdx.x;                          // every head's heaviest tile first (see the forward)
     const int n0 = kt * BM;
     const int j0 = n0 / BN;                            // first query tile that can see these keys
     const int n_tiles = S / BN - j0;
@@ -783,7 +785,7 @@ static int launch_fwd(const CUtensorMap &mq, const CUtensorMap &mk, const CUtens
     if (D == 64 && fwd128()) return attn_tc128::launch_fwd128(mq, mk, mv, mask, extra0, y, zsum, B, S, H, scale, clamp, y_transposed, st);
     static const int extra_smem = [] { const char *e = getenv("SPT_ATTN_EXTRA_SMEM"); return e ? atoi(e) : 0; }();   // diagnostics: forces 1 CTA / SM
     cudaFuncSetAttribute(attn_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dim<D>::FWD_SMEM + extra_smem);
-    attn_fwd_tc_kernel<D><<<dim3(S / BM, B), THREADS, Dim<D>::FWD_SMEM + extra_smem, st>>>(mq, mk, mv, mask, extra0, y, zsum, S, H,
+    attn_fwd_tc_kernel<D><<<dim3(B, S / BM), THREADS, Dim<D>::FWD_SMEM + extra_smem, st>>>(mq, mk, mv, mask, extra0, y, zsum, S, H,
                                                                               scale * LOG2E, clamp * LOG2E, y_transposed);
     return after_launch("attn_fwd_tc_kernel");
 }
@@ -810,13 +812,13 @@ static int launch_bwd(const CUtensorMap &mq, const CUtensorMap &mk, const CUtens
         if (rc != SPT_OK) return rc;
     } else {
         cudaFuncSetAttribute(attn_bwd_kv_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dim<D>::BWD_SMEM);
-        attn_bwd_kv_tc_kernel<D><<<dim3(S / BM, B), THREADS, Dim<D>::BWD_SMEM, st>>>(
+        attn_bwd_kv_tc_kernel<D><<<dim3(B, S / BM), THREADS, Dim<D>::BWD_SMEM, st>>>(
             mq, mk, mv, md, mask, extra0, delta, gk, gv, S, H, scale, scale * LOG2E, clamp * LOG2E);
         SPT_LAUNCH_CHECK("attn_bwd_kv_tc_kernel");
     }
     if (D == 64 && tile128()) return attn_tc128::launch_bwd_q128(mq, mk, mv, md, mask, extra0, delta, gq, B, S, H, scale, clamp, st);
     cudaFuncSetAttribute(attn_bwd_q_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dim<D>::BWD_SMEM);
-    attn_bwd_q_tc_kernel<D><<<dim3(S / BM, B), THREADS, Dim<D>::BWD_SMEM, st>>>(
+    attn_bwd_q_tc_kernel<D><<<dim3(B, S / BM), THREADS, Dim<D>::BWD_SMEM, st>>>(
         mq, mk, mv, md, mask, extra0, delta, gq, S, H, scale, scale * LOG2E, clamp * LOG2E);
     SPT_LAUNCH_CHECK("attn_bwd_q_tc_kernel");
     return SPT_OK;

@@ -301,8 +301,8 @@ lookup_bitmap_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__
     const size_t bits_bytes = mask_out ? (size_t)LK_ROWS * (S / 32) * 4 : 0;
     uint32_t *s_bits = mask_out ? reinterpret_cast<uint32_t *>(smem_raw + img_bytes) : nullptr;
     uint32_t *s_kb = reinterpret_cast<uint32_t *>(smem_raw + img_bytes + bits_bytes);
-    const int b = blockIdx.y;
-    const int tile = gridDim.x - 1 - blockIdx.x;  // heaviest (last) rows first
+    const int b = blockIdx.x;                      // grid (heads, row groups): every head's heaviest (last) row group first
+    const int tile = gridDim.y - 1 - blockIdx.y;
     const int r0 = tile * LK_ROWS;
     const int rl = threadIdx.x >> 2, t = threadIdx.x & 3;
     const int r = r0 + rl;
@@ -404,8 +404,8 @@ lookup_maskonly_kernel(const int32_t *__restrict__ query_codes, const uint32_t *
                        int32_t *__restrict__ extra0_out, int S, int nnz, int W, int H) {
     if (*flag) return;  // some key code >= 16: the generic kernel handles this call
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int b = blockIdx.y;
-    const int tile = gridDim.x - 1 - blockIdx.x;  // heaviest (last) rows first
+    const int b = blockIdx.x;                      // grid (heads, row groups): every head's heaviest (last) row group first
+    const int tile = gridDim.y - 1 - blockIdx.y;
     const int tw = tile + 1;                       // 128-key words a row of this group can see
     uint32_t *s_kb = reinterpret_cast<uint32_t *>(smem_raw);                 // [M][tw][16][4]
     uint32_t *s_pl = s_kb + (size_t)M * tw * LK_WORD_U32;                    // [2 tw][LKM_THREADS]
@@ -580,8 +580,8 @@ lookup_maskonly2_kernel(const int32_t *__restrict__ query_codes, const uint32_t 
                         int32_t *__restrict__ extra0_out, int S, int nnz, int W, int H) {
     if (*flag) return;  // some key code >= 16: the generic kernel handles this call
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int b = blockIdx.y;
-    const int tile = gridDim.x - 1 - blockIdx.x;  // heaviest (last) rows first
+    const int b = blockIdx.x;                      // grid (heads, row groups): every head's heaviest (last) row group first
+    const int tile = gridDim.y - 1 - blockIdx.y;
     const int tw = tile + 1;                       // 128-key words a row of this group can see
     uint32_t *s_kb = reinterpret_cast<uint32_t *>(smem_raw);                 // [M][tw][16][4]
     uint32_t *s_pl = s_kb + (size_t)M * tw * LK_WORD_U32;                    // [2 tw][LKM_THREADS]
@@ -794,7 +794,7 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
     const size_t smem = img + per_word * chunk_words;
     const size_t msmem = (per_word + 2 * LKM_THREADS * 4) * (size_t)W;
     if (mask_out && !output && (m == 8 || m == 16) && msmem <= 200 * 1024) {
-        const dim3 mgrid(S / LKM_ROWS, B);
+        const dim3 mgrid(B, S / LKM_ROWS);
         static const bool v1 = [] { const char *e = getenv("SPT_LOOKUP_MASK_V1"); return e && atoi(e) == 1; }();   // A/B switch
         if (v1) {
             if (m == 8) {
@@ -821,7 +821,7 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
     case MM:                                                                                                     \
         if (smem > 48 * 1024)                                                                                    \
             cudaFuncSetAttribute(lookup_bitmap_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        lookup_bitmap_kernel<MM><<<grid, LK_THREADS, smem, st>>>(query_codes, kb, flag, output, mask_out, extra0_out, S, \
+        lookup_bitmap_kernel<MM><<<dim3(B, tiles), LK_THREADS, smem, st>>>(query_codes, kb, flag, output, mask_out, extra0_out, S, \
                                                                  nnz, W, chunk_words, H);                        \
         break;
     switch (m) {
