@@ -28,6 +28,19 @@ constexpr int D = 64;
 constexpr int TILE = T * D * 2;              // 16 KB: one 128 x 64 bf16 operand tile
 constexpr int ST = 3;                        // pipeline stages of the "other" tiles
 
+// Static schedule: items are ordered heaviest first; round w hands items [w G, (w + 1) G) to the G CTAs, in reversed CTA
+// order on odd rounds so that no CTA collects the heaviest item of every round (backward 0.393 -> 0.380 ms against plain
+// round-robin; -DSPT_SCHED_PLAIN restores that).  -1 = done.
+__device__ __forceinline__ int sched_item(int round, int n_items) {
+    const int G = gridDim.x;
+#ifdef SPT_SCHED_PLAIN
+    const int item = round * G + (int)blockIdx.x;
+#else
+    const int item = round * G + ((round & 1) ? G - 1 - (int)blockIdx.x : (int)blockIdx.x);
+#endif
+    return item < n_items ? item : -1;
+}
+
 // elected arrive of a whole warp whose lanes have all executed the tcgen05 operation being signalled
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
     fence_before_sync();
@@ -100,7 +113,7 @@ attn_bwd_kv128_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (warp == W_TMA) {
         // ===== producer: owner tiles of the next item, query-side tiles + row data of every stage =====
         int g = 0, w = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+        for (int item; (item = sched_item(w, n_items)) >= 0; ++w) {
             const int kt = item / B, b = item % B;     // key tile 0 is the heaviest: items are ordered by key tile
             const int hn = b / H, hh = b % H, n0 = kt * T, n_tiles = n_own - kt;
             const size_t head = (size_t)b * S;
@@ -153,7 +166,7 @@ attn_bwd_kv128_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                        ddy0 = desc_kmajor(s_dy, 0), dqt0 = desc_mnmajor(s_q, 0, TILE), ddyt0 = desc_mnmajor(s_dy, 0, TILE);
         int g = 0, w = 0;
         PROF(Prof pf; pf.start(); const long long t0 = pf.last;)
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+        for (int item; (item = sched_item(w, n_items)) >= 0; ++w) {
             const int kt = item / B, n_tiles = n_own - kt;
             const int buf = w & 1;
             const uint64_t own_off = (uint64_t)((buf * TILE) >> 4);
@@ -213,7 +226,7 @@ attn_bwd_kv128_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const int c0 = cg * 32;                         // query rows c0 .. c0 + 31 of every tile
         int g = 0, w = 0;
         PROF(Prof pf; pf.start(); const long long t0 = pf.last;)
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+        for (int item; (item = sched_item(w, n_items)) >= 0; ++w) {
             const int kt = item / B, b = item % B;
             const int hn = b / H, hh = b % H, n0 = kt * T, n_tiles = n_own - kt;
             const bool key0 = (n0 + kk) == 0;
@@ -374,7 +387,7 @@ attn_bwd_q128_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     if (warp == W_TMA) {
         if (lane == 0) {
             int g = 0, w = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+            for (int item; (item = sched_item(w, n_items)) >= 0; ++w) {
                 const int qt = n_own - 1 - item / B, b = item % B;       // the last query tile sees the most keys
                 const int hn = b / H, hh = b % H, n_tiles = qt + 1;
                 const int buf = w & 1;
@@ -398,7 +411,7 @@ attn_bwd_q128_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                        dv0 = desc_kmajor(s_v, 0), dkt0 = desc_mnmajor(s_k, 0, TILE);
         int g = 0, w = 0;
         PROF(Prof pf; pf.start(); const long long t0 = pf.last;)
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+        for (int item; (item = sched_item(w, n_items)) >= 0; ++w) {
             const int n_tiles = n_own - item / B;
             const int buf = w & 1;
             const uint64_t own_off = (uint64_t)((buf * TILE) >> 4);
@@ -454,7 +467,7 @@ attn_bwd_q128_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         int g = 0, w = 0;
         PROF(Prof pf; pf.start(); const long long t0 = pf.last;)
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+        for (int item; (item = sched_item(w, n_items)) >= 0; ++w) {
             const int qt = n_own - 1 - item / B, b = item % B;
             const int hn = b / H, hh = b % H, n_tiles = qt + 1;
             const int row = qt * T + rt;
@@ -574,7 +587,7 @@ attn_fwd128_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     if (warp == W_TMA) {
         if (lane == 0) {
             int g = 0, w = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+            for (int item; (item = sched_item(w, n_items)) >= 0; ++w) {
                 const int qt = n_own - 1 - item / B, b = item % B;
                 const int hn = b / H, hh = b % H, n_tiles = qt + 1;
                 const int buf = w & 1;
@@ -599,7 +612,7 @@ attn_fwd128_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const uint64_t dq0 = desc_kmajor(s_q, 0), dk0 = desc_kmajor(s_k, 0), dvt0 = desc_mnmajor(s_v, 0, TILE);
         int g = 0, w = 0;
         PROF(Prof pf; pf.start(); const long long t0 = pf.last;)
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+        for (int item; (item = sched_item(w, n_items)) >= 0; ++w) {
             const int n_tiles = n_own - item / B;
             const int buf = w & 1;
             const uint64_t own_off = (uint64_t)((buf * TILE) >> 4);
@@ -655,7 +668,7 @@ attn_fwd128_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         int g = 0, w = 0;
         PROF(Prof pf; pf.start(); const long long t0 = pf.last;)
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+        for (int item; (item = sched_item(w, n_items)) >= 0; ++w) {
             const int qt = n_own - 1 - item / B, b = item % B;
             const int hn = b / H, hh = b % H, n_tiles = qt + 1;
             const int row = qt * T + rt;
