@@ -672,6 +672,169 @@ lookup_maskonly2_kernel(const int32_t *__restrict__ query_codes, const uint32_t 
     }
 }
 
+// ---- mask-only path for long sequences ---------------------------------------------------------------
+// lookup_maskonly2_kernel keeps two bit-planes per (thread, word) between its passes: 4 KB per word and block, i.e. its
+// shared memory runs out beyond S 4096 (m 8).  This variant stores NO planes: pass 1 only counts, pass 2 evaluates the
+// adder tree again (the bitmaps are in shared memory anyway) and selects; the selected words leave through a 16-word
+// staging area.  ~1.7x the instructions per word of the plane kernel, but S 8192 no longer falls back to the
+// index-emitting kernel (1.7 - 2.3 ms per 8192 tokens there).
+constexpr int LKB_CHUNK = 16;
+
+template <int M>
+__device__ __forceinline__ void lkb_planes(const uint32_t *pw, const uint32_t (&koff)[M], bool any_bad, uint32_t badq,
+                                           uint32_t &lo, uint32_t &hi, uint32_t &g1o, uint32_t &g3o) {
+    constexpr int DIV = M / 4;
+    uint32_t x[M];
+#pragma unroll
+    for (int s = 0; s < M; ++s) x[s] = pw[koff[s]];
+    if (any_bad) {
+#pragma unroll
+        for (int s = 0; s < M; ++s) x[s] = ((badq >> s) & 1u) ? 0u : x[s];
+    }
+    uint32_t bits[BitCount<M>::NB];
+    BitCount<M>::run(x, bits);
+    const uint32_t g1 = ge_const(bits, DIV), g2 = ge_const(bits, 2 * DIV), g3 = ge_const(bits, 3 * DIV);
+    lo = g1 ^ g2 ^ g3;
+    hi = g2;
+    g1o = g1;
+    g3o = g3;
+}
+
+template <int M>
+__global__ void __launch_bounds__(LKM_THREADS)
+lookup_maskonly_big_kernel(const int32_t *__restrict__ query_codes, const uint32_t *__restrict__ kb,
+                           const int *__restrict__ flag, uint32_t *__restrict__ mask_out,
+                           int32_t *__restrict__ extra0_out, int S, int nnz, int W, int H) {
+    if (*flag) return;  // some key code >= 16: the generic kernel handles this call
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x;                      // grid (heads, row groups): every head's heaviest (last) row group first
+    const int tile = gridDim.y - 1 - blockIdx.y;
+    const int tw = tile + 1;                       // 128-key words a row of this group can see
+    uint32_t *s_kb = reinterpret_cast<uint32_t *>(smem_raw);                 // [M][tw][16][4]
+    uint32_t *s_out = s_kb + (size_t)M * tw * LK_WORD_U32;                   // [LKB_CHUNK][LKM_THREADS]
+    const int tid = threadIdx.x;
+    const int rl = tid >> 2, t = tid & 3;
+    const int r = tile * LKM_ROWS + rl;
+    const int quarter = nnz / 4;
+    const int nkeys = r >= t ? (r - t) / 4 + 1 : 0;
+    const int lim = min(r + 1, nnz);
+    const int n_t = lim > t ? (lim - t + 3) / 4 : 0;
+    const uint32_t last_valid = valid_mask(tw - 1, nkeys);
+    {
+        const uint32_t *kb_head = kb + (size_t)b * M * W * LK_WORD_U32;
+        const int per_s = tw * LK_WORD_U32 / 4;  // uint4 per subspace
+        for (int i = tid; i < M * per_s; i += LKM_THREADS) {
+            const int s = i / per_s, o = i - s * per_s;
+            reinterpret_cast<uint4 *>(s_kb)[i] = reinterpret_cast<const uint4 *>(kb_head + (size_t)s * W * LK_WORD_U32)[o];
+        }
+    }
+    uint32_t koff[M];
+    uint32_t badq = 0;
+    {
+        const int32_t *qp = query_codes + (((size_t)(b / H) * S + r) * H + (b % H)) * M;
+#pragma unroll
+        for (int s = 0; s < M; ++s) {
+            const unsigned qc = (unsigned)qp[s] & 0xffffu;
+            badq |= (qc >= (unsigned)LK_CV) ? (1u << s) : 0u;
+            koff[s] = (uint32_t)((s * tw * LK_CV + (qc & (LK_CV - 1))) * 4 + t);
+        }
+    }
+    const bool any_bad = __any_sync(FULL, badq != 0);
+    __syncthreads();
+
+    // pass 1: bucket sizes
+    int len1 = 0, len2 = 0, len3 = 0;
+    {
+        const uint32_t *pw = s_kb;
+#pragma unroll 1
+        for (int w = 0; w < tw; ++w, pw += LK_WORD_U32) {
+            uint32_t lo, hi, g1, g3;
+            lkb_planes<M>(pw, koff, any_bad, badq, lo, hi, g1, g3);
+            const uint32_t valid = (w == tw - 1) ? last_valid : 0xffffffffu;
+            len3 += __popc(g3 & valid);
+            len2 += __popc(hi & valid);
+            len1 += __popc(g1 & valid);
+        }
+    }
+    LaneState st;
+    st.len[3] = len3;
+    st.len[2] = len2 - len3;
+    st.len[1] = len1 - len2;
+    st.len[0] = nkeys - len1;
+    plan_lane(st, t, n_t, quarter);
+
+    // pass 2: planes again, selection, chunked flush
+    uint32_t F[4];
+    int q[4];
+    bool cut[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        F[s] = (st.take[s] == st.len[s] && st.len[s] > 0) ? 0xffffffffu : 0u;
+        cut[s] = st.take[s] > 0 && st.take[s] < st.len[s];
+        q[s] = st.take[s];
+    }
+    const bool track = __any_sync(FULL, st.s_need >= 0 || st.track >= 0);
+    int j_old = -1, last_j = -1;
+    uint4 *dst = reinterpret_cast<uint4 *>(mask_out + ((size_t)b * S + (size_t)tile * LKM_ROWS) * (S / 32));
+    for (int c0 = 0; c0 < tw; c0 += LKB_CHUNK) {
+        const int c1 = min(tw, c0 + LKB_CHUNK);
+        const uint32_t *pw = s_kb + (size_t)c0 * LK_WORD_U32;
+#pragma unroll 1
+        for (int w = c0; w < c1; ++w, pw += LK_WORD_U32) {
+            uint32_t lo, hi, g1, g3;
+            lkb_planes<M>(pw, koff, any_bad, badq, lo, hi, g1, g3);
+            const uint32_t valid = (w == tw - 1) ? last_valid : 0xffffffffu;
+            const uint32_t fa = (lo & F[3]) | (~lo & F[2]), fb = (lo & F[1]) | (~lo & F[0]);
+            uint32_t sel = ((hi & fa) | (~hi & fb)) & valid;
+#pragma unroll
+            for (int s = 3; s >= 0; --s) {
+                if (cut[s] && q[s] > 0) {
+                    const uint32_t ms = ((s & 2) ? hi : ~hi) & ((s & 1) ? lo : ~lo) & valid;
+                    const int c = __popc(ms);
+                    if (c <= q[s]) {
+                        sel |= ms;
+                        q[s] -= c;
+                    } else {
+                        sel |= lowest_bits(ms, q[s]);
+                        q[s] = 0;
+                    }
+                }
+            }
+            s_out[(w - c0) * LKM_THREADS + tid] = sel;
+            if (track) {
+                if (st.s_need >= 0) {
+                    const uint32_t ms = ((st.s_need & 2) ? hi : ~hi) & ((st.s_need & 1) ? lo : ~lo) & sel;
+                    if (ms) j_old = 4 * (32 * w + 31 - __clz(ms)) + t;
+                }
+                if (st.track >= 0) {
+                    const uint32_t mt = ((st.track & 2) ? hi : ~hi) & ((st.track & 1) ? lo : ~lo) & valid;
+                    if (mt) last_j = 4 * (32 * w + 31 - __clz(mt)) + t;
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < LKM_ROWS * (c1 - c0); i += LKM_THREADS) {
+            const int w = i / LKM_ROWS, row = i - w * LKM_ROWS;
+            dst[(size_t)row * W + c0 + w] = *reinterpret_cast<const uint4 *>(s_out + (size_t)w * LKM_THREADS + row * 4);
+        }
+        __syncthreads();
+    }
+    // words the group cannot see are zero
+    for (int i = tid; i < LKM_ROWS * (W - tw); i += LKM_THREADS) {
+        const int w = i / LKM_ROWS, row = i - w * LKM_ROWS;
+        dst[(size_t)row * W + tw + w] = make_uint4(0, 0, 0, 0);
+    }
+    // clobber fix-up (see lookup_maskonly_kernel) on the flushed words: this thread's word of key j is mask word
+    // 4 (j >> 7) + t of its row (every flush above is ordered before by the __syncthreads)
+    const int recv = __shfl_xor_sync(FULL, last_j, 3);
+    const int swap_old = (st.s_need >= 0 && recv >= 0 && j_old >= 0 && (recv >> 2) > (j_old >> 2)) ? j_old : -1;
+    const int partner_swapped = __shfl_xor_sync(FULL, swap_old >= 0 ? 1 : 0, 3);
+    uint32_t *my_row = mask_out + ((size_t)b * S + r) * (S / 32);
+    if (swap_old >= 0) my_row[4 * (swap_old >> 7) + t] &= ~(1u << mask_bit(swap_old));
+    if (partner_swapped && last_j >= 0) my_row[4 * (last_j >> 7) + t] |= 1u << mask_bit(last_j);
+    store_extra0(st, extra0_out, b, r, S, nnz, true, t);
+}
+
 // ---- generic path ----------------------------------------------------------------------------
 // smem: [ out image ][ query codes LK_ROWS * m u16 ]
 __global__ void __launch_bounds__(LK_THREADS)
@@ -812,6 +975,23 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
             lookup_maskonly2_kernel<16><<<mgrid, LKM_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H);
         }
         SPT_LAUNCH_CHECK("lookup_maskonly_kernel");
+        lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, mask_out,
+                                                                  extra0_out, S, m, nnz, H);
+        SPT_LAUNCH_CHECK("lookup_generic_kernel(fallback)");
+        return SPT_OK;
+    }
+    const size_t bsmem = per_word * (size_t)W + (size_t)LKB_CHUNK * LKM_THREADS * 4;
+    if (mask_out && !output && (m == 8 || m == 16) && bsmem <= 200 * 1024) {
+        // long sequences: the plane-free mask-only kernel (S 8192 at m 8)
+        const dim3 mgrid(B, S / LKM_ROWS);
+        if (m == 8) {
+            cudaFuncSetAttribute(lookup_maskonly_big_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+            lookup_maskonly_big_kernel<8><<<mgrid, LKM_THREADS, bsmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H);
+        } else {
+            cudaFuncSetAttribute(lookup_maskonly_big_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+            lookup_maskonly_big_kernel<16><<<mgrid, LKM_THREADS, bsmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H);
+        }
+        SPT_LAUNCH_CHECK("lookup_maskonly_big_kernel");
         lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, mask_out,
                                                                   extra0_out, S, m, nnz, H);
         SPT_LAUNCH_CHECK("lookup_generic_kernel(fallback)");
