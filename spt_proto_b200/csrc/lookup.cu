@@ -499,6 +499,13 @@ lookup_maskonly_kernel(const int32_t *__restrict__ query_codes, const uint32_t *
     }
 }
 
+#ifndef SPT_LKM_UNROLL
+#define SPT_LKM_UNROLL 2     // pass 1 of the mask-only kernel: 1 -> 0.1077 ms, 2 -> 0.104, 4 -> 0.105 at the bench shape
+#endif
+#ifndef SPT_LKM_UNROLL2
+#define SPT_LKM_UNROLL2 2    // pass 2
+#endif
+constexpr int LKM_UNROLL_P1 = SPT_LKM_UNROLL, LKM_UNROLL_P2 = SPT_LKM_UNROLL2;   // loop unroll factors of the two passes (A/B)
 // ---- mask-only path, second version ---------------------------------------------------------------
 // Same algorithm and shared-memory layout as lookup_maskonly_kernel, written for instruction count (that kernel spends
 // ~270 warp instructions per (thread, 32-key word); ncu: integer-issue bound):
@@ -538,7 +545,7 @@ __device__ __forceinline__ void lkm2_select(uint32_t *s_pl, int tw, int tid, uin
         cut[s] = take[s] > 0 && take[s] < len[s];
         q[s] = take[s];
     }
-#pragma unroll 1
+#pragma unroll LKM_UNROLL_P2
     for (int w = 0; w < tw; ++w) {
         const uint32_t lo = s_pl[(2 * w) * LKM_THREADS + tid], hi = s_pl[(2 * w + 1) * LKM_THREADS + tid];
         const uint32_t valid = (w == tw - 1) ? last_valid : 0xffffffffu;
@@ -621,7 +628,7 @@ lookup_maskonly2_kernel(const int32_t *__restrict__ query_codes, const uint32_t 
     constexpr int DIV = M / 4;
     int len1 = 0, len2 = 0, len3 = 0;
     const uint32_t *pw = s_kb;                      // warp-uniform word base
-#pragma unroll 1
+#pragma unroll LKM_UNROLL_P1
     for (int w = 0; w < tw; ++w, pw += LK_WORD_U32) {
         uint32_t x[M];
 #pragma unroll
