@@ -289,6 +289,13 @@ int spt_rope_bf16(const void *x, const void *cos, const void *sin, void *out, in
  * Returns the number of records (at most `cap` are written), or a negative spt_status. */
 int spt_grouped_gemm_plan(const int32_t *tile_group, int n_m_tiles, int tiles_n, int32_t *out, int cap);
 
+/* Gated unit of the plain RoutedLLaMaFFN: h = silu(gate) * side (layers/sparse/feedforward.py:172-176 with the LLaMA
+ * activation), bf16 in / out with fp32 math, and its backward (both gradients in one pass).  n elements, multiple of 8,
+ * 16-byte aligned. */
+int spt_silu_mul_fwd(const void *gate, const void *side, void *h, int64_t n, spt_stream_t stream);
+int spt_silu_mul_bwd(const void *gate, const void *side, const void *grad_h, void *grad_gate, void *grad_side, int64_t n,
+                     spt_stream_t stream);
+
 /* Fused elementwise stages of the LoRA-routed FFN (naive_gpt/layers/tuning/lora_ffn.py:87-115,201-222).
  * coeff [R] fp32 = 2 * router probability of the bucket row.  dtypes: SPT_F32 / SPT_BF16.  C % 4 == 0.
  *   scale_add: out = coeff[r] * a + b;   bwd: da = coeff[r] * dout (a's dtype), dcoeff[r] = sum_c dout * a.

@@ -68,6 +68,8 @@ def _load() -> ctypes.CDLL:
     sig["spt_scale_add_fwd"] = (i32, [vp, vp, i32, vp, i32, vp, i32, i64, i32, vp])
     sig["spt_scale_add_bwd"] = (i32, [vp, vp, i32, vp, i32, vp, vp, i64, i32, vp])
     sig["spt_lora_glu_fwd"] = (i32, [vp] * 6 + [i64, i32, vp])
+    sig["spt_silu_mul_fwd"] = (i32, [vp] * 3 + [i64, vp])
+    sig["spt_silu_mul_bwd"] = (i32, [vp] * 5 + [i64, vp])
     sig["spt_lora_glu_bwd"] = (i32, [vp] * 11 + [i64, i32, vp])
     sig["spt_route_bucket_workspace_bytes"] = (sz, [i64, i32])
     sig["spt_route_bucket"] = (i32, [vp] * 8 + [i64, i32, i32, i64, vp])

@@ -179,6 +179,11 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
     return d;
 }
 
+#ifndef SPT_PQ_ENC_UNROLL
+#define SPT_PQ_ENC_UNROLL 2
+#endif
+constexpr int PQ_ENC_UNROLL = SPT_PQ_ENC_UNROLL;   // codeword pairs in flight per thread (independent accumulation chains)
+
 template <typename T, int DC>
 __global__ void __launch_bounds__(CDIST_THREADS)
 pq_encode_kernel(const T *__restrict__ z0, const T *__restrict__ z1, const float *__restrict__ table,
@@ -216,7 +221,7 @@ pq_encode_kernel(const T *__restrict__ z0, const T *__restrict__ z1, const float
         int min_index = 0;
         float min_distance = 1e13f;
         const uint64_t *tp = reinterpret_cast<const uint64_t *>(s_table) + s;
-#pragma unroll 2
+#pragma unroll PQ_ENC_UNROLL
         for (int wp = 0; wp < cp; ++wp, tp += (size_t)DC * m) {
             uint64_t acc = 0;   // (+0.0f, +0.0f)
 #pragma unroll

@@ -154,6 +154,41 @@ lora_glu_bwd_kernel(const float *__restrict__ coeff, const float *__restrict__ b
     if (threadIdx.x == 0) dcoeff[row] = acc;
 }
 
+// plain gated unit of RoutedLLaMaFFN (layers/sparse/feedforward.py:172-176, `act(gate) * side` with act = SiLU): bf16 in / out,
+// fp32 math, 8 elements (16 bytes) per thread; the backward gives both gradients in one pass
+__global__ void __launch_bounds__(THREADS)
+silu_mul_fwd_kernel(const __nv_bfloat16 *__restrict__ g, const __nv_bfloat16 *__restrict__ s, __nv_bfloat16 *__restrict__ h,
+                    int64_t n8) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        float a[8], b[8], o[8];
+        Vec16<__nv_bfloat16>::load(g + 8 * i, a);
+        Vec16<__nv_bfloat16>::load(s + 8 * i, b);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = a[u] * sigmoidf_(a[u]) * b[u];
+        Vec16<__nv_bfloat16>::store(h + 8 * i, o);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+silu_mul_bwd_kernel(const __nv_bfloat16 *__restrict__ g, const __nv_bfloat16 *__restrict__ s,
+                    const __nv_bfloat16 *__restrict__ dh, __nv_bfloat16 *__restrict__ dg, __nv_bfloat16 *__restrict__ ds,
+                    int64_t n8) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        float a[8], b[8], gh[8], o1[8], o2[8];
+        Vec16<__nv_bfloat16>::load(g + 8 * i, a);
+        Vec16<__nv_bfloat16>::load(s + 8 * i, b);
+        Vec16<__nv_bfloat16>::load(dh + 8 * i, gh);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float sg = sigmoidf_(a[u]);
+            o1[u] = gh[u] * b[u] * sg * (1.0f + a[u] * (1.0f - sg));      // d silu / dg
+            o2[u] = gh[u] * a[u] * sg;
+        }
+        Vec16<__nv_bfloat16>::store(dg + 8 * i, o1);
+        Vec16<__nv_bfloat16>::store(ds + 8 * i, o2);
+    }
+}
+
 }  // namespace lfuse
 }  // namespace spt
 
@@ -232,4 +267,33 @@ extern "C" int spt_lora_glu_bwd(const float *coeff, const float *bg, const float
     lfuse::lora_glu_bwd_kernel<<<(unsigned)R, lfuse::THREADS, 0, as_stream(stream)>>>(
         coeff, bg, lg, bs, ls, (const __nv_bfloat16 *)dh, d_bg, d_lg, d_bs, d_ls, dcoeff, C);
     return after_launch("lora_glu_bwd_kernel");
+}
+
+static unsigned silu_grid(int64_t n8) {
+    const int64_t want = (n8 + spt::lfuse::THREADS - 1) / spt::lfuse::THREADS;
+    const int64_t cap = (int64_t)spt::num_sms() * 16;
+    return (unsigned)(want < cap ? want : cap);
+}
+
+extern "C" int spt_silu_mul_fwd(const void *gate, const void *side, void *h, int64_t n, spt_stream_t stream) {
+    SPT_REQUIRE(gate && side && h, "silu_mul_fwd: null pointer");
+    SPT_REQUIRE(n >= 0 && n % 8 == 0, "silu_mul_fwd: element count must be a multiple of 8 (got %lld)", (long long)n);
+    SPT_REQUIRE(((uintptr_t)gate | (uintptr_t)side | (uintptr_t)h) % 16 == 0, "silu_mul_fwd: operands must be 16-byte aligned");
+    if (n == 0) return SPT_OK;
+    using bf = __nv_bfloat16;
+    lfuse::silu_mul_fwd_kernel<<<silu_grid(n / 8), lfuse::THREADS, 0, as_stream(stream)>>>((const bf *)gate, (const bf *)side, (bf *)h, n / 8);
+    return after_launch("silu_mul_fwd_kernel");
+}
+
+extern "C" int spt_silu_mul_bwd(const void *gate, const void *side, const void *grad_h, void *grad_gate, void *grad_side,
+                                int64_t n, spt_stream_t stream) {
+    SPT_REQUIRE(gate && side && grad_h && grad_gate && grad_side, "silu_mul_bwd: null pointer");
+    SPT_REQUIRE(n >= 0 && n % 8 == 0, "silu_mul_bwd: element count must be a multiple of 8 (got %lld)", (long long)n);
+    SPT_REQUIRE(((uintptr_t)gate | (uintptr_t)side | (uintptr_t)grad_h | (uintptr_t)grad_gate | (uintptr_t)grad_side) % 16 == 0,
+                "silu_mul_bwd: operands must be 16-byte aligned");
+    if (n == 0) return SPT_OK;
+    using bf = __nv_bfloat16;
+    lfuse::silu_mul_bwd_kernel<<<silu_grid(n / 8), lfuse::THREADS, 0, as_stream(stream)>>>(
+        (const bf *)gate, (const bf *)side, (const bf *)grad_h, (bf *)grad_gate, (bf *)grad_side, n / 8);
+    return after_launch("silu_mul_bwd_kernel");
 }

@@ -574,6 +574,29 @@ def scale_add_bwd(coeff: torch.Tensor, a: torch.Tensor, grad: torch.Tensor):
     return da, dcoeff
 
 
+def silu_mul_fwd(gate: torch.Tensor, side: torch.Tensor) -> torch.Tensor:
+    """h = silu(gate) * side, bf16 tensors of the same shape (fp32 math, one rounding)."""
+    for t, n in ((gate, "gate"), (side, "side")):
+        _check_type(t, torch.bfloat16, n)
+    if gate.shape != side.shape or not gate.is_contiguous() or not side.is_contiguous() or gate.numel() % 8:
+        raise RuntimeError("silu_mul: gate / side must be contiguous, equal-shaped, with a multiple of 8 elements")
+    h = torch.empty_like(gate)
+    with _on_device(gate):
+        check(lib.spt_silu_mul_fwd(_p(gate), _p(side), _p(h), gate.numel(), _stream(gate)))
+    return h
+
+
+def silu_mul_bwd(gate: torch.Tensor, side: torch.Tensor, grad_h: torch.Tensor):
+    """-> (grad_gate, grad_side) bf16."""
+    _check_type(grad_h, torch.bfloat16, "grad_h")
+    if grad_h.shape != gate.shape or not grad_h.is_contiguous():
+        raise RuntimeError("silu_mul_bwd: shape mismatch")
+    dg, ds = torch.empty_like(gate), torch.empty_like(side)
+    with _on_device(gate):
+        check(lib.spt_silu_mul_bwd(_p(gate), _p(side), _p(grad_h), _p(dg), _p(ds), gate.numel(), _stream(gate)))
+    return dg, ds
+
+
 def lora_glu_fwd(coeff, bg, lg, bs, ls) -> torch.Tensor:
     """h (bf16) = silu(coeff * bg + lg) * (coeff * bs + ls); all inputs fp32 [R, C], coeff [R]."""
     R, C = _rows_cols(bg, "bg")

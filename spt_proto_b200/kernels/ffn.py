@@ -250,6 +250,24 @@ class LoraGLU(autograd.Function):
         return dcoeff, d_bg, d_lg, d_bs, d_ls
 
 
+class SiluMul(autograd.Function):
+    """h = silu(gate) * side in one pass each way (the plain RoutedLLaMaFFN's `act(gate) * side`)."""
+
+    @staticmethod
+    def forward(ctx, gate, side):
+        ctx.save_for_backward(gate, side)
+        return ext.silu_mul_fwd(gate, side)
+
+    @staticmethod
+    def backward(ctx, grad):
+        gate, side = ctx.saved_tensors
+        return ext.silu_mul_bwd(gate, side, grad.contiguous())
+
+
+def silu_mul(gate, side):
+    return SiluMul.apply(gate, side)
+
+
 def scale_add(coeff, a, b, out_dtype):
     return ScaleAdd.apply(coeff, a, b, out_dtype)
 

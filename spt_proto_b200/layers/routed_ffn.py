@@ -98,7 +98,10 @@ class RoutedLLaMaFFN(LLaMaFeedforward):
         xp = F.gather(x2.to(torch.bfloat16).contiguous(), bucket)
         g = F.blocked_linear_rows(xp, self.gate.weight, None, bucket, self.block_size)
         s = F.blocked_linear_rows(xp, self.side.weight, None, bucket, self.block_size)
-        h = self.activation(g) * s
+        if isinstance(self.activation, nn.SiLU) and g.dtype == torch.bfloat16 and g.numel() % 8 == 0:
+            h = F.silu_mul(g, s)                      # one kernel each way instead of the eager act(g) * s chain
+        else:
+            h = self.activation(g) * s
         yp = F.blocked_linear_cols(h, self.down.weight, bucket, self.block_size)
         y = F.combine(yp, bucket, None, x.dtype)
         return y.view(x_size)

@@ -489,3 +489,20 @@ def test_route_bucket_nan_and_inf_rows():
     assert member[3, :k].all() and member[7, :k].all() and member[T - 1, :k].all()   # all-equal rows: lowest indices
     tr = b.token_rows.cpu()
     assert ((tr >= 0) & (tr < b.R)).all()
+
+
+def test_silu_mul_matches_torch_autograd():
+    """The fused gated unit of the plain RoutedLLaMaFFN (act(gate) * side, feedforward.py:172-176) against torch in fp32."""
+    from spt_proto_b200.kernels import ffn as F
+    torch.manual_seed(5)
+    g = (torch.randn(300, 512, device=DEV) * 2).bfloat16().requires_grad_()
+    s = torch.randn(300, 512, device=DEV).bfloat16().requires_grad_()
+    dh = torch.randn(300, 512, device=DEV).bfloat16()
+    h = F.silu_mul(g, s)
+    h.backward(dh)
+    gf, sf = g.detach().float().requires_grad_(), s.detach().float().requires_grad_()
+    hf = torch.nn.functional.silu(gf) * sf
+    hf.backward(dh.float())
+    assert torch.allclose(h.float(), hf, atol=2e-2, rtol=1e-2)
+    assert torch.allclose(g.grad.float(), gf.grad, atol=2e-2, rtol=2e-2)
+    assert torch.allclose(s.grad.float(), sf.grad, atol=2e-2, rtol=2e-2)
