@@ -145,17 +145,67 @@ sddmm_scalar_kernel(const int32_t *__restrict__ indptr, const int32_t *__restric
     }
 }
 
+// 32 bytes per lane through ONE 256-bit load (sm_100 LDG.E.256): a bf16 d = 64 row takes 4 lanes instead of 8 (fp32: 8
+// instead of 16), i.e. twice the gathered rows per load instruction and half the shuffles / index arithmetic per pair —
+// the gather kernels are LSU- and issue-bound, not bandwidth-bound
+__device__ __forceinline__ void ldg256_u32(const void *p, uint32_t (&u)[8]) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "l"(p));
+}
+template <typename T>
+struct Vec32;
+template <>
+struct Vec32<float> {
+    static constexpr int N = 8;
+    __device__ __forceinline__ static void load(const float *p, float (&o)[8]) {
+        uint32_t u[8];
+        ldg256_u32(p, u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(u[i]);
+    }
+};
+template <>
+struct Vec32<__nv_bfloat16> {
+    static constexpr int N = 16;
+    __device__ __forceinline__ static void load(const __nv_bfloat16 *p, float (&o)[16]) {
+        uint32_t u[8];
+        ldg256_u32(p, u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            o[2 * i] = __uint_as_float(u[i] << 16);
+            o[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+        }
+    }
+};
+// N fp32 values -> N consecutive elements of TO (16-byte stores)
+template <typename TO, int N>
+__device__ __forceinline__ void store_vec(TO *p, const float (&o)[N]) {
+    constexpr int V = Vec16<TO>::N;
+    if constexpr (N % V == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += V) {
+            float t[V];
+#pragma unroll
+            for (int u = 0; u < V; ++u) t[u] = o[i + u];
+            Vec16<TO>::store(p + i, t);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = from_f32<TO>(o[i]);
+    }
+}
+
 // ---- spmm (y = A x) and transposed spmm (y = A^T x through the CSC) ------------------------------
 // One warp per output row.  TRANS = false: entries e in [indptr[r], indptr[r+1]), source row
 // indices[b,e], weight values[b,e].  TRANS = true: entries e' in [col_ptr[b,c], col_ptr[b,c+1]),
 // source row row_idx[b,e'], weight values[b, perm[b,e']].  Accumulation order inside a group is the
 // entry order; groups are combined by a fixed butterfly => deterministic.
-template <typename T, typename TO, int L, bool TRANS>
+template <typename T, typename TO, int L, bool TRANS, typename VT = Vec16<T>>
 __global__ void __launch_bounds__(CSR_WARPS * 32)
 spmm_kernel(const int32_t *__restrict__ ptr, const int32_t *__restrict__ src_idx, const int32_t *__restrict__ perm,
             const float *__restrict__ values, const T *__restrict__ x, TO *__restrict__ y, int B, int S, int d,
             int64_t nnz) {
-    constexpr int VEC = Vec16<T>::N;
+    constexpr int VEC = VT::N;
     constexpr int G = 32 / L;
     const int lane = threadIdx.x & 31;
     const int64_t row_id = (int64_t)blockIdx.x * CSR_WARPS + (threadIdx.x >> 5);
@@ -189,7 +239,7 @@ spmm_kernel(const int32_t *__restrict__ ptr, const int32_t *__restrict__ src_idx
             const float w = __shfl_sync(FULL, my_val, src);  // 0 for padding lanes
             if (has) {
                 float xv[VEC];
-                Vec16<T>::load(xb + (size_t)col * d + sub * VEC, xv);
+                VT::load(xb + (size_t)col * d + sub * VEC, xv);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w, xv[i], acc[i]);
             }
@@ -200,21 +250,7 @@ spmm_kernel(const int32_t *__restrict__ ptr, const int32_t *__restrict__ src_idx
 #pragma unroll
         for (int o = L; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
     }
-    if (grp == 0 && has) {
-        TO *yp = y + ((size_t)b * S + r) * d + sub * VEC;
-        if constexpr (sizeof(TO) == 4 && VEC == 8) {
-            float lo[4] = {acc[0], acc[1], acc[2], acc[3]}, hi[4] = {acc[4], acc[5], acc[6], acc[7]};
-            Vec16<float>::store(reinterpret_cast<float *>(yp), lo);
-            Vec16<float>::store(reinterpret_cast<float *>(yp) + 4, hi);
-        } else if constexpr (sizeof(TO) == 4) {
-            Vec16<float>::store(reinterpret_cast<float *>(yp), acc);
-        } else if constexpr (VEC == 8) {
-            Vec16<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16 *>(yp), acc);
-        } else {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) yp[i] = from_f32<TO>(acc[i]);
-        }
-    }
+    if (grp == 0 && has) store_vec<TO, VEC>(y + ((size_t)b * S + r) * d + sub * VEC, acc);
 }
 
 template <typename T, typename TO, bool TRANS>
@@ -644,11 +680,11 @@ spmm_t_block_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restri
 // partial sums are added in warp order.  Same per-entry arithmetic and order inside a warp as above.
 // (Also tried for both products: all row loads of a batch issued before any arithmetic + packed fma.rn.f32x2 — 102
 // registers, 23 % occupancy, 1.4x SLOWER than the simple loop; dropped.)
-template <typename T, int L, bool PERM>
-__device__ __forceinline__ void spmm_accumulate(float (&acc)[Vec16<T>::N], const int32_t *__restrict__ ip,
+template <typename T, int L, bool PERM, typename VT>
+__device__ __forceinline__ void spmm_accumulate(float (&acc)[VT::N], const int32_t *__restrict__ ip,
                                                 const int32_t *__restrict__ pm, const float *__restrict__ vp,
                                                 const T *__restrict__ xb, int e0, int e1, int lane, int d, bool has) {
-    constexpr int VEC = Vec16<T>::N, G = 32 / L;
+    constexpr int VEC = VT::N, G = 32 / L;
     const int sub = lane % L, grp = lane / L;
     for (int base = e0; base < e1; base += 32) {
         const int e = base + lane;
@@ -667,7 +703,7 @@ __device__ __forceinline__ void spmm_accumulate(float (&acc)[Vec16<T>::N], const
             const float w = __shfl_sync(FULL, my_val, src);  // 0 for padding lanes
             if (has) {
                 float xv[VEC];
-                Vec16<T>::load(xb + (size_t)row * d + sub * VEC, xv);
+                VT::load(xb + (size_t)row * d + sub * VEC, xv);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w, xv[i], acc[i]);
             }
@@ -680,29 +716,12 @@ __device__ __forceinline__ void spmm_accumulate(float (&acc)[Vec16<T>::N], const
     }
 }
 
-template <typename T, typename TO>
-__device__ __forceinline__ void spmm_store(TO *yp, const float (&out)[Vec16<T>::N]) {
-    constexpr int VEC = Vec16<T>::N;
-    if constexpr (sizeof(TO) == 4 && VEC == 8) {
-        float lo[4] = {out[0], out[1], out[2], out[3]}, hi[4] = {out[4], out[5], out[6], out[7]};
-        Vec16<float>::store(reinterpret_cast<float *>(yp), lo);
-        Vec16<float>::store(reinterpret_cast<float *>(yp) + 4, hi);
-    } else if constexpr (sizeof(TO) == 4) {
-        Vec16<float>::store(reinterpret_cast<float *>(yp), out);
-    } else if constexpr (VEC == 8) {
-        Vec16<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16 *>(yp), out);
-    } else {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) yp[i] = from_f32<TO>(out[i]);
-    }
-}
-
 constexpr int SPMM_T_HEAVY = 1024;
-template <typename T, typename TO, int L>
+template <typename T, typename TO, int L, typename VT = Vec16<T>>
 __global__ void __launch_bounds__(CSR_WARPS * 32)
 spmm2_t_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ row_idx, const int32_t *__restrict__ perm,
                const float *__restrict__ values, const T *__restrict__ x, TO *__restrict__ y, int S, int d, int64_t nnz) {
-    constexpr int VEC = Vec16<T>::N;
+    constexpr int VEC = VT::N;
     __shared__ float s_part[CSR_WARPS][L * VEC];
     __shared__ int s_len[CSR_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -723,8 +742,8 @@ spmm2_t_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ 
             float acc[VEC];
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[i] = 0.0f;
-            spmm_accumulate<T, L, true>(acc, ip, pm, vp, xb, c0, c1, lane, d, has);
-            if (lane < L && has) spmm_store<T, TO>(y + ((size_t)b * S + c) * d + sub * VEC, acc);
+            spmm_accumulate<T, L, true, VT>(acc, ip, pm, vp, xb, c0, c1, lane, d, has);
+            if (lane < L && has) store_vec<TO, VEC>(y + ((size_t)b * S + c) * d + sub * VEC, acc);
         }
     }
     __syncthreads();
@@ -737,7 +756,7 @@ spmm2_t_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ 
         float acc[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = 0.0f;
-        spmm_accumulate<T, L, true>(acc, ip, pm, vp, xb, e0, e1, lane, d, has);
+        spmm_accumulate<T, L, true, VT>(acc, ip, pm, vp, xb, e0, e1, lane, d, has);
         if (lane < L) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) s_part[wid][sub * VEC + i] = acc[i];
@@ -752,7 +771,7 @@ spmm2_t_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ 
                 for (int w = 0; w < CSR_WARPS; ++w) t += s_part[w][sub * VEC + i];
                 sum[i] = t;
             }
-            spmm_store<T, TO>(y + ((size_t)b * S + c) * d + sub * VEC, sum);
+            store_vec<TO, VEC>(y + ((size_t)b * S + c) * d + sub * VEC, sum);
         }
         __syncthreads();
     }
@@ -832,6 +851,33 @@ static int launch_spmm(const int32_t *ptr, const int32_t *src_idx, const int32_t
             return csr_mma::launch_spmm(TRANS, ptr, src_idx, perm, values, x, y, sizeof(TO) == 2, B, S, d, nnz, st);
     }
     const unsigned grid = (unsigned)((rows + CSR_WARPS - 1) / CSR_WARPS);
+    {
+        // 256-bit lane loads when the rows allow it (see Vec32)
+        static const bool narrow = [] { const char *e = getenv("SPT_SPMM_NARROW"); return e && atoi(e) == 1; }();   // A/B switch
+        constexpr int WV = Vec32<T>::N;
+        // measured at the bench shapes: CSR product 0.84 -> 0.73 ms (bf16), 0.33 -> 0.27 (fp32); transposed product
+        // 1.10 -> 0.94 ms (fp32) but 1.33 -> 1.52 (bf16: 4 lanes per row leave a 3-step, 16-value reduction per column)
+        const bool use_wide = !narrow && (!TRANS || sizeof(T) == 4);
+        if (use_wide && d % WV == 0 && d <= 16 * WV && ((uintptr_t)x % 32 == 0) && ((uintptr_t)y % 16 == 0) && rows < ((int64_t)1 << 31)) {
+            const unsigned tgrid = (unsigned)(B * ((S + CSR_WARPS - 1) / CSR_WARPS));
+#define SPT_SPMM_WIDE(LL)                                                                                        \
+    case LL:                                                                                                     \
+        if (TRANS)                                                                                               \
+            spmm2_t_kernel<T, TO, LL, Vec32<T>><<<tgrid, CSR_WARPS * 32, 0, st>>>(ptr, src_idx, perm, values, x, y, S, d, nnz); \
+        else                                                                                                     \
+            spmm_kernel<T, TO, LL, false, Vec32<T>><<<grid, CSR_WARPS * 32, 0, st>>>(ptr, src_idx, perm, values, x, y, B, S, d, nnz); \
+        break;
+            switch (lanes_for(d, WV)) {
+                SPT_SPMM_WIDE(1)
+                SPT_SPMM_WIDE(2)
+                SPT_SPMM_WIDE(4)
+                SPT_SPMM_WIDE(8)
+                SPT_SPMM_WIDE(16)
+            }
+#undef SPT_SPMM_WIDE
+            return after_launch("spmm_kernel(wide)");
+        }
+    }
     const bool vec_ok = (d % VEC == 0) && (d <= 32 * VEC) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
     if (!vec_ok) {
         spmm_scalar_kernel<T, TO, TRANS><<<grid, CSR_WARPS * 32, 0, st>>>(ptr, src_idx, perm, values, x, y, B, S, d, nnz);
