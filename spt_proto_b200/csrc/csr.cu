@@ -492,7 +492,8 @@ __global__ void __launch_bounds__(C2C_WARPS * 32)
 csr2csc_place_staged_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                             const int32_t *__restrict__ tile_cnt, const int32_t *__restrict__ col_ptr,
                             int32_t *__restrict__ row_idx, int32_t *__restrict__ perm, int S, int64_t nnz,
-                            int n_tiles, int CAP) {
+                            int n_tiles, int CAP, const int *__restrict__ run_if) {
+    if (run_if && *run_if == 0) return;      // the bit-matrix placement below handled this call
     extern __shared__ __align__(16) unsigned char c2c_smem[];
     __shared__ int32_t s_warp[32];
     __shared__ int32_t s_carry;
@@ -593,6 +594,145 @@ csr2csc_place_staged_kernel(const int32_t *__restrict__ indptr, const int32_t *_
             s_goff[c] += next - s_lstart[c];
         }
         __syncthreads();
+    }
+}
+
+// Placement through a per-tile BIT MATRIX (the common pattern: S <= 2048, rows of up to 256 entries, no column repeated
+// inside a row except column 0 — what the lookup stage emits: distinct keys + zero padding).  For the tile's 64 rows,
+//   MT[c]   (64 bits)  = the rows that contain column c        (shared-memory atomicOr, order-free)
+//   P[r][c] (1 byte)   = position of column c inside row r
+// give everything the sorted output needs without sorting: after an exclusive scan of popc(MT[c]) over the columns, output
+// slot i of the tile belongs to the column found by a binary search over the scan, its row is the rank-th set bit of
+// MT[c], its CSR position comes from P — consecutive threads write consecutive slots of a column's run.  Column 0 (zero
+// padding: many entries per row) goes through a row-major list built with warp ballots.  No per-warp counters, no
+// tags, no __match_any, 32 warps per block instead of 8.  Anything else (a repeated non-zero column, a longer row) raises
+// `fallback` and the staged kernel above redoes the call: deterministic and stable either way.
+constexpr int C2B_THREADS = 1024;
+constexpr int C2B_SLOTS = C2C_TR * 256;          // entries of a tile
+
+__global__ void __launch_bounds__(C2B_THREADS)
+csr2csc_place_bits_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                          const int32_t *__restrict__ tile_cnt, const int32_t *__restrict__ col_ptr,
+                          int32_t *__restrict__ row_idx, int32_t *__restrict__ perm, int S, int64_t nnz, int n_tiles,
+                          int *__restrict__ fallback) {
+    extern __shared__ __align__(16) unsigned char c2b_smem[];
+    __shared__ int32_t s_warp[32];
+    __shared__ int32_t s_carry;
+    __shared__ int32_t s_indptr[C2C_TR + 1];
+    __shared__ int32_t s_cnt0[C2C_TR], s_zstart[C2C_TR + 1];
+    uint32_t *mt_lo = reinterpret_cast<uint32_t *>(c2b_smem);          // [S] rows 0 .. 31 of the tile; later: global offset of slot 0 of the column
+    uint32_t *mt_hi = mt_lo + S;                                       // [S] rows 32 .. 63
+    int32_t *lstart = reinterpret_cast<int32_t *>(mt_hi + S);          // [S] exclusive scan of the column counts
+    uint16_t *s_col = reinterpret_cast<uint16_t *>(lstart + S);        // [slots] column of a sorted slot
+    uint8_t *s_row = reinterpret_cast<uint8_t *>(s_col + C2B_SLOTS);   // [slots] its row inside the tile
+    uint8_t *s_pos = s_row + C2B_SLOTS;                                // [slots] its position inside the row
+    uint8_t *P = s_pos + C2B_SLOTS;                                    // [C2C_TR][S]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tile = blockIdx.x, b = blockIdx.y;
+    const int r0 = tile * C2C_TR, r1 = min(S, r0 + C2C_TR), n_rows = r1 - r0;
+    const int32_t *ip = indices + (size_t)b * nnz;
+    for (int c = threadIdx.x; c < S; c += C2B_THREADS) mt_lo[c] = mt_hi[c] = 0u;
+    for (int i = threadIdx.x; i <= n_rows; i += C2B_THREADS) s_indptr[i] = indptr[r0 + i];
+    if (threadIdx.x < C2C_TR) s_cnt0[threadIdx.x] = 0;
+    __syncthreads();
+    // pass 1: bit matrix, positions, zero counts; one warp per row
+    bool bad = false;
+    for (int r = wid; r < n_rows; r += C2B_THREADS / 32) {
+        const int e0 = s_indptr[r];
+        int e1 = s_indptr[r + 1];
+        if (e1 - e0 > 256) {                                         // positions would not fit a byte: fallback (warp-uniform)
+            bad = true;
+            e1 = e0 + 256;
+        }
+        uint32_t *word = r < 32 ? mt_lo : mt_hi;
+        const uint32_t bit = 1u << (r & 31);
+        int zeros = 0;
+        for (int base = e0; base < e1; base += 32) {
+            const int e = base + lane;
+            const int c = e < e1 ? ip[e] : -1;
+            const bool ok = (unsigned)c < (unsigned)S;               // out-of-range columns are dropped (as in the count kernel)
+            zeros += __popc(__ballot_sync(FULL, ok && c == 0));
+            if (ok && c != 0) {
+                const uint32_t old = atomicOr(&word[c], bit);
+                bad |= (old & bit) != 0;                               // the column twice in one row
+                P[(size_t)r * S + c] = (uint8_t)(e - e0);
+            }
+        }
+        if (lane == 0) s_cnt0[r] = zeros;
+    }
+    if (__any_sync(FULL, bad)) {
+        if (lane == 0) atomicOr(fallback, 1);
+    }
+    __syncthreads();
+    // column counts -> exclusive scan; zero-list offsets per row
+    if (wid == 0) {
+        int run = 0;
+        for (int base = 0; base < C2C_TR; base += 32) {
+            const int v = base + lane < n_rows ? s_cnt0[base + lane] : 0;
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (base + lane < C2C_TR) s_zstart[base + lane] = run + inc - v;
+            run += __shfl_sync(FULL, inc, 31);
+        }
+        if (lane == 0) s_zstart[C2C_TR] = run;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < S; c += C2B_THREADS) lstart[c] = c == 0 ? s_zstart[C2C_TR] : __popc(mt_lo[c]) + __popc(mt_hi[c]);
+    __syncthreads();
+    const int total = block_exclusive_scan(lstart, S, s_warp, &s_carry);
+    // pass 2: the column-0 entries in row-major order take the first slots
+    for (int r = wid; r < n_rows; r += C2B_THREADS / 32) {
+        if (s_cnt0[r] == 0) continue;                                  // warp-uniform
+        const int e0 = s_indptr[r], e1 = min(s_indptr[r + 1], e0 + 256);
+        int at = s_zstart[r];
+        for (int base = e0; base < e1; base += 32) {
+            const int e = base + lane;
+            const bool z = e < e1 && ip[e] == 0;
+            const unsigned m = __ballot_sync(FULL, z);
+            if (z) {
+                const int slot = at + __popc(m & ((1u << lane) - 1u));
+                s_row[slot] = (uint8_t)r;
+                s_pos[slot] = (uint8_t)(e - e0);
+                s_col[slot] = 0;
+            }
+            at += __popc(m);
+        }
+    }
+    // expand: every other column lists its rows (ascending) into its slots
+    const int32_t *tc = tile_cnt + ((size_t)b * n_tiles + tile) * S;
+    const int32_t *cp = col_ptr + (size_t)b * (S + 1);
+    for (int c = threadIdx.x; c < S; c += C2B_THREADS) {
+        const int first = lstart[c];
+        if (c != 0) {
+            int slot = first;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t m = half ? mt_hi[c] : mt_lo[c];
+                while (m) {
+                    const int r = 32 * half + __ffs(m) - 1;
+                    m &= m - 1;
+                    s_row[slot] = (uint8_t)r;
+                    s_pos[slot] = P[(size_t)r * S + c];
+                    s_col[slot] = (uint16_t)c;
+                    ++slot;
+                }
+            }
+        }
+        mt_lo[c] = (uint32_t)(cp[c] + tc[c] - first);                  // global position of the column's slot 0 minus its first slot
+    }
+    __syncthreads();
+    if (*reinterpret_cast<volatile int *>(fallback)) return;           // some block of this launch bailed out: the staged kernel redoes everything
+    // write-out: consecutive threads -> consecutive slots of a column's run
+    int32_t *ro = row_idx + (size_t)b * nnz, *po = perm + (size_t)b * nnz;
+    for (int i = threadIdx.x; i < total; i += C2B_THREADS) {
+        const int r = s_row[i];
+        const int g = (int)mt_lo[s_col[i]] + i;
+        ro[g] = r0 + r;
+        po[g] = s_indptr[r] + s_pos[i];
     }
 }
 
@@ -1027,7 +1167,7 @@ extern "C" int spt_softmax_bwd(const int32_t *indptr, const int32_t *indices, co
 extern "C" size_t spt_csr2csc_workspace_bytes(int B, int S, int64_t nnz) {
     (void)nnz;
     const size_t n_tiles = (size_t)(S + C2C_TR - 1) / C2C_TR;
-    return (size_t)B * n_tiles * S * sizeof(int32_t);
+    return (size_t)B * n_tiles * S * sizeof(int32_t) + 16;     // tile counts + the placement kernels' fallback flag
 }
 
 extern "C" int spt_csr2csc(const int32_t *indptr, const int32_t *indices, int32_t *col_ptr, int32_t *row_idx,
@@ -1056,9 +1196,23 @@ extern "C" int spt_csr2csc(const int32_t *indptr, const int32_t *indices, int32_
     const size_t smem_st = (size_t)S * 8 + (size_t)cap * 4 + (size_t)C2C_WARPS * S * 4 + (size_t)cap * 2 + (size_t)cap +
                            (size_t)C2C_WARPS * S;
     if (smem_st <= 220 * 1024) {
+        // bit-matrix placement first (S <= 2048); it raises the flag behind the tile counts when the pattern is not its
+        // kind, and the staged kernel then redoes the call (it returns at once otherwise)
+        static const bool no_bits = [] { const char *e = getenv("SPT_CSR2CSC_BITS"); return e && atoi(e) == 0; }();   // A/B switch
+        const size_t smem_b = (size_t)S * 12 + (size_t)C2B_SLOTS * 4 + (size_t)C2C_TR * S;
+        int *flag = nullptr;
+        if (!no_bits && S <= 2048 && S % 4 == 0 && smem_b <= 220 * 1024) {
+            flag = reinterpret_cast<int *>(reinterpret_cast<char *>(workspace) + (size_t)B * n_tiles * S * sizeof(int32_t));
+            cudaError_t e = cudaMemsetAsync(flag, 0, 16, st);
+            if (e != cudaSuccess) return fail(SPT_ERR_CUDA, "csr2csc: memset: %s", cudaGetErrorString(e));
+            cudaFuncSetAttribute(csr2csc_place_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+            csr2csc_place_bits_kernel<<<dim3(n_tiles, B), C2B_THREADS, smem_b, st>>>(indptr, indices, tile_cnt, col_ptr, row_idx,
+                                                                                   perm, S, nnz, n_tiles, flag);
+            SPT_LAUNCH_CHECK("csr2csc_place_bits_kernel");
+        }
         cudaFuncSetAttribute(csr2csc_place_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st);
         csr2csc_place_staged_kernel<<<dim3(n_tiles, B), C2C_WARPS * 32, smem_st, st>>>(indptr, indices, tile_cnt, col_ptr,
-                                                                                      row_idx, perm, S, nnz, n_tiles, cap);
+                                                                                      row_idx, perm, S, nnz, n_tiles, cap, flag);
         SPT_LAUNCH_CHECK("csr2csc_place_staged_kernel");
         return SPT_OK;
     }

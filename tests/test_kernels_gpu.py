@@ -290,6 +290,21 @@ def test_csr2csc_bit_exact(B, S, k):
     assert torch.equal(cp.cpu(), cp_o) and torch.equal(ri.cpu(), ri_o) and torch.equal(pm.cpu(), pm_o)
 
 
+@pytest.mark.parametrize("B,S,k,kind", [(2, 128, 16, "dup"), (2, 512, 64, "dup"), (1, 512, 320, "long"), (2, 2048, 64, "dup")])
+def test_csr2csc_fallback_patterns(B, S, k, kind):
+    """Patterns the bit-matrix placement hands back to the staged kernel: a non-zero column repeated inside a row,
+    rows longer than 256 entries.  Same stable order (rows ascending per column, CSR order among duplicates)."""
+    g = torch.Generator().manual_seed(S * 7 + k)
+    indptr, indices = _random_csr(B, S, k, causal=False, gen=g)
+    if kind == "dup":
+        for r in (5, S // 2, S - 1):
+            indices[:, r * k + 1] = indices[:, r * k + 3]           # the same non-zero column twice in row r
+            indices[0, r * k + 4 : r * k + 7] = 9
+    cp_o, ri_o, pm_o = O.csr2csc(indptr, indices, S)
+    cp, ri, pm = _ext().csr2csc(indptr.to(DEV), indices.to(DEV))
+    assert torch.equal(cp.cpu(), cp_o) and torch.equal(ri.cpu(), ri_o) and torch.equal(pm.cpu(), pm_o)
+
+
 def test_transposed_spmm_is_deterministic():
     g = torch.Generator().manual_seed(1)
     B, S, k, d = 4, 512, 64, 64
