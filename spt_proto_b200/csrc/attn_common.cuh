@@ -314,9 +314,9 @@ struct Prof {
             for (int i = 0; i < 8; ++i) atomicAdd(&g_prof[kernel][base + i], (unsigned long long)t[i]);
     }
 };
-#define PROF(x) x
+#define PROF(...) __VA_ARGS__
 #else
-#define PROF(x)
+#define PROF(...)
 #endif
 
 struct Smem {
@@ -351,6 +351,10 @@ int launch_bwd_kv128(const CUtensorMap &mq, const CUtensorMap &mk, const CUtenso
 int launch_bwd_q128(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const CUtensorMap &md,
                     const uint32_t *mask, const int32_t *extra0, const float *ndelta, __nv_bfloat16 *gq, int B, int S,
                     int H, float scale, float clamp, cudaStream_t st);
+int launch_bwd_fused128(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const CUtensorMap &md,
+                        const uint32_t *mask, const int32_t *extra0, const float *ndelta, float *dq_acc,
+                        __nv_bfloat16 *gq, __nv_bfloat16 *gk, __nv_bfloat16 *gv, int B, int S, int H, float scale,
+                        float clamp, cudaStream_t st);
 int launch_fwd128(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const uint32_t *mask,
                   const int32_t *extra0, __nv_bfloat16 *y, float *zsum, int B, int S, int H, float scale, float clamp,
                   int y_transposed, cudaStream_t st);

@@ -773,6 +773,11 @@ static bool tile128() {
     static const bool on = [] { const char *e = getenv("SPT_ATTN_TILE"); return !(e && atoi(e) == 64); }();
     return on;
 }
+// one-pass backward (dK, dV and dQ from the same score tiles, attn_bwd_fused128_kernel): opt-in, SPT_ATTN_BWD_FUSED=1
+static bool bwd_fused() {
+    static const bool on = [] { const char *e = getenv("SPT_ATTN_BWD_FUSED"); return e && atoi(e) == 1; }();
+    return on;
+}
 static bool fwd128() {
     static const bool on = [] { const char *e = getenv("SPT_ATTN_FWD128"); return e && atoi(e) == 1; }();
     return on;
@@ -805,8 +810,10 @@ static int launch_prep(const __nv_bfloat16 *y, const __nv_bfloat16 *grad_y, cons
 
 template <int D>
 static int launch_bwd(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const CUtensorMap &md,
-                      const uint32_t *mask, const int32_t *extra0, const float *delta, __nv_bfloat16 *gq,
+                      const uint32_t *mask, const int32_t *extra0, const float *delta, float *dq_acc, __nv_bfloat16 *gq,
                       __nv_bfloat16 *gk, __nv_bfloat16 *gv, int B, int S, int H, float scale, float clamp, cudaStream_t st) {
+    if (D == 64 && tile128() && bwd_fused())
+        return attn_tc128::launch_bwd_fused128(mq, mk, mv, md, mask, extra0, delta, dq_acc, gq, gk, gv, B, S, H, scale, clamp, st);
     if (D == 64 && tile128()) {
         const int rc = attn_tc128::launch_bwd_kv128(mq, mk, mv, md, mask, extra0, delta, gk, gv, B, S, H, scale, clamp, st);
         if (rc != SPT_OK) return rc;
@@ -880,9 +887,10 @@ extern "C" int spt_debug_attn_prof(unsigned long long *out48, int reset) {
 #endif
 }
 
-// workspace: delta' [B, S] fp32, then dO' (bf16, same shape as grad_y; sized for the largest head dim)
+// workspace: delta' [B, S] fp32, then dO' (bf16, same shape as grad_y; sized for the largest head dim), then the fp32
+// dQ scratch of the one-pass backward (head dim 64)
 extern "C" size_t spt_sparse_attn_bwd_workspace_bytes(int B, int S) {
-    return (size_t)B * S * sizeof(float) + (size_t)B * S * 128 * 2;
+    return (size_t)B * S * sizeof(float) + (size_t)B * S * 128 * 2 + (size_t)B * S * 64 * sizeof(float);
 }
 
 extern "C" int spt_sparse_attn_bwd(const void *q, const void *k, const void *v, const void *y, const void *grad_y,
@@ -907,6 +915,7 @@ extern "C" int spt_sparse_attn_bwd_ex(const void *q, const void *k, const void *
     using bf = __nv_bfloat16;
     float *delta = (float *)workspace;
     bf *dys = (bf *)((char *)workspace + (size_t)B * S * sizeof(float));
+    float *dq_acc = (float *)((char *)workspace + (size_t)B * S * sizeof(float) + (size_t)B * S * 128 * 2);
     // the row kernel goes first: besides producing dO' and delta' it is a runtime-API launch, which binds the
     // device's primary context to this (autograd worker) thread before the driver-API tensor-map encoder runs
     rc = d == 64 ? attn_tc::launch_prep<64>((const bf *)y, (const bf *)grad_y, zsum, delta, dys, B, S, H, yt, as_stream(stream))
@@ -918,8 +927,8 @@ extern "C" int spt_sparse_attn_bwd_ex(const void *q, const void *k, const void *
     if ((rc = attn_tc::make_map(&mv, v, B / H, S, H, d)) != SPT_OK) return rc;
     if ((rc = attn_tc::make_map(&md, dys, B / H, S, H, d)) != SPT_OK) return rc;
     if (d == 64)
-        return attn_tc::launch_bwd<64>(mq, mk, mv, md, mask, extra0, delta, (bf *)grad_q, (bf *)grad_k, (bf *)grad_v, B, S,
-                                       H, scale, clamp, as_stream(stream));
-    return attn_tc::launch_bwd<128>(mq, mk, mv, md, mask, extra0, delta, (bf *)grad_q, (bf *)grad_k, (bf *)grad_v, B, S, H,
-                                    scale, clamp, as_stream(stream));
+        return attn_tc::launch_bwd<64>(mq, mk, mv, md, mask, extra0, delta, dq_acc, (bf *)grad_q, (bf *)grad_k, (bf *)grad_v,
+                                       B, S, H, scale, clamp, as_stream(stream));
+    return attn_tc::launch_bwd<128>(mq, mk, mv, md, mask, extra0, delta, dq_acc, (bf *)grad_q, (bf *)grad_k, (bf *)grad_v, B,
+                                    S, H, scale, clamp, as_stream(stream));
 }

@@ -274,3 +274,19 @@ def test_config1_layer_matches_oracle():
         assert rel(y.detach(), y_ref.detach()) < 1e-2
         for got, want in ((qd.grad, qf.grad), (kd.grad, kf.grad), (vd.grad, vf.grad)):
             assert rel(got, want) < 2e-2
+
+
+def test_one_pass_backward_opt_in_matches_oracle():
+    """The opt-in one-pass backward (SPT_ATTN_BWD_FUSED=1: dK, dV and dQ from the same score tiles, dQ through TMA
+    add-reductions) is selected once per process, so the oracle comparison of the d = 64 cases runs in a child
+    process with the switch set."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SPT_ATTN_BWD_FUSED="1")
+    res = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(root, "tests", "test_fused_gpu.py"),
+                          "-k", "test_fused_attention_matches_oracle and 64"], cwd=root, env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert " passed" in res.stdout and "failed" not in res.stdout
