@@ -925,6 +925,12 @@ int launch_sddmm(const int32_t *indptr, const int32_t *indices, const __nv_bfloa
 int launch_spmm(bool trans, const int32_t *ptr, const int32_t *src_idx, const int32_t *perm, const float *values,
                 const __nv_bfloat16 *x, void *y, bool y_bf16, int B, int S, int d, int64_t nnz, cudaStream_t st);
 }  // namespace csr_mma
+// dense 64 x 64 tiles from the CSC pattern (csr_dense.cu): the transposed product at attention densities
+namespace csr_dense {
+bool supported(int d, int S, const void *x, const void *y);
+int launch_spmm_t(const int32_t *col_ptr, const int32_t *row_idx, const int32_t *perm, const float *values,
+                  const __nv_bfloat16 *x, void *y, bool y_bf16, int B, int S, int d, int64_t nnz, cudaStream_t st);
+}  // namespace csr_dense
 
 // ---- launch helpers ------------------------------------------------------------------------------
 static inline int lanes_for(int d, int vec) {
@@ -983,6 +989,12 @@ static int launch_spmm(const int32_t *ptr, const int32_t *src_idx, const int32_t
                        const T *x, TO *y, int B, int S, int d, int64_t nnz, cudaStream_t st) {
     constexpr int VEC = Vec16<T>::N;
     const int64_t rows = (int64_t)B * S;
+    if constexpr (sizeof(T) == 2 && TRANS) {
+        if (csr_dense::supported(d, S, x, y) && rows < ((int64_t)1 << 31) && nnz < ((int64_t)1 << 31)) {
+            const int rc = csr_dense::launch_spmm_t(ptr, src_idx, perm, values, x, y, sizeof(TO) == 2, B, S, d, nnz, st);
+            if (rc != SPT_ERR_UNSUPPORTED) return rc;              // unaligned lists: the gathered kernel below
+        }
+    }
     if constexpr (sizeof(T) == 2) {
         // the tensor-core spmm is correct but measured slower than the SIMT kernels (its B-fragment layout forces
         // 16-byte loads that coalesce per 32 bytes only: 4 LSU wavefronts per gathered row); opt-in for experiments

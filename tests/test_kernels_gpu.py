@@ -479,3 +479,58 @@ def test_sddmm_scaled_matches_eager_clamp_chain():
     assert (v2.detach().abs() >= 10.0).any() and (v2.detach().abs() < 10.0).any()
     assert torch.allclose(v1, v2, atol=1e-5, rtol=1e-5)
     assert torch.allclose(g1[0], q.grad, atol=1e-4, rtol=1e-4) and torch.allclose(g1[1], kk.grad, atol=1e-4, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------- dense-tile transposed product
+def _spmm_t_want(indptr, indices, vals, x):
+    """fp64 dense restatement of y = A^T x for a fixed-stride CSR (duplicates add up)."""
+    B, S, d = x.shape
+    k = indices.shape[1] // S
+    a = torch.zeros(B, S, S, dtype=torch.float64)
+    a.scatter_add_(2, indices.view(B, S, k).long(), vals.view(B, S, k).double())
+    return torch.einsum("brc,brd->bcd", a, x.double())
+
+
+@pytest.mark.parametrize("B,S,k,d,pad_rows,hot_cols", [(2, 2048, 256, 64, 256, 0), (2, 512, 64, 128, 64, 0), (1, 4096, 32, 64, 32, 3),
+                                                       (3, 200, 24, 64, 30, 0)])
+def test_spmm_t_dense_tiles_match_dense_product(B, S, k, d, pad_rows, hot_cols):
+    """bf16 x, head dim 64 / 128: the transposed product runs on dense 64 x 64 tiles built from the CSC lists
+    (csr_dense.cu).  pad_rows: rows r < pad_rows keep r + 1 keys and pad the rest with column 0 (the lookup's zero
+    padding: column 0's list is tens of thousands of entries long and goes through the strip); hot_cols: that many
+    columns are selected by EVERY row (more long lists than strips); S = 200: ragged last tile."""
+    g = torch.Generator().manual_seed(S + k + d)
+    indptr, indices = _random_csr(B, S, k, causal=True, gen=g)
+    idx = indices.view(B, S, k)
+    for r in range(min(pad_rows, k - 1)):
+        idx[:, r, r + 1:] = 0
+    for c in range(hot_cols):
+        idx[:, :, c] = 7 * c + 1
+    vals = torch.randn(B, S * k, generator=g)
+    x = torch.randn(B, S, d, generator=g).bfloat16()
+    want = _spmm_t_want(indptr, indices, vals, x.float())
+    csc = _ext().csr2csc(indptr.to(DEV), indices.to(DEV))
+    for out_dtype in (torch.float32, torch.bfloat16):
+        got = _ext().spmm_csc(csc, vals.to(DEV), x.to(DEV), out_dtype=out_dtype)
+        err = (got.double().cpu() - want).norm() / want.norm()
+        assert err < (2e-5 if out_dtype == torch.float32 else 4e-3), err     # hi + lo bf16 weights: ~16 mantissa bits
+        tol = dict(atol=2e-3, rtol=1e-4) if out_dtype == torch.float32 else dict(atol=2e-2 * want.abs().max().item(), rtol=2e-2)
+        assert torch.allclose(got.double().cpu(), want, **tol)
+
+
+def test_spmm_t_dense_tiles_unsorted_lists_fall_back():
+    """A CSC whose column lists are NOT in ascending row order (not an spt_csr2csc output) still gives the product:
+    blocks that meet such a list redo their columns with the gathered loop."""
+    g = torch.Generator().manual_seed(5)
+    B, S, k, d = 2, 256, 32, 64
+    indptr, indices = _random_csr(B, S, k, causal=False, gen=g)
+    vals = torch.randn(B, S * k, generator=g)
+    x = torch.randn(B, S, d, generator=g).bfloat16()
+    want = _spmm_t_want(indptr, indices, vals, x.float())
+    cp, ri, pm = (t.cpu() for t in _ext().csr2csc(indptr.to(DEV), indices.to(DEV)))
+    for b in range(B):                                   # reverse every column's list
+        for c in range(0, S, 3):
+            e0, e1 = int(cp[b, c]), int(cp[b, c + 1])
+            ri[b, e0:e1] = ri[b, e0:e1].flip(0)
+            pm[b, e0:e1] = pm[b, e0:e1].flip(0)
+    got = _ext().spmm_csc((cp.to(DEV), ri.to(DEV), pm.to(DEV)), vals.to(DEV), x.to(DEV), out_dtype=torch.float32)
+    assert torch.allclose(got.double().cpu(), want, atol=2e-3, rtol=1e-4)
