@@ -3,7 +3,8 @@ import os, sys; sys.path.insert(0, '.')
 import torch
 from spt_proto_b200 import ext
 dev = 'cuda'
-B, S, d, k = 128, 2048, 64, 256
+import os
+B, S, d, k = int(os.environ.get("B", 128)), 2048, 64, 256
 g = torch.Generator().manual_seed(7)
 q = torch.randn(B, S, d, generator=g).to(dev, torch.bfloat16); kk = torch.randn(B, S, d, generator=g).to(dev, torch.bfloat16)
 w = torch.randn(8, 16, 8, generator=g).to(dev)

@@ -198,46 +198,62 @@ pq_encode_kernel(const T *__restrict__ z0, const T *__restrict__ z1, const float
     __syncthreads();
     const T *z = blockIdx.y ? z1 : z0;
     int32_t *codes = blockIdx.y ? codes1 : codes0;
-    // grid-stride over (row, subspace) items: the codebook is staged once per resident block
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    // grid-stride over (row, subspace) items: the codebook is staged once per resident block.  A thread takes TWO items
+    // of the same subspace per trip (g and g + stride; the stride is a multiple of m), so that every codebook word it
+    // reads from shared memory serves both: per (dimension, codeword pair) 1 LDS.64 + 2 x (packed subtract + two FADD
+    // with the |x| operand modifier) = 7 issue slots for 4 distances terms (one item per trip with a 64-bit AND for the
+    // absolute values: 5 slots for 2).  Every distance is still the reference's i-ascending fp32 sum => codes bit-exact.
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool pair_ok = stride % m == 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += pair_ok ? 2 * stride : stride) {
         const int s = (int)(g % m);
-        float qv[DC];
-        const T *zp = z + (size_t)g * DC;
-        if constexpr (DC % Vec16<T>::N == 0) {
+        const bool has_b = pair_ok && g + stride < total;
+        uint64_t qa[DC], qb[DC];   // (q_i, q_i)
 #pragma unroll
-            for (int i = 0; i < DC; i += Vec16<T>::N) {
-                float tmp[Vec16<T>::N];
-                Vec16<T>::load(zp + i, tmp);
+        for (int it = 0; it < 2; ++it) {
+            float qv[DC];
+            const T *zp = z + (size_t)(it && has_b ? g + stride : g) * DC;
+            if constexpr (DC % Vec16<T>::N == 0) {
 #pragma unroll
-                for (int j = 0; j < Vec16<T>::N; ++j) qv[i + j] = tmp[j];
+                for (int i = 0; i < DC; i += Vec16<T>::N) {
+                    float tmp[Vec16<T>::N];
+                    Vec16<T>::load(zp + i, tmp);
+#pragma unroll
+                    for (int j = 0; j < Vec16<T>::N; ++j) qv[i + j] = tmp[j];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < DC; ++i) qv[i] = to_f32(zp[i]);
             }
-        } else {
 #pragma unroll
-            for (int i = 0; i < DC; ++i) qv[i] = to_f32(zp[i]);
+            for (int i = 0; i < DC; ++i) {
+                const uint64_t v = ((uint64_t)__float_as_uint(qv[i]) << 32) | __float_as_uint(qv[i]);
+                if (it) qb[i] = v;
+                else qa[i] = v;
+            }
         }
-        uint64_t q2[DC];   // (q_i, q_i)
-#pragma unroll
-        for (int i = 0; i < DC; ++i) q2[i] = ((uint64_t)__float_as_uint(qv[i]) << 32) | __float_as_uint(qv[i]);
-        int min_index = 0;
-        float min_distance = 1e13f;
+        int ia = 0, ib = 0;
+        float ma = 1e13f, mb = 1e13f;
         const uint64_t *tp = reinterpret_cast<const uint64_t *>(s_table) + s;
 #pragma unroll PQ_ENC_UNROLL
         for (int wp = 0; wp < cp; ++wp, tp += (size_t)DC * m) {
-            uint64_t acc = 0;   // (+0.0f, +0.0f)
+            float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
 #pragma unroll
-            for (int i = 0; i < DC; ++i)
-                acc = add_f32x2(acc, sub_f32x2(q2[i], tp[(size_t)i * m]) & 0x7fffffff7fffffffull);
-            const float d0 = __uint_as_float((uint32_t)acc), d1 = __uint_as_float((uint32_t)(acc >> 32));
-            if (d0 < min_distance) {
-                min_distance = d0;
-                min_index = 2 * wp;
+            for (int i = 0; i < DC; ++i) {
+                const uint64_t t2 = tp[(size_t)i * m];
+                const uint64_t da = sub_f32x2(qa[i], t2), db = sub_f32x2(qb[i], t2);
+                a0 += fabsf(__uint_as_float((uint32_t)da));
+                a1 += fabsf(__uint_as_float((uint32_t)(da >> 32)));
+                b0 += fabsf(__uint_as_float((uint32_t)db));
+                b1 += fabsf(__uint_as_float((uint32_t)(db >> 32)));
             }
-            if (d1 < min_distance) {   // an odd c pairs its last codeword with +inf: never selected
-                min_distance = d1;
-                min_index = 2 * wp + 1;
-            }
+            if (a0 < ma) { ma = a0; ia = 2 * wp; }
+            if (a1 < ma) { ma = a1; ia = 2 * wp + 1; }   // an odd c pairs its last codeword with +inf: never selected
+            if (b0 < mb) { mb = b0; ib = 2 * wp; }
+            if (b1 < mb) { mb = b1; ib = 2 * wp + 1; }
         }
-        codes[g] = min_index;
+        codes[g] = ia;
+        if (has_b) codes[g + stride] = ib;
     }
 }
 

@@ -64,7 +64,8 @@ __device__ __forceinline__ void store2<bf16>(bf16 *p, float a, float b) { *reint
 template <int D, typename TO>
 __global__ void __launch_bounds__(DT_THREADS, 4)
 spmm_t_dense_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restrict__ row_idx, const int32_t *__restrict__ perm,
-                    const float *__restrict__ values, const bf16 *__restrict__ x, TO *__restrict__ y, int B, int S, int64_t nnz) {
+                    const float *__restrict__ values, const bf16 *__restrict__ x, TO *__restrict__ y, int B, int S, int64_t nnz,
+                    int paired) {
     constexpr int XS = (D + 8) * 2;            // bytes per staged x row (16-byte pad: conflict-free ldmatrix)
     constexpr int NT = D / 16;                 // n-tiles (8 features) per warp: a warp owns 16 columns x D / 2 features
     extern __shared__ __align__(16) unsigned char smem[];
@@ -76,13 +77,20 @@ spmm_t_dense_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restri
     __shared__ int s_nheavy, s_rmin, s_rmax, s_bad;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x % B, c0 = (blockIdx.x / B) * DT;      // column tile 0 (the longest lists) of every head first
+    // paired (opt-in): a block takes column tiles p and n_tiles - 1 - p of one head, one after the other
+    const int n_tiles = (S + DT - 1) / DT;
+    const int b = blockIdx.x % B, pair = blockIdx.x / B;
     const int32_t *pp = col_ptr + (size_t)b * (S + 1);
     const int32_t *ip = row_idx + (size_t)b * nnz;
     const int32_t *pm = perm + (size_t)b * nnz;
     const float *vp = values + (size_t)b * nnz;
     const bf16 *xb = x + (size_t)b * S * D;
 
+  for (int pass = 0; pass < (paired ? 2 : 1); ++pass) {
+    const int tile = pass ? n_tiles - 1 - pair : pair;
+    if (pass && tile <= pair) break;                               // odd tile count: the middle tile is done once
+    const int c0 = tile * DT;
+    __syncthreads();                                               // the previous pass is done with the shared state
     if (tid <= DT) s_cp[tid] = pp[min(c0 + tid, S)];
     if (tid == 0) {
         s_nheavy = 0;
@@ -111,7 +119,13 @@ spmm_t_dense_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restri
         __syncthreads();
         const int e0 = s_cp[s_heavy[h]], e1 = s_cp[s_heavy[h] + 1];
         int lo = INT_MAX, hi = -1;
-        for (int e = e0 + tid; e < e1; e += 4 * DT_THREADS) {      // four independent (row, position -> value) chains in flight
+        // Four independent (row, position -> value) chains per thread and trip.  The list is sorted by row and column 0's
+        // holds each early row hundreds of times (zero padding): fp32 shared-memory atomics are CAS loops
+        // (ATOMS.CAST.SPIN), so 32 lanes adding to one address serialise 32-fold — the first version of this loop was
+        // the critical path of the whole kernel (0.6 ms for one block).  Each warp first sums the runs of adjacent equal
+        // rows among its 32 entries with shuffles; only the last lane of a run touches the strip.
+        const int e_round = e0 + ((e1 - e0 + 4 * DT_THREADS - 1) / (4 * DT_THREADS)) * (4 * DT_THREADS);
+        for (int e = e0 + tid; e < e_round; e += 4 * DT_THREADS) {
             int r[4], q[4];
             float v[4];
 #pragma unroll
@@ -121,11 +135,21 @@ spmm_t_dense_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restri
                 q[i] = ok ? pm[e + i * DT_THREADS] : 0;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = vp[q[i]];
+            for (int i = 0; i < 4; ++i) v[i] = r[i] >= 0 ? vp[q[i]] : 0.0f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if ((unsigned)r[i] < (unsigned)S) {
-                    atomicAdd(sp + r[i], v[i]);
+                const int prev = __shfl_up_sync(0xffffffffu, r[i], 1), next = __shfl_down_sync(0xffffffffu, r[i], 1);
+                int start = (lane == 0 || prev != r[i]) ? lane : 0;           // first lane of this lane's run
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) start = max(start, __shfl_up_sync(0xffffffffu, start, d) * (lane >= d));
+                float sum = v[i];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const float up = __shfl_up_sync(0xffffffffu, sum, d);
+                    if (lane - d >= start) sum += up;
+                }
+                if ((lane == 31 || next != r[i]) && (unsigned)r[i] < (unsigned)S) {
+                    atomicAdd(sp + r[i], sum);
                     lo = min(lo, r[i]);
                     hi = max(hi, r[i]);
                 }
@@ -216,7 +240,9 @@ spmm_t_dense_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restri
             for (int i = 0; i < 4; ++i) {
                 if (i < take && q0 + i >= cur) {
                     const int cell = rw[i] - r0;
-                    if (cell >= 0) atomicAdd(P + cl * PS + cell, v[i]);
+                    // adjacent entries of one cell (duplicates) are summed in registers: one atomic per run and lane
+                    if (i < 3 && i + 1 < take && rw[i + 1] == rw[i]) v[i + 1] += v[i];
+                    else if (cell >= 0) atomicAdd(P + cl * PS + cell, v[i]);
                     else s_bad = 1;                                  // a row below the chunk: the list is not ascending
                 }
             }
@@ -276,7 +302,7 @@ spmm_t_dense_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restri
 #pragma unroll
             for (int i = 0; i < F; i += 2) store2<TO>(y + ((size_t)b * S + c) * D + lane * F + i, a[i], a[i + 1]);
         }
-        return;
+        continue;
     }
     // epilogue: rows g / g + 8 of the warp's 16 columns, features nh D/2 + 8 j + 2 t
 #pragma unroll
@@ -288,6 +314,7 @@ spmm_t_dense_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restri
             for (int j = 0; j < NT; ++j) store2<TO>(dst + 8 * j, acc[j][2 * half], acc[j][2 * half + 1]);
         }
     }
+  }
 }
 
 static size_t smem_bytes(int D, int S) { return (size_t)DT * PS * 4 + (size_t)DT * (D + 8) * 2 + (size_t)DT_MAXH * S * 4; }
@@ -306,8 +333,13 @@ static int launch_d(const int32_t *col_ptr, const int32_t *row_idx, const int32_
                     TO *y, int B, int S, int64_t nnz, cudaStream_t st) {
     const size_t smem = smem_bytes(D, S);
     cudaFuncSetAttribute(spmm_t_dense_kernel<D, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int64_t blocks = (int64_t)B * ((S + DT - 1) / DT);
-    spmm_t_dense_kernel<D, TO><<<(unsigned)blocks, DT_THREADS, smem, st>>>(col_ptr, row_idx, perm, values, x, y, B, S, nnz);
+    // SPT_SPMM_T_PAIR=1: a block takes column tiles p and n - 1 - p (equal chunk counts under a causal pattern).  Measured
+    // at S 2048: no gain — 128 heads 0.82 ms paired against 0.76 ms, 32 heads 0.43 against 0.42 (a block's duration is
+    // set by the latency of its window passes, not by the balance) — so one tile per block is the default.
+    static const int paired = [] { const char *e = getenv("SPT_SPMM_T_PAIR"); return e && atoi(e) == 1 ? 1 : 0; }();
+    const int n_tiles = (S + DT - 1) / DT;
+    const int64_t blocks = (int64_t)B * (paired ? (n_tiles + 1) / 2 : n_tiles);
+    spmm_t_dense_kernel<D, TO><<<(unsigned)blocks, DT_THREADS, smem, st>>>(col_ptr, row_idx, perm, values, x, y, B, S, nnz, paired);
     return after_launch("spmm_t_dense_kernel");
 }
 
