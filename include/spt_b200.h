@@ -129,8 +129,12 @@ int spt_clamp_scale_bwd(const float *grad, const float *clamped, float *out, int
  * trans = 1: y[b, c, :]  = sum_{e : indices[b,e] = c} values[b, e] * x[b, row(e), :]
  *            (the reference's CUSPARSE_OPERATION_TRANSPOSE path used for dK / dV).
  * x, y [B, S, d]; x is (dtype), y is (out_dtype).  trans = 1 needs the CSC built by
- * spt_csr2csc (col_ptr, row_idx, perm); summation order is (row ascending, CSR order inside a
- * row) => bit-reproducible run to run, unlike the atomics-based cuSPARSE path.
+ * spt_csr2csc (col_ptr, row_idx, perm).  Summation order: fp32 x (and every shape the dense-tile
+ * kernel does not take): row ascending, CSR order inside a row => bit-reproducible run to run,
+ * unlike the atomics-based cuSPARSE path.  bf16 x with d 64 / 128: 64-row chunks ascending,
+ * tensor-core order inside a chunk, fp32 weights kept as bf16 hi + lo (~16 bits); deterministic
+ * except for the order in which DUPLICATE entries of one (row, column) cell add up.  Lists that
+ * are not in ascending row order are accepted (slower gathered loop for the blocks concerned).
  * ------------------------------------------------------------------------------------------ */
 int spt_spmm_fwd(const int32_t *indptr, const int32_t *indices, const float *values, const void *x,
                  void *y, int B, int S, int d, int64_t nnz, int dtype, int out_dtype,
