@@ -34,6 +34,8 @@
 // other CTA's MMAs and barrier round trips are in flight.  Score tiles of the next iteration are
 // issued while the current one is still in the math phase (double-buffered S in the forward; in the
 // dQ kernel the score columns are released as soon as they are in registers).
+#include <mutex>
+
 #include "attn_common.cuh"
 
 namespace spt {
@@ -778,6 +780,33 @@ static bool bwd_fused() {
     static const bool on = [] { const char *e = getenv("SPT_ATTN_BWD_FUSED"); return e && atoi(e) == 1; }();
     return on;
 }
+// dK/dV and dQ kernels on two streams (SPT_ATTN_BWD_STREAMS=0: one after the other on the caller's stream)
+static bool bwd_two_streams() {
+    static const bool on = [] { const char *e = getenv("SPT_ATTN_BWD_STREAMS"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+// one side stream + event pair per device, created on first use (never inside a capture: creation is not a stream operation)
+static SideStream *side_stream() {
+    static SideStream table[64];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    SideStream &s = table[dev];
+    if (!s.stream) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+            s.stream = nullptr;
+            return nullptr;
+        }
+    }
+    return &s;
+}
 static bool fwd128() {
     static const bool on = [] { const char *e = getenv("SPT_ATTN_FWD128"); return e && atoi(e) == 1; }();
     return on;
@@ -814,6 +843,23 @@ static int launch_bwd(const CUtensorMap &mq, const CUtensorMap &mk, const CUtens
                       __nv_bfloat16 *gk, __nv_bfloat16 *gv, int B, int S, int H, float scale, float clamp, cudaStream_t st) {
     if (D == 64 && tile128() && bwd_fused())
         return attn_tc128::launch_bwd_fused128(mq, mk, mv, md, mask, extra0, delta, dq_acc, gq, gk, gv, B, S, H, scale, clamp, st);
+    if (D == 64 && tile128() && bwd_two_streams()) {
+        // The dK/dV and the dQ kernel are independent: the dQ kernel goes to a side stream (fork / join with events, which
+        // a stream capture records as graph edges), so its CTAs start on each SM as that SM's dK/dV CTA retires instead of
+        // after the whole grid has drained (both are one-CTA-per-SM persistent grids: they never share an SM).
+        SideStream *ss = side_stream();
+        if (ss) {
+            if (cudaEventRecord(ss->fork, st) != cudaSuccess || cudaStreamWaitEvent(ss->stream, ss->fork, 0) != cudaSuccess)
+                return fail(SPT_ERR_CUDA, "sparse_attn_bwd: fork to the side stream failed");
+            int rc = attn_tc128::launch_bwd_kv128(mq, mk, mv, md, mask, extra0, delta, gk, gv, B, S, H, scale, clamp, st);
+            if (rc != SPT_OK) return rc;
+            rc = attn_tc128::launch_bwd_q128(mq, mk, mv, md, mask, extra0, delta, gq, B, S, H, scale, clamp, ss->stream);
+            if (rc != SPT_OK) return rc;
+            if (cudaEventRecord(ss->join, ss->stream) != cudaSuccess || cudaStreamWaitEvent(st, ss->join, 0) != cudaSuccess)
+                return fail(SPT_ERR_CUDA, "sparse_attn_bwd: join of the side stream failed");
+            return SPT_OK;
+        }
+    }
     if (D == 64 && tile128()) {
         const int rc = attn_tc128::launch_bwd_kv128(mq, mk, mv, md, mask, extra0, delta, gk, gv, B, S, H, scale, clamp, st);
         if (rc != SPT_OK) return rc;

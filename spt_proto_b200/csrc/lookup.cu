@@ -847,7 +847,8 @@ lookup_maskonly_big_kernel(const int32_t *__restrict__ query_codes, const uint32
 __global__ void __launch_bounds__(LK_THREADS)
 lookup_generic_kernel(const int32_t *__restrict__ query_codes, const int32_t *__restrict__ key_codes,
                       const int *__restrict__ flag, int flag_expect, int32_t *__restrict__ out,
-                      uint32_t *__restrict__ mask_out, int32_t *__restrict__ extra0_out, int S, int m, int nnz, int H) {
+                      uint32_t *__restrict__ mask_out, int32_t *__restrict__ extra0_out, int S, int m, int nnz, int H,
+                      int tiles, int nb) {
     if (flag && (*flag != 0) != (flag_expect != 0)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t *s_out = reinterpret_cast<uint16_t *>(smem_raw);
@@ -855,8 +856,11 @@ lookup_generic_kernel(const int32_t *__restrict__ query_codes, const int32_t *__
     const size_t bits_bytes = mask_out ? (size_t)LK_ROWS * (S / 32) * 4 : 0;
     uint32_t *s_bits = mask_out ? reinterpret_cast<uint32_t *>(smem_raw + img_bytes) : nullptr;
     uint16_t *s_q = reinterpret_cast<uint16_t *>(smem_raw + img_bytes + bits_bytes);
-    const int b = blockIdx.y;
-    const int tile = gridDim.x - 1 - blockIdx.x;
+    // items = (head, row tile), the block strides over them: as the flag-guarded fallback behind the bitmap kernels it is
+    // launched with a few hundred blocks (an early exit of one block per item cost 6 us per lookup at 128 heads)
+    for (int item = blockIdx.x; item < tiles * nb; item += gridDim.x) {
+    const int b = item / tiles;
+    const int tile = tiles - 1 - item % tiles;
     const int r0 = tile * LK_ROWS;
     const int rl = threadIdx.x >> 2, t = threadIdx.x & 3;
     const int r = r0 + rl;
@@ -904,6 +908,8 @@ lookup_generic_kernel(const int32_t *__restrict__ query_codes, const int32_t *__
     __syncthreads();
     flush_rows(s_out, out, b, r0, S, nnz);
     if (s_bits) flush_mask(s_bits, mask_out, b, r0, S);
+    __syncthreads();
+    }
 }
 
 static bool bitmap_m_supported(int m) { return m == 4 || m == 8 || m == 10 || m == 12 || m == 16 || m == 32; }
@@ -934,7 +940,8 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
     SPT_REQUIRE(!mask_out || (S % 128 == 0 && extra0_out), "lookup_fwd: bitmask output needs S %% 128 == 0 and extra0");
     cudaStream_t st = as_stream(stream);
     const int tiles = (S + LK_ROWS - 1) / LK_ROWS;
-    dim3 grid(tiles, B);
+    const unsigned grid = (unsigned)tiles * B;                                            // one block per (head, row tile)
+    const unsigned fb_grid = grid < 2u * num_sms() ? grid : 2u * num_sms();               // the flag-guarded fallback
     const size_t img = out_image_bytes(nnz) + (mask_out ? (size_t)LK_ROWS * (S / 32) * 4 : 0);
     const size_t gen_smem = img + (size_t)LK_ROWS * m * 2;
     SPT_REQUIRE(gen_smem <= 200 * 1024, "lookup_fwd: nnz=%d / S=%d too large for the shared-memory row images", nnz, S);
@@ -943,7 +950,7 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
 
     if (!bitmap_m_supported(m)) {
         lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, nullptr, 0, output, mask_out,
-                                                                  extra0_out, S, m, nnz, H);
+                                                                  extra0_out, S, m, nnz, H, tiles, B);
         SPT_LAUNCH_CHECK("lookup_generic_kernel");
         return SPT_OK;
     }
@@ -982,8 +989,8 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
             lookup_maskonly2_kernel<16><<<mgrid, LKM_THREADS, msmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H);
         }
         SPT_LAUNCH_CHECK("lookup_maskonly_kernel");
-        lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, mask_out,
-                                                                  extra0_out, S, m, nnz, H);
+        lookup_generic_kernel<<<fb_grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, mask_out,
+                                                                  extra0_out, S, m, nnz, H, tiles, B);
         SPT_LAUNCH_CHECK("lookup_generic_kernel(fallback)");
         return SPT_OK;
     }
@@ -999,8 +1006,8 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
             lookup_maskonly_big_kernel<16><<<mgrid, LKM_THREADS, bsmem, st>>>(query_codes, kb, flag, mask_out, extra0_out, S, nnz, W, H);
         }
         SPT_LAUNCH_CHECK("lookup_maskonly_big_kernel");
-        lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, mask_out,
-                                                                  extra0_out, S, m, nnz, H);
+        lookup_generic_kernel<<<fb_grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, mask_out,
+                                                                  extra0_out, S, m, nnz, H, tiles, B);
         SPT_LAUNCH_CHECK("lookup_generic_kernel(fallback)");
         return SPT_OK;
     }
@@ -1023,8 +1030,8 @@ static int lookup_impl(const int32_t *query_codes, const int32_t *key_codes, int
     }
 #undef SPT_LK_CASE
     SPT_LAUNCH_CHECK("lookup_bitmap_kernel");
-    lookup_generic_kernel<<<grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, mask_out,
-                                                              extra0_out, S, m, nnz, H);
+    lookup_generic_kernel<<<fb_grid, LK_THREADS, gen_smem, st>>>(query_codes, key_codes, flag, 1, output, mask_out,
+                                                              extra0_out, S, m, nnz, H, tiles, B);
     SPT_LAUNCH_CHECK("lookup_generic_kernel(fallback)");
     return SPT_OK;
 }
