@@ -176,19 +176,34 @@ spmm_t_dense_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restri
     int cur = s_cp[cl];
     const int e_end = my_strip >= 0 ? cur : s_cp[cl + 1];          // strip columns have nothing to walk
     int wbase = cur & ~15;
-    int rw[4], ps[4];
-    auto fetch = [&]() {
-        const int q0 = wbase + 4 * sub;
+    // Two windows in flight (the first version fetched a window and gathered its values only when a chunk asked for them:
+    // two dependent DRAM latencies per pass, which made a block's duration the critical path — 0.42 ms for 32 heads):
+    // the CURRENT window holds rows + the gathered VALUES, the NEXT one rows + positions.  Advancing turns the next window
+    // into the current one (its value gathers go out, their addresses are there already) and fetches a new next window;
+    // all of it completes under the MMAs of the chunks in between.
+    int rw[4], rwn[4], psn[4];
+    float wv[4];
+    auto load_idx = [&](int base, int (&r)[4], int (&p)[4]) {
+        const int q0 = base + 4 * sub;
         if (q0 < e_end && (int64_t)q0 + 4 <= nnz) {
             const int4 r4 = __ldg(reinterpret_cast<const int4 *>(ip + q0)), p4 = __ldg(reinterpret_cast<const int4 *>(pm + q0));
-            rw[0] = r4.x; rw[1] = r4.y; rw[2] = r4.z; rw[3] = r4.w;
-            ps[0] = p4.x; ps[1] = p4.y; ps[2] = p4.z; ps[3] = p4.w;
+            r[0] = r4.x; r[1] = r4.y; r[2] = r4.z; r[3] = r4.w;
+            p[0] = p4.x; p[1] = p4.y; p[2] = p4.z; p[3] = p4.w;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if (q0 + i >= e_end) rw[i] = INT_MAX;                  // beyond the list: never consumed
+            if (q0 + i >= e_end) {                                 // beyond the list: never consumed
+                r[i] = INT_MAX;
+                p[i] = 0;
+            }
     };
-    fetch();
+    auto gather = [&](const int (&r)[4], const int (&p)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wv[i] = r[i] != INT_MAX ? vp[p[i]] : 0.0f;
+    };
+    load_idx(wbase, rw, psn);
+    gather(rw, psn);
+    load_idx(wbase + 16, rwn, psn);
 
     // MMA roles: warp -> 16 columns (mt) x half of the features (nh)
     const int g = lane >> 2, t = lane & 3;
@@ -232,10 +247,7 @@ spmm_t_dense_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restri
             const uint32_t full = (__ballot_sync(0xffffffffu, mine == 4) >> quad_shift) & 15u;
             const int lead = __ffs(~full & 15u | 16u) - 1;            // lanes 0 .. lead - 1 of the quad are all-in
             const int take = sub <= lead ? mine : 0;
-            float v[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (i < take && q0 + i >= cur) v[i] = vp[ps[i]];
+            float v[4] = {wv[0], wv[1], wv[2], wv[3]};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (i < take && q0 + i >= cur) {
@@ -253,7 +265,10 @@ spmm_t_dense_kernel(const int32_t *__restrict__ col_ptr, const int32_t *__restri
             cur = ncur;
             if (next_window) {
                 wbase += 16;
-                fetch();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rw[i] = rwn[i];
+                gather(rw, psn);
+                load_idx(wbase + 16, rwn, psn);
             }
             if (__ballot_sync(0xffffffffu, next_window) == 0) break;  // warp-uniform: every quad has reached its chunk's end
         }
