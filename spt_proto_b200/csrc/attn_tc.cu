@@ -790,14 +790,17 @@ struct SideStream {
     cudaEvent_t fork = nullptr, join = nullptr;
 };
 // one side stream + event pair per device, created on first use (never inside a capture: creation is not a stream operation)
-static SideStream *side_stream() {
+static std::mutex g_side_mu;   // held while a fork / launch / join sequence is enqueued: callers on different streams share the side stream
+static SideStream *side_stream(cudaStream_t caller) {   // g_side_mu held
     static SideStream table[64];
-    static std::mutex mu;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
     SideStream &s = table[dev];
     if (!s.stream) {
+        // never create streams / events while the caller's stream is being captured (an API call that is not a stream
+        // operation can invalidate a global-mode capture): that one call runs the two kernels back to back
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(caller, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return nullptr;
         if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
@@ -847,7 +850,8 @@ static int launch_bwd(const CUtensorMap &mq, const CUtensorMap &mk, const CUtens
         // The dK/dV and the dQ kernel are independent: the dQ kernel goes to a side stream (fork / join with events, which
         // a stream capture records as graph edges), so its CTAs start on each SM as that SM's dK/dV CTA retires instead of
         // after the whole grid has drained (both are one-CTA-per-SM persistent grids: they never share an SM).
-        SideStream *ss = side_stream();
+        std::lock_guard<std::mutex> lock(g_side_mu);
+        SideStream *ss = side_stream(st);
         if (ss) {
             if (cudaEventRecord(ss->fork, st) != cudaSuccess || cudaStreamWaitEvent(ss->stream, ss->fork, 0) != cudaSuccess)
                 return fail(SPT_ERR_CUDA, "sparse_attn_bwd: fork to the side stream failed");
