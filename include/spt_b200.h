@@ -143,6 +143,26 @@ int spt_spmm_t_fwd(const int32_t *col_ptr, const int32_t *row_idx, const int32_t
                    const float *values, const void *x, void *y, int B, int S, int d, int64_t nnz,
                    int dtype, int out_dtype, spt_stream_t stream);
 
+/* (5b) tile index of the pattern + the transposed product on it — the form the backward passes
+ * (reference kernels/spmm.py:42-47, kernels/sddmm.py:44-49: cuSPARSE TRANSPOSE) use for bf16 x with
+ * head dim 64 / 128.  Instead of a full CSR -> CSC transposition the index only buckets the entries
+ * by (64-column tile, 64-row chunk):
+ *   tile_ptr [B, n*n + 1] int32, n = ceil(S / 64): bucket (ct, rc) of head b = entries
+ *            tile_ptr[b][ct*n + rc] .. tile_ptr[b][ct*n + rc + 1] of tile_ent[b]
+ *   tile_ent [B, nnz] uint32: c_local | r_local << 6 | e << 12, e = position in the head's CSR
+ * (so a head holds at most 2^20 entries and S <= 8192: spt_csr_tiles_supported).  The SET of entries
+ * of a bucket is deterministic, their order inside it is not (shared-memory atomics).
+ * spt_spmm_t_tiles_fwd: y[b, c, :] = sum_{e : indices[b,e] = c} values[b, e] * x[b, row(e), :],
+ * x bf16 [B, S, d], d 64 / 128, y bf16 or fp32; fp32 weights enter the tensor cores as bf16 hi + lo
+ * (~16 bits), accumulation fp32; duplicates of one (row, column) cell add up in an unspecified order. */
+int spt_csr_tiles_supported(int S, int64_t nnz);
+int64_t spt_csr_tiles_ptr_len(int S);
+int spt_csr_tiles(const int32_t *indptr, const int32_t *indices, int32_t *tile_ptr, uint32_t *tile_ent,
+                  int B, int S, int64_t nnz, spt_stream_t stream);
+int spt_spmm_t_tiles_fwd(const int32_t *tile_ptr, const uint32_t *tile_ent, const float *values,
+                         const void *x, void *y, int B, int S, int d, int64_t nnz, int dtype,
+                         int out_dtype, spt_stream_t stream);
+
 /* (a-7) CSR -> CSC (implicit in the reference's transposed cuSPARSE calls, explicit in
  * legacy/csr2csc.cpp:3-54).  indptr [S+1] shared, indices [B, nnz] ->
  * col_ptr [B, S+1], row_idx [B, nnz], perm [B, nnz] (values_csc = values[perm]).

@@ -44,6 +44,10 @@ def _load() -> ctypes.CDLL:
         "spt_clamp_scale_bwd": (i32, [vp, vp, vp, i64, f32, f32, vp]),
         "spt_spmm_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, vp]),
         "spt_spmm_t_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, vp]),
+        "spt_csr_tiles_supported": (i32, [i32, i64]),
+        "spt_csr_tiles_ptr_len": (i64, [i32]),
+        "spt_csr_tiles": (i32, [vp, vp, vp, vp, i32, i32, i64, vp]),
+        "spt_spmm_t_tiles_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, vp]),
         "spt_csr2csc_workspace_bytes": (sz, [i32, i32, i64]),
         "spt_csr2csc": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp]),
         "spt_softmax_fwd": (i32, [vp, vp, vp, vp, i32, i32, i64, vp]),

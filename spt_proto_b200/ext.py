@@ -319,6 +319,48 @@ def spmm_csc(csc, values: torch.Tensor, x: torch.Tensor, out_dtype=None) -> torc
     return y
 
 
+def csr_tiles_supported(indices: torch.Tensor, x: torch.Tensor) -> bool:
+    """Can the transposed product A^T x run on the tile index (csr_tiles / spmm_tiles)?  bf16 x, head dim 64 / 128,
+    at most 2^20 entries per head, S <= 8192."""
+    return bool(x.dtype == torch.bfloat16 and x.dim() == 3 and x.size(-1) in (64, 128) and x.is_contiguous()
+                and lib.spt_csr_tiles_supported(x.size(1), indices.size(-1)))
+
+
+def csr_tiles(indptr: torch.Tensor, indices: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (tile_ptr [B, n*n + 1] int32, tile_ent [B, nnz] int32 bit patterns): the entries of every head bucketed by
+    (64-column tile, 64-row chunk) — what the transposed product needs of a CSC, at a fraction of its cost."""
+    S = indptr.size(-1) - 1
+    _check_csr(indptr, indices, S)
+    B, nnz = indices.shape
+    if not lib.spt_csr_tiles_supported(S, nnz):
+        raise RuntimeError(f"csr_tiles: S={S} / nnz={nnz} beyond the tile index format (S <= 8192, nnz <= 2^20 per head)")
+    tile_ptr = torch.empty((B, lib.spt_csr_tiles_ptr_len(S)), dtype=torch.int32, device=indices.device)
+    tile_ent = torch.empty((B, nnz), dtype=torch.int32, device=indices.device)
+    with _on_device(indices):
+        check(lib.spt_csr_tiles(_p(indptr), _p(indices), _p(tile_ptr), _p(tile_ent), B, S, nnz, _stream(indices)))
+    return tile_ptr, tile_ent
+
+
+def spmm_tiles(tiles, values: torch.Tensor, x: torch.Tensor, out_dtype=None) -> torch.Tensor:
+    """y = A^T x on a tile index from csr_tiles(); values stay in CSR order."""
+    tile_ptr, tile_ent = tiles
+    _check_dim(x, 3, "x")
+    _check_dim(values, 2, "values")
+    _check_type(values, torch.float32, "values")
+    B, S, d = x.shape
+    nnz = values.size(-1)
+    if tile_ent.shape != values.shape or tile_ptr.size(0) != B:
+        raise RuntimeError("spmm_tiles: tile index / values / x shape mismatch")
+    code = _float_code(x, "x")
+    if out_dtype is None:
+        out_dtype = x.dtype
+    y = torch.empty((B, S, d), dtype=out_dtype, device=x.device)
+    with _on_device(x):
+        check(lib.spt_spmm_t_tiles_fwd(_p(tile_ptr), _p(tile_ent), _p(values), _p(x), _p(y), B, S, d, nnz, code,
+                                       _DTYPES[out_dtype], _stream(x)))
+    return y
+
+
 def spmm_forward_cuda(trans_lhs, trans_rhs, indptr, indices, values, x) -> torch.Tensor:
     """y = op(A) x, A = batched CSR with shared indptr (extension/spmm.cpp:3-72).  trans_lhs=True is
     the transposed product of the backward passes; it builds the CSC on the fly (callers that need

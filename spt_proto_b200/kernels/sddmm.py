@@ -5,7 +5,7 @@ backward: dQ = spmm(dvalues, K);  dK = spmm^T(dvalues, Q) through the cached CSC
 from torch import autograd
 
 from .. import ext
-from ._csc import get_csc
+from ._csc import transposed_product
 
 
 class SDDMM(autograd.Function):
@@ -22,7 +22,7 @@ class SDDMM(autograd.Function):
         if ctx.needs_input_grad[2]:
             grad_query = ext.spmm_forward_cuda(False, False, indptr, indices, grad_output, key)
         if ctx.needs_input_grad[3]:
-            grad_key = ext.spmm_csc(get_csc(indptr, indices), grad_output, query)
+            grad_key = transposed_product(indptr, indices, grad_output, query)
         return None, None, grad_query, grad_key
 
 
@@ -50,7 +50,7 @@ class SDDMMScaled(autograd.Function):
         if ctx.needs_input_grad[2]:
             grad_query = ext.spmm_forward_cuda(False, False, indptr, indices, grad_raw, key)
         if ctx.needs_input_grad[3]:
-            grad_key = ext.spmm_csc(get_csc(indptr, indices), grad_raw, query)
+            grad_key = transposed_product(indptr, indices, grad_raw, query)
         return None, None, grad_query, grad_key, None, None
 
 

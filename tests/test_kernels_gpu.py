@@ -534,3 +534,63 @@ def test_spmm_t_dense_tiles_unsorted_lists_fall_back():
             pm[b, e0:e1] = pm[b, e0:e1].flip(0)
     got = _ext().spmm_csc((cp.to(DEV), ri.to(DEV), pm.to(DEV)), vals.to(DEV), x.to(DEV), out_dtype=torch.float32)
     assert torch.allclose(got.double().cpu(), want, atol=2e-3, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------- tile index + product on it
+@pytest.mark.parametrize("B,S,k,d,pad_rows,hot_cols", [(2, 2048, 256, 64, 256, 0), (2, 512, 64, 128, 64, 0), (1, 4096, 32, 64, 32, 3),
+                                                       (3, 200, 24, 64, 30, 0), (2, 64, 8, 64, 4, 0)])
+def test_csr_tiles_and_product(B, S, k, d, pad_rows, hot_cols):
+    """The tile index buckets every entry by (64-column tile, 64-row chunk): bucket sizes and bucket CONTENTS (as sets:
+    the order inside a bucket is that of shared-memory atomics) are checked against a numpy restatement, the transposed
+    product on it against the fp64 dense product (same cases as the CSC kernel: padding column, hot columns, ragged S)."""
+    import numpy as np
+    g = torch.Generator().manual_seed(S * 3 + k + d)
+    indptr, indices = _random_csr(B, S, k, causal=True, gen=g)
+    idx = indices.view(B, S, k)
+    for r in range(min(pad_rows, k - 1)):
+        idx[:, r, r + 1:] = 0
+    for c in range(hot_cols):
+        idx[:, :, c] = 7 * c + 1
+    vals = torch.randn(B, S * k, generator=g)
+    x = torch.randn(B, S, d, generator=g).bfloat16()
+    tile_ptr, tile_ent = _ext().csr_tiles(indptr.to(DEV), indices.to(DEV))
+    n = (S + 63) // 64
+    tp, te = tile_ptr.cpu().numpy(), tile_ent.cpu().numpy().view(np.uint32)
+    cols = indices.numpy().astype(np.int64)
+    rows = np.repeat(np.arange(S, dtype=np.int64), k)[None, :].repeat(B, 0)
+    pos = np.arange(S * k, dtype=np.int64)
+    for b in range(B):
+        assert tp[b, 0] == 0 and tp[b, -1] == S * k
+        bucket = (cols[b] // 64) * n + rows[b] // 64
+        want_counts = np.bincount(bucket, minlength=n * n)
+        assert np.array_equal(np.diff(tp[b]), want_counts)
+        want_words = (cols[b] % 64) | ((rows[b] % 64) << 6) | (pos << 12)
+        order = np.argsort(bucket, kind="stable")
+        got_sorted = np.concatenate([np.sort(te[b, tp[b, i]:tp[b, i + 1]].astype(np.int64)) for i in range(n * n)])
+        want_sorted = np.concatenate([np.sort(want_words[order][tp[b, i]:tp[b, i + 1]]) for i in range(n * n)])
+        assert np.array_equal(got_sorted, want_sorted)
+    want = _spmm_t_want(indptr, indices, vals, x.float())
+    for out_dtype in (torch.float32, torch.bfloat16):
+        got = _ext().spmm_tiles((tile_ptr, tile_ent), vals.to(DEV), x.to(DEV), out_dtype=out_dtype)
+        err = (got.double().cpu() - want).norm() / want.norm()
+        assert err < (2e-5 if out_dtype == torch.float32 else 4e-3), err
+        tol = dict(atol=2e-3, rtol=1e-4) if out_dtype == torch.float32 else dict(atol=2e-2 * want.abs().max().item(), rtol=2e-2)
+        assert torch.allclose(got.double().cpu(), want, **tol)
+
+
+def test_csr_tiles_ragged_rows_and_limits():
+    """General CSR (ragged indptr, empty rows, duplicated columns) through the tile index; sizes beyond the 32-bit entry
+    format are refused."""
+    indptr = torch.tensor([0, 0, 3, 4, 9, 9, 12], dtype=torch.int32)
+    indices = torch.tensor([[0, 0, 1, 2, 0, 0, 0, 3, 3, 5, 5, 4],
+                            [1, 1, 1, 0, 3, 2, 1, 0, 0, 4, 5, 5]], dtype=torch.int32)
+    g = torch.Generator().manual_seed(0)
+    vals = torch.randn(2, 12, generator=g)
+    x = torch.randn(2, 6, 64, generator=g).bfloat16()
+    want = O.spmm_forward(True, indptr, indices, vals, x.float())
+    tiles = _ext().csr_tiles(indptr.to(DEV), indices.to(DEV))
+    got = _ext().spmm_tiles(tiles, vals.to(DEV), x.to(DEV), out_dtype=torch.float32)
+    assert torch.allclose(got.cpu(), want, atol=1e-3)
+    big = torch.zeros(1, (1 << 20) + 4, dtype=torch.int32, device=DEV)
+    with pytest.raises(RuntimeError):
+        _ext().csr_tiles(torch.tensor([0, (1 << 20) + 4], dtype=torch.int32, device=DEV), big)
