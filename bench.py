@@ -146,7 +146,7 @@ def base_config(n_seq: int, world: int, fused: bool = True) -> dict:
             "l2": "inputs+intermediates per step exceed L2 (>1 GB vs 126 MB); no explicit flush",
             "path": ("fused: pq_encode(q,k) -> lookup(bitmask) -> masked-dense-tile attention fwd/bwd "
                      "(tcgen05 + TMEM + TMA, bf16)" if fused else
-                     "stage kernels (pq_encode, lookup, sddmm, softmax, spmm, csr2csc, spmm_t)"),
+                     "stage kernels (pq_encode, lookup, sddmm, softmax, spmm, tile index, transposed spmm)"),
             "pq_train": "off (fwd+bwd of the layer as configs[1] words it; the one-shot PQ loss the reference's "
                         "training loop arms per step is part of the finetune_step section)",
             "output_layout": "reference (the shipped layer's [N*H, E, S] memory viewed as [N, S, H, E])",
@@ -221,8 +221,10 @@ STAGE_BOUND = {
     "softmax_fwd": "hbm",
     "softmax_bwd": "hbm",
     "csr2csc": "shared-memory bit-matrix build + scan per 64-row tile (one CTA of 1024 threads per SM); index read + write",
+    "csr_tiles": "two passes over the indices (count, place) with shared-memory histograms over the column tiles",
+    "spmm_t_tiles": "LSU data pipe: one value gather per entry + tile scatter / fragment loads; latency of the first column tile's long buckets",
 }
-STAGE_PATH = ["pq_encode", "lookup", "sddmm", "softmax_fwd", "spmm", "softmax_bwd", "csr2csc", "spmm_t"]
+STAGE_PATH = ["pq_encode", "lookup", "sddmm", "softmax_fwd", "spmm", "softmax_bwd", "csr_tiles", "spmm_t_tiles"]
 
 
 def stage_roofline(n_seq: int, dev, hbm_gbs: float, tensor_tflops: float):
@@ -244,6 +246,7 @@ def stage_roofline(n_seq: int, dev, hbm_gbs: float, tensor_tflops: float):
     sc = torch.clamp(vals * d ** -0.5, -10, 10)
     p = ext.softmax_forward_cuda(indptr, idx, sc)
     csc = ext.csr2csc(indptr, idx)
+    tiles = ext.csr_tiles(indptr, idx)
     dy = torch.randn(B, S, d, generator=g).to(dev, torch.bfloat16)
     Sd, Sk = S * d * e, S * k * 4
     stages = {
@@ -256,6 +259,10 @@ def stage_roofline(n_seq: int, dev, hbm_gbs: float, tensor_tflops: float):
         "softmax_bwd": (lambda: ext.softmax_backward_cuda(indptr, idx, p, sc), 4 * Sk),
         "csr2csc": (lambda: ext.csr2csc(indptr, idx), 4 * Sk + S * 4),
         "spmm_t": (lambda: ext.spmm_csc(csc, p, dy), 3 * Sk + 2 * Sd),
+        # what the bf16 stage path runs instead of the two rows above: the tile index (indices read, one word per entry
+        # written) and the transposed product on it (entry word + value per entry, x read, y written)
+        "csr_tiles": (lambda: ext.csr_tiles(indptr, idx), 2 * Sk + S * 4),
+        "spmm_t_tiles": (lambda: ext.spmm_tiles(tiles, p, dy), 2 * Sk + 2 * Sd),
     }
     mask, extra0, _ = ext.lookup_mask(qc, kc, COEFF)
     y_f, z_f = ext.sparse_attn_fwd(q, kk, v, mask, extra0, d ** -0.5)

@@ -114,17 +114,23 @@ tiles_place_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
     const uint32_t lt = (1u << lane) - 1;
     for (int r = rc * DT + warp; r < min(S, rc * DT + DT); r += THREADS / 32) {
         const int e0 = indptr[r], e1 = indptr[r + 1];
-        for (int base = e0; base < e1; base += 32) {                  // warp-uniform trip count
-            const int e = base + lane;
-            const int c = e < e1 ? ix[e] : -1;
-            const bool ok = (unsigned)c < (unsigned)S;
-            const int key = ok ? (c >> 6) : (MAX_CT + lane);           // lanes without an entry: a group of their own
-            const uint32_t peers = __match_any_sync(0xffffffffu, key);
-            const int leader = __ffs(peers) - 1;
-            int slot = 0;
-            if (ok && lane == leader) slot = atomicAdd(&cursor[key], __popc(peers));
-            slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(peers & lt);
-            if (ok) out[slot] = (uint32_t)(c & 63) | ((uint32_t)(r - rc * DT) << 6) | ((uint32_t)e << 12);
+        for (int base = e0; base < e1; base += 4 * 32) {              // warp-uniform trip count; four index loads in flight
+            int cs[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cs[j] = base + j * 32 + lane < e1 ? ix[base + j * 32 + lane] : -1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (base + j * 32 >= e1) break;
+                const int e = base + j * 32 + lane, c = cs[j];
+                const bool ok = (unsigned)c < (unsigned)S;
+                const int key = ok ? (c >> 6) : (MAX_CT + lane);       // lanes without an entry: a group of their own
+                const uint32_t peers = __match_any_sync(0xffffffffu, key);
+                const int leader = __ffs(peers) - 1;
+                int slot = 0;
+                if (ok && lane == leader) slot = atomicAdd(&cursor[key], __popc(peers));
+                slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(peers & lt);
+                if (ok) out[slot] = (uint32_t)(c & 63) | ((uint32_t)(r - rc * DT) << 6) | ((uint32_t)e << 12);
+            }
         }
     }
 }
