@@ -369,6 +369,8 @@ def spmm_forward_cuda(trans_lhs, trans_rhs, indptr, indices, values, x) -> torch
         raise RuntimeError("spmm_forward_cuda: trans_rhs=True is not supported")
     B, S, d, nnz, code = _check_spmm(indptr, indices, values, x)
     if _flag(trans_lhs):
+        if csr_tiles_supported(indices, x):      # bf16, head dim 64 / 128: tile index instead of a CSC
+            return spmm_tiles(csr_tiles(indptr, indices), values, x, out_dtype=x.dtype)
         return spmm_csc(csr2csc(indptr, indices), values, x, out_dtype=x.dtype)
     y = torch.empty_like(x)
     with _on_device(x):

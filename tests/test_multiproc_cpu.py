@@ -56,8 +56,12 @@ def _worker(rank, world, port, ret):
         xs = torch.full((2, 8), float(rank + 1 + step))
         reducer.zero_grad()
         h = net[1](net[0](xs)) * extra.float()
-        (net[2](h.float()).sum() * (rank + 1)).backward()
-        local = {id(p): p.grad.clone() for p in trainable}
+        loss = net[2](h.float()).sum() * (rank + 1)
+        # this rank's own gradients, taken WITHOUT accumulation (no hooks fire): once backward() runs, the hooks reduce
+        # the flat buffer in place and asynchronously, so p.grad must not be read between backward() and finish()
+        own = torch.autograd.grad(loss, trainable, allow_unused=True, retain_graph=True)
+        local = {id(p): (torch.zeros_like(p) if g is None else g.clone()) for p, g in zip(trainable, own)}
+        loss.backward()
         n_coll = reducer.finish()
         ok_reducer &= n_coll == reducer.n_buckets
         for p in trainable:
