@@ -162,6 +162,11 @@ int spt_csr_tiles(const int32_t *indptr, const int32_t *indices, int32_t *tile_p
 int spt_spmm_t_tiles_fwd(const int32_t *tile_ptr, const uint32_t *tile_ent, const float *values,
                          const void *x, void *y, int B, int S, int d, int64_t nnz, int dtype,
                          int out_dtype, spt_stream_t stream);
+/* both directions on the same index: trans = 0 is y[b, r, :] = sum_{e in row r} values[b, e] *
+ * x[b, indices[b, e], :] (the spt_spmm_fwd product), trans = 1 the one above */
+int spt_spmm_tiles_fwd(const int32_t *tile_ptr, const uint32_t *tile_ent, const float *values,
+                       const void *x, void *y, int B, int S, int d, int64_t nnz, int dtype,
+                       int out_dtype, int trans, spt_stream_t stream);
 
 /* (a-7) CSR -> CSC (implicit in the reference's transposed cuSPARSE calls, explicit in
  * legacy/csr2csc.cpp:3-54).  indptr [S+1] shared, indices [B, nnz] ->

@@ -24,6 +24,8 @@ def ev(fn, n=5):
 csc = ext.csr2csc(indptr, idx)
 tiles = ext.csr_tiles(indptr, idx)
 print("B", B, "csr2csc ms %.3f" % ev(lambda: ext.csr2csc(indptr, idx)), "csr_tiles ms %.3f" % ev(lambda: ext.csr_tiles(indptr, idx)),
-      "spmm_csc ms %.3f" % ev(lambda: ext.spmm_csc(csc, p, q)), "spmm_tiles ms %.3f" % ev(lambda: ext.spmm_tiles(tiles, p, q)))
+      "spmm_csc ms %.3f" % ev(lambda: ext.spmm_csc(csc, p, q)), "spmm_tiles ms %.3f" % ev(lambda: ext.spmm_tiles(tiles, p, q)),
+      "| direct: gathered ms %.3f" % ev(lambda: ext.spmm_forward_cuda(False, False, indptr, idx, p, q)),
+      "tiles ms %.3f" % ev(lambda: ext.spmm_tiles(tiles, p, q, trans=False)))
 a, b = ext.spmm_csc(csc, p, q, out_dtype=torch.float32), ext.spmm_tiles(tiles, p, q, out_dtype=torch.float32)
 print("max |csc - tiles| %.3e  rel %.3e" % ((a - b).abs().max().item(), ((a - b).norm() / a.norm()).item()))

@@ -163,6 +163,7 @@ template <>
 __device__ __forceinline__ void store2<bf16>(bf16 *p, float a, float b) { *reinterpret_cast<__nv_bfloat162 *>(p) = __floats2bfloat162_rn(a, b); }
 
 // one warp-wide batch of 32 consecutive bucket entries -> the tile.  cell = c_local | r_local << 6 (or -1: no entry).
+template <bool TRANS>
 __device__ __forceinline__ void scatter_batch(float *P, int cell, float v, int lane) {
     const int prev = __shfl_up_sync(0xffffffffu, cell, 1), next = __shfl_down_sync(0xffffffffu, cell, 1);
     const bool head = lane == 0 || prev != cell;
@@ -177,21 +178,27 @@ __device__ __forceinline__ void scatter_batch(float *P, int cell, float v, int l
         }
         if (lane != 31 && next == cell) cell = -1;                   // only the last lane of a run adds
     }
-    if (cell >= 0) atomicAdd(P + (cell & 63) * PS + (cell >> 6), v);
+    // tile row = the owner's index (column for the transposed product, row for the direct one), tile column = contraction
+    if (cell >= 0) atomicAdd(P + (TRANS ? (cell & 63) * PS + (cell >> 6) : (cell >> 6) * PS + (cell & 63)), v);
 }
 
-template <int D, typename TO>
+// TRANS: y[c] = sum_r A[r, c] x[r] (owner = column tile, walks row chunks); !TRANS: y[r] = sum_c A[r, c] x[c] (owner = row
+// tile, walks column chunks).  Same index, same buckets: only the walk and the orientation of the tile differ.
+template <int D, typename TO, bool TRANS>
 __global__ void __launch_bounds__(THREADS, 4)
-spmm_t_tiles_kernel(const int32_t *__restrict__ tile_ptr, const uint32_t *__restrict__ tile_ent, const float *__restrict__ values,
-                    const bf16 *__restrict__ x, TO *__restrict__ y, int B, int S, int64_t nnz, int n_ct, int n_rc) {
+spmm_tiles_kernel(const int32_t *__restrict__ tile_ptr, const uint32_t *__restrict__ tile_ent, const float *__restrict__ values,
+                  const bf16 *__restrict__ x, TO *__restrict__ y, int B, int S, int64_t nnz, int n_ct, int n_rc) {
     constexpr int XS = (D + 8) * 2;            // bytes per staged x row
     constexpr int NT = D / 16;
     extern __shared__ __align__(16) unsigned char smem[];
     float *P0 = reinterpret_cast<float *>(smem);                                   // [2][64 columns][PS]
     unsigned char *X0 = smem + 2 * DT * PS * 4;                                    // [2][64 rows][XS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x % B, ct = blockIdx.x / B;             // column tile 0 (every chunk non-empty) of every head first
-    const int32_t *tp = tile_ptr + (size_t)b * (n_ct * n_rc + 1) + (size_t)ct * n_rc;
+    // the heaviest owner of every head first: under a causal pattern column tile 0 / the last row tile touch every chunk
+    const int b = blockIdx.x % B, ct = TRANS ? blockIdx.x / B : n_rc - 1 - blockIdx.x / B;       // ct = the owner's tile index
+    const int32_t *tp = tile_ptr + (size_t)b * (n_ct * n_rc + 1) + (TRANS ? (size_t)ct * n_rc : (size_t)ct);
+    constexpr int one = 1;
+    const int tstep = TRANS ? one : n_rc;                          // bucket (owner, other) -> tp[other * tstep]
     const uint32_t *ent = tile_ent + (size_t)b * nnz;
     const float *vp = values + (size_t)b * nnz;
     const bf16 *xb = x + (size_t)b * S * D;
@@ -220,13 +227,13 @@ spmm_t_tiles_kernel(const int32_t *__restrict__ tile_ptr, const uint32_t *__rest
     };
     // next non-empty bucket at or after rc
     auto next_chunk = [&](int rc) {
-        while (rc < n_rc && tp[rc + 1] == tp[rc]) ++rc;
+        while (rc < n_rc && tp[(size_t)rc * tstep + 1] == tp[(size_t)rc * tstep]) ++rc;
         return rc;
     };
     int cell_n[PRE];
     float val_n[PRE];
     auto prefetch = [&](int rc) {                                     // the first PRE * THREADS entries of bucket rc
-        const int p0 = tp[rc], p1 = tp[rc + 1];
+        const int p0 = tp[(size_t)rc * tstep], p1 = tp[(size_t)rc * tstep + 1];
 #pragma unroll
         for (int j = 0; j < PRE; ++j) {
             const int q = p0 + j * THREADS + tid;
@@ -248,10 +255,10 @@ spmm_t_tiles_kernel(const int32_t *__restrict__ tile_ptr, const uint32_t *__rest
         float *P = P0 + buf * DT * PS;
         // (A) this bucket -> tile[buf]
         {
-            const int p0 = tp[rc], p1 = tp[rc + 1];
+            const int p0 = tp[(size_t)rc * tstep], p1 = tp[(size_t)rc * tstep + 1];
 #pragma unroll
             for (int j = 0; j < PRE; ++j)
-                if (p0 + j * THREADS + (tid & ~31) < p1) scatter_batch(P, cell_n[j], val_n[j], lane);      // warp-uniform
+                if (p0 + j * THREADS + (tid & ~31) < p1) scatter_batch<TRANS>(P, cell_n[j], val_n[j], lane);      // warp-uniform
             // long buckets (the padding column's early chunks hold 16 k entries): four independent entry -> value chains
             // per thread and trip (one chain at a time made the first column tile's block the critical path of the kernel)
             for (int q0 = p0 + PRE * THREADS + (tid & ~31); q0 < p1; q0 += 4 * THREADS) {
@@ -266,7 +273,7 @@ spmm_t_tiles_kernel(const int32_t *__restrict__ tile_ptr, const uint32_t *__rest
                 for (int j = 0; j < 4; ++j) v[j] = w[j] != 0xffffffffu ? vp[w[j] >> 12] : 0.0f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (q0 + j * THREADS < p1) scatter_batch(P, w[j] != 0xffffffffu ? (int)(w[j] & 0xfffu) : -1, v[j], lane);
+                    if (q0 + j * THREADS < p1) scatter_batch<TRANS>(P, w[j] != 0xffffffffu ? (int)(w[j] & 0xfffu) : -1, v[j], lane);
             }
         }
         const int rc_next = next_chunk(rc + 1);
@@ -311,15 +318,21 @@ spmm_t_tiles_kernel(const int32_t *__restrict__ tile_ptr, const uint32_t *__rest
     }
 }
 
-template <int D, typename TO>
-static int launch_d(const int32_t *tile_ptr, const uint32_t *tile_ent, const float *values, const bf16 *x, TO *y, int B, int S,
-                    int64_t nnz, cudaStream_t st) {
+template <int D, typename TO, bool TRANS>
+static int launch_dt(const int32_t *tile_ptr, const uint32_t *tile_ent, const float *values, const bf16 *x, TO *y, int B, int S,
+                     int64_t nnz, cudaStream_t st) {
     const int n_ct = (S + DT - 1) / DT, n_rc = n_ct;
     const size_t smem = 2 * (size_t)DT * PS * 4 + 2 * (size_t)DT * (D + 8) * 2;
-    cudaFuncSetAttribute(spmm_t_tiles_kernel<D, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    spmm_t_tiles_kernel<D, TO><<<(unsigned)((int64_t)B * n_ct), THREADS, smem, st>>>(tile_ptr, tile_ent, values, x, y, B, S, nnz,
-                                                                                   n_ct, n_rc);
-    return after_launch("spmm_t_tiles_kernel");
+    cudaFuncSetAttribute(spmm_tiles_kernel<D, TO, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    spmm_tiles_kernel<D, TO, TRANS><<<(unsigned)((int64_t)B * n_ct), THREADS, smem, st>>>(tile_ptr, tile_ent, values, x, y, B, S,
+                                                                                        nnz, n_ct, n_rc);
+    return after_launch("spmm_tiles_kernel");
+}
+template <int D, typename TO>
+static int launch_d(bool trans, const int32_t *tile_ptr, const uint32_t *tile_ent, const float *values, const bf16 *x, TO *y,
+                    int B, int S, int64_t nnz, cudaStream_t st) {
+    return trans ? launch_dt<D, TO, true>(tile_ptr, tile_ent, values, x, y, B, S, nnz, st)
+                 : launch_dt<D, TO, false>(tile_ptr, tile_ent, values, x, y, B, S, nnz, st);
 }
 
 }  // namespace csr_tiles
@@ -352,18 +365,24 @@ extern "C" int spt_csr_tiles(const int32_t *indptr, const int32_t *indices, int3
     return after_launch("tiles_place_kernel");
 }
 
-extern "C" int spt_spmm_t_tiles_fwd(const int32_t *tile_ptr, const uint32_t *tile_ent, const float *values, const void *x, void *y,
-                                    int B, int S, int d, int64_t nnz, int dtype, int out_dtype, spt_stream_t stream) {
-    SPT_REQUIRE(tile_ptr && tile_ent && values && x && y, "spmm_t_tiles_fwd: null pointer");
-    SPT_REQUIRE(B >= 1 && S >= 1 && nnz >= 0, "spmm_t_tiles_fwd: bad sizes B=%d S=%d nnz=%lld", B, S, (long long)nnz);
+extern "C" int spt_spmm_tiles_fwd(const int32_t *tile_ptr, const uint32_t *tile_ent, const float *values, const void *x, void *y,
+                                  int B, int S, int d, int64_t nnz, int dtype, int out_dtype, int trans, spt_stream_t stream) {
+    SPT_REQUIRE(tile_ptr && tile_ent && values && x && y, "spmm_tiles_fwd: null pointer");
+    SPT_REQUIRE(B >= 1 && S >= 1 && nnz >= 0, "spmm_tiles_fwd: bad sizes B=%d S=%d nnz=%lld", B, S, (long long)nnz);
     if (dtype != SPT_BF16 || (d != 64 && d != 128) || !spt_csr_tiles_supported(S, nnz) || (out_dtype != SPT_BF16 && out_dtype != SPT_F32))
-        return fail(SPT_ERR_UNSUPPORTED, "spmm_t_tiles_fwd: bf16 x with head dim 64 / 128 only (dtype %d, d %d)", dtype, d);
-    SPT_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)y % 8 == 0, "spmm_t_tiles_fwd: x must be 16-byte, y 8-byte aligned");
+        return fail(SPT_ERR_UNSUPPORTED, "spmm_tiles_fwd: bf16 x with head dim 64 / 128 only (dtype %d, d %d)", dtype, d);
+    SPT_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)y % 8 == 0, "spmm_tiles_fwd: x must be 16-byte, y 8-byte aligned");
     using bf = __nv_bfloat16;
     cudaStream_t st = as_stream(stream);
+    const bool t = trans != 0;
     if (d == 64)
-        return out_dtype == SPT_BF16 ? csr_tiles::launch_d<64, bf>(tile_ptr, tile_ent, values, (const bf *)x, (bf *)y, B, S, nnz, st)
-                                     : csr_tiles::launch_d<64, float>(tile_ptr, tile_ent, values, (const bf *)x, (float *)y, B, S, nnz, st);
-    return out_dtype == SPT_BF16 ? csr_tiles::launch_d<128, bf>(tile_ptr, tile_ent, values, (const bf *)x, (bf *)y, B, S, nnz, st)
-                                 : csr_tiles::launch_d<128, float>(tile_ptr, tile_ent, values, (const bf *)x, (float *)y, B, S, nnz, st);
+        return out_dtype == SPT_BF16 ? csr_tiles::launch_d<64, bf>(t, tile_ptr, tile_ent, values, (const bf *)x, (bf *)y, B, S, nnz, st)
+                                     : csr_tiles::launch_d<64, float>(t, tile_ptr, tile_ent, values, (const bf *)x, (float *)y, B, S, nnz, st);
+    return out_dtype == SPT_BF16 ? csr_tiles::launch_d<128, bf>(t, tile_ptr, tile_ent, values, (const bf *)x, (bf *)y, B, S, nnz, st)
+                                 : csr_tiles::launch_d<128, float>(t, tile_ptr, tile_ent, values, (const bf *)x, (float *)y, B, S, nnz, st);
+}
+
+extern "C" int spt_spmm_t_tiles_fwd(const int32_t *tile_ptr, const uint32_t *tile_ent, const float *values, const void *x, void *y,
+                                    int B, int S, int d, int64_t nnz, int dtype, int out_dtype, spt_stream_t stream) {
+    return spt_spmm_tiles_fwd(tile_ptr, tile_ent, values, x, y, B, S, d, nnz, dtype, out_dtype, 1, stream);
 }

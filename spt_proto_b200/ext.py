@@ -341,8 +341,8 @@ def csr_tiles(indptr: torch.Tensor, indices: torch.Tensor) -> Tuple[torch.Tensor
     return tile_ptr, tile_ent
 
 
-def spmm_tiles(tiles, values: torch.Tensor, x: torch.Tensor, out_dtype=None) -> torch.Tensor:
-    """y = A^T x on a tile index from csr_tiles(); values stay in CSR order."""
+def spmm_tiles(tiles, values: torch.Tensor, x: torch.Tensor, out_dtype=None, trans: bool = True) -> torch.Tensor:
+    """y = A^T x (trans, the default) or y = A x on a tile index from csr_tiles(); values stay in CSR order."""
     tile_ptr, tile_ent = tiles
     _check_dim(x, 3, "x")
     _check_dim(values, 2, "values")
@@ -356,8 +356,8 @@ def spmm_tiles(tiles, values: torch.Tensor, x: torch.Tensor, out_dtype=None) -> 
         out_dtype = x.dtype
     y = torch.empty((B, S, d), dtype=out_dtype, device=x.device)
     with _on_device(x):
-        check(lib.spt_spmm_t_tiles_fwd(_p(tile_ptr), _p(tile_ent), _p(values), _p(x), _p(y), B, S, d, nnz, code,
-                                       _DTYPES[out_dtype], _stream(x)))
+        check(lib.spt_spmm_tiles_fwd(_p(tile_ptr), _p(tile_ent), _p(values), _p(x), _p(y), B, S, d, nnz, code,
+                                     _DTYPES[out_dtype], 1 if trans else 0, _stream(x)))
     return y
 
 

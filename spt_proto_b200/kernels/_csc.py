@@ -7,8 +7,11 @@ import torch
 
 from .. import ext
 
+import os
+
 _CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 _MAX = 4
+_TILES_DIRECT = os.environ.get("SPT_SPMM_TILES_DIRECT", "1") != "0"    # A/B switch: the CSR-direction product on the tile index
 
 
 def get_csc(indptr: torch.Tensor, indices: torch.Tensor):
@@ -25,25 +28,37 @@ def get_csc(indptr: torch.Tensor, indices: torch.Tensor):
     return csc
 
 
+def get_tiles(indptr: torch.Tensor, indices: torch.Tensor):
+    """The cached tile index of the pattern (entries bucketed by 64-column tile and 64-row chunk: 0.2 ms to build at the
+    bench shape against 1.13 ms for the CSC); one index serves both directions of the product."""
+    key = ("tiles", indptr.data_ptr(), indices.data_ptr(), indices._version, tuple(indices.shape),
+           indices.device.index, torch.cuda.current_stream(indices.device).cuda_stream)
+    hit = _CACHE.get(key)
+    if hit is not None and hit[0] is indices:
+        _CACHE.move_to_end(key)
+        return hit[1]
+    tiles = ext.csr_tiles(indptr, indices)
+    _CACHE[key] = (indices, tiles)
+    while len(_CACHE) > _MAX:
+        _CACHE.popitem(last=False)
+    return tiles
+
+
 def transposed_product(indptr: torch.Tensor, indices: torch.Tensor, values: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """y = A^T x for the backward passes.  bf16 x with head dim 64 / 128 runs on the cached TILE INDEX (entries bucketed
-    by 64-column tile and 64-row chunk: 0.25 ms to build at the bench shape against 1.15 ms for the CSC); everything else
-    goes through the cached CSC."""
+    """y = A^T x for the backward passes.  bf16 x with head dim 64 / 128 runs on the tile index; everything else goes
+    through the cached CSC."""
     x = x.contiguous()
     if ext.csr_tiles_supported(indices, x):
-        key = ("tiles", indptr.data_ptr(), indices.data_ptr(), indices._version, tuple(indices.shape),
-               indices.device.index, torch.cuda.current_stream(indices.device).cuda_stream)
-        hit = _CACHE.get(key)
-        if hit is not None and hit[0] is indices:
-            _CACHE.move_to_end(key)
-            tiles = hit[1]
-        else:
-            tiles = ext.csr_tiles(indptr, indices)
-            _CACHE[key] = (indices, tiles)
-            while len(_CACHE) > _MAX:
-                _CACHE.popitem(last=False)
-        return ext.spmm_tiles(tiles, values, x)
+        return ext.spmm_tiles(get_tiles(indptr, indices), values, x, trans=True)
     return ext.spmm_csc(get_csc(indptr, indices), values, x)
+
+
+def direct_product(indptr: torch.Tensor, indices: torch.Tensor, values: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """y = A x (forward of spmm, dQ of sddmm): on the tile index when it applies, else the gathered CSR kernel."""
+    x = x.contiguous()
+    if _TILES_DIRECT and ext.csr_tiles_supported(indices, x):
+        return ext.spmm_tiles(get_tiles(indptr, indices), values, x, trans=False)
+    return ext.spmm_forward_cuda(False, False, indptr, indices, values, x)
 
 
 def clear():

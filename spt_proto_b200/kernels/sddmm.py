@@ -5,7 +5,7 @@ backward: dQ = spmm(dvalues, K);  dK = spmm^T(dvalues, Q) through the cached CSC
 from torch import autograd
 
 from .. import ext
-from ._csc import transposed_product
+from ._csc import direct_product, transposed_product
 
 
 class SDDMM(autograd.Function):
@@ -20,7 +20,7 @@ class SDDMM(autograd.Function):
         grad_output = grad_output.contiguous()
         grad_query = grad_key = None
         if ctx.needs_input_grad[2]:
-            grad_query = ext.spmm_forward_cuda(False, False, indptr, indices, grad_output, key)
+            grad_query = direct_product(indptr, indices, grad_output, key)
         if ctx.needs_input_grad[3]:
             grad_key = transposed_product(indptr, indices, grad_output, query)
         return None, None, grad_query, grad_key
@@ -48,7 +48,7 @@ class SDDMMScaled(autograd.Function):
         grad_raw = ext.clamp_scale_bwd(grad_output.contiguous(), values, ctx.scale, ctx.clamp)
         grad_query = grad_key = None
         if ctx.needs_input_grad[2]:
-            grad_query = ext.spmm_forward_cuda(False, False, indptr, indices, grad_raw, key)
+            grad_query = direct_product(indptr, indices, grad_raw, key)
         if ctx.needs_input_grad[3]:
             grad_key = transposed_product(indptr, indices, grad_raw, query)
         return None, None, grad_query, grad_key, None, None

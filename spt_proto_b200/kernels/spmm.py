@@ -4,14 +4,14 @@ backward: dA = sddmm(dy, x) on the pattern;  dx = A^T dy through the cached CSC.
 from torch import autograd
 
 from .. import ext
-from ._csc import transposed_product
+from ._csc import direct_product, transposed_product
 
 
 class SPMM(autograd.Function):
     @staticmethod
     def forward(ctx, indptr, indices, values, x):
         ctx.save_for_backward(indptr, indices, values, x)
-        return ext.spmm_forward_cuda(False, False, indptr, indices, values, x)
+        return direct_product(indptr, indices, values, x)
 
     @staticmethod
     def backward(ctx, grad_output):

@@ -569,13 +569,15 @@ def test_csr_tiles_and_product(B, S, k, d, pad_rows, hot_cols):
         got_sorted = np.concatenate([np.sort(te[b, tp[b, i]:tp[b, i + 1]].astype(np.int64)) for i in range(n * n)])
         want_sorted = np.concatenate([np.sort(want_words[order][tp[b, i]:tp[b, i + 1]]) for i in range(n * n)])
         assert np.array_equal(got_sorted, want_sorted)
-    want = _spmm_t_want(indptr, indices, vals, x.float())
-    for out_dtype in (torch.float32, torch.bfloat16):
-        got = _ext().spmm_tiles((tile_ptr, tile_ent), vals.to(DEV), x.to(DEV), out_dtype=out_dtype)
-        err = (got.double().cpu() - want).norm() / want.norm()
-        assert err < (2e-5 if out_dtype == torch.float32 else 4e-3), err
-        tol = dict(atol=2e-3, rtol=1e-4) if out_dtype == torch.float32 else dict(atol=2e-2 * want.abs().max().item(), rtol=2e-2)
-        assert torch.allclose(got.double().cpu(), want, **tol)
+    a = torch.zeros(B, S, S, dtype=torch.float64)
+    a.scatter_add_(2, indices.view(B, S, k).long(), vals.view(B, S, k).double())
+    for trans, want in ((True, torch.einsum("brc,brd->bcd", a, x.double())), (False, torch.einsum("brc,bcd->brd", a, x.double()))):
+        for out_dtype in (torch.float32, torch.bfloat16):
+            got = _ext().spmm_tiles((tile_ptr, tile_ent), vals.to(DEV), x.to(DEV), out_dtype=out_dtype, trans=trans)
+            err = (got.double().cpu() - want).norm() / want.norm()
+            assert err < (2e-5 if out_dtype == torch.float32 else 4e-3), (trans, err)
+            tol = dict(atol=2e-3, rtol=1e-4) if out_dtype == torch.float32 else dict(atol=2e-2 * want.abs().max().item(), rtol=2e-2)
+            assert torch.allclose(got.double().cpu(), want, **tol)
 
 
 def test_csr_tiles_ragged_rows_and_limits():
@@ -591,6 +593,8 @@ def test_csr_tiles_ragged_rows_and_limits():
     tiles = _ext().csr_tiles(indptr.to(DEV), indices.to(DEV))
     got = _ext().spmm_tiles(tiles, vals.to(DEV), x.to(DEV), out_dtype=torch.float32)
     assert torch.allclose(got.cpu(), want, atol=1e-3)
+    got = _ext().spmm_tiles(tiles, vals.to(DEV), x.to(DEV), out_dtype=torch.float32, trans=False)
+    assert torch.allclose(got.cpu(), O.spmm_forward(False, indptr, indices, vals, x.float()), atol=1e-3)
     big = torch.zeros(1, (1 << 20) + 4, dtype=torch.int32, device=DEV)
     with pytest.raises(RuntimeError):
         _ext().csr_tiles(torch.tensor([0, (1 << 20) + 4], dtype=torch.int32, device=DEV), big)
