@@ -146,7 +146,7 @@ def base_config(n_seq: int, world: int, fused: bool = True) -> dict:
             "l2": "inputs+intermediates per step exceed L2 (>1 GB vs 126 MB); no explicit flush",
             "path": ("fused: pq_encode(q,k) -> lookup(bitmask) -> masked-dense-tile attention fwd/bwd "
                      "(tcgen05 + TMEM + TMA, bf16)" if fused else
-                     "stage kernels (pq_encode, lookup, sddmm, softmax, spmm, tile index, transposed spmm)"),
+                     "stage kernels (pq_encode, lookup, tile index, sddmm / spmm / transposed spmm on dense tiles, softmax)"),
             "pq_train": "off (fwd+bwd of the layer as configs[1] words it; the one-shot PQ loss the reference's "
                         "training loop arms per step is part of the finetune_step section)",
             "output_layout": "reference (the shipped layer's [N*H, E, S] memory viewed as [N, S, H, E])",
@@ -222,9 +222,11 @@ STAGE_BOUND = {
     "softmax_bwd": "hbm",
     "csr2csc": "shared-memory bit-matrix build + scan per 64-row tile (one CTA of 1024 threads per SM); index read + write",
     "csr_tiles": "two passes over the indices (count, place) with shared-memory histograms over the column tiles",
+    "sddmm_tiles": "LSU data pipe: one index word read + one 4-byte store per entry, score tile through shared memory",
+    "spmm_tiles": "LSU data pipe: one value gather per entry + tile scatter / fragment loads",
     "spmm_t_tiles": "LSU data pipe: one value gather per entry + tile scatter / fragment loads; latency of the first column tile's long buckets",
 }
-STAGE_PATH = ["pq_encode", "lookup", "sddmm", "softmax_fwd", "spmm", "softmax_bwd", "csr_tiles", "spmm_t_tiles"]
+STAGE_PATH = ["pq_encode", "lookup", "sddmm_tiles", "softmax_fwd", "spmm_tiles", "softmax_bwd", "csr_tiles", "spmm_t_tiles"]
 
 
 def stage_roofline(n_seq: int, dev, hbm_gbs: float, tensor_tflops: float):
@@ -263,6 +265,8 @@ def stage_roofline(n_seq: int, dev, hbm_gbs: float, tensor_tflops: float):
         # written) and the transposed product on it (entry word + value per entry, x read, y written)
         "csr_tiles": (lambda: ext.csr_tiles(indptr, idx), 2 * Sk + S * 4),
         "spmm_t_tiles": (lambda: ext.spmm_tiles(tiles, p, dy), 2 * Sk + 2 * Sd),
+        "spmm_tiles": (lambda: ext.spmm_tiles(tiles, p, v, trans=False), 2 * Sk + 2 * Sd),
+        "sddmm_tiles": (lambda: ext.sddmm_tiles(tiles, q, kk, d ** -0.5, 10.0), 2 * Sd + 2 * Sk),
     }
     mask, extra0, _ = ext.lookup_mask(qc, kc, COEFF)
     y_f, z_f = ext.sparse_attn_fwd(q, kk, v, mask, extra0, d ** -0.5)

@@ -162,6 +162,12 @@ int spt_csr_tiles(const int32_t *indptr, const int32_t *indices, int32_t *tile_p
 int spt_spmm_t_tiles_fwd(const int32_t *tile_ptr, const uint32_t *tile_ent, const float *values,
                          const void *x, void *y, int B, int S, int d, int64_t nnz, int dtype,
                          int out_dtype, spt_stream_t stream);
+/* values[b, e] = clamp(scale * <query[b, row(e)], key[b, col(e)]>) on the same index (the spt_sddmm_fwd
+ * product, bf16 operands, head dim 64 / 128): dense 64 x 64 score tiles on the tensor cores, every
+ * entry picks its cell. */
+int spt_sddmm_tiles_fwd(const int32_t *tile_ptr, const uint32_t *tile_ent, const void *query,
+                        const void *key, float *values, int B, int S, int d, int64_t nnz, float scale,
+                        float clamp, int dtype, spt_stream_t stream);
 /* both directions on the same index: trans = 0 is y[b, r, :] = sum_{e in row r} values[b, e] *
  * x[b, indices[b, e], :] (the spt_spmm_fwd product), trans = 1 the one above */
 int spt_spmm_tiles_fwd(const int32_t *tile_ptr, const uint32_t *tile_ent, const float *values,

@@ -26,6 +26,8 @@ tiles = ext.csr_tiles(indptr, idx)
 print("B", B, "csr2csc ms %.3f" % ev(lambda: ext.csr2csc(indptr, idx)), "csr_tiles ms %.3f" % ev(lambda: ext.csr_tiles(indptr, idx)),
       "spmm_csc ms %.3f" % ev(lambda: ext.spmm_csc(csc, p, q)), "spmm_tiles ms %.3f" % ev(lambda: ext.spmm_tiles(tiles, p, q)),
       "| direct: gathered ms %.3f" % ev(lambda: ext.spmm_forward_cuda(False, False, indptr, idx, p, q)),
-      "tiles ms %.3f" % ev(lambda: ext.spmm_tiles(tiles, p, q, trans=False)))
+      "tiles ms %.3f" % ev(lambda: ext.spmm_tiles(tiles, p, q, trans=False)),
+      "| sddmm: gathered ms %.3f" % ev(lambda: ext.sddmm_scaled(indptr, idx, q, kk, 0.125, 10.0)),
+      "tiles ms %.3f" % ev(lambda: ext.sddmm_tiles(tiles, q, kk, 0.125, 10.0)))
 a, b = ext.spmm_csc(csc, p, q, out_dtype=torch.float32), ext.spmm_tiles(tiles, p, q, out_dtype=torch.float32)
 print("max |csc - tiles| %.3e  rel %.3e" % ((a - b).abs().max().item(), ((a - b).norm() / a.norm()).item()))

@@ -49,6 +49,7 @@ def _load() -> ctypes.CDLL:
         "spt_csr_tiles": (i32, [vp, vp, vp, vp, i32, i32, i64, vp]),
         "spt_spmm_t_tiles_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, vp]),
         "spt_spmm_tiles_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, i32, vp]),
+        "spt_sddmm_tiles_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i64, f32, f32, i32, vp]),
         "spt_csr2csc_workspace_bytes": (sz, [i32, i32, i64]),
         "spt_csr2csc": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp]),
         "spt_softmax_fwd": (i32, [vp, vp, vp, vp, i32, i32, i64, vp]),

@@ -335,6 +335,132 @@ static int launch_d(bool trans, const int32_t *tile_ptr, const uint32_t *tile_en
                  : launch_dt<D, TO, false>(tile_ptr, tile_ent, values, x, y, B, S, nnz, st);
 }
 
+
+// ---- sddmm on the tile index -------------------------------------------------------------------------------------------
+// values[e] = clamp(scale <q[row(e)], k[col(e)]>).  A block owns a 64-row tile of one head (its Q rows stay in shared
+// memory, their A fragments in registers for head dim 64) and walks the non-empty buckets of its row: S = Q K_chunk^T on
+// mma.sync (bf16 operands are exact, fp32 accumulation) into a double-buffered fp32 tile, then every entry of the bucket
+// picks its cell and stores it at its CSR position.  The gathered kernel (csr_mma.cu) moves a 128-byte key row per entry
+// through L2; this one reads a 4-byte index word and writes 4 bytes per entry — the key chunk is staged once per 64 rows.
+// One block barrier per chunk.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+template <int D>
+__global__ void __launch_bounds__(THREADS, D == 64 ? 3 : 2)
+sddmm_tiles_kernel(const int32_t *__restrict__ tile_ptr, const uint32_t *__restrict__ tile_ent, const bf16 *__restrict__ q,
+                   const bf16 *__restrict__ k, float *__restrict__ values, int B, int S, int64_t nnz, int n_ct, int n_rc,
+                   float scale, float clamp) {
+    constexpr int XS = (D + 8) * 2;            // bytes per staged row
+    constexpr int KS = D / 16;                 // k-steps
+    constexpr bool HOLD_A = D == 64;           // Q fragments live in registers across chunks
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned char *Q0 = smem;                                                        // [64 rows][XS]
+    unsigned char *K0 = smem + DT * XS;                                              // [2][64 keys][XS]
+    float *S0 = reinterpret_cast<float *>(smem + 3 * DT * XS);                       // [2][64 rows][PS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x % B, rt = n_rc - 1 - blockIdx.x / B;   // under a causal pattern the last row tile is the heaviest
+    const int32_t *tp = tile_ptr + (size_t)b * (n_ct * n_rc + 1) + rt;               // bucket (ct, rt) -> tp[ct * n_rc]
+    const uint32_t *ent = tile_ent + (size_t)b * nnz;
+    float *vp = values + (size_t)b * nnz;
+    const bf16 *qb = q + (size_t)b * S * D, *kb = k + (size_t)b * S * D;
+    const uint32_t q_s = (uint32_t)__cvta_generic_to_shared(Q0), k_s = (uint32_t)__cvta_generic_to_shared(K0);
+
+    auto load_rows = [&](uint32_t dst, const bf16 *src, int r0) {                     // 64 rows -> shared memory, zero beyond S
+        for (int i = tid; i < DT * (D / 8); i += THREADS) {
+            const int rr = i / (D / 8), ch = i % (D / 8);
+            const bool ok = r0 + rr < S;
+            cp_async16(dst + rr * XS + ch * 16, src + (size_t)(ok ? r0 + rr : 0) * D + ch * 8, ok);
+        }
+    };
+    auto next_chunk = [&](int ct) {
+        while (ct < n_ct && tp[(size_t)ct * n_rc + 1] == tp[(size_t)ct * n_rc]) ++ct;
+        return ct;
+    };
+    const int g = lane >> 2, t = lane & 3;
+    const int mt = warp & 3, nh = warp >> 2;                                         // 16 rows x 32 columns of the tile per warp
+    const uint32_t a_addr = q_s + (mt * 16 + (lane & 15)) * XS + (lane >> 4) * 16;
+    const uint32_t b_off = (nh * 32 + (lane & 7) + ((lane >> 4) & 1) * 8) * XS + ((lane >> 3) & 1) * 16;
+
+    int ct = next_chunk(0), it = 0;
+    if (ct >= n_ct) return;                                                          // a row tile without entries (block-uniform)
+    load_rows(q_s, qb, rt * DT);
+    load_rows(k_s, kb, ct * DT);
+    cp_async_wait_all();
+    __syncthreads();
+    uint32_t qa[HOLD_A ? KS : 1][4];
+    if (HOLD_A) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) ldmatrix_x4(a_addr + ks * 32, qa[HOLD_A ? ks : 0]);
+    }
+    for (; ct < n_ct; ++it) {
+        const int buf = it & 1;
+        const int ct_next = next_chunk(ct + 1);
+        if (ct_next < n_ct) load_rows(k_s + (buf ^ 1) * DT * XS, kb, ct_next * DT);  // its last readers finished before the previous barrier
+        const int p0 = tp[(size_t)ct * n_rc], p1 = tp[(size_t)ct * n_rc + 1];
+        uint32_t w[PRE];                                                             // this bucket's first entries, under the MMAs
+#pragma unroll
+        for (int j = 0; j < PRE; ++j) w[j] = p0 + j * THREADS + tid < p1 ? ent[p0 + j * THREADS + tid] : 0xffffffffu;
+        // S[buf] = Q K_chunk^T
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t a[4];
+            if (HOLD_A) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = qa[HOLD_A ? ks : 0][i];
+            } else {
+                ldmatrix_x4(a_addr + ks * 32, a);
+            }
+#pragma unroll
+            for (int jp = 0; jp < 2; ++jp) {
+                uint32_t bb[4];
+                ldmatrix_x4(k_s + buf * DT * XS + b_off + jp * 16 * XS + ks * 32, bb);
+                mma16816(acc[2 * jp], a, bb[0], bb[1]);
+                mma16816(acc[2 * jp + 1], a, bb[2], bb[3]);
+            }
+        }
+        float *Sb = S0 + buf * DT * PS;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float *dst = Sb + (mt * 16 + g) * PS + nh * 32 + j * 8 + 2 * t;
+            *reinterpret_cast<float2 *>(dst) = make_float2(acc[j][0], acc[j][1]);
+            *reinterpret_cast<float2 *>(dst + 8 * PS) = make_float2(acc[j][2], acc[j][3]);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        // every entry of the bucket takes its cell
+        auto emit = [&](uint32_t word) {
+            if (word != 0xffffffffu) {
+                float v = Sb[((word >> 6) & 63u) * PS + (word & 63u)] * scale;
+                if (clamp > 0.0f) v = fminf(fmaxf(v, -clamp), clamp);
+                vp[word >> 12] = v;
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < PRE; ++j) emit(w[j]);
+        for (int qi = p0 + PRE * THREADS + tid; qi < p1; qi += THREADS) emit(ent[qi]);
+        ct = ct_next;
+    }
+}
+
+template <int D>
+static int launch_sddmm_d(const int32_t *tile_ptr, const uint32_t *tile_ent, const bf16 *q, const bf16 *k, float *values, int B,
+                          int S, int64_t nnz, float scale, float clamp, cudaStream_t st) {
+    const int n_t = (S + DT - 1) / DT;
+    const size_t smem = 3 * (size_t)DT * (D + 8) * 2 + 2 * (size_t)DT * PS * 4;
+    cudaFuncSetAttribute(sddmm_tiles_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sddmm_tiles_kernel<D><<<(unsigned)((int64_t)B * n_t), THREADS, smem, st>>>(tile_ptr, tile_ent, q, k, values, B, S, nnz, n_t, n_t,
+                                                                             scale, clamp);
+    return after_launch("sddmm_tiles_kernel");
+}
+
 }  // namespace csr_tiles
 }  // namespace spt
 
@@ -385,4 +511,21 @@ extern "C" int spt_spmm_tiles_fwd(const int32_t *tile_ptr, const uint32_t *tile_
 extern "C" int spt_spmm_t_tiles_fwd(const int32_t *tile_ptr, const uint32_t *tile_ent, const float *values, const void *x, void *y,
                                     int B, int S, int d, int64_t nnz, int dtype, int out_dtype, spt_stream_t stream) {
     return spt_spmm_tiles_fwd(tile_ptr, tile_ent, values, x, y, B, S, d, nnz, dtype, out_dtype, 1, stream);
+}
+
+/* values[b, e] = clamp(scale * <query[b, row(e)], key[b, col(e)]>, -clamp, clamp) (clamp <= 0: none) for every entry of
+ * the tile index — the spt_sddmm_fwd product for bf16 operands with head dim 64 / 128.  Entries whose column is outside
+ * [0, S) are not in the index: their values are left untouched. */
+extern "C" int spt_sddmm_tiles_fwd(const int32_t *tile_ptr, const uint32_t *tile_ent, const void *query, const void *key,
+                                   float *values, int B, int S, int d, int64_t nnz, float scale, float clamp, int dtype,
+                                   spt_stream_t stream) {
+    SPT_REQUIRE(tile_ptr && tile_ent && query && key && values, "sddmm_tiles_fwd: null pointer");
+    SPT_REQUIRE(B >= 1 && S >= 1 && nnz >= 0, "sddmm_tiles_fwd: bad sizes B=%d S=%d nnz=%lld", B, S, (long long)nnz);
+    if (dtype != SPT_BF16 || (d != 64 && d != 128) || !spt_csr_tiles_supported(S, nnz))
+        return fail(SPT_ERR_UNSUPPORTED, "sddmm_tiles_fwd: bf16 operands with head dim 64 / 128 only (dtype %d, d %d)", dtype, d);
+    SPT_REQUIRE((uintptr_t)query % 16 == 0 && (uintptr_t)key % 16 == 0, "sddmm_tiles_fwd: operands must be 16-byte aligned");
+    using bf = __nv_bfloat16;
+    cudaStream_t st = as_stream(stream);
+    return d == 64 ? csr_tiles::launch_sddmm_d<64>(tile_ptr, tile_ent, (const bf *)query, (const bf *)key, values, B, S, nnz, scale, clamp, st)
+                   : csr_tiles::launch_sddmm_d<128>(tile_ptr, tile_ent, (const bf *)query, (const bf *)key, values, B, S, nnz, scale, clamp, st);
 }

@@ -341,6 +341,25 @@ def csr_tiles(indptr: torch.Tensor, indices: torch.Tensor) -> Tuple[torch.Tensor
     return tile_ptr, tile_ent
 
 
+def sddmm_tiles(tiles, query: torch.Tensor, key: torch.Tensor, scale: float = 1.0, clamp: float = 0.0) -> torch.Tensor:
+    """values[b, e] = clamp(scale * <query[b, row(e)], key[b, col(e)]>) for the entries of a tile index (bf16, d 64 / 128)."""
+    tile_ptr, tile_ent = tiles
+    _check_dim(key, 3, "key")
+    _check_dim(query, 3, "query")
+    if query.shape != key.shape or query.dtype != key.dtype:
+        raise RuntimeError("query and key must have the same shape and dtype")
+    B, S, d = query.shape
+    nnz = tile_ent.size(-1)
+    if tile_ent.size(0) != B:
+        raise RuntimeError("sddmm_tiles: tile index batch must match query batch")
+    code = _float_code(query, "query")
+    values = torch.empty((B, nnz), dtype=torch.float32, device=query.device)   # every entry of a valid pattern is in the index
+    with _on_device(query):
+        check(lib.spt_sddmm_tiles_fwd(_p(tile_ptr), _p(tile_ent), _p(query), _p(key), _p(values), B, S, d, nnz,
+                                      float(scale), float(clamp), code, _stream(query)))
+    return values
+
+
 def spmm_tiles(tiles, values: torch.Tensor, x: torch.Tensor, out_dtype=None, trans: bool = True) -> torch.Tensor:
     """y = A^T x (trans, the default) or y = A x on a tile index from csr_tiles(); values stay in CSR order."""
     tile_ptr, tile_ent = tiles

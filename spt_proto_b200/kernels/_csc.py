@@ -12,6 +12,7 @@ import os
 _CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 _MAX = 4
 _TILES_DIRECT = os.environ.get("SPT_SPMM_TILES_DIRECT", "1") != "0"    # A/B switch: the CSR-direction product on the tile index
+_TILES_SDDMM = os.environ.get("SPT_SDDMM_TILES", "1") != "0"           # A/B switch: sddmm on the tile index
 
 
 def get_csc(indptr: torch.Tensor, indices: torch.Tensor):
@@ -59,6 +60,15 @@ def direct_product(indptr: torch.Tensor, indices: torch.Tensor, values: torch.Te
     if _TILES_DIRECT and ext.csr_tiles_supported(indices, x):
         return ext.spmm_tiles(get_tiles(indptr, indices), values, x, trans=False)
     return ext.spmm_forward_cuda(False, False, indptr, indices, values, x)
+
+
+def sddmm_product(indptr: torch.Tensor, indices: torch.Tensor, query: torch.Tensor, key: torch.Tensor,
+                  scale: float = 1.0, clamp: float = 0.0) -> torch.Tensor:
+    """values = clamp(scale * sddmm(q, k)): dense score tiles on the tile index when it applies, else the gathered kernel."""
+    query, key = query.contiguous(), key.contiguous()
+    if _TILES_SDDMM and key.dtype == query.dtype and ext.csr_tiles_supported(indices, query):
+        return ext.sddmm_tiles(get_tiles(indptr, indices), query, key, scale, clamp)
+    return ext.sddmm_scaled(indptr, indices, query, key, scale, clamp)
 
 
 def clear():

@@ -5,14 +5,14 @@ backward: dQ = spmm(dvalues, K);  dK = spmm^T(dvalues, Q) through the cached CSC
 from torch import autograd
 
 from .. import ext
-from ._csc import direct_product, transposed_product
+from ._csc import direct_product, sddmm_product, transposed_product
 
 
 class SDDMM(autograd.Function):
     @staticmethod
     def forward(ctx, indptr, indices, query, key):
         ctx.save_for_backward(indptr, indices, query, key)
-        return ext.sddmm_forward_cuda(False, True, indptr, indices, query, key)
+        return sddmm_product(indptr, indices, query, key)
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -37,7 +37,7 @@ class SDDMMScaled(autograd.Function):
 
     @staticmethod
     def forward(ctx, indptr, indices, query, key, scale, clamp):
-        values = ext.sddmm_scaled(indptr, indices, query, key, scale, clamp)
+        values = sddmm_product(indptr, indices, query, key, scale, clamp)
         ctx.save_for_backward(indptr, indices, query, key, values)
         ctx.scale, ctx.clamp = float(scale), float(clamp)
         return values

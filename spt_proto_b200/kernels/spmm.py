@@ -4,7 +4,7 @@ backward: dA = sddmm(dy, x) on the pattern;  dx = A^T dy through the cached CSC.
 from torch import autograd
 
 from .. import ext
-from ._csc import direct_product, transposed_product
+from ._csc import direct_product, sddmm_product, transposed_product
 
 
 class SPMM(autograd.Function):
@@ -19,7 +19,7 @@ class SPMM(autograd.Function):
         grad_output = grad_output.contiguous()
         grad_a = grad_x = None
         if ctx.needs_input_grad[2]:
-            grad_a = ext.sddmm_forward_cuda(False, True, indptr, indices, grad_output, x)
+            grad_a = sddmm_product(indptr, indices, grad_output, x)
         if ctx.needs_input_grad[3]:
             grad_x = transposed_product(indptr, indices, values, grad_output)
         return None, None, grad_a, grad_x

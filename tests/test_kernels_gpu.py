@@ -569,6 +569,16 @@ def test_csr_tiles_and_product(B, S, k, d, pad_rows, hot_cols):
         got_sorted = np.concatenate([np.sort(te[b, tp[b, i]:tp[b, i + 1]].astype(np.int64)) for i in range(n * n)])
         want_sorted = np.concatenate([np.sort(want_words[order][tp[b, i]:tp[b, i + 1]]) for i in range(n * n)])
         assert np.array_equal(got_sorted, want_sorted)
+    # sddmm on the same index: every entry picks its cell of the dense score tile
+    y = torch.randn(B, S, d, generator=g).bfloat16()
+    dense = torch.einsum("brd,bcd->brc", x.double(), y.double())
+    want_v = torch.gather(dense, 2, indices.view(B, S, k).long()).view(B, S * k)
+    got_v = _ext().sddmm_tiles((tile_ptr, tile_ent), x.to(DEV), y.to(DEV))
+    assert torch.allclose(got_v.double().cpu(), want_v, atol=2e-4 * d ** 0.5, rtol=1e-5)
+    got_v = _ext().sddmm_tiles((tile_ptr, tile_ent), x.to(DEV), y.to(DEV), scale=0.5, clamp=3.0)
+    assert torch.allclose(got_v.double().cpu(), (want_v * 0.5).clamp(-3.0, 3.0), atol=2e-4 * d ** 0.5, rtol=1e-5)
+    assert torch.equal(got_v, _ext().sddmm_scaled(indptr.to(DEV), indices.to(DEV), x.to(DEV), y.to(DEV), 0.5, 3.0)) or \
+        torch.allclose(got_v, _ext().sddmm_scaled(indptr.to(DEV), indices.to(DEV), x.to(DEV), y.to(DEV), 0.5, 3.0), atol=1e-4, rtol=1e-5)
     a = torch.zeros(B, S, S, dtype=torch.float64)
     a.scatter_add_(2, indices.view(B, S, k).long(), vals.view(B, S, k).double())
     for trans, want in ((True, torch.einsum("brc,brd->bcd", a, x.double())), (False, torch.einsum("brc,bcd->brd", a, x.double()))):
