@@ -206,6 +206,22 @@ def _time_cuda(fn, iters=5, warm=2, prequeue=True):
     return statistics.median(ts)
 
 
+def _time_back_to_back(fn, iters=10, warm=3):
+    """Average device time of `iters` calls launched back to back behind a short device-side spin (no sync between
+    them): the steady state of a loop whose host side runs ahead of the GPU."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(2_000_000)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    b.synchronize()
+    return a.elapsed_time(b) * 1e-3 / iters
+
+
 FUSED_PATH = ["pq_encode", "lookup_mask", "attn_fwd", "attn_bwd"]
 # what bounds each kernel according to its ncu capture (profiles/README.md, DESIGN.md section 4): the HBM fraction
 # reported beside it is NOT the target for the issue-bound ones
@@ -317,9 +333,13 @@ def ffn_bench(dev, tensor_tflops: float):
                 p.grad = None
             ffn(x).backward(dy)
 
-        t_eager = _time_cuda(step, iters=5, warm=3, prequeue=False)   # eager = with host launch gaps
-        # The eager step is bound by ~45 Python-side launches (GPU busy ~0.85 ms of ~1.1 ms).  Routing and bucketing
-        # are device-side (no host sync), so the whole forward + backward is capturable: replay one CUDA graph.
+        # eager, two readings: `isolated` = one step launched into an idle GPU and waited for (host launch time of
+        # ~25 launches + autograd shows in full), `steady` = ten steps launched back to back the way a training loop
+        # runs them (the host stays ahead of the device; what is left are the device-side gaps between ~25 kernels).
+        t_isolated = _time_cuda(step, iters=5, warm=3, prequeue=False)
+        t_eager = _time_back_to_back(step, iters=10, warm=3)
+        # Routing and bucketing are device-side (no host sync), so the whole forward + backward is capturable:
+        # replay one CUDA graph.
         t, graphed = t_eager, False
         try:
             side = torch.cuda.Stream()
@@ -336,7 +356,8 @@ def ffn_bench(dev, tensor_tflops: float):
             print(f"[bench] routed FFN graph capture failed: {exc!r}", file=sys.stderr)
             torch.cuda.synchronize()
         flops = 12 * T * 0.5 * F * d          # fwd 4 T rho F d, bwd dX 4 ..., bwd dW 4 ...
-        out[f"block_{bs}"] = {"ms": t * 1e3, "ms_eager": t_eager * 1e3, "cuda_graph": graphed, "tokens_per_s": T / t,
+        out[f"block_{bs}"] = {"ms": t * 1e3, "ms_eager": t_eager * 1e3, "ms_eager_isolated": t_isolated * 1e3,
+                              "cuda_graph": graphed, "tokens_per_s": T / t,
                               "algorithmic_TFLOPs": flops / t / 1e12,
                               "frac_tensor": flops / t / 1e12 / tensor_tflops, "T": T, "d": d, "ffn": F,
                               "n_blocks": F // bs, "active": (F // bs) // 2}

@@ -318,6 +318,13 @@ int spt_rmsnorm_bwd_bf16(const void *g, const void *x, const void *w, const floa
 int spt_rope_bf16(const void *x, const void *cos, const void *sin, void *out, int64_t rows, int S, int H, int E,
                   int transpose, spt_stream_t stream);
 
+/* Layout copies of the stage path: the reference layer's `transpose(1, 2).contiguous()` of q / k / v and of the
+ * product (naive_gpt/layers/sparse/attention.py:92-95, 138-142) as 16-byte-word row moves.
+ *   swap_dims12    : out[a, c, b, :] = in[a, b, c, :]; rows of row_bytes (multiple of 16), both 16-byte aligned.
+ *   transpose_last2: out[b, c, r] = in[b, r, c], elements of 2 or 4 bytes (the shipped layer's output layout). */
+int spt_swap_dims12(const void *in, void *out, int64_t A, int64_t B, int64_t C, int64_t row_bytes, spt_stream_t stream);
+int spt_transpose_last2(const void *in, void *out, int64_t batch, int R, int C, int elem_bytes, spt_stream_t stream);
+
 /* Host-side replay of the CTA-pair grouped GEMM's mode-0 schedule (no GPU needed; used by the CPU tests).
  * tile_group is a HOST array [n_m_tiles] (n_m_tiles <= 1024).  One record of 6 ints per (unit, CTA rank):
  *   unit, rank, group, m_tile, n_tile, role | mma << 4     (role: 0 idle, 1 active, 2 zero-fill).

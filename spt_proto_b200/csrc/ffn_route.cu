@@ -189,33 +189,53 @@ combine_kernel(const TP *__restrict__ part, const int32_t *__restrict__ token_ro
 
 // out[g, c] = sum over rows bucket_ptr[g] .. bucket_ptr[g+1] of x[row, c]; two deterministic stages
 constexpr int CS_SPLIT = 64;
-// thread = 8 consecutive columns (one 16-byte load per row: a warp reads 512 contiguous bytes), 64 row parts per group
-__global__ void __launch_bounds__(128)
+// block = 8 warps over one 256-column strip of one row part: lane = 8 consecutive columns (one 16-byte load per row, a warp
+// reads 512 contiguous bytes), warp w takes rows a + w, a + w + 8, ... four at a time (independent loads in flight: with one
+// load per thread and 128 blocks the kernel ran at a quarter of the HBM rate); the eight warps' sums meet in shared memory
+// in warp order, so the result is deterministic.
+constexpr int CS_WARPS = 8;
+__global__ void __launch_bounds__(32 * CS_WARPS)
 colsum_stage1(const __nv_bfloat16 *__restrict__ x, const int32_t *__restrict__ bucket_ptr, float *__restrict__ partial,
               int C) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    __shared__ float red[CS_WARPS][256 + 8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 256 + lane * 8;
     const int part = blockIdx.y, g = blockIdx.z;
-    if (c >= C) return;
     const int r0 = bucket_ptr[g], r1 = bucket_ptr[g + 1];
     const int per = (r1 - r0 + CS_SPLIT - 1) / CS_SPLIT;
     const int a = r0 + part * per, b = min(r1, a + per);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float *out = partial + ((long long)g * CS_SPLIT + part) * C + c;
     if (c + 8 <= C && (C % 8 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0)) {
-        for (int r = a; r < b; ++r) {
+        const __nv_bfloat16 *px = x + c;
+        int r = a + w;
+        for (; r + 3 * CS_WARPS < b; r += 4 * CS_WARPS) {
+            float v[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) Vec16<__nv_bfloat16>::load(px + (long long)(r + u * CS_WARPS) * C, v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += v[u][i];
+        }
+        for (; r < b; r += CS_WARPS) {
             float v[8];
-            Vec16<__nv_bfloat16>::load(x + (long long)r * C + c, v);
+            Vec16<__nv_bfloat16>::load(px + (long long)r * C, v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] += v[i];
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) out[i] = acc[i];
     } else {
-        for (int i = 0; i < 8 && c + i < C; ++i) {
-            float t = 0.0f;
-            for (int r = a; r < b; ++r) t += __bfloat162float(x[(long long)r * C + c + i]);
-            out[i] = t;
-        }
+        for (int i = 0; i < 8 && c + i < C; ++i)
+            for (int r = a + w; r < b; r += CS_WARPS) acc[i] += __bfloat162float(x[(long long)r * C + c + i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = acc[i];
+    __syncthreads();
+    const int cc = blockIdx.x * 256 + threadIdx.x;
+    if (cc < C) {
+        float t = 0.0f;
+#pragma unroll
+        for (int u = 0; u < CS_WARPS; ++u) t += red[u][threadIdx.x];
+        partial[((long long)g * CS_SPLIT + part) * C + cc] = t;
     }
 }
 __global__ void __launch_bounds__(128)
@@ -305,8 +325,8 @@ extern "C" int spt_group_colsum_bf16(const void *x, const int32_t *bucket_ptr, f
     SPT_REQUIRE(x && bucket_ptr && out && workspace, "group_colsum: null pointer");
     SPT_REQUIRE(n_groups >= 1 && n_groups <= 65535 && C >= 1, "group_colsum: bad sizes");
     cudaStream_t st = as_stream(stream);
-    dim3 g1((C + 1023) / 1024, route::CS_SPLIT, n_groups);
-    route::colsum_stage1<<<g1, 128, 0, st>>>((const __nv_bfloat16 *)x, bucket_ptr, (float *)workspace, C);
+    dim3 g1((C + 255) / 256, route::CS_SPLIT, n_groups);
+    route::colsum_stage1<<<g1, 32 * route::CS_WARPS, 0, st>>>((const __nv_bfloat16 *)x, bucket_ptr, (float *)workspace, C);
     SPT_LAUNCH_CHECK("colsum_stage1");
     route::colsum_stage2<<<dim3((C + 127) / 128, n_groups), 128, 0, st>>>((const float *)workspace, out, C);
     return after_launch("colsum_stage2");

@@ -1,0 +1,98 @@
+// Layout copies of the stage path: the reference layer moves q, k, v to head-major with
+// `transpose(1, 2).contiguous()` before its kernels and the product back afterwards
+// (naive_gpt/layers/sparse/attention.py:92-95, 138-142).  torch's strided copy reads 2-byte elements one by one
+// (44 us per 33.5 MB operand = 1.5 TB/s); here a row of E elements moves as 16-byte words, four rows in flight per
+// thread, and the last-two-dims transpose of the shipped output layout goes through a padded shared-memory tile.
+// (The fused path needs neither: its kernels stride over [N, S, H, E] through 4-D tensor maps.)
+#include "common.cuh"
+
+namespace spt {
+namespace layout {
+
+// out[a, c, b, :] = in[a, b, c, :], rows of `w16` 16-byte words.  One thread per (output row, word), consecutive threads
+// = consecutive words of consecutive output rows (stores fully coalesced, loads in whole rows of >= 64 bytes).
+constexpr int SW_UNROLL = 4;
+__global__ void __launch_bounds__(256)
+swap12_kernel(const int4 *__restrict__ in, int4 *__restrict__ out, long long n_words, int Bd, int Cd, int w16) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (SW_UNROLL - 1) * stride < n_words; i += SW_UNROLL * stride) {
+        int4 v[SW_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SW_UNROLL; ++u) {
+            const long long o = i + u * stride;
+            const long long row = o / w16;
+            const int w = (int)(o - row * w16);
+            const long long ac = row / Bd;           // output row = (a, c, b)
+            const int b = (int)(row - ac * Bd);
+            const long long a = ac / Cd;
+            const int c = (int)(ac - a * Cd);
+            v[u] = ld_stream(in + (((a * Bd + b) * Cd + c) * w16 + w));
+        }
+#pragma unroll
+        for (int u = 0; u < SW_UNROLL; ++u) st_stream(out + i + u * stride, v[u]);
+    }
+    for (; i < n_words; i += stride) {
+        const long long row = i / w16;
+        const int w = (int)(i - row * w16);
+        const long long ac = row / Bd;
+        const int b = (int)(row - ac * Bd);
+        const long long a = ac / Cd;
+        const int c = (int)(ac - a * Cd);
+        st_stream(out + i, ld_stream(in + (((a * Bd + b) * Cd + c) * w16 + w)));
+    }
+}
+
+// out[b, c, r] = in[b, r, c] for 2-byte (T = uint16_t) or 4-byte elements: 64 x 64 tiles through shared memory
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_tile_kernel(const T *__restrict__ in, T *__restrict__ out, int R, int C) {
+    __shared__ T tile[64][64 + (sizeof(T) == 2 ? 2 : 1)];
+    const long long base = (long long)blockIdx.z * R * C;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
+#pragma unroll 4
+    for (int j = ty; j < 64; j += 4)
+        if (r0 + j < R && c0 + tx < C) tile[j][tx] = in[base + (long long)(r0 + j) * C + c0 + tx];
+    __syncthreads();
+#pragma unroll 4
+    for (int j = ty; j < 64; j += 4)
+        if (c0 + j < C && r0 + tx < R) out[base + (long long)(c0 + j) * R + r0 + tx] = tile[tx][j];
+}
+
+}  // namespace layout
+}  // namespace spt
+
+using namespace spt;
+
+extern "C" int spt_swap_dims12(const void *in, void *out, int64_t A, int64_t B, int64_t C, int64_t row_bytes,
+                               spt_stream_t stream) {
+    SPT_REQUIRE(in && out, "swap_dims12: null pointer");
+    SPT_REQUIRE(A >= 1 && B >= 1 && C >= 1 && B < (1ll << 31) && C < (1ll << 31), "swap_dims12: bad sizes");
+    SPT_REQUIRE(row_bytes >= 16 && row_bytes % 16 == 0 && row_bytes / 16 < (1 << 20),
+                "swap_dims12: rows must be a multiple of 16 bytes (got %lld)", (long long)row_bytes);
+    SPT_REQUIRE(((uintptr_t)in | (uintptr_t)out) % 16 == 0, "swap_dims12: operands must be 16-byte aligned");
+    const int w16 = (int)(row_bytes / 16);
+    const long long n_words = (long long)A * B * C * w16;
+    long long blocks = (n_words + 256ll * layout::SW_UNROLL - 1) / (256ll * layout::SW_UNROLL);
+    const long long cap = (long long)num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    layout::swap12_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((const int4 *)in, (int4 *)out, n_words, (int)B,
+                                                                          (int)C, w16);
+    return after_launch("swap12_kernel");
+}
+
+extern "C" int spt_transpose_last2(const void *in, void *out, int64_t batch, int R, int C, int elem_bytes,
+                                   spt_stream_t stream) {
+    SPT_REQUIRE(in && out, "transpose_last2: null pointer");
+    SPT_REQUIRE(batch >= 1 && batch <= 65535 && R >= 1 && C >= 1, "transpose_last2: bad sizes");
+    SPT_REQUIRE((R + 63) / 64 <= 65535, "transpose_last2: too many rows");
+    const dim3 grid((C + 63) / 64, (R + 63) / 64, (unsigned)batch);
+    if (elem_bytes == 2)
+        layout::transpose_tile_kernel<uint16_t><<<grid, 256, 0, as_stream(stream)>>>((const uint16_t *)in, (uint16_t *)out, R, C);
+    else if (elem_bytes == 4)
+        layout::transpose_tile_kernel<uint32_t><<<grid, 256, 0, as_stream(stream)>>>((const uint32_t *)in, (uint32_t *)out, R, C);
+    else
+        return fail(SPT_ERR_INVALID_ARGUMENT, "transpose_last2: element size %d not supported (2 or 4)", elem_bytes);
+    return after_launch("transpose_tile_kernel");
+}

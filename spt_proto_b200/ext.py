@@ -730,3 +730,35 @@ def rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, transpose: bool 
     with _on_device(x):
         check(lib.spt_rope_bf16(_p(x), _p(cos), _p(sin), _p(out), N * S * H, S, H, E, int(transpose), _stream(x)))
     return out
+
+
+def swap12_supported(x: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dim() == 4 and x.is_contiguous() and x.numel() > 0
+            and (x.size(3) * x.element_size()) % 16 == 0 and x.data_ptr() % 16 == 0)
+
+
+def swap12(x: torch.Tensor) -> torch.Tensor:
+    """x [A, B, C, E] contiguous -> x.transpose(1, 2).contiguous() = [A, C, B, E] (16-byte-word row moves)."""
+    if not swap12_supported(x):
+        raise RuntimeError("swap12: need a contiguous 4-D CUDA tensor with rows of a multiple of 16 bytes")
+    A, B, C, E = x.shape
+    out = torch.empty(A, C, B, E, dtype=x.dtype, device=x.device)
+    with _on_device(x):
+        check(lib.spt_swap_dims12(_p(x), _p(out), A, B, C, E * x.element_size(), _stream(x)))
+    return out
+
+
+def transpose_last2_supported(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dim() == 3 and x.is_contiguous() and x.numel() > 0 and x.element_size() in (2, 4) \
+        and x.size(0) <= 65535
+
+
+def transpose_last2(x: torch.Tensor) -> torch.Tensor:
+    """x [B, R, C] contiguous -> x.transpose(1, 2).contiguous() = [B, C, R]."""
+    if not transpose_last2_supported(x):
+        raise RuntimeError("transpose_last2: need a contiguous 3-D CUDA tensor of 2- or 4-byte elements")
+    B, R, C = x.shape
+    out = torch.empty(B, C, R, dtype=x.dtype, device=x.device)
+    with _on_device(x):
+        check(lib.spt_transpose_last2(_p(x), _p(out), B, R, C, x.element_size(), _stream(x)))
+    return out

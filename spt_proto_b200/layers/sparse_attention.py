@@ -10,6 +10,7 @@ from __future__ import annotations
 import torch
 
 from .. import ext, kernels
+from ..kernels import layout
 from .basic import PQV1, PQV2, RotaryAttention, VanillaAttention
 
 
@@ -97,7 +98,7 @@ class _SparseV2Mixin:
 
     @staticmethod
     def _to_heads(x: torch.Tensor) -> torch.Tensor:  # [N, S, H, E] -> [N*H, S, E]
-        x = x.transpose(1, 2).contiguous()
+        x = layout.swap12(x)                         # transpose(1, 2).contiguous() as 16-byte-word row moves
         return x.view(-1, x.size(-2), x.size(-1))
 
     def _fused_ok(self, q) -> bool:
@@ -149,9 +150,8 @@ class _SparseV2Mixin:
         indptr, indices, values = attn
         y = kernels.spmm(indptr, indices, values, self._to_heads(v))
         if self.reference_output_layout:
-            return y.transpose(1, 2).contiguous().view(v_size)
-        y = y.view(v_size[0], v_size[2], v_size[1], v_size[3]).transpose(1, 2).contiguous()
-        return y.view(v_size)
+            return layout.transpose_last2(y).view(v_size)
+        return layout.swap12(y.view(v_size[0], v_size[2], v_size[1], v_size[3])).view(v_size)
 
 
 class SparseVanillaAttentionV2(_SparseV2Mixin, VanillaAttention):

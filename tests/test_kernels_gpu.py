@@ -457,6 +457,40 @@ def test_rope_fused_matches_torch_expression(shape):
     assert torch.equal(res[True][1], res[False][1])
 
 
+# ------------------------------------------------------------------------------ layout copies of the stage layer (layout.cu)
+@pytest.mark.parametrize("shape,dtype", [((2, 256, 12, 64), torch.float32), ((4, 2048, 32, 64), torch.bfloat16),
+                                         ((1, 70, 3, 128), torch.bfloat16), ((3, 5, 7, 8), torch.bfloat16),
+                                         ((2, 33, 5, 4), torch.float32)])
+def test_swap12_is_transpose_contiguous(shape, dtype):
+    """kernels.layout.swap12 == x.transpose(1, 2).contiguous() (reference attention.py:92-95), bit for bit, both ways."""
+    from spt_proto_b200.kernels import layout
+    from spt_proto_b200 import ext
+    g = torch.Generator(device="cpu").manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g).to(DEV).to(dtype)
+    assert ext.swap12_supported(x)
+    xi = x.clone().requires_grad_()
+    y = layout.swap12(xi)
+    assert y.is_contiguous() and torch.equal(y.detach(), x.transpose(1, 2).contiguous())
+    go = torch.randn(*y.shape, generator=g).to(DEV).to(dtype)
+    y.backward(go)
+    assert torch.equal(xi.grad, go.transpose(1, 2).contiguous())
+
+
+@pytest.mark.parametrize("shape,dtype", [((24, 256, 64), torch.float32), ((128, 2048, 64), torch.bfloat16),
+                                         ((3, 100, 20), torch.float32), ((5, 77, 129), torch.bfloat16), ((1, 1, 1), torch.bfloat16)])
+def test_transpose_last2_is_transpose_contiguous(shape, dtype):
+    """kernels.layout.transpose_last2 == y.transpose(1, 2).contiguous() (the shipped layer's output, attention.py:138-142)."""
+    from spt_proto_b200.kernels import layout
+    g = torch.Generator(device="cpu").manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g).to(DEV).to(dtype)
+    xi = x.clone().requires_grad_()
+    y = layout.transpose_last2(xi)
+    assert y.is_contiguous() and torch.equal(y.detach(), x.transpose(1, 2).contiguous())
+    go = torch.randn(*y.shape, generator=g).to(DEV).to(dtype)
+    y.backward(go)
+    assert torch.equal(xi.grad, go.transpose(1, 2).contiguous())
+
+
 def test_sddmm_scaled_matches_eager_clamp_chain():
     """kernels.sddmm_scaled (one kernel each way) == the reference's eager chain clamp_(scaling * sddmm(q, k), -10, 10)
     (layers/sparse/attention.py:122-127) incl. the clamp's zero gradient; scores scaled so that some are clamped."""
