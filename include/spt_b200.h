@@ -199,6 +199,12 @@ int spt_softmax_bwd(const int32_t *indptr, const int32_t *indices, const float *
 int spt_softmax_bwd_ex(const int32_t *indptr, const int32_t *indices, const float *output,
                        const float *grad_output, float *grad_values, int B, int S, int64_t nnz,
                        int reference_clamp, spt_stream_t stream);
+/* softmax backward through v = clamp(scale * raw, -clamp, clamp) (the layer's eager `clamp_(scaling * values, -10, 10)`,
+ * naive_gpt/layers/sparse/attention.py:125-127, in front of the softmax): grad_raw = scale * dv where |clamped| < clamp,
+ * else 0, with dv as above — spt_softmax_bwd_ex followed by spt_clamp_scale_bwd in one pass, bit-identical. */
+int spt_softmax_clamp_bwd(const int32_t *indptr, const int32_t *indices, const float *output,
+                          const float *grad_output, const float *clamped, float *grad_raw, int B, int S,
+                          int64_t nnz, float scale, float clamp, int reference_clamp, spt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused sparse attention (fast path of SparseVanillaAttentionV2 / SparseRotaryAttentionV2,

@@ -310,7 +310,8 @@ softmax_fwd_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
 __global__ void __launch_bounds__(CSR_WARPS * 32)
 softmax_bwd_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                    const float *__restrict__ output, const float *__restrict__ grad_output,
-                   float *__restrict__ grad_values, int B, int S, int64_t nnz, int reference_clamp) {
+                   float *__restrict__ grad_values, int B, int S, int64_t nnz, int reference_clamp,
+                   const float *__restrict__ clamped, float scale, float clamp) {
     const int lane = threadIdx.x & 31;
     const int64_t row_id = (int64_t)blockIdx.x * CSR_WARPS + (threadIdx.x >> 5);
     if (row_id >= (int64_t)B * S) return;
@@ -320,6 +321,10 @@ softmax_bwd_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
     const float *yp = output + (size_t)b * nnz;
     const float *gp = grad_output + (size_t)b * nnz;
     float *op = grad_values + (size_t)b * nnz;
+    // clamped != nullptr: the input of the softmax was v = clamp(scale * raw, -clamp, clamp) (the stage layer's scores) and the
+    // gradient w.r.t. raw is wanted: the clamp's zero-gradient mask and the scale are applied to the stored value (same
+    // roundings as softmax_bwd followed by clamp_scale_bwd: one pass instead of two over the nnz arrays)
+    const float *cp = clamped ? clamped + (size_t)b * nnz : nullptr;
     constexpr int KEEP = 8;
     float ys[KEEP], gs[KEEP];
     float sum = 0.0f;
@@ -337,7 +342,9 @@ softmax_bwd_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
         float yv, gv;
         if (it < KEEP) { yv = ys[it]; gv = gs[it]; }
         else { yv = (ip[e] <= r) ? yp[e] : 0.0f; gv = gp[e]; }
-        op[e] = yv * (gv - sum);
+        float o = yv * (gv - sum);
+        if (cp) o = (clamp <= 0.0f || fabsf(cp[e]) < clamp) ? o * scale : 0.0f;
+        op[e] = o;
     }
 }
 
@@ -1166,7 +1173,19 @@ extern "C" int spt_softmax_bwd_ex(const int32_t *indptr, const int32_t *indices,
     if (nnz == 0) return SPT_OK;
     const int64_t rows = (int64_t)B * S;
     softmax_bwd_kernel<<<(unsigned)((rows + CSR_WARPS - 1) / CSR_WARPS), CSR_WARPS * 32, 0, as_stream(stream)>>>(
-        indptr, indices, output, grad_output, grad_values, B, S, nnz, reference_clamp);
+        indptr, indices, output, grad_output, grad_values, B, S, nnz, reference_clamp, nullptr, 1.0f, 0.0f);
+    return after_launch("softmax_bwd_kernel");
+}
+
+extern "C" int spt_softmax_clamp_bwd(const int32_t *indptr, const int32_t *indices, const float *output,
+                                     const float *grad_output, const float *clamped, float *grad_raw, int B, int S,
+                                     int64_t nnz, float scale, float clamp, int reference_clamp, spt_stream_t stream) {
+    SPT_REQUIRE(indptr && indices && output && grad_output && clamped && grad_raw, "softmax_clamp_bwd: null pointer");
+    SPT_CHECK_CSR("softmax_clamp_bwd");
+    if (nnz == 0) return SPT_OK;
+    const int64_t rows = (int64_t)B * S;
+    softmax_bwd_kernel<<<(unsigned)((rows + CSR_WARPS - 1) / CSR_WARPS), CSR_WARPS * 32, 0, as_stream(stream)>>>(
+        indptr, indices, output, grad_output, grad_raw, B, S, nnz, reference_clamp, clamped, scale, clamp);
     return after_launch("softmax_bwd_kernel");
 }
 

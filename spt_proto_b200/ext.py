@@ -433,6 +433,24 @@ def softmax_backward_cuda(indptr, indices, output, grad_output) -> torch.Tensor:
     return grad_values
 
 
+def softmax_clamp_bwd(indptr, indices, output, grad_output, clamped, scale: float, clamp: float) -> torch.Tensor:
+    """softmax_backward_cuda followed by clamp_scale_bwd in one pass: the gradient w.r.t. the raw sddmm scores of
+    softmax(clamp(scale * raw, -clamp, clamp)), bit-identical to the two-kernel chain."""
+    _check_csr(indptr, indices, indptr.size(-1) - 1)
+    for name, t in (("output", output), ("grad_output", grad_output), ("clamped", clamped)):
+        _check_dim(t, 2, name)
+        _check_type(t, torch.float32, name)
+        if t.shape != indices.shape or not t.is_contiguous():
+            raise RuntimeError(f"{name} must be contiguous with the shape of indices")
+    B, nnz = indices.shape
+    S = indptr.size(-1) - 1
+    grad_raw = torch.empty_like(output)
+    with _on_device(output):
+        check(lib.spt_softmax_clamp_bwd(_p(indptr), _p(indices), _p(output), _p(grad_output), _p(clamped), _p(grad_raw), B, S,
+                                        nnz, float(scale), float(clamp), int(REFERENCE_SOFTMAX_CLAMP), _stream(output)))
+    return grad_raw
+
+
 def launch_count() -> int:
     """Kernel launches issued through libspt_b200 by this process so far."""
     return int(lib.spt_launch_count())

@@ -3,8 +3,8 @@
 from .cdist import cdist
 from .lookup import lookup
 from .softmax import softmax
-from .sddmm import sddmm, sddmm_scaled
+from .sddmm import sddmm, sddmm_scaled, sddmm_softmax
 from .spmm import spmm
 from .fused import sparse_attention
 
-__all__ = ["cdist", "lookup", "softmax", "sddmm", "sddmm_scaled", "spmm", "sparse_attention"]
+__all__ = ["cdist", "lookup", "softmax", "sddmm", "sddmm_scaled", "sddmm_softmax", "spmm", "sparse_attention"]

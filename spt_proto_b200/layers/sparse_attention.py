@@ -141,8 +141,9 @@ class _SparseV2Mixin:
         csr_indices = topk.flatten(start_dim=1)
         indptr = self._fixed_indptr(seq_length, seq_length // self.sparse_coeff, q.device)
         # sddmm + scale + clamp(-10, 10) of attention.py:122-127 in one kernel each way (no eager elementwise passes)
-        values = kernels.sddmm_scaled(indptr, csr_indices, q, k, self.scaling, 10.0)
-        values = kernels.softmax(indptr, csr_indices, values=values)
+        # (kernels.sddmm_softmax = kernels.sddmm_scaled + kernels.softmax with a one-pass backward from the gradient of
+        # the probabilities to the gradient of the raw scores)
+        values = kernels.sddmm_softmax(indptr, csr_indices, q, k, self.scaling, 10.0)
         return indptr, csr_indices, values
 
     def _apply_attn(self, attn, v):

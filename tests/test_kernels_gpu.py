@@ -515,6 +515,34 @@ def test_sddmm_scaled_matches_eager_clamp_chain():
     assert torch.allclose(g1[0], q.grad, atol=1e-4, rtol=1e-4) and torch.allclose(g1[1], kk.grad, atol=1e-4, rtol=1e-4)
 
 
+@pytest.mark.parametrize("dtype,B,S,d,k", [(torch.float32, 3, 256, 64, 32), (torch.bfloat16, 2, 512, 64, 64),
+                                           (torch.bfloat16, 2, 256, 128, 32)])
+def test_sddmm_softmax_is_the_two_function_chain(dtype, B, S, d, k):
+    """kernels.sddmm_softmax (what the stage layer calls) == kernels.softmax(kernels.sddmm_scaled(...)) of the reference's
+    _get_attn chain (layers/sparse/attention.py:122-130): same probabilities, and the one-pass backward (softmax backward +
+    clamp mask + scale) gives bit-identical gradients.  Scores are scaled so that some are clamped; rows see
+    future keys, so the causal predicate is exercised too."""
+    from spt_proto_b200 import kernels
+    torch.manual_seed(5 + S)
+    q = (torch.randn(B, S, d, device=DEV) * 3.0).to(dtype).requires_grad_()
+    kk = (torch.randn(B, S, d, device=DEV) * 3.0).to(dtype).requires_grad_()
+    idx = torch.stack([torch.stack([torch.randperm(S, device=DEV)[:k].sort().values for _ in range(S)]) for _ in range(B)])
+    idx = idx.to(torch.int32).flatten(1).contiguous()
+    indptr = torch.arange(0, k * S + 1, k, dtype=torch.int32, device=DEV)
+    g = torch.randn(B, S * k, device=DEV)
+    scale = d ** -0.5
+    p1 = kernels.sddmm_softmax(indptr, idx, q, kk, scale, 10.0)
+    p1.backward(g)
+    g1 = (q.grad.clone(), kk.grad.clone())
+    q.grad = kk.grad = None
+    v2 = kernels.sddmm_scaled(indptr, idx, q, kk, scale, 10.0)
+    p2 = kernels.softmax(indptr, idx, v2)
+    p2.backward(g)
+    assert (v2.detach().abs() >= 10.0).any() and (v2.detach().abs() < 10.0).any()
+    assert torch.equal(p1, p2)
+    assert torch.equal(g1[0], q.grad) and torch.equal(g1[1], kk.grad)
+
+
 # ---------------------------------------------------------------------------------- dense-tile transposed product
 def _spmm_t_want(indptr, indices, vals, x):
     """fp64 dense restatement of y = A^T x for a fixed-stride CSR (duplicates add up)."""
