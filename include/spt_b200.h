@@ -272,6 +272,11 @@ size_t spt_route_bucket_workspace_bytes(int64_t T, int nb);
 int spt_route_bucket(const float *prob, int32_t *bucket_ptr, int32_t *bucket_rows, int32_t *tile_group,
                      int32_t *row_token, float *row_prob, int32_t *token_rows, void *workspace,
                      int64_t T, int nb, int k_active, int64_t R, spt_stream_t stream);
+/* Router gradient of the LoRA-routed FFN (naive_gpt/layers/tuning/lora_ffn.py:92,206: the block outputs are scaled by
+ * 2 * prob[token, block]): grad_prob [T, nb] fp32 (cleared here) receives 2 * grad_coeff[r] at (row_token[r], block of
+ * row r) for every real bucket row — the backward of coeff = 2 * row_prob without torch's sort-based index_put. */
+int spt_row_coeff_bwd(const float *grad_coeff, const int32_t *row_token, const int32_t *tile_group,
+                      float *grad_prob, int64_t R, int64_t T, int nb, spt_stream_t stream);
 
 /* dst[r, :] = src[row_token[r], :] for r < R, zeros where row_token[r] < 0 (bf16, C % 8 == 0). */
 int spt_gather_rows_bf16(const void *src, const int32_t *row_token, void *dst, int64_t R, int C,

@@ -83,6 +83,7 @@ def _load() -> ctypes.CDLL:
     sig["spt_ffn_combine"] = (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp])
     sig["spt_group_colsum_workspace_bytes"] = (sz, [i32, i32])
     sig["spt_group_colsum_bf16"] = (i32, [vp, vp, vp, vp, i32, i32, vp])
+    sig["spt_row_coeff_bwd"] = (i32, [vp, vp, vp, vp, i64, i64, i32, vp])
     sig["spt_softmax_clamp_bwd"] = (i32, [vp] * 6 + [i32, i32, i64, f32, f32, i32, vp])
     sig["spt_swap_dims12"] = (i32, [vp, vp, i64, i64, i64, i64, vp])
     sig["spt_transpose_last2"] = (i32, [vp, vp, i64, i32, i32, i32, vp])

@@ -248,10 +248,32 @@ colsum_stage2(const float *__restrict__ partial, float *__restrict__ out, int C)
     out[(long long)g * C + c] = acc;
 }
 
+// router gradient of the LoRA-routed FFN: coeff[r] = 2 * prob[token(r), block(r)] (lora_ffn.py:92,206), so
+// grad_prob[token(r), block(r)] = 2 * grad_coeff[r]; every (token, block) pair owns at most one bucket row: plain stores
+__global__ void __launch_bounds__(256)
+row_coeff_bwd_kernel(const float *__restrict__ grad_coeff, const int32_t *__restrict__ row_token,
+                     const int32_t *__restrict__ tile_group, float *__restrict__ grad_prob, long long R, int nb) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int t = row_token[r], g = tile_group[r >> 7];
+    if (t >= 0 && g >= 0) grad_prob[(long long)t * nb + g] = 2.0f * grad_coeff[r];
+}
+
 }  // namespace route
 }  // namespace spt
 
 using namespace spt;
+
+extern "C" int spt_row_coeff_bwd(const float *grad_coeff, const int32_t *row_token, const int32_t *tile_group,
+                                 float *grad_prob, int64_t R, int64_t T, int nb, spt_stream_t stream) {
+    SPT_REQUIRE(grad_coeff && row_token && tile_group && grad_prob, "row_coeff_bwd: null pointer");
+    SPT_REQUIRE(R >= 128 && R % 128 == 0 && T >= 1 && nb >= 1 && nb <= 64, "row_coeff_bwd: bad sizes");
+    cudaStream_t st = as_stream(stream);
+    if (cudaMemsetAsync(grad_prob, 0, (size_t)T * nb * sizeof(float), st) != cudaSuccess)
+        return fail(SPT_ERR_CUDA, "row_coeff_bwd: memset failed");
+    route::row_coeff_bwd_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(grad_coeff, row_token, tile_group, grad_prob, R, nb);
+    return after_launch("row_coeff_bwd_kernel");
+}
 
 extern "C" size_t spt_route_bucket_workspace_bytes(int64_t T, int nb) {
     const size_t n_chunks = (size_t)(T + route::CHUNK - 1) / route::CHUNK;

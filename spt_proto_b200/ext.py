@@ -585,6 +585,18 @@ def route_bucket(prob: torch.Tensor, k_active: int) -> Bucket:
     return b
 
 
+def row_coeff_bwd(grad_coeff: torch.Tensor, bucket: "Bucket") -> torch.Tensor:
+    """grad_prob [T, nb] fp32 of coeff[r] = 2 * prob[token(r), block(r)] (zeros where a (token, block) pair is inactive)."""
+    _check_type(grad_coeff, torch.float32, "grad_coeff")
+    if grad_coeff.numel() != bucket.R or not grad_coeff.is_contiguous():
+        raise RuntimeError("grad_coeff must be a contiguous [R] tensor")
+    grad_prob = torch.empty(bucket.T, bucket.nb, dtype=torch.float32, device=grad_coeff.device)
+    with _on_device(grad_coeff):
+        check(lib.spt_row_coeff_bwd(_p(grad_coeff), _p(bucket.row_token), _p(bucket.tile_group), _p(grad_prob), bucket.R,
+                                    bucket.T, bucket.nb, _stream(grad_coeff)))
+    return grad_prob
+
+
 def gather_rows(src: torch.Tensor, row_token: torch.Tensor) -> torch.Tensor:
     """dst[r] = src[row_token[r]] (zeros for padding rows); src [T, C] bf16."""
     _check_dim(src, 2, "src")

@@ -19,6 +19,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from .. import ext
 from ..kernels import ffn as F
 from .basic import Feedforward, LLaMaFeedforward
 from .routed_ffn import RoutedFFN, RoutedLLaMaFFN, _route
@@ -51,7 +52,11 @@ class LoRALinear(nn.Linear):
 
     def forward(self, x):
         y = nn.functional.linear(x, self.weight, self.bias)
-        return y + (x @ self.lora.left.weight) @ self.lora.right.weight.t()
+        # y + (x L) R^T with the addition in the second product's epilogue (one pass less over y than a separate add)
+        # (in place on the fresh product: an out-of-place addmm would first copy y)
+        t = x.reshape(-1, x.size(-1)) @ self.lora.left.weight
+        y.view(-1, y.size(-1)).addmm_(t, self.lora.right.weight.t())
+        return y
 
 
 class LoRAEmbedding(nn.Embedding):
@@ -73,14 +78,25 @@ class LoRAEmbedding(nn.Embedding):
         return nn.functional.embedding(x, self.weight) + self.lora.left(x) @ self.lora.right.weight.t()
 
 
+class _RowCoeff(torch.autograd.Function):
+    """coeff[r] = 2 * prob[token(r), block(r)] for real bucket rows, 0 for padding — differentiable in prob (this is how
+    the router is trained, lora_ffn.py:92,206).  route_bucket already gathered prob[token, block] per row (row_prob), so
+    the forward is one multiply; the backward writes 2 * grad to the row's (token, block) cell with plain stores (every
+    pair owns at most one row) instead of torch's index chain and sort-based index_put backward (~25 small kernels)."""
+
+    @staticmethod
+    def forward(ctx, prob, bucket):
+        ctx.bucket, ctx.p_dtype = bucket, prob.dtype
+        return bucket.row_prob * 2.0
+
+    @staticmethod
+    def backward(ctx, grad):
+        return ext.row_coeff_bwd(grad.float().contiguous(), ctx.bucket).to(ctx.p_dtype), None
+
+
 def _row_coeff(prob: torch.Tensor, bucket) -> torch.Tensor:
-    """coeff[r] = 2 * prob[token(r), block(r)] for real bucket rows, 0 for padding — differentiable in prob
-    (this is how the router is trained, lora_ffn.py:92,206)."""
-    nb = prob.size(1)
-    group = bucket.tile_group.clamp(min=0).long().repeat_interleave(128)
-    valid = bucket.row_token >= 0
-    flat = bucket.row_token.clamp(min=0).long() * nb + group
-    return 2.0 * prob.reshape(-1)[flat] * valid
+    """prob [T, nb] must hold the values route_bucket() bucketed (its fp32 copy): coeff comes from bucket.row_prob."""
+    return _RowCoeff.apply(prob, bucket)
 
 
 def _bf16(t: torch.Tensor) -> torch.Tensor:

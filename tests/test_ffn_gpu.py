@@ -506,3 +506,26 @@ def test_silu_mul_matches_torch_autograd():
     assert torch.allclose(h.float(), hf, atol=2e-2, rtol=1e-2)
     assert torch.allclose(g.grad.float(), gf.grad, atol=2e-2, rtol=2e-2)
     assert torch.allclose(s.grad.float(), sf.grad, atol=2e-2, rtol=2e-2)
+
+
+def test_row_coeff_matches_torch_index_chain():
+    """layers.lora._row_coeff (2 * row_prob forward, spt_row_coeff_bwd backward) == the torch formulation it replaced:
+    coeff[r] = 2 * prob[token(r), block(r)] * valid(r), differentiable in prob (lora_ffn.py:92,206), bit for bit."""
+    from spt_proto_b200 import ext
+    from spt_proto_b200.layers.lora import _row_coeff
+    torch.manual_seed(11)
+    for T, nb, k in ((1000, 8, 4), (77, 16, 4), (2048, 4, 2)):
+        prob = torch.rand(T, nb, device=DEV).bfloat16().float()
+        bucket = ext.route_bucket(prob.contiguous(), k)
+        g = torch.randn(bucket.R, device=DEV)
+        p1 = prob.clone().requires_grad_()
+        c1 = _row_coeff(p1, bucket)
+        c1.backward(g)
+        p2 = prob.clone().requires_grad_()
+        group = bucket.tile_group.clamp(min=0).long().repeat_interleave(128)
+        valid = bucket.row_token >= 0
+        flat = bucket.row_token.clamp(min=0).long() * nb + group
+        c2 = 2.0 * p2.reshape(-1)[flat] * valid
+        c2.backward(g)
+        assert torch.equal(c1.detach(), c2.detach())
+        assert torch.equal(p1.grad, p2.grad)
