@@ -316,20 +316,24 @@ attn_bwd_prep_t_kernel(const __nv_bfloat16 *__restrict__ dyt, const __nv_bfloat1
     __shared__ __align__(16) __nv_bfloat16 s_y[D][LD];
     const int b = blockIdx.y, r0 = blockIdx.x * TR;
     const size_t base = (size_t)b * D * S + r0;
+    constexpr int EPT = D / 4;                       // features per thread
+    // the 16-byte row chunks of feature e sit at chunk index (c / 8) ^ (e / EPT): the four threads of a row read the
+    // same column of four features 16 * LD elements apart (the same bank without the swizzle: 4-way conflicts on
+    // every one of the 2 * EPT reads)
     for (int id = threadIdx.x; id < D * (TR / 8); id += 256) {
-        const int e = id / (TR / 8), c = (id % (TR / 8)) * 8;
-        *reinterpret_cast<uint4 *>(&s_dy[e][c]) = *reinterpret_cast<const uint4 *>(dyt + base + (size_t)e * S + c);
-        *reinterpret_cast<uint4 *>(&s_y[e][c]) = *reinterpret_cast<const uint4 *>(yt + base + (size_t)e * S + c);
+        const int e = id / (TR / 8), c = (id % (TR / 8)) * 8, cs = (((id % (TR / 8)) ^ (e / EPT)) & (TR / 8 - 1)) * 8;
+        *reinterpret_cast<uint4 *>(&s_dy[e][cs]) = *reinterpret_cast<const uint4 *>(dyt + base + (size_t)e * S + c);
+        *reinterpret_cast<uint4 *>(&s_y[e][cs]) = *reinterpret_cast<const uint4 *>(yt + base + (size_t)e * S + c);
     }
     __syncthreads();
     const int r = threadIdx.x >> 2, qd = threadIdx.x & 3;
-    constexpr int EPT = D / 4;                       // features per thread
+    const int rs = ((((r >> 3) ^ qd) & (TR / 8 - 1)) << 3) | (r & 7);
     float a[EPT];
     float acc = 0.0f;
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
-        a[i] = __bfloat162float(s_dy[qd * EPT + i][r]);
-        acc = fmaf(a[i], __bfloat162float(s_y[qd * EPT + i][r]), acc);
+        a[i] = __bfloat162float(s_dy[qd * EPT + i][rs]);
+        acc = fmaf(a[i], __bfloat162float(s_y[qd * EPT + i][rs]), acc);
     }
     acc = group_sum<4>(acc);
     const size_t grow = (size_t)b * S + r0 + r;
