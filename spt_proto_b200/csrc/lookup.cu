@@ -46,16 +46,37 @@ lookup_pack_kernel(const int32_t *__restrict__ key_codes, uint32_t *__restrict__
     // codes are [N, S, H, m] (heads interleaved; H = 1: [B, S, m])
     const int32_t *kp = key_codes + (((size_t)(b / H) * S + j) * H + (b % H)) * m;
     bool overflow = false;
-    for (int s = 0; s < m; ++s) {
-        const unsigned code = (j < S) ? ((unsigned)kp[s] & 0xffffu) : 0xffffu;
-        overflow |= (j < S) && (code >= (unsigned)LK_CV);
-        unsigned mine = 0;
+    // m = 8 / 16 (the PQ shapes of the layer): the key's codes are fetched with 16-byte loads up front — the loop below
+    // would otherwise issue one dependent 4-byte load per subspace between its ballots (a latency chain per block)
+    int32_t pre[16];
+    const bool fast = (m == 8 || m == 16) && (reinterpret_cast<uintptr_t>(key_codes) % 16 == 0);
+    if (fast && j < S) {
 #pragma unroll
-        for (int v = 0; v < LK_CV; ++v) {
-            const unsigned word = __ballot_sync(FULL, code == (unsigned)v);
-            if (i == v) mine = word;
+        for (int q = 0; q < 4; ++q)
+            if (q * 4 < m) {
+                const int4 v = *reinterpret_cast<const int4 *>(kp + q * 4);
+                pre[q * 4] = v.x; pre[q * 4 + 1] = v.y; pre[q * 4 + 2] = v.z; pre[q * 4 + 3] = v.w;
+            }
+    }
+#pragma unroll 1
+    for (int s0 = 0; s0 < m; s0 += 8) {
+#pragma unroll
+      for (int ss = 0; ss < 8; ++ss) {
+        const int s = s0 + ss;
+        if (s >= m) break;
+        const unsigned code = (j < S) ? ((unsigned)(fast ? pre[s0 == 0 ? ss : ss + 8] : kp[s]) & 0xffffu) : 0xffffu;
+        overflow |= (j < S) && (code >= (unsigned)LK_CV);
+        // lane v (< 16) wants the mask of keys whose code is v: four ballots over the code's bits, each lane keeps or
+        // complements them according to its own index (16 compare + ballot + select rounds took 770 instructions per warp)
+        static_assert(LK_CV == 16, "four code bits");
+        unsigned mine = __ballot_sync(FULL, code < (unsigned)LK_CV);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned bk = __ballot_sync(FULL, (code >> k) & 1u);
+            mine &= ((i >> k) & 1) ? bk : ~bk;
         }
         if (i < LK_CV) kb[(((size_t)b * m + s) * W + w) * LK_WORD_U32 + i * 4 + t] = mine;
+      }
     }
     if (__any_sync(FULL, overflow) && i == 0) atomicOr(flag, 1);
 }
