@@ -238,3 +238,21 @@ def test_pair_gemm_plan_rejects_bad_arguments():
     assert lib.spt_grouped_gemm_plan(tg.ctypes.data_as(ctypes.c_void_p), 0, 1, None, 0) < 0
     assert lib.spt_grouped_gemm_plan(tg.ctypes.data_as(ctypes.c_void_p), 4, 0, None, 0) < 0
     assert lib.spt_grouped_gemm_plan(tg.ctypes.data_as(ctypes.c_void_p), 2000, 1, None, 0) < 0
+
+
+def test_layout_helpers_fall_back_to_torch_on_cpu():
+    """kernels.layout.swap12 / transpose_last2 use the CUDA copy kernels only where they apply; anything else (CPU tensors
+    in the host-logic tests, odd row sizes) takes torch's own transpose(1, 2).contiguous() with the same result."""
+    from spt_proto_b200 import ext
+    from spt_proto_b200.kernels import layout
+    x = torch.randn(2, 5, 3, 8, requires_grad=True)
+    assert not ext.swap12_supported(x)
+    y = layout.swap12(x)
+    assert y.is_contiguous() and torch.equal(y, x.transpose(1, 2).contiguous())
+    y.sum().backward()
+    assert torch.equal(x.grad, torch.ones_like(x))
+    z = torch.randn(3, 7, 5)
+    assert not ext.transpose_last2_supported(z)
+    assert torch.equal(layout.transpose_last2(z), z.transpose(1, 2).contiguous())
+    with pytest.raises(RuntimeError):
+        ext.swap12(x.detach())          # the ext entry points themselves never fall back
