@@ -56,7 +56,7 @@ def build_model(dev, n_layers: int, d_lora: int):
 
 
 def run(dev, rank: int, world: int, steps: int = 5, warmup: int = 2, seq: int = 2048, batch: int = 1, n_layers: int = 4,
-        d_lora: int = 16, graph: bool = True, overlap: bool = True, n_buckets: int = 4) -> dict:
+        d_lora: int = 16, graph: bool = True, overlap: bool = True, n_buckets: int = 4, data_seed=None) -> dict:
     """Times the step on this rank's GPU (collective when world > 1: torch.distributed must be initialised) and
     returns the result line as a dict (identical on every rank; times are the max over ranks)."""
     import torch.distributed as dist
@@ -69,7 +69,7 @@ def run(dev, rank: int, world: int, steps: int = 5, warmup: int = 2, seq: int = 
     n_train = sum(p.numel() for p in trainable)
     reducer = GradReducer(trainable, n_buckets=n_buckets, overlap=overlap)
     opt = torch.optim.AdamW(trainable, lr=1e-4, weight_decay=1e-2, capturable=graph)
-    torch.manual_seed(1234 + rank)
+    torch.manual_seed(1234 + rank if data_seed is None else data_seed)   # every rank its own batch
     x = torch.randn(batch, seq, d_model, device=dev).bfloat16()
     target = torch.randn(batch, seq, d_model, device=dev).bfloat16()
 
@@ -186,6 +186,8 @@ def main():
                     help="capture forward + backward + all-reduce + optimizer of one step in a CUDA graph and replay it")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after backward instead of from backward hooks")
     ap.add_argument("--buckets", type=int, default=4)
+    ap.add_argument("--data-seed", type=int, default=None,
+                    help="seed of this rank's batch (default 1234 + rank): run one GPU on another rank's data")
     args = ap.parse_args()
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
@@ -197,7 +199,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     line = run(dev, rank, world, steps=args.steps, warmup=args.warmup, seq=args.seq, batch=args.batch,
                n_layers=args.layers, d_lora=args.d_lora, graph=args.graph, overlap=not args.no_overlap,
-               n_buckets=args.buckets)
+               n_buckets=args.buckets, data_seed=args.data_seed)
     if rank == 0:
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
