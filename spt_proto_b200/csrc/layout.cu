@@ -12,35 +12,30 @@ namespace layout {
 // out[a, c, b, :] = in[a, b, c, :], rows of `w16` 16-byte words.  One thread per (output row, word), consecutive threads
 // = consecutive words of consecutive output rows (stores fully coalesced, loads in whole rows of >= 64 bytes).
 constexpr int SW_UNROLL = 4;
+// I = unsigned where the word count fits 32 bits: the three divisions per word are the kernel's instruction budget
+// (62 % issue-active with 64-bit indices), 32-bit ones cost a quarter of that
+template <typename I>
+__device__ __forceinline__ I swap12_src(I o, I Bd, I Cd, I w16) {
+    const I row = o / w16, w = o - row * w16;
+    const I ac = row / Bd, b = row - ac * Bd;     // output row = (a, c, b)
+    const I a = ac / Cd, c = ac - a * Cd;
+    return ((a * Bd + b) * Cd + c) * w16 + w;
+}
+template <typename I>
 __global__ void __launch_bounds__(256)
-swap12_kernel(const int4 *__restrict__ in, int4 *__restrict__ out, long long n_words, int Bd, int Cd, int w16) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+swap12_kernel(const int4 *__restrict__ in, int4 *__restrict__ out, long long n_words_ll, int Bd_, int Cd_, int w16_) {
+    const I n_words = (I)n_words_ll, Bd = (I)Bd_, Cd = (I)Cd_, w16 = (I)w16_;
+    const I stride = (I)gridDim.x * blockDim.x;
+    I i = (I)blockIdx.x * blockDim.x + threadIdx.x;
+    // (i + 3 * stride cannot wrap: the launcher keeps n_words + 4 * stride below 2^32 for the 32-bit instance)
     for (; i + (SW_UNROLL - 1) * stride < n_words; i += SW_UNROLL * stride) {
         int4 v[SW_UNROLL];
 #pragma unroll
-        for (int u = 0; u < SW_UNROLL; ++u) {
-            const long long o = i + u * stride;
-            const long long row = o / w16;
-            const int w = (int)(o - row * w16);
-            const long long ac = row / Bd;           // output row = (a, c, b)
-            const int b = (int)(row - ac * Bd);
-            const long long a = ac / Cd;
-            const int c = (int)(ac - a * Cd);
-            v[u] = ld_stream(in + (((a * Bd + b) * Cd + c) * w16 + w));
-        }
+        for (int u = 0; u < SW_UNROLL; ++u) v[u] = ld_stream(in + swap12_src<I>(i + u * stride, Bd, Cd, w16));
 #pragma unroll
-        for (int u = 0; u < SW_UNROLL; ++u) st_stream(out + i + u * stride, v[u]);
+        for (int u = 0; u < SW_UNROLL; ++u) st_stream(out + (i + u * stride), v[u]);
     }
-    for (; i < n_words; i += stride) {
-        const long long row = i / w16;
-        const int w = (int)(i - row * w16);
-        const long long ac = row / Bd;
-        const int b = (int)(row - ac * Bd);
-        const long long a = ac / Cd;
-        const int c = (int)(ac - a * Cd);
-        st_stream(out + i, ld_stream(in + (((a * Bd + b) * Cd + c) * w16 + w)));
-    }
+    for (; i < n_words; i += stride) st_stream(out + i, ld_stream(in + swap12_src<I>(i, Bd, Cd, w16)));
 }
 
 // out[b, c, r] = in[b, r, c] for 2-byte (T = uint16_t) or 4-byte elements: 64 x 64 tiles through shared memory
@@ -77,8 +72,12 @@ extern "C" int spt_swap_dims12(const void *in, void *out, int64_t A, int64_t B, 
     long long blocks = (n_words + 256ll * layout::SW_UNROLL - 1) / (256ll * layout::SW_UNROLL);
     const long long cap = (long long)num_sms() * 32;
     if (blocks > cap) blocks = cap;
-    layout::swap12_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((const int4 *)in, (int4 *)out, n_words, (int)B,
-                                                                          (int)C, w16);
+    if (n_words + 4 * blocks * 256 < (1ll << 32))
+        layout::swap12_kernel<unsigned><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((const int4 *)in, (int4 *)out, n_words,
+                                                                                      (int)B, (int)C, w16);
+    else
+        layout::swap12_kernel<long long><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((const int4 *)in, (int4 *)out, n_words,
+                                                                                       (int)B, (int)C, w16);
     return after_launch("swap12_kernel");
 }
 
