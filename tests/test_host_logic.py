@@ -256,3 +256,23 @@ def test_layout_helpers_fall_back_to_torch_on_cpu():
     assert torch.equal(layout.transpose_last2(z), z.transpose(1, 2).contiguous())
     with pytest.raises(RuntimeError):
         ext.swap12(x.detach())          # the ext entry points themselves never fall back
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    """`bench.py --impl reference` (the oracle port on the host cores; no GPU, no /root/reference at run time) prints one
+    JSON line with the driver's keys, honours --steps / --warmup, and reports the same metric / unit as the GPU arm."""
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-heads", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "sparse_mha_fwd_bwd_tokens_per_s" and d["unit"] == "tokens/s"
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
