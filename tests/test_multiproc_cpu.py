@@ -70,7 +70,23 @@ def _worker(rank, world, port, ret):
             ok_reducer &= torch.allclose(p.grad, sum(parts) / world)
             ok_reducer &= any(p.grad.data_ptr() >= f.data_ptr() and
                               p.grad.data_ptr() < f.data_ptr() + f.numel() * f.element_size() for f in reducer.flats)
-    ret[rank] = (ok_shard, ok_grad, n_calls, bool(ok_reducer))
+    reducer.remove()
+
+    # (4) the non-overlapped form the 2-GPU measurements compare against: no hooks, ONE bucket,
+    # everything reduced by finish() after backward
+    torch.manual_seed(2)
+    lin = torch.nn.Linear(6, 3)
+    plain = GradReducer(list(lin.parameters()), n_buckets=1, overlap=False)
+    plain.zero_grad()
+    loss = lin(torch.full((4, 6), float(rank + 1))).sum() * (rank + 2)
+    own = torch.autograd.grad(loss, list(lin.parameters()), retain_graph=True)
+    loss.backward()
+    ok_plain = plain.n_buckets == 1 and plain.finish() == 1
+    for p, g in zip(lin.parameters(), own):
+        parts = [torch.zeros_like(g) for _ in range(world)]
+        dist.all_gather(parts, g.clone())
+        ok_plain &= torch.allclose(p.grad, sum(parts) / world)
+    ret[rank] = (ok_shard, ok_grad, n_calls, bool(ok_reducer) and bool(ok_plain))
     dist.destroy_process_group()
 
 
